@@ -1,0 +1,280 @@
+"""Model loading for the frame-upscale path.
+
+Two on-disk formats are understood:
+
+* the ncnn pair ``<name>.param`` (text graph) + ``<name>.bin`` (raw weight blob) that the
+  reference hands to ``ncnn.Net.load_param/load_model`` in ``init_worker``
+  (reference ``upscale/upscale_processing.py:70-71``; files ``models/*.param|.bin``);
+* ``<name>.b2sr`` -- this repo's own single-file container (JSON graph + little-endian arrays,
+  fp16 wherever that is lossless) produced by ``tools/convert_models.py`` from the ncnn pair.
+
+Both decode to the same in-memory :class:`Graph`.  The graph is then *recognised* as one of the network
+families the CUDA engine runs (``compact_desc``) and its parameters packed into the flat blob that
+``b2sr_create`` (``include/b2sr.h``) takes.
+
+ncnn text grammar (public ncnn format): line 1 magic ``7767517``; line 2 ``<layers> <blobs>``; then per layer
+``type name n_in n_out in... out... key=value...`` where a key ``-233xx`` introduces an array
+``count,v0,v1...`` for parameter id ``xx``.  ``.bin`` layout per Convolution: u32 tag (``0x01306B47`` -> fp16
+weights padded to 4 bytes, ``0`` -> raw fp32), weights in OIHW order, then fp32 bias when ``5=1``; PReLU:
+raw fp32 slopes with no tag.
+"""
+from __future__ import annotations
+
+import json
+import os
+import struct
+from dataclasses import dataclass, field
+
+import numpy as np
+
+NCNN_MAGIC = "7767517"
+FP16_TAG = 0x01306B47
+B2SR_MAGIC = b"B2SRv1\0\0"
+
+
+@dataclass
+class Layer:
+    type: str
+    name: str
+    bottoms: list
+    tops: list
+    params: dict = field(default_factory=dict)  # int id -> int | float | list
+    weights: dict = field(default_factory=dict)  # "weight" | "bias" | "slope" -> np.ndarray
+
+    def p(self, key, default=0):
+        return self.params.get(key, default)
+
+
+@dataclass
+class Graph:
+    layers: list
+    n_blobs: int = 0
+
+    def convs(self):
+        return [l for l in self.layers if l.type == "Convolution"]
+
+    def nbytes(self):
+        return sum(a.nbytes for l in self.layers for a in l.weights.values())
+
+
+def _parse_value(text):
+    try:
+        return int(text)
+    except ValueError:
+        return float(text)
+
+
+def parse_param(text: str) -> Graph:
+    lines = [ln.strip() for ln in text.splitlines() if ln.strip()]
+    if lines[0] != NCNN_MAGIC:
+        raise ValueError("not an ncnn param file (magic %r)" % lines[0])
+    n_layers, n_blobs = (int(v) for v in lines[1].split())
+    layers = []
+    for ln in lines[2:]:
+        tok = ln.split()
+        ltype, name, n_in, n_out = tok[0], tok[1], int(tok[2]), int(tok[3])
+        bottoms = tok[4 : 4 + n_in]
+        tops = tok[4 + n_in : 4 + n_in + n_out]
+        params = {}
+        for kv in tok[4 + n_in + n_out :]:
+            k, v = kv.split("=", 1)
+            k = int(k)
+            if k <= -23300:  # array parameter: "-233xx=count,v0,v1,..."
+                items = v.split(",")
+                params[-k - 23300] = [_parse_value(x) for x in items[1 : 1 + int(items[0])]]
+            else:
+                params[k] = _parse_value(v)
+        layers.append(Layer(ltype, name, bottoms, tops, params))
+    if len(layers) != n_layers:
+        raise ValueError("param file declares %d layers, found %d" % (n_layers, len(layers)))
+    return Graph(layers, n_blobs)
+
+
+def attach_bin(graph: Graph, blob: bytes) -> int:
+    """Consume ``blob`` in layer order; returns the number of bytes used (must equal len(blob))."""
+    off = 0
+    for l in graph.layers:
+        if l.type == "Convolution":
+            count = int(l.p(6))
+            (tag,) = struct.unpack_from("<I", blob, off)
+            off += 4
+            if tag == FP16_TAG:
+                w = np.frombuffer(blob, "<f2", count, off).copy()
+                off += (count * 2 + 3) & ~3
+            elif tag == 0:
+                w = np.frombuffer(blob, "<f4", count, off).copy()
+                off += count * 4
+            else:
+                raise ValueError("unsupported ncnn weight tag 0x%08x in %s" % (tag, l.name))
+            cout, k = int(l.p(0)), int(l.p(1))
+            cin = count // (cout * k * k)
+            l.weights["weight"] = w.reshape(cout, cin, k, k)
+            if l.p(5):
+                l.weights["bias"] = np.frombuffer(blob, "<f4", cout, off).copy()
+                off += cout * 4
+        elif l.type == "PReLU":
+            n = int(l.p(0))
+            l.weights["slope"] = np.frombuffer(blob, "<f4", n, off).copy()
+            off += n * 4
+    return off
+
+
+def load_ncnn(param_path: str, bin_path: str) -> Graph:
+    with open(param_path, "r") as f:
+        g = parse_param(f.read())
+    with open(bin_path, "rb") as f:
+        blob = f.read()
+    used = attach_bin(g, blob)
+    if used != len(blob):
+        raise ValueError("%s: consumed %d of %d bytes" % (bin_path, used, len(blob)))
+    return g
+
+
+# ----------------------------------------------------------------------------------------------
+# .b2sr container
+# ----------------------------------------------------------------------------------------------
+def _fp16_lossless(a: np.ndarray) -> bool:
+    return a.dtype == np.float32 and bool(np.array_equal(a.astype(np.float16).astype(np.float32), a))
+
+
+def save_b2sr(graph: Graph, path: str) -> None:
+    """Arrays keep the ncnn (OIHW) element order; weights are narrowed to fp16 only when that is exact."""
+    meta, chunks, off = [], [], 0
+    for l in graph.layers:
+        entry = {"type": l.type, "name": l.name, "bottoms": l.bottoms, "tops": l.tops,
+                 "params": {str(k): v for k, v in l.params.items()}, "arrays": {}}
+        for key, arr in l.weights.items():
+            if key == "weight" and _fp16_lossless(arr):
+                arr = arr.astype(np.float16)
+            raw = np.ascontiguousarray(arr).astype(arr.dtype.newbyteorder("<")).tobytes()
+            entry["arrays"][key] = {"dtype": arr.dtype.name, "shape": list(arr.shape), "offset": off,
+                                    "nbytes": len(raw)}
+            pad = (-len(raw)) % 16
+            chunks.append(raw + b"\0" * pad)
+            off += len(raw) + pad
+        meta.append(entry)
+    header = json.dumps({"n_blobs": graph.n_blobs, "layers": meta}, separators=(",", ":")).encode()
+    header += b" " * ((-(len(B2SR_MAGIC) + 4 + len(header))) % 16)
+    with open(path, "wb") as f:
+        f.write(B2SR_MAGIC)
+        f.write(struct.pack("<I", len(header)))
+        f.write(header)
+        for c in chunks:
+            f.write(c)
+
+
+def load_b2sr(path: str) -> Graph:
+    with open(path, "rb") as f:
+        data = f.read()
+    if data[:8] != B2SR_MAGIC:
+        raise ValueError("%s: not a b2sr model" % path)
+    (hlen,) = struct.unpack_from("<I", data, 8)
+    head = json.loads(data[12 : 12 + hlen].decode())
+    base = 12 + hlen
+    layers = []
+    for e in head["layers"]:
+        l = Layer(e["type"], e["name"], e["bottoms"], e["tops"], {int(k): v for k, v in e["params"].items()})
+        for key, a in e["arrays"].items():
+            arr = np.frombuffer(data, np.dtype(a["dtype"]).newbyteorder("<"), int(np.prod(a["shape"])),
+                                base + a["offset"])
+            l.weights[key] = arr.reshape(a["shape"]).astype(a["dtype"])
+        layers.append(l)
+    return Graph(layers, head.get("n_blobs", 0))
+
+
+def packaged_model_dir() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "models")
+
+
+def load_model(model_path: str, stem: str) -> Graph:
+    """Resolve ``<model_path>/<stem>`` the way ``init_worker`` names models (reference
+    ``upscale_processing.py:70-71``: ``str(scale) + model_file`` + ``.param``/``.bin``), preferring the
+    ncnn pair, then a ``.b2sr`` beside it, then the converted copy packaged with this repo."""
+    param = os.path.join(model_path, stem + ".param")
+    binf = os.path.join(model_path, stem + ".bin")
+    if os.path.exists(param) and os.path.exists(binf):
+        return load_ncnn(param, binf)
+    for d in (model_path, packaged_model_dir()):
+        cand = os.path.join(d, stem + ".b2sr")
+        if os.path.exists(cand):
+            return load_b2sr(cand)
+    raise FileNotFoundError("model %s(.param/.bin|.b2sr) not found under %s" % (stem, model_path))
+
+
+# ----------------------------------------------------------------------------------------------
+# Family recognition + blob packing for the C ABI
+# ----------------------------------------------------------------------------------------------
+FAMILY_COMPACT = 1  # SRVGGNetCompact: conv(cin->nf)+PReLU, n_mid x [conv(nf->nf)+PReLU], conv(nf->cin*r^2),
+#                     PixelShuffle(r) + nearest-upsample(input, r)   (reference models/2x_Compact_Pretrain.param:3-42)
+
+
+@dataclass
+class CompactDesc:
+    cin: int
+    nf: int
+    n_mid: int
+    scale: int
+    cout_last: int
+    input_blob: str
+    output_blob: str
+
+
+def compact_desc(graph: Graph) -> CompactDesc | None:
+    """Return the SRVGGNetCompact description of ``graph`` or None when it is some other topology
+    (e.g. the RRDB ``4x_Valar_v1``).  The check is structural and strict: every layer must be accounted for."""
+    ls = graph.layers
+    if len(ls) < 8 or ls[0].type != "Input" or ls[1].type != "Split" or len(ls[1].tops) != 2:
+        return None
+    skip_blob, x = ls[1].tops[0], ls[1].tops[1]
+    i, convs = 2, []
+    while i + 1 < len(ls) and ls[i].type == "Convolution" and ls[i + 1].type == "PReLU":
+        c, p = ls[i], ls[i + 1]
+        if c.bottoms != [x] or p.bottoms != c.tops:
+            return None
+        convs.append(c)
+        x = p.tops[0]
+        i += 2
+    if len(convs) < 2 or i + 3 >= len(ls):
+        return None
+    last, ps, interp, add = ls[i], ls[i + 1], ls[i + 2], ls[i + 3]
+    if (last.type, ps.type, interp.type, add.type) != ("Convolution", "PixelShuffle", "Interp", "BinaryOp"):
+        return None
+    if i + 4 != len(ls) or last.bottoms != [x] or ps.bottoms != last.tops:
+        return None
+    if interp.bottoms != [skip_blob] or sorted(add.bottoms) != sorted([ps.tops[0], interp.tops[0]]):
+        return None
+    r = int(ps.p(0, 1))
+    if ps.p(1, 0) != 0 or add.p(0, 0) != 0:  # PixelShuffle mode 0, BinaryOp op 0 (add)
+        return None
+    if r > 1 and (interp.p(0) != 1 or float(interp.p(1, 1.0)) != r or float(interp.p(2, 1.0)) != r):
+        return None
+    for c in convs + [last]:
+        if (c.p(1), c.p(2, 1), c.p(3, 1), c.p(4, 0), c.p(5, 0), c.p(9, 0)) != (3, 1, 1, 1, 1, 0):
+            return None
+    nf = int(convs[0].p(0))
+    cin = convs[0].weights["weight"].shape[1]
+    if any(c.weights["weight"].shape != (nf, nf, 3, 3) for c in convs[1:]):
+        return None
+    cout_last = int(last.p(0))
+    if cout_last != cin * r * r or last.weights["weight"].shape != (cout_last, nf, 3, 3):
+        return None
+    return CompactDesc(cin, nf, len(convs) - 1, r, cout_last, ls[0].tops[0], add.tops[0])
+
+
+def pack_compact_blob(graph: Graph) -> tuple:
+    """Flat fp32 blob for ``b2sr_create``: per conv in graph order ``weight[OIHW] | bias[O] | slope[O]``
+    (slope omitted for the last conv).  fp32 keeps the ABI trivially typed; the engine narrows weights to
+    fp16 itself and refuses (error) if that is not exact."""
+    d = compact_desc(graph)
+    if d is None:
+        raise ValueError("graph is not an SRVGGNetCompact")
+    parts = []
+    ls = graph.layers
+    for i, l in enumerate(ls):
+        if l.type != "Convolution":
+            continue
+        parts.append(l.weights["weight"].astype(np.float32).ravel())
+        parts.append(l.weights["bias"].astype(np.float32).ravel())
+        if i + 1 < len(ls) and ls[i + 1].type == "PReLU":
+            parts.append(ls[i + 1].weights["slope"].astype(np.float32).ravel())
+    return d, np.ascontiguousarray(np.concatenate(parts))

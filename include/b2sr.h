@@ -1,0 +1,142 @@
+/*
+ * b2sr.h -- C ABI of the B200 frame super-resolution engine (libb2sr.so).
+ *
+ * This is the drop-in boundary for the reference's per-frame worker loop.  The reference
+ * (davlee1972/upscale_video) has no FFI of its own: its worker functions call the third-party ncnn_vulkan
+ * object API.  Each entry point below replaces one group of those calls; file:line citations are into
+ * /root/reference/.
+ *
+ *   reference call site                                              replaced by
+ *   ---------------------------------------------------------------  ---------------------------------
+ *   ncnn.get_gpu_count / get_default_gpu_index / get_gpu_info         b2sr_device_count / b2sr_device_name
+ *     (test_gpus.py:47-67)
+ *   ncnn.Net(); opt.use_vulkan_compute; set_vulkan_device;            b2sr_create
+ *     load_param; load_model   (upscale/upscale_processing.py:65-71)
+ *   Mat.from_pixels + substract_mean_normalize + create_extractor +   b2sr_run_u8  (whole upscale_image
+ *     input + extract + np.array + *255 + canvas scatter + imwrite      tile loop :499-519, or apply_model
+ *     rounding   (upscale_processing.py:437-477, :487-519, :263-288)    :263-288 with tile = 0)
+ *   the same, up to `output_tile * 255` (float, unrounded)            b2sr_run_f32 (process_tile :437-462)
+ *     (upscale_processing.py:437-462)
+ *   pool of per-frame tasks on device-resident frames (no reference   b2sr_run_batch_device
+ *     equivalent: the reference moves pixels through PNG files)
+ *   ncnn.destroy_gpu_instance (upscale_processing.py:292, :458)       b2sr_destroy
+ *   exceptions caught at :289 / :454                                   negative return + b2sr_last_error
+ *
+ * Conventions: plain C types only; every function returning int returns 0 on success and a negative
+ * B2SR_E_* code on failure, with a thread-local message available from b2sr_last_error().  A context is
+ * bound to one CUDA device, owns its stream, weights, scratch and TMA descriptors, and is not thread-safe
+ * (one context per worker process, like the reference's process-global `net`, upscale_processing.py:22,57).
+ * There is no CPU fallback: creating a context without a usable sm_100 device fails.
+ *
+ * Pixel format everywhere: 8-bit, 3 interleaved channels in the order the caller has them (the reference
+ * feeds cv2's BGR unswapped as PIXEL_BGR, :265-270); the network is applied channel-for-channel.
+ */
+#ifndef B2SR_H
+#define B2SR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2SR_ABI_VERSION 1
+
+/* error codes */
+#define B2SR_OK 0
+#define B2SR_E_INVALID (-1)     /* bad argument / unsupported network description */
+#define B2SR_E_CUDA (-2)        /* CUDA runtime or driver error (message has the detail) */
+#define B2SR_E_NODEVICE (-3)    /* no CUDA device / device is not sm_100 */
+#define B2SR_E_NOMEM (-4)       /* host or device allocation failed */
+#define B2SR_E_UNSUPPORTED (-5) /* valid request this build cannot serve */
+
+/* network families */
+#define B2SR_FAMILY_COMPACT 1 /* SRVGGNetCompact: conv(cin->nf)+PReLU, n_mid x [conv(nf->nf)+PReLU], conv(nf->cin*scale^2),
+                                 PixelShuffle(scale) + nearest-upsample(input)  (models/2x_Compact_Pretrain.param:3-42) */
+
+/* where image buffers live */
+#define B2SR_MEM_HOST 0
+#define B2SR_MEM_DEVICE 1
+
+/* b2sr_set_option keys */
+#define B2SR_OPT_IMPL 1        /* 0 = auto (tcgen05 path where available), 1 = plain CUDA-core kernels, 2 = force tcgen05 */
+#define B2SR_OPT_PROFILE 2     /* 1 = bracket every kernel launch with CUDA events (see b2sr_get_stat) */
+#define B2SR_OPT_MAX_BATCH 3   /* frames per internal pass of b2sr_run_batch_device (0 = choose from free memory) */
+#define B2SR_OPT_DEBUG_DESC 4  /* bring-up only: UMMA descriptor variant */
+
+/* b2sr_get_stat keys */
+#define B2SR_STAT_LAUNCHES 1       /* kernels launched by this context since creation / last reset */
+#define B2SR_STAT_TC_LAUNCHES 2    /* ... of which tcgen05 convolution kernels */
+#define B2SR_STAT_TC_MID_MS 3      /* profile mode: summed device time of nf->nf tcgen05 conv launches, ms */
+#define B2SR_STAT_TC_MID_COUNT 4   /* profile mode: number of launches summed in B2SR_STAT_TC_MID_MS */
+#define B2SR_STAT_ALL_MS 5         /* profile mode: summed device time of every launch, ms */
+#define B2SR_STAT_TC_MID_PIXELS 6  /* profile mode: output pixels (exact, no halo/padding) those launches produced */
+
+typedef struct b2sr_ctx b2sr_ctx;
+
+typedef struct b2sr_net_desc {
+    int32_t family;    /* B2SR_FAMILY_* */
+    int32_t cin;       /* image channels (3) */
+    int32_t nf;        /* feature channels (64, 24) */
+    int32_t n_mid;     /* number of nf->nf convolutions (16, 8) */
+    int32_t scale;     /* pixel-shuffle factor 1, 2 or 4 */
+    int32_t reserved[11];
+} b2sr_net_desc;
+
+int b2sr_abi_version(void);
+
+/* Device enumeration (test_gpus.py:47-67). */
+int b2sr_device_count(void);
+int b2sr_default_device(void);
+int b2sr_device_name(int device, char *buf, int buflen);
+
+/*
+ * Create an engine on `device`.  `weights` is a host blob of fp32 values: for every convolution in graph
+ * order  weight[out][in][3][3] | bias[out] | slope[out]  (slope omitted after the last convolution).
+ * All weights must be exactly representable in fp16 (true for every Compact model the reference ships);
+ * otherwise B2SR_E_UNSUPPORTED.
+ */
+int b2sr_create(b2sr_ctx **out, int device, const void *weights, size_t nbytes, const b2sr_net_desc *desc);
+void b2sr_destroy(b2sr_ctx *ctx);
+
+/*
+ * One frame, u8 in -> u8 out ((h*scale) x (w*scale) x 3, round-half-even + saturate like cv2.imwrite).
+ * tile/halo = 960/10 reproduces the reference's tiling (zero padding at tile borders, upscale_processing.py
+ * :409-434); tile = 0 runs the frame as one piece (apply_model).  Strides are in bytes.  Synchronous.
+ */
+int b2sr_run_u8(b2sr_ctx *ctx, const uint8_t *in, int h, int w, int in_stride, uint8_t *out, int out_stride,
+                int tile, int halo, int memspace);
+
+/* Same, but the output is the float image the reference holds after `* 255` (unrounded), 3 floats/pixel. */
+int b2sr_run_f32(b2sr_ctx *ctx, const uint8_t *in, int h, int w, int in_stride, float *out, int out_stride,
+                 int tile, int halo, int memspace);
+
+/*
+ * n device-resident frames, packed (no row padding): in  n x h x w x 3, out  n x (h*scale) x (w*scale) x 3.
+ * Asynchronous on the context's stream unless `sync` is non-zero.
+ */
+int b2sr_run_batch_device(b2sr_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, int n, int h, int w, int tile,
+                          int halo, int sync);
+
+/* n host frames (pinned or pageable) through a double-buffered H2D -> run -> D2H pipeline; synchronous. */
+int b2sr_run_batch_host(b2sr_ctx *ctx, const uint8_t *h_in, uint8_t *h_out, int n, int h, int w, int tile,
+                        int halo);
+
+/* Bring-up aid: activations after convolution `layer` (0-based, post-PReLU) of a single untiled u8 image,
+ * as float h x w x nf on the host. */
+int b2sr_debug_layer(b2sr_ctx *ctx, const uint8_t *in, int h, int w, int layer, float *out);
+
+int b2sr_set_option(b2sr_ctx *ctx, int key, int64_t value);
+int b2sr_get_stat(b2sr_ctx *ctx, int key, double *value);
+int b2sr_reset_stats(b2sr_ctx *ctx);
+int b2sr_synchronize(b2sr_ctx *ctx);
+/* The CUDA stream (cudaStream_t) the context launches on, for callers that time with their own events. */
+void *b2sr_stream(b2sr_ctx *ctx);
+
+const char *b2sr_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2SR_H */

@@ -1,0 +1,406 @@
+// tc_conv.cuh -- 3x3 convolution as an im2col-free tcgen05 contraction (sm_100a).
+//
+// Replaces the Convolution(+PReLU) / PixelShuffle / Interp / BinaryOp layers that ncnn_vulkan executes for the
+// reference inside `ex.extract` (reference upscale/upscale_processing.py:278-281, :450-453; graph
+// models/2x_Compact_Pretrain.param:5-42).
+//
+// Layout.  Activations are channel-last fp16, CPIX channels per pixel (CPIX*2 = 32/64/128 bytes = one swizzle
+// row).  A work item is a band of `w` columns x `rows` rows of a plane.  The producer warp streams the band's
+// input rows (w+2 columns incl. halo; rows y0-1 .. y0+rows) with TMA into a shared-memory ring laid out as one
+// FLAT array of pixels with pitch `pitch` = band width + 2.  Because every pixel is exactly one swizzle row, the
+// A operand of filter tap (ky,kx) for the 128 consecutive flat output positions [p0, p0+128) is simply the 128
+// consecutive ring pixels starting at p0 + ky*pitch + kx: nine shifted UMMA descriptors over the same bytes,
+// no im2col, no data replication.  Flat positions that fall on the two halo columns produce junk rows of the
+// accumulator that are never stored (2/pitch of the tensor work).  TMA zero-fills out-of-plane coordinates,
+// which is exactly the convolution's zero padding at the plane (= reference tile) border.
+//
+// Ring wrap: the ring has R rows; the first MR rows are mirrored behind the last one (their TMA loads are
+// issued twice) so a 128-pixel operand that starts near the end never wraps.
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> bias/PReLU -> fp16 -> swizzled staging -> 128-bit coalesced stores, or
+// pixel-shuffle + nearest-upsampled residual + x255 + round-half-even/saturate for the last layer).
+// Two TMEM accumulators let the MMAs of tile i+1 overlap the epilogue of tile i.
+#pragma once
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace b2sr {
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_SLOTS = 64;
+constexpr int TC_TILE_M = 128;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a protocol bug must trap (and fail the launch) rather than hang the GPU box.
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity, int who) {
+    printf("b2sr: mbarrier timeout block %d thread %d bar 0x%x parity %u who %d\n", (int)blockIdx.x, (int)threadIdx.x,
+           bar, parity, who);
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) mbar_timeout(bar, parity, who);
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// compile-time geometry shared by host and device
+// ------------------------------------------------------------------------------------------------
+template <int CPIX, int NOUT, int SHUF>
+struct TcCfg {
+    static constexpr int PB = CPIX * 2;            // bytes per input pixel == swizzle row
+    static constexpr int KSLABS = CPIX / 16;       // K=16 MMAs per filter tap
+    static constexpr int WB = 9 * NOUT * PB;       // weight image bytes
+    static constexpr int OB = NOUT * 2;            // bytes per output pixel (PReLU epilogue)
+    static constexpr int CH = OB / 16;             // 16-byte chunks per output pixel
+    static constexpr int STG = SHUF == 0 ? 4 * 32 * OB : 0;
+    static constexpr int TCOLS = 2 * NOUT <= 32 ? 32 : (2 * NOUT <= 64 ? 64 : 128);
+    static constexpr uint32_t LAYOUT = CPIX == 64 ? 2u : (CPIX == 32 ? 4u : 6u);  // UMMA LayoutType: SW128 / SW64 / SW32
+    static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NOUT >> 3) << 17) | ((uint32_t)(TC_TILE_M >> 4) << 24);
+    static constexpr int MISC = 2 * NOUT * 4 + (2 * TC_MAX_SLOTS + 8) * 8 + 64;
+    static_assert(CPIX == 16 || CPIX == 32 || CPIX == 64, "one pixel must be one swizzle row");
+    static_assert(NOUT % 16 == 0 && NOUT >= 16 && NOUT <= 64, "UMMA M=128 needs N % 16 == 0");
+    static_assert((NOUT * PB) % (8 * PB) == 0, "per-tap weight tile must be whole swizzle atoms");
+    // bytes left for the input ring
+    static constexpr int ring_budget() { return B2SR_SMEM_LIMIT - 1024 - WB - STG - MISC; }
+    static constexpr int smem_bytes(int ring_rows, int pitch) {
+        return 1024 + WB + ((ring_rows * pitch * PB + 127) & ~127) + STG + MISC;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int CPIX, int NOUT, int SHUF /*0 = PReLU->fp16, else pixel-shuffle factor*/, bool F32OUT>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcParams P) {
+    using C = TcCfg<CPIX, NOUT, SHUF>;
+    constexpr int PB = C::PB;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (sbase - raw);
+
+    const int pitch = P.pitch, R = P.R, MR = P.MR;
+    const uint32_t rowbytes = (uint32_t)pitch * PB;
+    const uint32_t ringbytes = ((uint32_t)(R + MR) * rowbytes + 127u) & ~127u;
+    const uint32_t w_s = sbase;
+    const uint32_t ring_s = sbase + C::WB;
+    const uint32_t stg_off = C::WB + ringbytes;
+    const uint32_t fl_off = stg_off + C::STG;
+    float* s_bias = reinterpret_cast<float*>(gbase + fl_off);
+    float* s_slope = s_bias + NOUT;
+    const uint32_t bar_off = fl_off + 2 * NOUT * 4;
+    const uint32_t bar_s = sbase + bar_off;  // 8-byte aligned: all terms are multiples of 8
+    auto full_bar = [&](int s) { return bar_s + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_s + 8u * (TC_MAX_SLOTS + s); };
+    auto tfull_bar = [&](int b) { return bar_s + 8u * (2 * TC_MAX_SLOTS + b); };
+    auto tempty_bar = [&](int b) { return bar_s + 8u * (2 * TC_MAX_SLOTS + 2 + b); };
+    const uint32_t w_bar = bar_s + 8u * (2 * TC_MAX_SLOTS + 4);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + bar_off + 8 * (2 * TC_MAX_SLOTS + 5));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < R; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 4);
+        }
+        mbar_init(w_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                     "r"((uint32_t)C::TCOLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {
+        for (int i = threadIdx.x - 64; i < NOUT; i += 128) {
+            s_bias[i] = P.bias[i];
+            s_slope[i] = (SHUF == 0) ? P.slope[i] : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ======================= TMA producer =======================
+        if (lane == 0) {
+            mbar_expect_tx(w_bar, C::WB);
+            for (int t = 0; t < 9; ++t)
+                bulk_g2s(w_s + t * (NOUT * PB), P.wimg + (size_t)t * (NOUT * PB), NOUT * PB, w_bar);
+            int slot = 0;
+            uint32_t phase = 0;
+            for (int it = blockIdx.x; it < P.n_items; it += gridDim.x) {
+                const TcItem I = P.items[it];
+                const CUtensorMap* map = P.maps + (P.map_base + I.map);
+                const int rows_in = I.rows + 2;
+                for (int rho = 0; rho < rows_in; ++rho) {
+                    mbar_wait(empty_bar(slot), phase ^ 1u, 0);
+                    const bool mirror = slot < MR;
+                    mbar_expect_tx(full_bar(slot), mirror ? 2 * rowbytes : rowbytes);
+                    tma_load_4d(ring_s + slot * rowbytes, map, full_bar(slot), 0, I.x0 - 1, I.y0 - 1 + rho, I.plane);
+                    if (mirror)
+                        tma_load_4d(ring_s + (R + slot) * rowbytes, map, full_bar(slot), 0, I.x0 - 1, I.y0 - 1 + rho,
+                                    I.plane);
+                    if (++slot == R) {
+                        slot = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            const uint32_t desc_hi = ((8u * PB) >> 4) | (1u << 14) | (C::LAYOUT << 29);
+            const int RP = R * pitch;
+            int full_slot = 0, rel_slot = 0, slot0 = 0;
+            uint32_t full_phase = 0;
+            uint32_t tile_cnt = 0;
+            mbar_wait(w_bar, 0, 1);
+            for (int it = blockIdx.x; it < P.n_items; it += gridDim.x) {
+                const TcItem I = P.items[it];
+                const int rows_in = I.rows + 2;
+                const int nt = ((I.rows - 1) * pitch + I.w - 1) / TC_TILE_M + 1;
+                int n_full = 0, n_rel = 0;  // item-local counts of rows waited-for / released
+                for (int t = 0; t < nt; ++t) {
+                    const int p0 = t * TC_TILE_M;
+                    int need = (p0 + TC_TILE_M - 1 + 2 * pitch + 2) / pitch;
+                    if (need > rows_in - 1) need = rows_in - 1;
+                    while (n_full <= need) {
+                        mbar_wait(full_bar(full_slot), full_phase, 2);
+                        ++n_full;
+                        if (++full_slot == R) {
+                            full_slot = 0;
+                            full_phase ^= 1u;
+                        }
+                    }
+                    const uint32_t buf = tile_cnt & 1u;
+                    mbar_wait(tempty_bar(buf), ((tile_cnt >> 1) & 1u) ^ 1u, 3);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + buf * NOUT;
+                    const int fl = (slot0 * pitch + p0) % RP;
+                    uint32_t accum = 0;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            int f = fl + ky * pitch + kx;
+                            if (f >= RP) f -= RP;
+                            const uint32_t a_addr = ring_s + (uint32_t)f * PB;
+                            const uint32_t b_addr = w_s + (ky * 3 + kx) * (NOUT * PB);
+                            uint32_t hi_a = desc_hi;
+                            if (P.desc_mode == 1) hi_a |= ((a_addr >> 7) & 7u) << 17;
+#pragma unroll
+                            for (int k = 0; k < C::KSLABS; ++k) {
+                                const uint64_t adesc =
+                                    ((uint64_t)hi_a << 32) | (uint64_t)((((a_addr + k * 32) >> 4) & 0x3FFFu) | (1u << 16));
+                                const uint64_t bdesc =
+                                    ((uint64_t)desc_hi << 32) | (uint64_t)((((b_addr + k * 32) >> 4) & 0x3FFFu) | (1u << 16));
+                                umma_f16(tmem_d, adesc, bdesc, C::IDESC, accum);
+                                accum = 1;
+                            }
+                        }
+                    }
+                    umma_commit(tfull_bar(buf));
+                    ++tile_cnt;
+                    int lim = (t + 1 < nt) ? (p0 + TC_TILE_M) / pitch : rows_in;
+                    if (lim > rows_in) lim = rows_in;
+                    while (n_rel < lim) {
+                        umma_commit(empty_bar(rel_slot));
+                        ++n_rel;
+                        if (++rel_slot == R) rel_slot = 0;
+                    }
+                }
+                slot0 = (slot0 + rows_in) % R;
+            }
+        }
+    } else {
+        // ======================= epilogue =======================
+        const int q = warp & 3;  // TMEM lane quadrant this warp may read
+        uint32_t tile_cnt = 0;
+        const float scale_acc = P.acc_scale;
+        for (int it = blockIdx.x; it < P.n_items; it += gridDim.x) {
+            const TcItem I = P.items[it];
+            const int nt = ((I.rows - 1) * pitch + I.w - 1) / TC_TILE_M + 1;
+            for (int t = 0; t < nt; ++t, ++tile_cnt) {
+                const uint32_t buf = tile_cnt & 1u;
+                const int p = t * TC_TILE_M + q * 32 + lane;
+                const int r = p / pitch, c = p - r * pitch;
+                const bool valid = (c < I.w) && (r < I.rows);
+                mbar_wait(tfull_bar(buf), (tile_cnt >> 1) & 1u, 4);
+                tc_fence_after();
+                uint32_t acc[NOUT];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NOUT;
+#pragma unroll
+                for (int j = 0; j < NOUT; j += 16) tmem_ld16(taddr + j, acc + j);
+                tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(buf));
+
+                if constexpr (SHUF == 0) {
+                    // bias + PReLU -> fp16, via swizzled per-warp staging, then 128-bit coalesced global stores
+                    constexpr int CH = C::CH;
+                    uint4* stg = reinterpret_cast<uint4*>(gbase + stg_off + (warp - 2) * (32 * C::OB));
+                    const int off = valid ? ((I.y0 + r) * I.Wt + I.x0 + c) : -1;
+#pragma unroll
+                    for (int j = 0; j < NOUT; j += 8) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2) {
+                            float v0 = fmaf(__uint_as_float(acc[j + e]), scale_acc, s_bias[j + e]);
+                            float v1 = fmaf(__uint_as_float(acc[j + e + 1]), scale_acc, s_bias[j + e + 1]);
+                            v0 = v0 < 0.f ? v0 * s_slope[j + e] : v0;
+                            v1 = v1 < 0.f ? v1 * s_slope[j + e + 1] : v1;
+                            __half2 h = __floats2half2_rn(v0, v1);
+                            pk[e >> 1] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                        const int qi = lane * CH + (j >> 3);
+                        stg[qi ^ ((qi >> 3) & 7)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                    __syncwarp();
+                    uint8_t* outp = reinterpret_cast<uint8_t*>(P.out) + (size_t)I.pix_off * C::OB;
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) {
+                        const int qi = i * 32 + lane;
+                        const uint4 v = stg[qi ^ ((qi >> 3) & 7)];
+                        const int o = __shfl_sync(0xffffffffu, off, qi / CH);
+                        if (o >= 0) *reinterpret_cast<uint4*>(outp + (size_t)o * C::OB + (qi % CH) * 16) = v;
+                    }
+                    __syncwarp();
+                } else {
+                    // last layer: pixel shuffle + nearest-upsampled input residual + x255 (+ round/saturate)
+                    constexpr int S = SHUF;
+                    const int fy = I.fy0 + I.y0 + r, fx = I.fx0 + I.x0 + c;
+                    if (valid && fy >= I.cy0 && fy < I.cy1 && fx >= I.cx0 && fx < I.cx1) {
+                        const uint8_t* px = P.frames_in + ((size_t)((size_t)I.frame * P.frame_h + fy) * P.frame_w + fx) * 3;
+                        float xin[3];
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) xin[ch] = (float)px[ch] * (1.f / 255.f);
+                        const size_t OW = (size_t)P.frame_w * S;
+#pragma unroll
+                        for (int dy = 0; dy < S; ++dy) {
+                            float v[S * 3];
+#pragma unroll
+                            for (int dx = 0; dx < S; ++dx)
+#pragma unroll
+                                for (int ch = 0; ch < 3; ++ch) {
+                                    const int n = ch * S * S + dy * S + dx;
+                                    float t0 = fmaf(__uint_as_float(acc[n]), scale_acc, s_bias[n]);
+                                    t0 = t0 + xin[ch];
+                                    v[dx * 3 + ch] = t0 * 255.f;
+                                }
+                            const size_t o = (((size_t)I.frame * P.frame_h * S + (size_t)fy * S + dy) * OW + (size_t)fx * S) * 3;
+                            if constexpr (F32OUT) {
+                                float* dst = reinterpret_cast<float*>(P.out) + o;
+#pragma unroll
+                                for (int e = 0; e < S * 3; ++e) dst[e] = v[e];
+                            } else {
+                                uint8_t b[S * 3];
+#pragma unroll
+                                for (int e = 0; e < S * 3; ++e) {
+                                    int iv = __float2int_rn(v[e]);  // round half to even, like cv2's saturate_cast
+                                    b[e] = (uint8_t)min(max(iv, 0), 255);
+                                }
+                                uint8_t* dst = reinterpret_cast<uint8_t*>(P.out) + o;
+                                if constexpr (S == 4) {
+#pragma unroll
+                                    for (int e = 0; e < 3; ++e)
+                                        reinterpret_cast<uint32_t*>(dst)[e] = (uint32_t)b[4 * e] | ((uint32_t)b[4 * e + 1] << 8) |
+                                                                              ((uint32_t)b[4 * e + 2] << 16) |
+                                                                              ((uint32_t)b[4 * e + 3] << 24);
+                                } else if constexpr (S == 2) {
+#pragma unroll
+                                    for (int e = 0; e < 3; ++e)
+                                        reinterpret_cast<uint16_t*>(dst)[e] = (uint16_t)(b[2 * e] | (b[2 * e + 1] << 8));
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 3; ++e) dst[e] = b[e];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TCOLS)
+                     : "memory");
+    }
+}
+
+}  // namespace b2sr

@@ -63,7 +63,7 @@ extern "C" {
 #define B2SR_OPT_IMPL 1        /* 0 = auto (tcgen05 path where available), 1 = plain CUDA-core kernels, 2 = force tcgen05 */
 #define B2SR_OPT_PROFILE 2     /* 1 = bracket every kernel launch with CUDA events (see b2sr_get_stat) */
 #define B2SR_OPT_MAX_BATCH 3   /* frames per internal pass of b2sr_run_batch_device (0 = choose from free memory) */
-#define B2SR_OPT_DEBUG_DESC 4  /* bring-up only: UMMA descriptor variant */
+#define B2SR_OPT_DEBUG_DESC 4  /* bring-up only: 0 (default, verified on B200) = UMMA descriptors with base_offset 0; 1 = base_offset from address (wrong) */
 
 /* b2sr_get_stat keys */
 #define B2SR_STAT_LAUNCHES 1       /* kernels launched by this context since creation / last reset */

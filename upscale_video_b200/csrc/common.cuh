@@ -19,7 +19,7 @@ struct PlaneDev {
     int64_t pix_off;  // first pixel of this plane in the activation buffers
 };
 
-// Work item of the tcgen05 convolution kernel: a band of `w` columns x `rows` rows of one plane.
+// Work item of the tcgen05 convolution kernel: a band of `w` (<= 128) columns x `rows` rows of one plane.
 struct TcItem {
     int32_t map;    // index into the tensor-map array (plane group; the launch adds the ping/pong offset)
     int32_t plane;  // plane index inside its group (TMA coordinate 3)
@@ -47,8 +47,7 @@ struct TcParams {
     const uint8_t* frames_in;  // EPI_SHUFFLE_*: packed u8 input frames (residual branch)
     int32_t frame_h, frame_w;  // input frame size
     int32_t scale;             // pixel-shuffle factor
-    int32_t pitch;             // shared-memory row pitch in pixels (band width + 2 halo columns)
-    int32_t R, MR;             // ring rows, mirror rows
+    int32_t R;                 // shared-memory ring rows
     int32_t desc_mode;         // bring-up: 0 = base_offset 0 (absolute-address swizzle), 1 = base_offset from address
 };
 

@@ -1,0 +1,827 @@
+// engine.cu -- host side of libb2sr: the C ABI of include/b2sr.h over the sm_100a kernels in tc_conv.cuh /
+// simple_kernels.cuh.
+//
+// What it replaces in the reference (davlee1972/upscale_video): the ncnn_vulkan object surface used by the
+// frame-upscale worker loop -- Net/load_param/load_model (upscale/upscale_processing.py:65-71),
+// Mat.from_pixels + substract_mean_normalize + Extractor.input/extract (:265-281, :437-453) -- together with the
+// per-tile numpy glue of process_tile / upscale_image (:395-519): tiling with a 10-px halo, `* 255`, the crop
+// into the canvas and cv2.imwrite's rounding all happen on the device here.
+//
+// There is no CPU fallback in this file: every entry point that computes needs an sm_100 device.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/b2sr.h"
+#include "common.cuh"
+#include "simple_kernels.cuh"
+#include "tc_conv.cuh"
+
+using namespace b2sr;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                        \
+    do {                                                                                                      \
+        cudaError_t e_ = (expr);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(e_ == cudaErrorMemoryAllocation ? B2SR_E_NOMEM : B2SR_E_CUDA, "%s failed: %s (%s:%d)", \
+                        #expr, cudaGetErrorString(e_), __FILE__, __LINE__);                                   \
+    } while (0)
+
+#define TRY(expr)               \
+    do {                        \
+        int rc_ = (expr);       \
+        if (rc_ != 0) return rc_; \
+    } while (0)
+
+extern "C" const char* b2sr_last_error(void) { return g_err.c_str(); }
+extern "C" int b2sr_abi_version(void) { return B2SR_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------------
+// device enumeration (reference test_gpus.py:47-67)
+// ------------------------------------------------------------------------------------------------
+extern "C" int b2sr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+extern "C" int b2sr_default_device(void) { return b2sr_device_count() > 0 ? 0 : -1; }
+extern "C" int b2sr_device_name(int device, char* buf, int buflen) {
+    cudaDeviceProp p;
+    if (!buf || buflen <= 0) return fail(B2SR_E_INVALID, "b2sr_device_name: no buffer");
+    CUDA_TRY(cudaGetDeviceProperties(&p, device));
+    snprintf(buf, buflen, "%s (sm_%d%d, %d SMs, %.0f GiB)", p.name, p.major, p.minor, p.multiProcessorCount,
+             p.totalGlobalMem / 1073741824.0);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct LayerDev {
+    int cin = 0, cout = 0;    // real channels
+    int cinp = 0, noutp = 0;  // padded channels (kernel layout)
+    uint8_t* wimg = nullptr;  // swizzled shared-memory image [9][noutp][cinp] fp16
+    __half* wplain = nullptr; // [9][cinp][noutp] fp16 (simple path)
+    float* bias = nullptr;    // [noutp]
+    float* slope = nullptr;   // [noutp] (absent for the last layer)
+};
+
+struct Group {  // planes of identical size share one TMA tensor map per activation buffer
+    int Ht, Wt, count;
+    int64_t pix_base;
+};
+
+struct Plan {
+    int n = 0, h = 0, w = 0, tile = 0, halo = 0;
+    std::vector<PlaneDev> planes;
+    std::vector<Group> groups;
+    std::vector<TcItem> items;
+    TcItem* d_items = nullptr;
+    double out_px = 0;  // exact output pixels of all items
+    int64_t total_px = 0;
+    int max_plane_px = 0;
+    PlaneDev* d_planes = nullptr;
+    CUtensorMap* d_maps = nullptr;  // [3 buffers][groups]: 0 = in16, 1 = ping, 2 = pong
+    void* bound_in16 = nullptr;     // buffers the maps were encoded for
+    void* bound_ping = nullptr;
+    void* bound_pong = nullptr;
+    ~Plan() {
+        if (d_planes) cudaFree(d_planes);
+        if (d_maps) cudaFree(d_maps);
+        if (d_items) cudaFree(d_items);
+    }
+};
+
+struct ProfRec {
+    cudaEvent_t a, b;
+    int kind;  // 0 other, 1 tcgen05 mid conv
+    double px;
+};
+
+struct b2sr_ctx {
+    int device = 0, sms = 0;
+    cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
+    b2sr_net_desc desc{};
+    int CF = 0, NL = 0, cout_last = 0;
+    std::vector<LayerDev> layers;
+    // scratch
+    int64_t cap_px = 0;
+    __half *in16 = nullptr, *ping = nullptr, *pong = nullptr;
+    float* lastf = nullptr;
+    int64_t cap_lastf = 0;
+    uint8_t *d_in = nullptr, *d_out = nullptr;  // staging for host-memory calls
+    size_t cap_in = 0, cap_out = 0;
+    uint8_t *d_in2 = nullptr, *d_out2 = nullptr;  // second set for the double-buffered host pipeline
+    size_t cap_in2 = 0, cap_out2 = 0;
+    std::vector<std::unique_ptr<Plan>> plans;
+    // options
+    int impl = 0, profile = 0, max_batch = 0, desc_mode = 0;
+    // stats
+    double n_launch = 0, n_tc = 0;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled g_encode = nullptr;
+
+static int get_encode() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail(B2SR_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = (PFN_tmapEncodeTiled)fn;
+    return 0;
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static inline int pad_channels(int c) { return c <= 32 ? 32 : 64; }
+// canonical shared-memory swizzles (address based): 128B -> Swizzle<3,4,3>, 64B -> <2,4,3>, 32B -> <1,4,3>
+static inline uint32_t swizzle_addr(uint32_t a, int row_bytes) {
+    const uint32_t mask = row_bytes == 128 ? 7u : (row_bytes == 64 ? 3u : 1u);
+    return a ^ (((a >> 7) & mask) << 4);
+}
+
+static bool fp16_exact(float v) { return __half2float(__float2half_rn(v)) == v; }
+
+static void free_layers(b2sr_ctx* c) {
+    for (auto& L : c->layers) {
+        if (L.wimg) cudaFree(L.wimg);
+        if (L.wplain) cudaFree(L.wplain);
+        if (L.bias) cudaFree(L.bias);
+        if (L.slope) cudaFree(L.slope);
+    }
+    c->layers.clear();
+}
+
+extern "C" void b2sr_destroy(b2sr_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->plans.clear();
+    free_layers(c);
+    for (void* p : {(void*)c->in16, (void*)c->ping, (void*)c->pong, (void*)c->lastf, (void*)c->d_in, (void*)c->d_out,
+                    (void*)c->d_in2, (void*)c->d_out2})
+        if (p) cudaFree(p);
+    for (auto& r : c->prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_in) cudaStreamDestroy(c->copy_in);
+    if (c->copy_out) cudaStreamDestroy(c->copy_out);
+    delete c;
+}
+
+static int upload_layer(b2sr_ctx* c, const float* w, const float* bias, const float* slope, int cin, int cout,
+                        int cinp, int noutp) {
+    LayerDev L;
+    L.cin = cin;
+    L.cout = cout;
+    L.cinp = cinp;
+    L.noutp = noutp;
+    const int PB = cinp * 2;
+    std::vector<uint8_t> img((size_t)9 * noutp * PB, 0);
+    std::vector<__half> plain((size_t)9 * cinp * noutp, __float2half(0.f));
+    for (int o = 0; o < cout; ++o)
+        for (int i = 0; i < cin; ++i)
+            for (int t = 0; t < 9; ++t) {
+                const float v = w[((size_t)o * cin + i) * 9 + t];
+                if (!fp16_exact(v))
+                    return fail(B2SR_E_UNSUPPORTED, "weight %g (conv out %d in %d tap %d) is not exactly representable in fp16", v,
+                                o, i, t);
+                const __half hv = __float2half_rn(v);
+                // tile of tap t starts 1024-aligned; element (row o, channel i) sits at the swizzled address
+                const uint32_t a = swizzle_addr((uint32_t)(o * PB + i * 2), PB);
+                memcpy(&img[(size_t)t * noutp * PB + a], &hv, 2);
+                plain[((size_t)t * cinp + i) * noutp + o] = hv;
+            }
+    std::vector<float> b(noutp, 0.f), s(noutp, 0.f);
+    for (int o = 0; o < cout; ++o) {
+        b[o] = bias[o];
+        if (slope) s[o] = slope[o];
+    }
+    CUDA_TRY(cudaMalloc(&L.wimg, img.size()));
+    CUDA_TRY(cudaMemcpy(L.wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&L.wplain, plain.size() * 2));
+    CUDA_TRY(cudaMemcpy(L.wplain, plain.data(), plain.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&L.bias, noutp * 4));
+    CUDA_TRY(cudaMemcpy(L.bias, b.data(), noutp * 4, cudaMemcpyHostToDevice));
+    if (slope) {
+        CUDA_TRY(cudaMalloc(&L.slope, noutp * 4));
+        CUDA_TRY(cudaMemcpy(L.slope, s.data(), noutp * 4, cudaMemcpyHostToDevice));
+    }
+    c->layers.push_back(L);
+    return 0;
+}
+
+extern "C" int b2sr_create(b2sr_ctx** out, int device, const void* weights, size_t nbytes, const b2sr_net_desc* d) {
+    if (!out || !weights || !d) return fail(B2SR_E_INVALID, "b2sr_create: null argument");
+    *out = nullptr;
+    if (d->family != B2SR_FAMILY_COMPACT) return fail(B2SR_E_UNSUPPORTED, "network family %d is not supported", d->family);
+    if (d->cin != 3) return fail(B2SR_E_UNSUPPORTED, "cin = %d (only 3-channel images are supported)", d->cin);
+    if (d->nf < 8 || d->nf > 64 || d->nf % 8) return fail(B2SR_E_UNSUPPORTED, "nf = %d (need a multiple of 8, <= 64)", d->nf);
+    if (d->scale != 1 && d->scale != 2 && d->scale != 4) return fail(B2SR_E_UNSUPPORTED, "scale = %d (need 1, 2 or 4)", d->scale);
+    if (d->n_mid < 1 || d->n_mid > 64) return fail(B2SR_E_INVALID, "n_mid = %d", d->n_mid);
+    const int cin = d->cin, nf = d->nf, cl = cin * d->scale * d->scale;
+    const size_t need = ((size_t)nf * cin * 9 + 2 * nf + (size_t)d->n_mid * ((size_t)nf * nf * 9 + 2 * nf) + (size_t)cl * nf * 9 + cl) * 4;
+    if (nbytes != need) return fail(B2SR_E_INVALID, "weight blob is %zu bytes, network description needs %zu", nbytes, need);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B2SR_E_NODEVICE, "no CUDA device is visible (this library has no CPU path)");
+    }
+    if (device < 0 || device >= ndev) return fail(B2SR_E_NODEVICE, "device %d out of range (%d visible)", device, ndev);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(B2SR_E_NODEVICE, "device %d (%s) is sm_%d%d; this library contains sm_100a code only", device, prop.name,
+                    prop.major, prop.minor);
+    CUDA_TRY(cudaSetDevice(device));
+    TRY(get_encode());
+
+    b2sr_ctx* c = new b2sr_ctx();
+    c->device = device;
+    c->sms = prop.multiProcessorCount;
+    c->desc = *d;
+    c->CF = pad_channels(nf);
+    c->cout_last = cl;
+    c->NL = round_up(cl, 16);
+    int rc = 0;
+    do {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking) != cudaSuccess) {
+            rc = fail(B2SR_E_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        const float* p = (const float*)weights;
+        rc = upload_layer(c, p, p + (size_t)nf * cin * 9, p + (size_t)nf * cin * 9 + nf, cin, nf, 16, c->CF);
+        if (rc) break;
+        p += (size_t)nf * cin * 9 + 2 * nf;
+        for (int i = 0; i < d->n_mid && !rc; ++i) {
+            rc = upload_layer(c, p, p + (size_t)nf * nf * 9, p + (size_t)nf * nf * 9 + nf, nf, nf, c->CF, c->CF);
+            p += (size_t)nf * nf * 9 + 2 * nf;
+        }
+        if (rc) break;
+        rc = upload_layer(c, p, p + (size_t)cl * nf * 9, nullptr, nf, cl, c->CF, c->NL);
+    } while (0);
+    if (rc) {
+        std::string keep = g_err;
+        b2sr_destroy(c);
+        g_err = keep;
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// planning: planes (reference tiles), launch classes, work items, tensor maps
+// ------------------------------------------------------------------------------------------------
+static int build_plan(b2sr_ctx* c, int n, int h, int w, int tile, int halo, Plan** out) {
+    for (auto& p : c->plans)
+        if (p->n == n && p->h == h && p->w == w && p->tile == tile && p->halo == halo) {
+            *out = p.get();
+            return 0;
+        }
+    if (c->plans.size() > 8) c->plans.erase(c->plans.begin());
+    std::unique_ptr<Plan> P(new Plan());
+    P->n = n, P->h = h, P->w = w, P->tile = tile, P->halo = halo;
+    // reference process_tile :398-427 (tile = 0: the whole frame is one plane, apply_model :263-281)
+    struct Rect {
+        int iy0, iy1, ix0, ix1, cy0, cy1, cx0, cx1;
+    };
+    std::vector<Rect> rects;
+    if (tile <= 0) {
+        rects.push_back({0, h, 0, w, 0, h, 0, w});
+    } else {
+        const int ty = (h + tile - 1) / tile, tx = (w + tile - 1) / tile;
+        for (int y = 0; y < ty; ++y)
+            for (int x = 0; x < tx; ++x) {
+                const int sy = y * tile, ey = std::min(sy + tile, h), sx = x * tile, ex = std::min(sx + tile, w);
+                const int by0 = sy >= halo ? -halo : 0, by1 = ey <= h - halo ? halo : 0;
+                const int bx0 = sx >= halo ? -halo : 0, bx1 = ex <= w - halo ? halo : 0;
+                rects.push_back({sy + by0, ey + by1, sx + bx0, ex + bx1, sy, ey, sx, ex});
+            }
+    }
+    // groups by plane size
+    std::map<std::pair<int, int>, int> gidx;
+    for (auto& r : rects) {
+        auto key = std::make_pair(r.iy1 - r.iy0, r.ix1 - r.ix0);
+        if (!gidx.count(key)) {
+            gidx[key] = (int)P->groups.size();
+            P->groups.push_back({key.first, key.second, 0, 0});
+        }
+        P->groups[gidx[key]].count += n;
+    }
+    int64_t base = 0;
+    for (auto& g : P->groups) {
+        g.pix_base = base;
+        base += (int64_t)g.count * g.Ht * g.Wt;
+        P->max_plane_px = std::max(P->max_plane_px, g.Ht * g.Wt);
+    }
+    P->total_px = base;
+    // planes + items; plane index inside its group = frame-major
+    std::vector<int> fill(P->groups.size(), 0);
+    int64_t band_rows = 0;
+    for (auto& g : P->groups) band_rows += (int64_t)g.count * g.Ht * ((g.Wt + TC_BW - 1) / TC_BW);
+    const int RB = (int)std::min<int64_t>(64, std::max<int64_t>(8, (band_rows + (int64_t)c->sms * 6 - 1) / ((int64_t)c->sms * 6)));
+    for (int f = 0; f < n; ++f)
+        for (auto& r : rects) {
+            const int Ht = r.iy1 - r.iy0, Wt = r.ix1 - r.ix0;
+            const int gi = gidx[std::make_pair(Ht, Wt)];
+            Group& g = P->groups[gi];
+            const int pl = fill[gi]++;
+            PlaneDev pd{};
+            pd.frame = f, pd.fy0 = r.iy0, pd.fx0 = r.ix0, pd.Ht = Ht, pd.Wt = Wt;
+            pd.cy0 = r.cy0, pd.cy1 = r.cy1, pd.cx0 = r.cx0, pd.cx1 = r.cx1;
+            pd.pix_off = g.pix_base + (int64_t)pl * Ht * Wt;
+            P->planes.push_back(pd);
+            const int bw = TC_BW;
+            const int nchunks = (Ht + RB - 1) / RB, rows = (Ht + nchunks - 1) / nchunks;
+            for (int y0 = 0; y0 < Ht; y0 += rows)
+                for (int x0 = 0; x0 < Wt; x0 += bw) {
+                    TcItem it{};
+                    it.map = gi, it.plane = pl, it.x0 = x0, it.y0 = y0;
+                    it.rows = std::min(rows, Ht - y0), it.w = std::min(bw, Wt - x0);
+                    it.Ht = Ht, it.Wt = Wt, it.pix_off = pd.pix_off;
+                    it.frame = f, it.fy0 = r.iy0, it.fx0 = r.ix0;
+                    it.cy0 = r.cy0, it.cy1 = r.cy1, it.cx0 = r.cx0, it.cx1 = r.cx1;
+                    P->items.push_back(it);
+                    P->out_px += (double)it.rows * it.w;
+                }
+        }
+    CUDA_TRY(cudaMalloc(&P->d_planes, P->planes.size() * sizeof(PlaneDev)));
+    CUDA_TRY(cudaMemcpy(P->d_planes, P->planes.data(), P->planes.size() * sizeof(PlaneDev), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&P->d_items, P->items.size() * sizeof(TcItem)));
+    CUDA_TRY(cudaMemcpy(P->d_items, P->items.data(), P->items.size() * sizeof(TcItem), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&P->d_maps, 3 * P->groups.size() * sizeof(CUtensorMap)));
+    *out = P.get();
+    c->plans.push_back(std::move(P));
+    return 0;
+}
+
+static int ensure_scratch(b2sr_ctx* c, int64_t px) {
+    if (px <= c->cap_px) return 0;
+    cudaStreamSynchronize(c->stream);
+    for (void* p : {(void*)c->in16, (void*)c->ping, (void*)c->pong})
+        if (p) cudaFree(p);
+    c->in16 = c->ping = c->pong = nullptr;
+    c->cap_px = 0;
+    const int64_t cap = px + px / 16 + 1024;
+    CUDA_TRY(cudaMalloc(&c->in16, (size_t)cap * 16 * 2));
+    CUDA_TRY(cudaMalloc(&c->ping, (size_t)cap * c->CF * 2));
+    CUDA_TRY(cudaMalloc(&c->pong, (size_t)cap * c->CF * 2));
+    c->cap_px = cap;
+    return 0;
+}
+
+static int encode_maps(b2sr_ctx* c, Plan* P) {
+    if (P->bound_in16 == c->in16 && P->bound_ping == c->ping && P->bound_pong == c->pong) return 0;
+    const size_t G = P->groups.size();
+    std::vector<CUtensorMap> maps(3 * G);
+    for (int b = 0; b < 3; ++b) {
+        const int C = b == 0 ? 16 : c->CF;
+        __half* basep = b == 0 ? c->in16 : (b == 1 ? c->ping : c->pong);
+        const CUtensorMapSwizzle sw = C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+        for (size_t g = 0; g < G; ++g) {
+            const Group& gr = P->groups[g];
+            cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)gr.Wt, (cuuint64_t)gr.Ht, (cuuint64_t)gr.count};
+            cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)gr.Wt * C * 2, (cuuint64_t)gr.Ht * gr.Wt * C * 2};
+            cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)TC_PITCH, 1, 1};
+            cuuint32_t es[4] = {1, 1, 1, 1};
+            CUresult r = g_encode(&maps[b * G + g], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, basep + (size_t)gr.pix_base * C, dims,
+                                  strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS)
+                return fail(B2SR_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for buffer %d group %zu (%dx%dx%d)", (int)r, b, g, gr.Ht,
+                            gr.Wt, gr.count);
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(P->d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    P->bound_in16 = c->in16, P->bound_ping = c->ping, P->bound_pong = c->pong;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launches
+// ------------------------------------------------------------------------------------------------
+static int prof_begin(b2sr_ctx* c, int kind, double px) {
+    if (!c->profile) return 0;
+    ProfRec r;
+    r.kind = kind, r.px = px;
+    for (cudaEvent_t* e : {&r.a, &r.b}) {
+        if (!c->ev_pool.empty()) {
+            *e = c->ev_pool.back();
+            c->ev_pool.pop_back();
+        } else {
+            CUDA_TRY(cudaEventCreate(e));
+        }
+    }
+    CUDA_TRY(cudaEventRecord(r.a, c->stream));
+    c->prof.push_back(r);
+    return 0;
+}
+static int prof_end(b2sr_ctx* c) {
+    if (!c->profile) return 0;
+    CUDA_TRY(cudaEventRecord(c->prof.back().b, c->stream));
+    return 0;
+}
+
+template <int CPIX, int NOUT, int SHUF, bool F32OUT>
+static int launch_tc(b2sr_ctx* c, const Plan* plan, TcParams P) {
+    using Cfg = TcCfg<CPIX, NOUT, SHUF>;
+    constexpr int R = Cfg::ring_rows();
+    static_assert(R >= 4, "ring needs 3 live rows + 1 in flight");
+    P.R = R;
+    P.items = plan->d_items, P.n_items = (int)plan->items.size();
+    P.desc_mode = c->desc_mode;
+    const int smem = Cfg::smem_bytes(R);
+    auto kern = tc_conv_kernel<CPIX, NOUT, SHUF, F32OUT>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = std::min(P.n_items, c->sms);
+    kern<<<grid, TC_THREADS, smem, c->stream>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    c->n_launch += 1, c->n_tc += 1;
+    return 0;
+}
+
+static int tc_layer(b2sr_ctx* c, Plan* P, int li, int in_buf, void* out, const uint8_t* frames, int fh, int fw, bool f32out) {
+    const LayerDev& L = c->layers[li];
+    const bool first = li == 0, last = li == (int)c->layers.size() - 1;
+    {
+        const Plan* lc = P;
+        TcParams p{};
+        p.maps = P->d_maps;
+        p.map_base = in_buf * (int)P->groups.size();
+        p.wimg = L.wimg, p.bias = L.bias, p.slope = L.slope;
+        p.acc_scale = first ? (1.f / 255.f) : 1.f;
+        p.out = out;
+        p.frames_in = frames, p.frame_h = fh, p.frame_w = fw, p.scale = c->desc.scale;
+        TRY(prof_begin(c, (!first && !last) ? 1 : 0, P->out_px));
+        int rc = B2SR_E_UNSUPPORTED;
+        const int CF = c->CF, S = c->desc.scale;
+        if (first) {
+            rc = CF == 64 ? launch_tc<16, 64, 0, false>(c, lc, p) : launch_tc<16, 32, 0, false>(c, lc, p);
+        } else if (!last) {
+            rc = CF == 64 ? launch_tc<64, 64, 0, false>(c, lc, p) : launch_tc<32, 32, 0, false>(c, lc, p);
+        } else {
+#define LAST_CASE(cf, nl, s)                                                                            \
+    if (CF == cf && c->NL == nl && S == s)                                                              \
+        rc = f32out ? launch_tc<cf, nl, s, true>(c, lc, p) : launch_tc<cf, nl, s, false>(c, lc, p);
+            LAST_CASE(64, 16, 1)
+            LAST_CASE(64, 16, 2)
+            LAST_CASE(64, 48, 4)
+            LAST_CASE(32, 16, 1)
+            LAST_CASE(32, 16, 2)
+            LAST_CASE(32, 48, 4)
+#undef LAST_CASE
+            if (rc == B2SR_E_UNSUPPORTED) fail(rc, "no tcgen05 kernel for nf-pad %d, last-pad %d, scale %d", CF, c->NL, S);
+        }
+        TRY(rc);
+        TRY(prof_end(c));
+    }
+    return 0;
+}
+
+static int simple_layer(b2sr_ctx* c, Plan* P, int li, const __half* in, void* out) {
+    const LayerDev& L = c->layers[li];
+    const bool first = li == 0, last = li == (int)c->layers.size() - 1;
+    const int total = P->max_plane_px * (L.noutp / 8);
+    dim3 grid((unsigned)std::min(4096, (total + 255) / 256), (unsigned)P->planes.size());
+    TRY(prof_begin(c, 0, 0));
+    if (last)
+        simple_conv_kernel<true><<<grid, 256, 0, c->stream>>>(in, L.cinp, L.wplain, L.noutp, L.bias, L.slope,
+                                                              first ? 1.f / 255.f : 1.f, P->d_planes, out);
+    else
+        simple_conv_kernel<false><<<grid, 256, 0, c->stream>>>(in, L.cinp, L.wplain, L.noutp, L.bias, L.slope,
+                                                               first ? 1.f / 255.f : 1.f, P->d_planes, out);
+    CUDA_TRY(cudaGetLastError());
+    TRY(prof_end(c));
+    c->n_launch += 1;
+    return 0;
+}
+
+static bool use_tc(const b2sr_ctx* c) { return c->impl != 1; }
+
+// Runs layers [0, upto] for the planes of P; the final layer writes `out` (u8 or f32 frames).  Returns in *act the
+// buffer that holds the activations of layer `upto` when upto is not the last layer.
+static int run_plan(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, bool f32out, int upto, const __half** act) {
+    TRY(ensure_scratch(c, P->total_px));
+    TRY(encode_maps(c, P));
+    const int nl = (int)c->layers.size();
+    if (upto < 0 || upto >= nl) upto = nl - 1;
+    {
+        dim3 grid((unsigned)std::min(2048, (P->max_plane_px + 255) / 256), (unsigned)P->planes.size());
+        TRY(prof_begin(c, 0, 0));
+        prep_kernel<<<grid, 256, 0, c->stream>>>(d_frames, P->h, P->w, P->d_planes, c->in16);
+        CUDA_TRY(cudaGetLastError());
+        TRY(prof_end(c));
+        c->n_launch += 1;
+    }
+    int in_buf = 0;  // 0 in16, 1 ping, 2 pong
+    for (int li = 0; li <= upto; ++li) {
+        const bool last = li == nl - 1;
+        const int out_buf = in_buf == 1 ? 2 : 1;
+        const __half* inp = in_buf == 0 ? c->in16 : (in_buf == 1 ? c->ping : c->pong);
+        __half* outp = out_buf == 1 ? c->ping : c->pong;
+        if (use_tc(c)) {
+            TRY(tc_layer(c, P, li, in_buf, last ? d_out : (void*)outp, d_frames, P->h, P->w, f32out));
+        } else if (!last) {
+            TRY(simple_layer(c, P, li, inp, outp));
+        } else {
+            const LayerDev& L = c->layers[li];
+            if (c->cap_lastf < P->total_px) {
+                cudaStreamSynchronize(c->stream);
+                if (c->lastf) cudaFree(c->lastf);
+                c->lastf = nullptr, c->cap_lastf = 0;
+                CUDA_TRY(cudaMalloc(&c->lastf, (size_t)P->total_px * L.noutp * 4));
+                c->cap_lastf = P->total_px;
+            }
+            TRY(simple_layer(c, P, li, inp, c->lastf));
+            dim3 grid((unsigned)std::min(2048, (P->max_plane_px + 255) / 256), (unsigned)P->planes.size());
+            TRY(prof_begin(c, 0, 0));
+            if (f32out)
+                simple_shuffle_kernel<true><<<grid, 256, 0, c->stream>>>(c->lastf, L.noutp, P->d_planes, d_frames, P->h, P->w,
+                                                                        c->desc.scale, d_out);
+            else
+                simple_shuffle_kernel<false><<<grid, 256, 0, c->stream>>>(c->lastf, L.noutp, P->d_planes, d_frames, P->h, P->w,
+                                                                         c->desc.scale, d_out);
+            CUDA_TRY(cudaGetLastError());
+            TRY(prof_end(c));
+            c->n_launch += 1;
+        }
+        if (!last) {
+            if (act) *act = outp;
+            in_buf = out_buf;
+        }
+    }
+    return 0;
+}
+
+static int check_geom(int n, int h, int w, int tile, int halo) {
+    if (n < 1 || h < 1 || w < 1) return fail(B2SR_E_INVALID, "empty image (%d frames of %dx%d)", n, h, w);
+    if (h > 16384 || w > 16384) return fail(B2SR_E_INVALID, "image %dx%d too large", h, w);
+    if (tile < 0 || halo < 0 || (tile > 0 && halo >= tile)) return fail(B2SR_E_INVALID, "bad tiling: tile %d halo %d", tile, halo);
+    return 0;
+}
+
+static int frames_per_pass(const b2sr_ctx* c, int h, int w) {
+    if (c->max_batch > 0) return c->max_batch;
+    const double px = (double)h * w * 1.06;
+    return (int)std::max(1.0, std::min(16.0, floor(9.0e6 / px)));
+}
+
+static int run_batch_dev(b2sr_ctx* c, const uint8_t* d_in, void* d_out, bool f32out, int n, int h, int w, int tile, int halo) {
+    const int S = c->desc.scale;
+    const int B = frames_per_pass(c, h, w);
+    const size_t in_frame = (size_t)h * w * 3, out_frame = (size_t)h * S * w * S * 3 * (f32out ? 4 : 1);
+    for (int f = 0; f < n; f += B) {
+        const int nb = std::min(B, n - f);
+        Plan* P = nullptr;
+        TRY(build_plan(c, nb, h, w, tile, halo, &P));
+        TRY(run_plan(c, P, d_in + (size_t)f * in_frame, (uint8_t*)d_out + (size_t)f * out_frame, f32out, -1, nullptr));
+    }
+    return 0;
+}
+
+extern "C" int b2sr_run_batch_device(b2sr_ctx* c, const uint8_t* d_in, uint8_t* d_out, int n, int h, int w, int tile,
+                                     int halo, int sync) {
+    if (!c || !d_in || !d_out) return fail(B2SR_E_INVALID, "b2sr_run_batch_device: null argument");
+    TRY(check_geom(n, h, w, tile, halo));
+    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(run_batch_dev(c, d_in, d_out, false, n, h, w, tile, halo));
+    if (sync) CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int grow(uint8_t** p, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr, *cap = 0;
+    CUDA_TRY(cudaMalloc(p, need));
+    *cap = need;
+    return 0;
+}
+
+static int run_one(b2sr_ctx* c, const uint8_t* in, int h, int w, int in_stride, void* out, int out_stride, bool f32out,
+                   int tile, int halo, int memspace) {
+    if (!c || !in || !out) return fail(B2SR_E_INVALID, "b2sr_run: null argument");
+    TRY(check_geom(1, h, w, tile, halo));
+    const int S = c->desc.scale;
+    const size_t in_row = (size_t)w * 3, out_row = (size_t)w * S * 3 * (f32out ? 4 : 1);
+    if (in_stride == 0) in_stride = (int)in_row;
+    if (out_stride == 0) out_stride = (int)out_row;
+    if ((size_t)in_stride < in_row || (size_t)out_stride < out_row) return fail(B2SR_E_INVALID, "stride smaller than a row");
+    if (memspace != B2SR_MEM_HOST && memspace != B2SR_MEM_DEVICE) return fail(B2SR_E_INVALID, "memspace %d", memspace);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const bool packed = (size_t)in_stride == in_row && (size_t)out_stride == out_row;
+    const uint8_t* din = in;
+    void* dout = out;
+    if (memspace == B2SR_MEM_HOST || !packed) {
+        TRY(grow(&c->d_in, &c->cap_in, in_row * h));
+        TRY(grow(&c->d_out, &c->cap_out, out_row * h * S));
+        CUDA_TRY(cudaMemcpy2DAsync(c->d_in, in_row, in, in_stride, in_row, h,
+                                   memspace == B2SR_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
+        din = c->d_in, dout = c->d_out;
+    }
+    TRY(run_batch_dev(c, din, dout, f32out, 1, h, w, tile, halo));
+    if (dout != out)
+        CUDA_TRY(cudaMemcpy2DAsync(out, out_stride, dout, out_row, out_row, (size_t)h * S,
+                                   memspace == B2SR_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int b2sr_run_u8(b2sr_ctx* c, const uint8_t* in, int h, int w, int in_stride, uint8_t* out, int out_stride, int tile,
+                           int halo, int memspace) {
+    return run_one(c, in, h, w, in_stride, out, out_stride, false, tile, halo, memspace);
+}
+extern "C" int b2sr_run_f32(b2sr_ctx* c, const uint8_t* in, int h, int w, int in_stride, float* out, int out_stride, int tile,
+                            int halo, int memspace) {
+    return run_one(c, in, h, w, in_stride, out, out_stride, true, tile, halo, memspace);
+}
+
+// Host frames -> H2D -> network -> D2H, chunk by chunk, copies overlapped with compute on separate streams
+// (double-buffered staging).  The reference moves every frame through PNG files instead (upscale_processing.py:487,:519).
+extern "C" int b2sr_run_batch_host(b2sr_ctx* c, const uint8_t* h_in, uint8_t* h_out, int n, int h, int w, int tile, int halo) {
+    if (!c || !h_in || !h_out) return fail(B2SR_E_INVALID, "b2sr_run_batch_host: null argument");
+    TRY(check_geom(n, h, w, tile, halo));
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int S = c->desc.scale;
+    const int B = frames_per_pass(c, h, w);
+    const size_t in_frame = (size_t)h * w * 3, out_frame = in_frame * S * S;
+    TRY(grow(&c->d_in, &c->cap_in, in_frame * B));
+    TRY(grow(&c->d_out, &c->cap_out, out_frame * B));
+    TRY(grow(&c->d_in2, &c->cap_in2, in_frame * B));
+    TRY(grow(&c->d_out2, &c->cap_out2, out_frame * B));
+    uint8_t* din[2] = {c->d_in, c->d_in2};
+    uint8_t* dout[2] = {c->d_out, c->d_out2};
+    cudaEvent_t in_ready[2], compute_done[2], out_done[2];
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&in_ready[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&compute_done[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&out_done[i], cudaEventDisableTiming));
+    }
+    int rc = 0, k = 0;
+    for (int f = 0; f < n && !rc; f += B, ++k) {
+        const int nb = std::min(B, n - f), s = k & 1;
+        // staging slot s is free once the compute that read din[s] and the D2H that read dout[s] (chunk k-2) are done
+        if (k >= 2) {
+            cudaStreamWaitEvent(c->copy_in, compute_done[s], 0);
+            cudaStreamWaitEvent(c->stream, out_done[s], 0);
+        }
+        cudaMemcpyAsync(din[s], h_in + (size_t)f * in_frame, in_frame * nb, cudaMemcpyHostToDevice, c->copy_in);
+        cudaEventRecord(in_ready[s], c->copy_in);
+        cudaStreamWaitEvent(c->stream, in_ready[s], 0);
+        rc = run_batch_dev(c, din[s], dout[s], false, nb, h, w, tile, halo);
+        if (rc) break;
+        cudaEventRecord(compute_done[s], c->stream);
+        cudaStreamWaitEvent(c->copy_out, compute_done[s], 0);
+        cudaMemcpyAsync(h_out + (size_t)f * out_frame, dout[s], out_frame * nb, cudaMemcpyDeviceToHost, c->copy_out);
+        cudaEventRecord(out_done[s], c->copy_out);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(c->copy_in), e2 = cudaStreamSynchronize(c->stream), e3 = cudaStreamSynchronize(c->copy_out);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(in_ready[i]);
+        cudaEventDestroy(compute_done[i]);
+        cudaEventDestroy(out_done[i]);
+    }
+    if (rc) return rc;
+    for (cudaError_t e : {e1, e2, e3})
+        if (e != cudaSuccess) return fail(B2SR_E_CUDA, "b2sr_run_batch_host: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int b2sr_debug_layer(b2sr_ctx* c, const uint8_t* in, int h, int w, int layer, float* out) {
+    if (!c || !in || !out) return fail(B2SR_E_INVALID, "b2sr_debug_layer: null argument");
+    TRY(check_geom(1, h, w, 0, 0));
+    if (layer < 0 || layer >= (int)c->layers.size() - 1) return fail(B2SR_E_INVALID, "layer %d has no activation output", layer);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t in_bytes = (size_t)h * w * 3;
+    TRY(grow(&c->d_in, &c->cap_in, in_bytes));
+    CUDA_TRY(cudaMemcpyAsync(c->d_in, in, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    Plan* P = nullptr;
+    TRY(build_plan(c, 1, h, w, 0, 0, &P));
+    const __half* act = nullptr;
+    TRY(run_plan(c, P, c->d_in, nullptr, false, layer, &act));
+    const int nf = c->desc.nf;
+    const size_t npx = (size_t)h * w;
+    TRY(grow(&c->d_out, &c->cap_out, npx * nf * 4));
+    unpack_act_kernel<<<(unsigned)std::min<size_t>(4096, (npx * nf + 255) / 256), 256, 0, c->stream>>>(act, c->CF, nf, npx, (float*)c->d_out);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, c->d_out, npx * nf * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// options, stats
+// ------------------------------------------------------------------------------------------------
+extern "C" int b2sr_set_option(b2sr_ctx* c, int key, int64_t value) {
+    if (!c) return fail(B2SR_E_INVALID, "null context");
+    switch (key) {
+        case B2SR_OPT_IMPL:
+            if (value < 0 || value > 2) return fail(B2SR_E_INVALID, "impl %lld", (long long)value);
+            c->impl = (int)value;
+            return 0;
+        case B2SR_OPT_PROFILE:
+            c->profile = value != 0;
+            return 0;
+        case B2SR_OPT_MAX_BATCH:
+            if (value < 0 || value > 4096) return fail(B2SR_E_INVALID, "max_batch %lld", (long long)value);
+            c->max_batch = (int)value;
+            return 0;
+        case B2SR_OPT_DEBUG_DESC:
+            c->desc_mode = (int)value;
+            return 0;
+    }
+    return fail(B2SR_E_INVALID, "unknown option %d", key);
+}
+
+extern "C" int b2sr_reset_stats(b2sr_ctx* c) {
+    if (!c) return fail(B2SR_E_INVALID, "null context");
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->n_launch = c->n_tc = 0;
+    for (auto& r : c->prof) {
+        c->ev_pool.push_back(r.a);
+        c->ev_pool.push_back(r.b);
+    }
+    c->prof.clear();
+    return 0;
+}
+
+extern "C" int b2sr_get_stat(b2sr_ctx* c, int key, double* value) {
+    if (!c || !value) return fail(B2SR_E_INVALID, "null argument");
+    switch (key) {
+        case B2SR_STAT_LAUNCHES:
+            *value = c->n_launch;
+            return 0;
+        case B2SR_STAT_TC_LAUNCHES:
+            *value = c->n_tc;
+            return 0;
+        case B2SR_STAT_TC_MID_MS:
+        case B2SR_STAT_TC_MID_COUNT:
+        case B2SR_STAT_ALL_MS:
+        case B2SR_STAT_TC_MID_PIXELS: {
+            CUDA_TRY(cudaSetDevice(c->device));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            double mid_ms = 0, all_ms = 0, cnt = 0, px = 0;
+            for (auto& r : c->prof) {
+                float ms = 0;
+                CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+                all_ms += ms;
+                if (r.kind == 1) mid_ms += ms, cnt += 1, px += r.px;
+            }
+            *value = key == B2SR_STAT_TC_MID_MS ? mid_ms : key == B2SR_STAT_TC_MID_COUNT ? cnt : key == B2SR_STAT_ALL_MS ? all_ms : px;
+            return 0;
+        }
+    }
+    return fail(B2SR_E_INVALID, "unknown stat %d", key);
+}
+
+extern "C" int b2sr_synchronize(b2sr_ctx* c) {
+    if (!c) return fail(B2SR_E_INVALID, "null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" void* b2sr_stream(b2sr_ctx* c) { return c ? (void*)c->stream : nullptr; }

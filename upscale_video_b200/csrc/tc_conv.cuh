@@ -4,23 +4,20 @@
 // reference inside `ex.extract` (reference upscale/upscale_processing.py:278-281, :450-453; graph
 // models/2x_Compact_Pretrain.param:5-42).
 //
-// Layout.  Activations are channel-last fp16, CPIX channels per pixel (CPIX*2 = 32/64/128 bytes = one swizzle
-// row).  A work item is a band of `w` columns x `rows` rows of a plane.  The producer warp streams the band's
-// input rows (w+2 columns incl. halo; rows y0-1 .. y0+rows) with TMA into a shared-memory ring laid out as one
-// FLAT array of pixels with pitch `pitch` = band width + 2.  Because every pixel is exactly one swizzle row, the
-// A operand of filter tap (ky,kx) for the 128 consecutive flat output positions [p0, p0+128) is simply the 128
-// consecutive ring pixels starting at p0 + ky*pitch + kx: nine shifted UMMA descriptors over the same bytes,
-// no im2col, no data replication.  Flat positions that fall on the two halo columns produce junk rows of the
-// accumulator that are never stored (2/pitch of the tensor work).  TMA zero-fills out-of-plane coordinates,
-// which is exactly the convolution's zero padding at the plane (= reference tile) border.
-//
-// Ring wrap: the ring has R rows; the first MR rows are mirrored behind the last one (their TMA loads are
-// issued twice) so a 128-pixel operand that starts near the end never wraps.
+// Layout.  Activations are channel-last fp16, CPIX channels per pixel (CPIX*2 = 32/64/128 bytes = exactly one
+// swizzle row of the 32B/64B/128B shared-memory swizzle).  A work item is a band of `w` <= 128 columns x `rows`
+// rows of a plane.  The producer warp streams the band's input rows (columns x0-1 .. x0+TC_PITCH-2, rows
+// y0-1 .. y0+rows; TMA zero-fills outside the plane = the convolution's zero padding at the reference's tile
+// border) into a ring of R shared-memory rows of TC_PITCH pixels.  One M=128 accumulator tile = one band row:
+// because a pixel is one swizzle row, the A operand of filter tap (ky,kx) for output row t is the 128 consecutive
+// pixels of ring row t+ky starting at pixel kx -- nine shifted UMMA descriptors over the same bytes, no im2col,
+// no data replication.  The B operand of tap (ky,kx) is that tap's [NOUT][CPIX] weight slice, resident in shared
+// memory for the life of the CTA (pre-swizzled on the host).
 //
 // Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma issuer,
 // warps 2..5 = epilogue (tcgen05.ld -> bias/PReLU -> fp16 -> swizzled staging -> 128-bit coalesced stores, or
 // pixel-shuffle + nearest-upsampled residual + x255 + round-half-even/saturate for the last layer).
-// Two TMEM accumulators let the MMAs of tile i+1 overlap the epilogue of tile i.
+// Two TMEM accumulators let the MMAs of row t+1 overlap the epilogue of row t.
 #pragma once
 #include <stdio.h>
 
@@ -107,11 +104,15 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 // ------------------------------------------------------------------------------------------------
 // compile-time geometry shared by host and device
 // ------------------------------------------------------------------------------------------------
+constexpr int TC_BW = 128;     // output columns per band = UMMA M
+constexpr int TC_PITCH = 136;  // pixels per ring row: 130 needed (+-1 halo); 136 keeps every row swizzle-atom aligned
+
 template <int CPIX, int NOUT, int SHUF>
 struct TcCfg {
     static constexpr int PB = CPIX * 2;            // bytes per input pixel == swizzle row
     static constexpr int KSLABS = CPIX / 16;       // K=16 MMAs per filter tap
     static constexpr int WB = 9 * NOUT * PB;       // weight image bytes
+    static constexpr int ROWB = TC_PITCH * PB;     // bytes per ring row
     static constexpr int OB = NOUT * 2;            // bytes per output pixel (PReLU epilogue)
     static constexpr int CH = OB / 16;             // 16-byte chunks per output pixel
     static constexpr int STG = SHUF == 0 ? 4 * 32 * OB : 0;
@@ -121,12 +122,14 @@ struct TcCfg {
     static constexpr int MISC = 2 * NOUT * 4 + (2 * TC_MAX_SLOTS + 8) * 8 + 64;
     static_assert(CPIX == 16 || CPIX == 32 || CPIX == 64, "one pixel must be one swizzle row");
     static_assert(NOUT % 16 == 0 && NOUT >= 16 && NOUT <= 64, "UMMA M=128 needs N % 16 == 0");
-    static_assert((NOUT * PB) % (8 * PB) == 0, "per-tap weight tile must be whole swizzle atoms");
-    // bytes left for the input ring
-    static constexpr int ring_budget() { return B2SR_SMEM_LIMIT - 1024 - WB - STG - MISC; }
-    static constexpr int smem_bytes(int ring_rows, int pitch) {
-        return 1024 + WB + ((ring_rows * pitch * PB + 127) & ~127) + STG + MISC;
+    static_assert((NOUT * PB) % 1024 == 0, "per-tap weight tile must keep 1024-byte (swizzle atom) alignment");
+    static_assert(ROWB % (8 * PB) == 0, "ring rows must start on a swizzle atom");
+    // ring rows that fit beside the weights
+    static constexpr int ring_rows() {
+        int r = (B2SR_SMEM_LIMIT - 1024 - WB - STG - MISC) / ROWB;
+        return r > 16 ? 16 : r;
     }
+    static constexpr int smem_bytes(int ring_rows) { return 1024 + WB + ring_rows * ROWB + STG + MISC; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -136,17 +139,16 @@ template <int CPIX, int NOUT, int SHUF /*0 = PReLU->fp16, else pixel-shuffle fac
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcParams P) {
     using C = TcCfg<CPIX, NOUT, SHUF>;
     constexpr int PB = C::PB;
+    constexpr uint32_t ROWB = C::ROWB;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (sbase - raw);
 
-    const int pitch = P.pitch, R = P.R, MR = P.MR;
-    const uint32_t rowbytes = (uint32_t)pitch * PB;
-    const uint32_t ringbytes = ((uint32_t)(R + MR) * rowbytes + 127u) & ~127u;
+    const int R = P.R;
     const uint32_t w_s = sbase;
     const uint32_t ring_s = sbase + C::WB;
-    const uint32_t stg_off = C::WB + ringbytes;
+    const uint32_t stg_off = C::WB + (uint32_t)R * ROWB;
     const uint32_t fl_off = stg_off + C::STG;
     float* s_bias = reinterpret_cast<float*>(gbase + fl_off);
     float* s_slope = s_bias + NOUT;
@@ -204,12 +206,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 const int rows_in = I.rows + 2;
                 for (int rho = 0; rho < rows_in; ++rho) {
                     mbar_wait(empty_bar(slot), phase ^ 1u, 0);
-                    const bool mirror = slot < MR;
-                    mbar_expect_tx(full_bar(slot), mirror ? 2 * rowbytes : rowbytes);
-                    tma_load_4d(ring_s + slot * rowbytes, map, full_bar(slot), 0, I.x0 - 1, I.y0 - 1 + rho, I.plane);
-                    if (mirror)
-                        tma_load_4d(ring_s + (R + slot) * rowbytes, map, full_bar(slot), 0, I.x0 - 1, I.y0 - 1 + rho,
-                                    I.plane);
+                    mbar_expect_tx(full_bar(slot), ROWB);
+                    tma_load_4d(ring_s + slot * ROWB, map, full_bar(slot), 0, I.x0 - 1, I.y0 - 1 + rho, I.plane);
                     if (++slot == R) {
                         slot = 0;
                         phase ^= 1u;
@@ -221,21 +219,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         // ======================= MMA issuer =======================
         if (lane == 0) {
             const uint32_t desc_hi = ((8u * PB) >> 4) | (1u << 14) | (C::LAYOUT << 29);
-            const int RP = R * pitch;
-            int full_slot = 0, rel_slot = 0, slot0 = 0;
+            int full_slot = 0;  // next ring slot to wait for
             uint32_t full_phase = 0;
+            int rs = 0;  // ring slot of input row t of the current item
             uint32_t tile_cnt = 0;
             mbar_wait(w_bar, 0, 1);
             for (int it = blockIdx.x; it < P.n_items; it += gridDim.x) {
                 const TcItem I = P.items[it];
-                const int rows_in = I.rows + 2;
-                const int nt = ((I.rows - 1) * pitch + I.w - 1) / TC_TILE_M + 1;
-                int n_full = 0, n_rel = 0;  // item-local counts of rows waited-for / released
-                for (int t = 0; t < nt; ++t) {
-                    const int p0 = t * TC_TILE_M;
-                    int need = (p0 + TC_TILE_M - 1 + 2 * pitch + 2) / pitch;
-                    if (need > rows_in - 1) need = rows_in - 1;
-                    while (n_full <= need) {
+                int n_full = 0;  // input rows of this item already waited for
+                for (int t = 0; t < I.rows; ++t) {
+                    while (n_full < t + 3) {  // output row t reads input rows t, t+1, t+2
                         mbar_wait(full_bar(full_slot), full_phase, 2);
                         ++n_full;
                         if (++full_slot == R) {
@@ -247,15 +240,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                     mbar_wait(tempty_bar(buf), ((tile_cnt >> 1) & 1u) ^ 1u, 3);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + buf * NOUT;
-                    const int fl = (slot0 * pitch + p0) % RP;
                     uint32_t accum = 0;
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
+                        int s = rs + ky;
+                        if (s >= R) s -= R;
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
-                            int f = fl + ky * pitch + kx;
-                            if (f >= RP) f -= RP;
-                            const uint32_t a_addr = ring_s + (uint32_t)f * PB;
+                            const uint32_t a_addr = ring_s + (uint32_t)s * ROWB + (uint32_t)kx * PB;
                             const uint32_t b_addr = w_s + (ky * 3 + kx) * (NOUT * PB);
                             uint32_t hi_a = desc_hi;
                             if (P.desc_mode == 1) hi_a |= ((a_addr >> 7) & 7u) << 17;
@@ -272,15 +264,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                     }
                     umma_commit(tfull_bar(buf));
                     ++tile_cnt;
-                    int lim = (t + 1 < nt) ? (p0 + TC_TILE_M) / pitch : rows_in;
-                    if (lim > rows_in) lim = rows_in;
-                    while (n_rel < lim) {
-                        umma_commit(empty_bar(rel_slot));
-                        ++n_rel;
-                        if (++rel_slot == R) rel_slot = 0;
+                    // input row t is dead once these MMAs retire; the last tile also frees the two trailing rows
+                    const int nrel = (t + 1 < I.rows) ? 1 : 3;
+                    for (int j = 0; j < nrel; ++j) {
+                        umma_commit(empty_bar(rs));
+                        if (++rs == R) rs = 0;
                     }
                 }
-                slot0 = (slot0 + rows_in) % R;
             }
         }
     } else {
@@ -288,14 +278,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         const int q = warp & 3;  // TMEM lane quadrant this warp may read
         uint32_t tile_cnt = 0;
         const float scale_acc = P.acc_scale;
+        const int c = q * 32 + lane;  // column inside the band
         for (int it = blockIdx.x; it < P.n_items; it += gridDim.x) {
             const TcItem I = P.items[it];
-            const int nt = ((I.rows - 1) * pitch + I.w - 1) / TC_TILE_M + 1;
-            for (int t = 0; t < nt; ++t, ++tile_cnt) {
+            const bool valid = c < I.w;
+            for (int t = 0; t < I.rows; ++t, ++tile_cnt) {
                 const uint32_t buf = tile_cnt & 1u;
-                const int p = t * TC_TILE_M + q * 32 + lane;
-                const int r = p / pitch, c = p - r * pitch;
-                const bool valid = (c < I.w) && (r < I.rows);
                 mbar_wait(tfull_bar(buf), (tile_cnt >> 1) & 1u, 4);
                 tc_fence_after();
                 uint32_t acc[NOUT];
@@ -311,7 +299,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                     // bias + PReLU -> fp16, via swizzled per-warp staging, then 128-bit coalesced global stores
                     constexpr int CH = C::CH;
                     uint4* stg = reinterpret_cast<uint4*>(gbase + stg_off + (warp - 2) * (32 * C::OB));
-                    const int off = valid ? ((I.y0 + r) * I.Wt + I.x0 + c) : -1;
+                    const int off = valid ? ((I.y0 + t) * I.Wt + I.x0 + c) : -1;
 #pragma unroll
                     for (int j = 0; j < NOUT; j += 8) {
                         uint32_t pk[4];
@@ -340,7 +328,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 } else {
                     // last layer: pixel shuffle + nearest-upsampled input residual + x255 (+ round/saturate)
                     constexpr int S = SHUF;
-                    const int fy = I.fy0 + I.y0 + r, fx = I.fx0 + I.x0 + c;
+                    const int fy = I.fy0 + I.y0 + t, fx = I.fx0 + I.x0 + c;
                     if (valid && fy >= I.cy0 && fy < I.cy1 && fx >= I.cx0 && fx < I.cx1) {
                         const uint8_t* px = P.frames_in + ((size_t)((size_t)I.frame * P.frame_h + fy) * P.frame_w + fx) * 3;
                         float xin[3];
@@ -397,6 +385,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
+        __syncwarp();
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TCOLS)
                      : "memory");

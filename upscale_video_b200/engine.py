@@ -1,0 +1,198 @@
+"""ctypes binding of libb2sr.so (C ABI: include/b2sr.h) -- the object the worker functions hold instead of the
+reference's process-global ``ncnn.Net`` (reference upscale/upscale_processing.py:22,57-73).
+
+There is deliberately no CPU implementation behind this class: if the shared library is missing or no sm_100
+device is visible, construction raises :class:`EngineError`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import ncnn_model
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2sr.so")
+
+MEM_HOST, MEM_DEVICE = 0, 1
+OPT_IMPL, OPT_PROFILE, OPT_MAX_BATCH, OPT_DEBUG_DESC = 1, 2, 3, 4
+STAT_LAUNCHES, STAT_TC_LAUNCHES, STAT_TC_MID_MS, STAT_TC_MID_COUNT, STAT_ALL_MS, STAT_TC_MID_PIXELS = 1, 2, 3, 4, 5, 6
+IMPL_AUTO, IMPL_SIMPLE, IMPL_TCGEN05 = 0, 1, 2
+
+# every symbol include/b2sr.h declares (tests check the library exports exactly these)
+SYMBOLS = [
+    "b2sr_abi_version", "b2sr_device_count", "b2sr_default_device", "b2sr_device_name", "b2sr_create", "b2sr_destroy",
+    "b2sr_run_u8", "b2sr_run_f32", "b2sr_run_batch_device", "b2sr_run_batch_host", "b2sr_debug_layer",
+    "b2sr_set_option", "b2sr_get_stat", "b2sr_reset_stats", "b2sr_synchronize", "b2sr_stream", "b2sr_last_error",
+]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class NetDesc(ctypes.Structure):
+    _fields_ = [("family", ctypes.c_int32), ("cin", ctypes.c_int32), ("nf", ctypes.c_int32), ("n_mid", ctypes.c_int32),
+                ("scale", ctypes.c_int32), ("reserved", ctypes.c_int32 * 11)]
+
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen libb2sr.so and declare prototypes.  Never falls back to anything else."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise EngineError("libb2sr.so not built (%s); run `python -m upscale_video_b200.build`" % path)
+    lib = ctypes.CDLL(path)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+    lib.b2sr_abi_version.restype = i32
+    lib.b2sr_device_count.restype = i32
+    lib.b2sr_default_device.restype = i32
+    lib.b2sr_device_name.argtypes = [i32, ctypes.c_char_p, i32]
+    lib.b2sr_create.argtypes = [ctypes.POINTER(vp), i32, vp, ctypes.c_size_t, ctypes.POINTER(NetDesc)]
+    lib.b2sr_destroy.argtypes = [vp]
+    lib.b2sr_destroy.restype = None
+    lib.b2sr_run_u8.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, i32, i32]
+    lib.b2sr_run_f32.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, i32, i32]
+    lib.b2sr_run_batch_device.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32]
+    lib.b2sr_run_batch_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32]
+    lib.b2sr_debug_layer.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.b2sr_set_option.argtypes = [vp, i32, i64]
+    lib.b2sr_get_stat.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double)]
+    lib.b2sr_reset_stats.argtypes = [vp]
+    lib.b2sr_synchronize.argtypes = [vp]
+    lib.b2sr_stream.argtypes = [vp]
+    lib.b2sr_stream.restype = vp
+    lib.b2sr_last_error.restype = ctypes.c_char_p
+    if lib.b2sr_abi_version() != 1:
+        raise EngineError("libb2sr.so ABI version %d, expected 1" % lib.b2sr_abi_version())
+    _lib = lib
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise EngineError("%s failed (%d): %s" % (what, rc, load_library().b2sr_last_error().decode(errors="replace")))
+
+
+def device_count() -> int:
+    """``ncnn.get_gpu_count()`` (reference test_gpus.py:47)."""
+    return load_library().b2sr_device_count()
+
+
+def default_device() -> int:
+    """``ncnn.get_default_gpu_index()`` (reference test_gpus.py:53)."""
+    return load_library().b2sr_default_device()
+
+
+def device_name(dev: int) -> str:
+    """``ncnn.get_gpu_info(i).device_name()`` (reference test_gpus.py:59-66)."""
+    buf = ctypes.create_string_buffer(256)
+    _check(load_library().b2sr_device_name(dev, buf, 256), "b2sr_device_name")
+    return buf.value.decode()
+
+
+def _ptr(a):
+    """Host numpy array, torch tensor (host or cuda) or raw integer address -> (void*, is_device)."""
+    if isinstance(a, np.ndarray):
+        return ctypes.c_void_p(a.ctypes.data), False
+    if isinstance(a, int):
+        return ctypes.c_void_p(a), True
+    if hasattr(a, "data_ptr"):
+        return ctypes.c_void_p(a.data_ptr()), bool(getattr(a, "is_cuda", False))
+    raise TypeError("unsupported buffer type %r" % type(a))
+
+
+class Engine:
+    """One network bound to one GPU (one per worker process, like the reference's ``net``)."""
+
+    def __init__(self, graph: ncnn_model.Graph, device: int = 0):
+        self._h = None
+        self._lib = load_library()
+        desc, blob = ncnn_model.pack_compact_blob(graph)
+        self.desc = desc
+        self.scale = desc.scale
+        self.device = device
+        nd = NetDesc(family=ncnn_model.FAMILY_COMPACT, cin=desc.cin, nf=desc.nf, n_mid=desc.n_mid, scale=desc.scale)
+        h = ctypes.c_void_p()
+        _check(self._lib.b2sr_create(ctypes.byref(h), device, blob.ctypes.data, blob.nbytes, ctypes.byref(nd)), "b2sr_create")
+        self._h = h
+
+    @classmethod
+    def from_files(cls, model_path: str, stem: str, device: int = 0) -> "Engine":
+        return cls(ncnn_model.load_model(model_path, stem), device)
+
+    def close(self):
+        if self._h is not None:
+            self._lib.b2sr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- single frame -------------------------------------------------------------------------
+    def run_u8(self, img: np.ndarray, tile: int = 960, halo: int = 10) -> np.ndarray:
+        """u8 HWC frame -> u8 HWC frame, the image the reference's ``cv2.imwrite(output)`` stores
+        (upscale_image :487-519 with tile=960/halo=10; apply_model :263-288 with tile=0)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w, ch = img.shape
+        assert ch == 3
+        out = np.empty((h * self.scale, w * self.scale, 3), np.uint8)
+        _check(self._lib.b2sr_run_u8(self._h, img.ctypes.data, h, w, 0, out.ctypes.data, 0, tile, halo, MEM_HOST), "b2sr_run_u8")
+        return out
+
+    def run_f32(self, img: np.ndarray, tile: int = 960, halo: int = 10) -> np.ndarray:
+        """The float canvas before imwrite (``output_tile * 255`` scattered into ``output``, :462-477)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w, ch = img.shape
+        assert ch == 3
+        out = np.empty((h * self.scale, w * self.scale, 3), np.float32)
+        _check(self._lib.b2sr_run_f32(self._h, img.ctypes.data, h, w, 0, out.ctypes.data, 0, tile, halo, MEM_HOST), "b2sr_run_f32")
+        return out
+
+    # ---- batches ------------------------------------------------------------------------------
+    def run_batch_device(self, d_in, d_out, n: int, h: int, w: int, tile: int = 960, halo: int = 10, sync: bool = False):
+        """Device-resident packed frames (torch cuda uint8 tensors or raw device addresses)."""
+        pi, _ = _ptr(d_in)
+        po, _ = _ptr(d_out)
+        _check(self._lib.b2sr_run_batch_device(self._h, pi, po, n, h, w, tile, halo, int(sync)), "b2sr_run_batch_device")
+
+    def run_batch_host(self, h_in, h_out, n: int, h: int, w: int, tile: int = 960, halo: int = 10):
+        """Host frames (ideally pinned) through the double-buffered H2D -> network -> D2H pipeline."""
+        pi, _ = _ptr(h_in)
+        po, _ = _ptr(h_out)
+        _check(self._lib.b2sr_run_batch_host(self._h, pi, po, n, h, w, tile, halo), "b2sr_run_batch_host")
+
+    # ---- bring-up / measurement ---------------------------------------------------------------
+    def debug_layer(self, img: np.ndarray, layer: int) -> np.ndarray:
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w, _ = img.shape
+        out = np.empty((h, w, self.desc.nf), np.float32)
+        _check(self._lib.b2sr_debug_layer(self._h, img.ctypes.data, h, w, layer, out.ctypes.data), "b2sr_debug_layer")
+        return out
+
+    def set_option(self, key: int, value: int):
+        _check(self._lib.b2sr_set_option(self._h, key, value), "b2sr_set_option")
+
+    def stat(self, key: int) -> float:
+        v = ctypes.c_double()
+        _check(self._lib.b2sr_get_stat(self._h, key, ctypes.byref(v)), "b2sr_get_stat")
+        return v.value
+
+    def reset_stats(self):
+        _check(self._lib.b2sr_reset_stats(self._h), "b2sr_reset_stats")
+
+    def synchronize(self):
+        _check(self._lib.b2sr_synchronize(self._h), "b2sr_synchronize")
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.b2sr_stream(self._h) or 0)

@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py -- 1080p frames/s of the frame-upscale hot path (2x_Compact_Pretrain) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A *step* is one pass of the hot path (reference upscale_frames -> upscale_image -> process_tile -> network,
+upscale/upscale_processing.py:480-598) over one batch of B synthetic 1920x1080 BGR u8 frames per GPU, with the
+reference's 960-px tiling + 10-px halo reproduced on the device (4 planes per frame).  Frames shard across
+ranks with no data-path collective (weak scaling: B frames per rank); NCCL only broadcasts the packed weight
+blob from rank 0 at start-up.
+
+The one JSON line printed by rank 0 follows the contract in the task statement:
+  value      frames/s with inputs and outputs resident in HBM (CUDA events on the engine's stream, max over ranks)
+  e2e        frames/s through Engine.run_batch_host: pinned host buffers, H2D and D2H inside the timed region
+  roofline   the dominant kernel (tcgen05 64->64 conv): algorithmic FLOPs per launch / mean launch time
+             (per-launch CUDA events recorded on the engine's stream inside the timed region)
+  cpu_baseline  the CPU oracle (oracle/, a port of the reference graph + glue -- ncnn itself is not installable)
+             timed on the host cores on a bounded sample of the same workload
+`--impl reference` times that CPU port alone, with every host thread, on the same config (rank 0 only).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = "2x_Compact_Pretrain"
+H, W, SCALE = 1080, 1920, 2
+TILE, HALO = 960, 10
+MAC_PER_PX_MID = 64 * 64 * 9                 # one nf->nf convolution
+MAC_PER_PX_NET = 598464                      # whole 2x_Compact graph
+METRIC = "1080p frames/sec (2x_Compact_Pretrain)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap", nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_port_fps(sample_hw=(270, 480), reps=1, threads=None):
+    """Times the CPU oracle (f32, what ncnn's CPU path computes in) on a crop of one synthetic frame and scales
+    by area to frames/s.  Returns (fps, threads, description, seconds)."""
+    from oracle import oracle
+    from upscale_video_b200 import ncnn_model
+    threads = threads or os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    layers = oracle.read_model(ncnn_model.packaged_model_dir(), MODEL)
+    rng = np.random.default_rng(0)
+    h, w = sample_hw
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    oracle.upscale_image_array(layers, img[:32, :64], SCALE, "f32")  # warm the library
+    t0 = time.time()
+    for _ in range(reps):
+        oracle.upscale_image_array(layers, img, SCALE, "f32", TILE, HALO)
+    dt = (time.time() - t0) / reps
+    fps = (h * w) / float(H * W) / dt
+    return fps, threads, "%dx%d crop (1/%.1f of a 1080p frame), f32 C oracle with OpenMP, scaled by area" % (
+        h, w, H * W / float(h * w)), dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's arithmetic on the host CPU (port: ncnn_vulkan cannot be installed)."""
+    if rank != 0:
+        return
+    fps_list = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        fps, threads, desc, dt = cpu_port_fps(reps=1)
+        if i >= args.warmup:
+            fps_list.append(fps)
+        info = (threads, desc, dt)
+    fps = float(np.mean(fps_list))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * info[2], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "synthetic 1080p RGB batch, 2x_Compact_Pretrain, reference tiling 960+10", "step": info[1]},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": info[0], "kind": "port", "sample": info[1]},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16, help="frames per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    from upscale_video_b200 import engine as E
+    from upscale_video_b200 import ncnn_model
+    from upscale_video_b200 import parallel
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path to time)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # rank 0 reads the model; everyone else receives the packed blob over NCCL (north_star: weight broadcast)
+    packed = parallel.broadcast_packed_model(
+        (lambda: ncnn_model.pack_compact_blob(ncnn_model.load_model(ncnn_model.packaged_model_dir(), MODEL))),
+        rank, world, device=torch.device("cuda", local_rank))
+    eng = E.Engine(device=local_rank, packed=packed)
+
+    B = args.batch
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    d_in = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device="cuda", generator=gen)
+    d_out = torch.empty((B, H * SCALE, W * SCALE, 3), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        eng.run_batch_device(d_in, d_out, B, H, W, TILE, HALO, sync=False)
+
+    for _ in range(args.warmup):
+        step()
+    eng.synchronize()
+    eng.set_option(E.OPT_PROFILE, 1)
+    eng.reset_stats()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record()
+    for _ in range(args.steps):
+        step()
+    with torch.cuda.stream(stream):
+        ev1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.stat(E.STAT_LAUNCHES)
+    mid_ms, mid_n = eng.stat(E.STAT_TC_MID_MS), eng.stat(E.STAT_TC_MID_COUNT)
+    all_ms = eng.stat(E.STAT_ALL_MS)
+    eng.set_option(E.OPT_PROFILE, 0)
+    eng.reset_stats()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max / 1000.0)
+
+    # ---- end to end: pinned host frames in, pinned host frames out, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        h_in = torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()
+        h_in.copy_(d_in.cpu())
+        h_out = torch.empty((B, H * SCALE, W * SCALE, 3), dtype=torch.uint8).pin_memory()
+        for _ in range(2):
+            eng.run_batch_host(h_in, h_out, B, H, W, TILE, HALO)
+        barrier()
+        t0 = time.perf_counter()
+        e_steps = max(3, args.steps // 2)
+        for _ in range(e_steps):
+            eng.run_batch_host(h_in, h_out, B, H, W, TILE, HALO)  # synchronous: returns when the last D2H landed
+        barrier()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        checksum = int(h_out[0, ::97, ::89].to(torch.int64).sum())
+        e2e = {"value": world * B * e_steps / float(te.item()), "unit": "frames/s", "h2d_bytes_per_step": int(h_in.numel()),
+               "d2h_bytes_per_step": int(h_out.numel()), "steps": e_steps, "timer": "host perf_counter around synchronous calls",
+               "result_checksum": checksum}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = load_peaks()
+    # frames one launch covers (the engine splits a batch into passes); exact frame pixels: no halo, no padding, no junk
+    frames_per_launch = B * args.steps * 16.0 / max(mid_n, 1)
+    flop_launch = 2.0 * MAC_PER_PX_MID * frames_per_launch * H * W
+    ach = flop_launch / (mid_ms / max(mid_n, 1) * 1e-3) / 1e12 if mid_n else None
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    roofline = {
+        "bound": "tensor", "kernel": "tc_conv_kernel<64,64,0> (3x3 conv 64->64 + bias + PReLU, tcgen05 kind::f16)",
+        "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak if ach else None),
+        "peak_source": peak_src + ", bf16_tflops_sustained (kernel timed inside a long step)",
+        "frac_of_burst_peak": (ach / peaks["bf16_tflops"] if ach else None),
+        "flop_per_launch": flop_launch, "frames_per_launch": frames_per_launch, "launches_timed": mid_n, "mean_launch_ms": mid_ms / max(mid_n, 1),
+        "share_of_step": (mid_ms / all_ms if all_ms else None),
+        "whole_net_tflops": value / world * 2.0 * MAC_PER_PX_NET * H * W / 1e12,
+        "traffic": None,
+    }
+    cpu = None
+    if not args.no_cpu_baseline:
+        fps, threads, desc, dt = cpu_port_fps(reps=1)
+        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": desc, "seconds": dt}
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 storage / f32 accumulate", "data": "synthetic",
+        "config": {"workload": "synthetic 1080p RGB batch, 2x_Compact_Pretrain, 1xB200 per rank (BASELINE configs[1])",
+                   "frames_per_gpu_per_step": B, "frame": [H, W, 3], "tile": TILE, "halo": HALO,
+                   "l2": "inputs+outputs per step are %d MB per GPU, larger than the 126 MB L2" % ((d_in.numel() + d_out.numel()) >> 20),
+                   "parallelism": "frames sharded over %d rank(s), no data-path collective; weights NCCL-broadcast" % world},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,82 @@
+"""CPU: the C-ABI shared library builds, loads without a GPU driver, exports every symbol include/b2sr.h declares,
+and fails loudly (no CPU fallback) when asked to compute without a device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from upscale_video_b200 import build, engine
+    build.build_lib()
+    return engine.load_library()
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "b2sr.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2sr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_exports_every_declared_symbol(lib):
+    from upscale_video_b200 import engine
+    declared = _header_functions()
+    assert declared == sorted(engine.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.b2sr_abi_version() == 1
+
+
+def test_no_libcuda_link_dependency():
+    """The library must dlopen on a box without the NVIDIA driver (driver API is resolved at run time)."""
+    import subprocess
+    from upscale_video_b200 import engine
+    out = subprocess.run(["ldd", engine.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libcuda.so" not in out and "libcudart" not in out and "not found" not in out
+
+
+def test_net_desc_layout():
+    from upscale_video_b200 import engine
+    assert ctypes.sizeof(engine.NetDesc) == 16 * 4
+
+
+def test_argument_validation_without_device(lib):
+    from upscale_video_b200 import engine
+    h = ctypes.c_void_p()
+    nd = engine.NetDesc(family=99, cin=3, nf=64, n_mid=16, scale=2)
+    blob = np.zeros(4, np.float32)
+    assert lib.b2sr_create(ctypes.byref(h), 0, blob.ctypes.data, blob.nbytes, ctypes.byref(nd)) == -5
+    assert b"family" in lib.b2sr_last_error()
+    nd = engine.NetDesc(family=1, cin=3, nf=64, n_mid=16, scale=3)
+    assert lib.b2sr_create(ctypes.byref(h), 0, blob.ctypes.data, blob.nbytes, ctypes.byref(nd)) == -5
+    nd = engine.NetDesc(family=1, cin=3, nf=64, n_mid=16, scale=2)
+    assert lib.b2sr_create(ctypes.byref(h), 0, blob.ctypes.data, blob.nbytes, ctypes.byref(nd)) == -1  # blob size
+    assert h.value is None
+    assert lib.b2sr_run_u8(None, None, 1, 1, 0, None, 0, 0, 0, 0) == -1
+
+
+def test_no_cpu_fallback(model_dir):
+    """Without a visible sm_100 device the engine must refuse to exist (never compute on the CPU)."""
+    import torch
+    from upscale_video_b200 import engine
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible; the refusal path is covered on the CPU box")
+    assert engine.device_count() == 0 and engine.default_device() == -1
+    with pytest.raises(engine.EngineError, match="no CUDA device"):
+        engine.Engine.from_files(model_dir, "2x_Compact_Pretrain", 0)
+
+
+def test_product_code_never_imports_oracle():
+    """oracle/ is test infrastructure: nothing under upscale_video_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "upscale_video_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "liboracle" not in src, f

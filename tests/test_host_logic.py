@@ -1,0 +1,163 @@
+"""CPU: host-side logic of the drop-in worker module (upscale_video_b200/upscale_processing.py) and the
+multi-process plumbing (gloo, world_size 2)."""
+import logging
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from upscale_video_b200 import parallel
+from upscale_video_b200 import upscale_processing as up
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_get_frames():
+    assert up.get_frames("1,4-6,9") == [1, 4, 5, 6, 9]
+    assert up.get_frames("7") == [7]
+
+
+@pytest.mark.parametrize("h,w", [(1080, 1920), (540, 960), (1278, 1920), (24, 1000), (969, 961), (1930, 975), (5, 5), (960, 960), (970, 1940)])
+def test_tile_rect_matches_oracle(h, w):
+    """tile_rect restates reference process_tile :398-427; the oracle restates it independently."""
+    import math
+    rects = {(r[0], r[1]): r[2:] for r in oracle.tile_rects(h, w)}
+    for y in range(math.ceil(h / 960)):
+        for x in range(math.ceil(w / 960)):
+            (iy0, iy1, ix0, ix1), (cy0, cy1, cx0, cx1) = up.tile_rect(y, x, 960, h, w)
+            assert (iy0, iy1, ix0, ix1, cy0, cy1, cx0, cx1) == rects[(y, x)]
+    assert len(rects) == math.ceil(h / 960) * math.ceil(w / 960)
+
+
+def test_logging_callback_exits_on_error(caplog):
+    with caplog.at_level(logging.DEBUG):
+        up.logging_callback([["debug", "d"], ["info", "i"]])
+    assert "i" in caplog.text
+    with pytest.raises(SystemExit):
+        up.logging_callback([["info", "ok"], ["error", "boom"], ["info", "never"]])
+
+
+class _FakeNet:
+    """Stands in for the engine in host-logic tests only (no arithmetic is checked with it)."""
+    scale = 2
+
+    def __init__(self, fail=False):
+        self.fail, self.calls, self.closed = fail, [], False
+
+    def run_u8(self, img, tile=960, halo=10):
+        self.calls.append(("u8", img.shape, tile, halo))
+        if self.fail:
+            raise RuntimeError("device lost")
+        return np.zeros((img.shape[0] * self.scale, img.shape[1] * self.scale, 3), np.uint8)
+
+    def run_f32(self, img, tile=960, halo=10):
+        self.calls.append(("f32", img.shape, tile, halo))
+        if self.fail:
+            raise RuntimeError("device lost")
+        return np.full((img.shape[0] * self.scale, img.shape[1] * self.scale, 3), 7.0, np.float32)
+
+    def close(self):
+        self.closed = True
+
+
+@pytest.fixture
+def frame_png(tmp_path):
+    import cv2
+    p = str(tmp_path / "3.extract.png")
+    cv2.imwrite(p, np.random.default_rng(0).integers(0, 256, (30, 1000, 3), dtype=np.uint8))
+    return p
+
+
+def test_upscale_image_contract(frame_png, tmp_path, monkeypatch):
+    import cv2
+    net = _FakeNet()
+    monkeypatch.setattr(up, "net", net)
+    out = str(tmp_path / "3.png")
+    items = up.upscale_image(frame_png, out, 2, 1, 3, 10, remove=True)
+    assert net.calls == [("u8", (30, 1000, 3), 960, 10)]
+    assert items[:2] == [["debug", "Processing Tile: 1/2"], ["debug", "Processing Tile: 2/2"]]
+    assert items[-1] == ["info", "Upscaling Batch: 1 : Upscaled 3/10"]
+    assert not os.path.exists(frame_png) and cv2.imread(out).shape == (60, 2000, 3)
+
+
+def test_upscale_image_variants(frame_png, monkeypatch):
+    monkeypatch.setattr(up, "net", _FakeNet())
+    items = up.upscale_image(frame_png, None, 2, None, 3, 10, remove=False)  # test_gpus.py usage
+    assert items[-1] == ["info", "Upscaled 3/10"] and os.path.exists(frame_png)
+    items = up.upscale_image(frame_png, "x.png", 2, [3, 4], 3, 10, remove=False)
+    assert items[-1] == ["info", "Upscaled x.png"]
+    os.remove("x.png")
+
+
+def test_errors_become_log_items(frame_png, monkeypatch):
+    net = _FakeNet(fail=True)
+    monkeypatch.setattr(up, "net", net)
+    items = up.upscale_image(frame_png, None, 2, None, 1, 1, remove=True)
+    assert [i[0] for i in items[-2:]] == ["error", "error"] and items[-2][1] == "Upscale failed"
+    assert os.path.exists(frame_png), "input must survive a failed frame (resume contract)"
+    assert net.closed and up.net is None
+    monkeypatch.setattr(up, "net", _FakeNet(fail=True))
+    items = up.apply_model(frame_png, "o.png", True)
+    assert items[0] == ["error", "Model processing failed"] and os.path.exists(frame_png)
+    # wrong scale is an error item too, not an exception
+    monkeypatch.setattr(up, "net", _FakeNet())
+    assert up.upscale_image(frame_png, None, 4, None, 1, 1, remove=False)[-2][0] == "error"
+
+
+def test_process_tile_scatter(monkeypatch):
+    net = _FakeNet()
+    monkeypatch.setattr(up, "net", net)
+    img = np.zeros((30, 1000, 3), np.uint8)
+    canvas = np.zeros((60, 2000, 3))
+    items = []
+    assert up.process_tile(img, 960, 2, 0, 1, 30, 1000, canvas, items) is None
+    assert net.calls == [("f32", (30, 50, 3), 0, 0)]  # 40 core columns + 10 halo on the left
+    assert (canvas[:, 1920:] == 7.0).all() and (canvas[:, :1920] == 0).all()
+    monkeypatch.setattr(up, "net", _FakeNet(fail=True))
+    assert up.process_tile(img, 960, 2, 0, 0, 30, 1000, canvas, items) == -1 and items[0][0] == "error"
+
+
+def test_shard_frames():
+    frames = list(range(1, 12))
+    parts = [parallel.shard_frames(frames, r, 4) for r in range(4)]
+    assert sorted(sum(parts, [])) == frames and parts[1] == [2, 6, 10]
+
+
+def _gloo_worker(rank, world, port, model_dir, q):
+    import torch.distributed as dist
+    from upscale_video_b200 import ncnn_model
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    loads = []
+
+    def load():
+        loads.append(1)
+        return ncnn_model.pack_compact_blob(ncnn_model.load_model(model_dir, "2x_Compact_Pretrain"))
+
+    desc, blob = parallel.broadcast_packed_model(load, rank, world, device=None)
+    q.put((rank, len(loads), (desc.cin, desc.nf, desc.n_mid, desc.scale, desc.input_blob), float(blob.sum()), blob.size,
+           parallel.shard_frames(range(10), rank, world)))
+    dist.destroy_process_group()
+
+
+def test_weight_broadcast_gloo_world2(model_dir):
+    """N>1 path on CPU: rank 0 alone reads the model, rank 1 receives identical bytes; frames shard disjointly."""
+    import multiprocessing as mp
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, model_dir, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    (r0, l0, d0, s0, n0, f0), (r1, l1, d1, s1, n1, f1) = res
+    assert (l0, l1) == (1, 0) and d0 == d1 == (3, 64, 16, 2, "input") and s0 == s1 and n0 == n1 == 598464 + 1100 + 1088
+    assert sorted(f0 + f1) == list(range(10)) and not set(f0) & set(f1)

@@ -1,0 +1,133 @@
+"""CPU: model loading (upscale_video_b200/ncnn_model.py) -- ncnn text/bin grammar, .b2sr container, family
+recognition and blob packing for b2sr_create.  The product loader is checked against the oracle's independent
+reader on the packaged models."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import HURR
+from oracle import oracle
+from upscale_video_b200 import ncnn_model as M
+
+
+def _tiny_ncnn(tmp_path, nf=8, n_mid=2, r=2, fp16=True):
+    rng = np.random.default_rng(3)
+    lines, blob = [], b""
+    names = iter(range(100))
+
+    def conv(name, bottom, top, cin, cout):
+        nonlocal blob
+        w = (rng.integers(-64, 64, cout * cin * 9) / 64.0).astype(np.float32)
+        if fp16:
+            raw = w.astype("<f2").tobytes()
+            blob += struct.pack("<I", 0x01306B47) + raw + b"\0" * ((-len(raw)) % 4)
+        else:
+            blob += struct.pack("<I", 0) + w.astype("<f4").tobytes()
+        b = (rng.integers(-32, 32, cout) / 32.0).astype("<f4")
+        blob += b.tobytes()
+        lines.append("Convolution %s 1 1 %s %s 0=%d 1=3 4=1 5=1 6=%d" % (name, bottom, top, cout, cout * cin * 9))
+        return w.reshape(cout, cin, 3, 3), b
+
+    def prelu(name, bottom, top, n):
+        nonlocal blob
+        s = (rng.integers(0, 32, n) / 64.0).astype("<f4")
+        blob += s.tobytes()
+        lines.append("PReLU %s 1 1 %s %s 0=%d" % (name, bottom, top, n))
+
+    lines.append("Input input 0 1 input")
+    lines.append("Split splitncnn_0 1 2 input input_s0 input_s1")
+    x = "input_s1"
+    conv("c0", x, "b0", 3, nf)
+    prelu("p0", "b0", "a0", nf)
+    x = "a0"
+    for i in range(n_mid):
+        conv("c%d" % (i + 1), x, "b%d" % (i + 1), nf, nf)
+        prelu("p%d" % (i + 1), "b%d" % (i + 1), "a%d" % (i + 1), nf)
+        x = "a%d" % (i + 1)
+    conv("clast", x, "y", nf, 3 * r * r)
+    lines.append("PixelShuffle ps 1 1 y ys 0=%d" % r)
+    lines.append("Interp up 1 1 input_s0 xs 0=1 1=%d.000000e+00 2=%d.000000e+00" % (r, r))
+    lines.append("BinaryOp add 2 1 ys xs output")
+    text = "7767517\n%d %d\n" % (len(lines), len(lines) + 2) + "\n".join(lines) + "\n"
+    p = tmp_path / "t.param"
+    p.write_text(text)
+    (tmp_path / "t.bin").write_bytes(blob)
+    return str(p), str(tmp_path / "t.bin")
+
+
+@pytest.mark.parametrize("fp16", [True, False])
+def test_parse_ncnn_pair_and_recognise(tmp_path, fp16):
+    param, binf = _tiny_ncnn(tmp_path, fp16=fp16)
+    g = M.load_ncnn(param, binf)
+    d = M.compact_desc(g)
+    assert (d.cin, d.nf, d.n_mid, d.scale, d.cout_last, d.input_blob, d.output_blob) == (3, 8, 2, 2, 12, "input", "output")
+    d2, blob = M.pack_compact_blob(g)
+    assert blob.dtype == np.float32 and blob.size == 8 * 3 * 9 + 16 + 2 * (8 * 8 * 9 + 16) + 12 * 8 * 9 + 12
+    # the oracle's own reader sees the same numbers
+    layers = oracle.read_ncnn(param, binf)
+    convs = [L for L in layers if L["type"] == "Convolution"]
+    assert np.array_equal(convs[0]["arrays"]["weight"], g.convs()[0].weights["weight"].astype(np.float32))
+    assert np.array_equal(blob[:8 * 3 * 9], convs[0]["arrays"]["weight"].ravel())
+
+
+def test_bin_must_be_fully_consumed(tmp_path):
+    param, binf = _tiny_ncnn(tmp_path)
+    with open(binf, "ab") as f:
+        f.write(b"\0\0\0\0")
+    with pytest.raises(ValueError):
+        M.load_ncnn(param, binf)
+
+
+def test_bad_magic():
+    with pytest.raises(ValueError):
+        M.parse_param("12345\n1 1\nInput input 0 1 input\n")
+
+
+def test_b2sr_roundtrip(tmp_path):
+    param, binf = _tiny_ncnn(tmp_path, fp16=False)
+    g = M.load_ncnn(param, binf)
+    out = str(tmp_path / "t.b2sr")
+    M.save_b2sr(g, out)
+    g2 = M.load_b2sr(out)
+    assert [l.name for l in g.layers] == [l.name for l in g2.layers]
+    for a, b in zip(g.layers, g2.layers):
+        assert a.params == b.params
+        for k in a.weights:
+            assert np.array_equal(a.weights[k].astype(np.float32), b.weights[k].astype(np.float32))
+    # fp32-stored weights that are fp16-exact are narrowed (lossless), like 4x_Compact_Pretrain
+    assert g2.convs()[0].weights["weight"].dtype == np.float16
+
+
+def test_non_compact_graph_is_rejected(tmp_path):
+    param, binf = _tiny_ncnn(tmp_path)
+    g = M.load_ncnn(param, binf)
+    g.layers[-1].params[0] = 2  # BinaryOp mul instead of add
+    assert M.compact_desc(g) is None
+    with pytest.raises(ValueError):
+        M.pack_compact_blob(g)
+
+
+@pytest.mark.parametrize("stem,expect", [
+    ("2x_Compact_Pretrain", (3, 64, 16, 2, 12)),
+    ("4x_Compact_Pretrain", (3, 64, 16, 4, 48)),
+    (HURR, (3, 24, 8, 1, 3)),
+])
+def test_packaged_models(model_dir, stem, expect):
+    g = M.load_model(model_dir, stem)
+    d = M.compact_desc(g)
+    assert (d.cin, d.nf, d.n_mid, d.scale, d.cout_last) == expect
+    _, blob = M.pack_compact_blob(g)
+    # every parameter the reference ships for the Compact family is exactly representable in fp16
+    assert np.array_equal(blob.astype(np.float16).astype(np.float32), blob)
+    # product loader == oracle's independent reader
+    layers = oracle.read_model(model_dir, stem)
+    ow = [L["arrays"]["weight"] for L in layers if L["type"] == "Convolution"]
+    pw = [l.weights["weight"].astype(np.float32) for l in g.convs()]
+    assert len(ow) == len(pw) and all(np.array_equal(a, b) for a, b in zip(ow, pw))
+
+
+def test_mac_count_matches_survey(model_dir):
+    g = M.load_model(model_dir, "2x_Compact_Pretrain")
+    assert sum(l.weights["weight"].size for l in g.convs()) == 598464

@@ -1,0 +1,88 @@
+"""CPU: the oracle (oracle/oracle.py + oracle.c) against the frozen known-answer vectors in tests/golden/.
+
+The goldens were produced by tools/make_goldens.py from the reference's ORIGINAL ncnn .param/.bin files; here the
+oracle reads this repo's converted .b2sr containers, so the test also pins the conversion.  (The reference itself
+ships no expected outputs -- "parity unpinned", see oracle/oracle.py.)
+"""
+import numpy as np
+import pytest
+
+from conftest import HURR, golden
+from oracle import oracle
+
+
+@pytest.mark.parametrize("name,model,scale", [
+    ("compact2x_crop", "2x_Compact_Pretrain", 2),
+    ("compact2x_noise_a", "2x_Compact_Pretrain", 2),
+    ("compact2x_noise_ragged", "2x_Compact_Pretrain", 2),
+    ("compact4x_crop", "4x_Compact_Pretrain", 4),
+])
+def test_upscale_goldens_f64_exact(name, model, scale, oracle_models):
+    g = golden(name)
+    y = oracle.upscale_image_array(oracle_models(model), g["x"], scale, "f64")
+    assert y.dtype == np.uint8 and np.array_equal(y, g["y"])
+
+
+def test_seam_x_golden(oracle_models):
+    """1000-px-wide strip: two tiles in x with the reference's 10-px halo (process_tile :409-427)."""
+    g = golden("compact2x_seam_x")
+    y = oracle.upscale_image_array(oracle_models("2x_Compact_Pretrain"), g["x"], 2, "f64")
+    assert np.array_equal(y, g["y"])
+
+
+def test_hurr_and_chain_goldens(oracle_models):
+    g = golden("hurr1x_crop")
+    y1 = oracle.apply_model_array(oracle_models(HURR), g["x"], "f64")
+    assert np.array_equal(y1, g["y"])
+    c = golden("chain_hurr_compact2x")
+    y2 = oracle.upscale_image_array(oracle_models("2x_Compact_Pretrain"), y1, 2, "f64")
+    assert np.array_equal(y2, c["y"])
+    n = golden("hurr1x_noise")
+    assert np.array_equal(oracle.apply_model_array(oracle_models(HURR), n["x"], "f64"), n["y"])
+
+
+def test_f32_oracle_within_one_lsb(oracle_models):
+    g = golden("compact2x_crop")
+    y = oracle.upscale_image_array(oracle_models("2x_Compact_Pretrain"), g["x"], 2, "f32")
+    assert np.array_equal(y, g["y_f32"])
+    assert np.abs(y.astype(int) - g["y"].astype(int)).max() <= 1
+
+
+def test_canvas_golden(oracle_models):
+    g = golden("compact2x_canvas_f64")
+    y = oracle.upscale_canvas(oracle_models("2x_Compact_Pretrain"), g["x"], 2, "f64")
+    assert np.allclose(y, g["y"], atol=2e-4)
+
+
+def test_layer_semantics_small():
+    """Known answers for the ncnn layer restatements, by hand."""
+    x = np.arange(2 * 2 * 4, dtype=np.float64).reshape(2, 2, 4)  # HWC, C = 1*r*r
+    ps = oracle.pixelshuffle(x, 2)
+    assert ps.shape == (4, 4, 1)
+    # out[y*2+dy][x*2+dx] = in[y][x][dy*2+dx]
+    assert ps[0, 0, 0] == x[0, 0, 0] and ps[0, 1, 0] == x[0, 0, 1] and ps[1, 0, 0] == x[0, 0, 2] and ps[3, 3, 0] == x[1, 1, 3]
+    up = oracle.nearest(np.arange(6, dtype=np.float64).reshape(2, 3, 1), 2.0, 2.0)
+    assert up.shape == (4, 6, 1) and np.array_equal(up[:, :, 0], np.repeat(np.repeat(np.arange(6).reshape(2, 3), 2, 0), 2, 1))
+    # 3x3 conv, zero padding: an all-ones kernel over an all-ones image counts the in-image taps
+    w = np.ones((1, 1, 3, 3), np.float32)
+    y = oracle.conv(np.ones((3, 4, 1)), w, np.zeros(1, np.float32), 1)
+    assert np.array_equal(y[:, :, 0], np.array([[4, 6, 6, 4], [6, 9, 9, 6], [4, 6, 6, 4]], float))
+    # cv2.imwrite rounding: half to even, saturate
+    assert list(oracle.saturate_u8(np.array([0.5, 1.5, 2.5, 254.5, 255.5, -3.0, 300.0]))) == [0, 2, 2, 254, 255, 0, 255]
+
+
+def test_saturate_matches_cv2(tmp_path):
+    """The rounding the oracle applies is what cv2.imwrite does to a float image (reference :288, :519)."""
+    import cv2
+    vals = np.linspace(-2, 258, 3 * 64 * 5).reshape(5, 64, 3)
+    vals[0, :7, 0] = [0.5, 1.5, 2.5, 254.5, 255.5, 127.5, 128.5]
+    p = str(tmp_path / "r.png")
+    cv2.imwrite(p, vals)
+    assert np.array_equal(cv2.imread(p), oracle.saturate_u8(vals))
+
+
+def test_tile_rects_1080p():
+    rects = list(oracle.tile_rects(1080, 1920))
+    shapes = [(r[3] - r[2], r[5] - r[4]) for r in rects]
+    assert shapes == [(970, 970), (970, 970), (130, 970), (130, 970)]
+    assert [(r[3] - r[2], r[5] - r[4]) for r in oracle.tile_rects(540, 960)] == [(540, 960)]

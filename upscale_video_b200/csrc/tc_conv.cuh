@@ -14,10 +14,11 @@
 // no data replication.  The B operand of tap (ky,kx) is that tap's [NOUT][CPIX] weight slice, resident in shared
 // memory for the life of the CTA (pre-swizzled on the host).
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma issuer,
-// warps 2..5 = epilogue (tcgen05.ld -> bias/PReLU -> fp16 -> swizzled staging -> 128-bit coalesced stores, or
-// pixel-shuffle + nearest-upsampled residual + x255 + round-half-even/saturate for the last layer).
-// Two TMEM accumulators let the MMAs of row t+1 overlap the epilogue of row t.
+// Roles (320 threads): warp 0 = TMA producer; warp 1 = TMEM owner + tcgen05.mma issuer (the whole warp runs the
+// control flow so descriptors live in uniform registers, one elected lane issues); warps 2..5 and 6..9 = two
+// epilogue sets that take alternate rows (tcgen05.ld -> bias/PReLU -> fp16 -> swizzled staging -> 128-bit coalesced
+// stores, or pixel-shuffle + nearest-upsampled residual + x255 + round-half-even/saturate for the last layer).
+// Each set owns one TMEM accumulator, so the MMAs of row t+1 overlap the epilogue of row t.
 #pragma once
 #include <stdio.h>
 
@@ -25,7 +26,8 @@
 
 namespace b2sr {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_NSETS = 2;                       // epilogue warp sets == TMEM accumulator buffers
+constexpr int TC_THREADS = 64 + 128 * TC_NSETS;    // producer warp + MMA warp + 4 epilogue warps per set
 constexpr int TC_MAX_SLOTS = 64;
 constexpr int TC_TILE_M = 128;
 
@@ -99,6 +101,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
@@ -115,11 +126,11 @@ struct TcCfg {
     static constexpr int ROWB = TC_PITCH * PB;     // bytes per ring row
     static constexpr int OB = NOUT * 2;            // bytes per output pixel (PReLU epilogue)
     static constexpr int CH = OB / 16;             // 16-byte chunks per output pixel
-    static constexpr int STG = SHUF == 0 ? 4 * 32 * OB : 0;
-    static constexpr int TCOLS = 2 * NOUT <= 32 ? 32 : (2 * NOUT <= 64 ? 64 : 128);
+    static constexpr int STG = SHUF == 0 ? TC_NSETS * 4 * 32 * OB : 0;
+    static constexpr int TCOLS = TC_NSETS * NOUT <= 32 ? 32 : (TC_NSETS * NOUT <= 64 ? 64 : (TC_NSETS * NOUT <= 128 ? 128 : 256));
     static constexpr uint32_t LAYOUT = CPIX == 64 ? 2u : (CPIX == 32 ? 4u : 6u);  // UMMA LayoutType: SW128 / SW64 / SW32
     static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NOUT >> 3) << 17) | ((uint32_t)(TC_TILE_M >> 4) << 24);
-    static constexpr int MISC = 2 * NOUT * 4 + (2 * TC_MAX_SLOTS + 8) * 8 + 64;
+    static constexpr int MISC = 2 * NOUT * 4 + (2 * TC_MAX_SLOTS + 2 * TC_NSETS + 4) * 8 + 64;
     static_assert(CPIX == 16 || CPIX == 32 || CPIX == 64, "one pixel must be one swizzle row");
     static_assert(NOUT % 16 == 0 && NOUT >= 16 && NOUT <= 64, "UMMA M=128 needs N % 16 == 0");
     static_assert((NOUT * PB) % 1024 == 0, "per-tap weight tile must keep 1024-byte (swizzle atom) alignment");
@@ -157,9 +168,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     auto full_bar = [&](int s) { return bar_s + 8u * s; };
     auto empty_bar = [&](int s) { return bar_s + 8u * (TC_MAX_SLOTS + s); };
     auto tfull_bar = [&](int b) { return bar_s + 8u * (2 * TC_MAX_SLOTS + b); };
-    auto tempty_bar = [&](int b) { return bar_s + 8u * (2 * TC_MAX_SLOTS + 2 + b); };
-    const uint32_t w_bar = bar_s + 8u * (2 * TC_MAX_SLOTS + 4);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + bar_off + 8 * (2 * TC_MAX_SLOTS + 5));
+    auto tempty_bar = [&](int b) { return bar_s + 8u * (2 * TC_MAX_SLOTS + TC_NSETS + b); };
+    const uint32_t w_bar = bar_s + 8u * (2 * TC_MAX_SLOTS + 2 * TC_NSETS);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + bar_off + 8 * (2 * TC_MAX_SLOTS + 2 * TC_NSETS + 1));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -168,7 +179,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < TC_NSETS; ++b) {
             mbar_init(tfull_bar(b), 1);
             mbar_init(tempty_bar(b), 4);
         }
@@ -182,7 +193,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < NOUT; i += 128) {
+        for (int i = threadIdx.x - 64; i < NOUT; i += TC_THREADS - 64) {
             s_bias[i] = P.bias[i];
             s_slope[i] = (SHUF == 0) ? P.slope[i] : 0.f;
         }
@@ -217,65 +228,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
-        if (lane == 0) {
-            const uint32_t desc_hi = ((8u * PB) >> 4) | (1u << 14) | (C::LAYOUT << 29);
-            int full_slot = 0;  // next ring slot to wait for
-            uint32_t full_phase = 0;
-            int rs = 0;  // ring slot of input row t of the current item
-            uint32_t tile_cnt = 0;
-            mbar_wait(w_bar, 0, 1);
-            for (int it = blockIdx.x; it < P.n_items; it += gridDim.x) {
-                const TcItem I = P.items[it];
-                int n_full = 0;  // input rows of this item already waited for
-                for (int t = 0; t < I.rows; ++t) {
-                    while (n_full < t + 3) {  // output row t reads input rows t, t+1, t+2
-                        mbar_wait(full_bar(full_slot), full_phase, 2);
-                        ++n_full;
-                        if (++full_slot == R) {
-                            full_slot = 0;
-                            full_phase ^= 1u;
-                        }
+        // Every lane runs the (warp-uniform) control flow; one elected lane issues the tcgen05 instructions.
+        const uint32_t desc_hi = ((8u * PB) >> 4) | (1u << 14) | (C::LAYOUT << 29);  // SBO | version | swizzle mode
+        const uint32_t w_lo = (w_s >> 4) | (1u << 16);                                // start address | LBO(unused)=1
+        const uint32_t ring_lo = (ring_s >> 4) | (1u << 16);
+        int full_slot = 0;  // next ring slot to wait for
+        uint32_t full_phase = 0;
+        int rs = 0;  // ring slot of input row t of the current item
+        uint32_t tile_cnt = 0;
+        mbar_wait(w_bar, 0, 1);
+        for (int it = blockIdx.x; it < P.n_items; it += gridDim.x) {
+            const int rows = P.items[it].rows;
+            int n_full = 0;  // input rows of this item already waited for
+            for (int t = 0; t < rows; ++t) {
+                while (n_full < t + 3) {  // output row t reads input rows t, t+1, t+2
+                    mbar_wait(full_bar(full_slot), full_phase, 2);
+                    ++n_full;
+                    if (++full_slot == R) {
+                        full_slot = 0;
+                        full_phase ^= 1u;
                     }
-                    const uint32_t buf = tile_cnt & 1u;
-                    mbar_wait(tempty_bar(buf), ((tile_cnt >> 1) & 1u) ^ 1u, 3);
-                    tc_fence_after();
+                }
+                const uint32_t buf = tile_cnt % TC_NSETS;
+                mbar_wait(tempty_bar(buf), ((tile_cnt / TC_NSETS) & 1u) ^ 1u, 3);
+                tc_fence_after();
+                const int s1 = rs + 1 >= R ? rs + 1 - R : rs + 1;
+                const int s2 = s1 + 1 >= R ? s1 + 1 - R : s1 + 1;
+                const int nrel = (t + 1 < rows) ? 1 : 3;  // the last row of an item also frees its two trailing rows
+                if (elect_one_sync()) {
                     const uint32_t tmem_d = tmem_base + buf * NOUT;
-                    uint32_t accum = 0;
-#pragma unroll
+                    int sk = rs;  // ring slot of input row t + ky
+                    // base_offset stays 0 although kx shifts the start inside a swizzle atom: the hardware swizzles
+                    // on absolute shared-memory address bits, like TMA did when it wrote the row
+#pragma unroll 1
                     for (int ky = 0; ky < 3; ++ky) {
-                        int s = rs + ky;
-                        if (s >= R) s -= R;
+                        const uint64_t a0 = ((uint64_t)desc_hi << 32) | (ring_lo + (uint32_t)sk * (ROWB >> 4));
+                        sk = sk + 1 >= R ? sk + 1 - R : sk + 1;
+                        const uint64_t b0 = ((uint64_t)desc_hi << 32) | (w_lo + (uint32_t)(ky * ((3 * NOUT * PB) >> 4)));
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
-                            const uint32_t a_addr = ring_s + (uint32_t)s * ROWB + (uint32_t)kx * PB;
-                            const uint32_t b_addr = w_s + (ky * 3 + kx) * (NOUT * PB);
-                            uint32_t hi_a = desc_hi;
-                            if (P.desc_mode == 1) hi_a |= ((a_addr >> 7) & 7u) << 17;
 #pragma unroll
                             for (int k = 0; k < C::KSLABS; ++k) {
-                                const uint64_t adesc =
-                                    ((uint64_t)hi_a << 32) | (uint64_t)((((a_addr + k * 32) >> 4) & 0x3FFFu) | (1u << 16));
-                                const uint64_t bdesc =
-                                    ((uint64_t)desc_hi << 32) | (uint64_t)((((b_addr + k * 32) >> 4) & 0x3FFFu) | (1u << 16));
-                                umma_f16(tmem_d, adesc, bdesc, C::IDESC, accum);
-                                accum = 1;
+                                umma_f16(tmem_d, a0 + (uint32_t)((kx * PB + k * 32) >> 4),
+                                         b0 + (uint32_t)((kx * (NOUT * PB) + k * 32) >> 4), C::IDESC, (ky | kx | k) != 0);
                             }
                         }
                     }
                     umma_commit(tfull_bar(buf));
-                    ++tile_cnt;
-                    // input row t is dead once these MMAs retire; the last tile also frees the two trailing rows
-                    const int nrel = (t + 1 < I.rows) ? 1 : 3;
-                    for (int j = 0; j < nrel; ++j) {
-                        umma_commit(empty_bar(rs));
-                        if (++rs == R) rs = 0;
+                    umma_commit(empty_bar(rs));
+                    if (nrel == 3) {
+                        umma_commit(empty_bar(s1));
+                        umma_commit(empty_bar(s2));
                     }
                 }
+                __syncwarp();
+                ++tile_cnt;
+                rs += nrel;
+                if (rs >= R) rs -= R;
             }
         }
     } else {
         // ======================= epilogue =======================
-        const int q = warp & 3;  // TMEM lane quadrant this warp may read
+        const int q = warp & 3;             // TMEM lane quadrant this warp may read
+        const uint32_t set = (warp - 2) >> 2;  // this warp's epilogue set == its TMEM buffer
         uint32_t tile_cnt = 0;
         const float scale_acc = P.acc_scale;
         const int c = q * 32 + lane;  // column inside the band
@@ -283,8 +298,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             const TcItem I = P.items[it];
             const bool valid = c < I.w;
             for (int t = 0; t < I.rows; ++t, ++tile_cnt) {
-                const uint32_t buf = tile_cnt & 1u;
-                mbar_wait(tfull_bar(buf), (tile_cnt >> 1) & 1u, 4);
+                const uint32_t buf = tile_cnt % TC_NSETS;
+                if (buf != set) continue;
+                mbar_wait(tfull_bar(buf), (tile_cnt / TC_NSETS) & 1u, 4);
                 tc_fence_after();
                 uint32_t acc[NOUT];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NOUT;
@@ -300,15 +316,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                     constexpr int CH = C::CH;
                     uint4* stg = reinterpret_cast<uint4*>(gbase + stg_off + (warp - 2) * (32 * C::OB));
                     const int off = valid ? ((I.y0 + t) * I.Wt + I.x0 + c) : -1;
+                    const float4* sb4 = reinterpret_cast<const float4*>(s_bias);
+                    const float4* ss4 = reinterpret_cast<const float4*>(s_slope);
 #pragma unroll
                     for (int j = 0; j < NOUT; j += 8) {
+                        const float4 b0 = sb4[j >> 2], b1 = sb4[(j >> 2) + 1], l0 = ss4[j >> 2], l1 = ss4[(j >> 2) + 1];
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        const float sl[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
                         uint32_t pk[4];
 #pragma unroll
                         for (int e = 0; e < 8; e += 2) {
-                            float v0 = fmaf(__uint_as_float(acc[j + e]), scale_acc, s_bias[j + e]);
-                            float v1 = fmaf(__uint_as_float(acc[j + e + 1]), scale_acc, s_bias[j + e + 1]);
-                            v0 = v0 < 0.f ? v0 * s_slope[j + e] : v0;
-                            v1 = v1 < 0.f ? v1 * s_slope[j + e + 1] : v1;
+                            float v0 = fmaf(__uint_as_float(acc[j + e]), scale_acc, bb[e]);
+                            float v1 = fmaf(__uint_as_float(acc[j + e + 1]), scale_acc, bb[e + 1]);
+                            v0 = v0 < 0.f ? v0 * sl[e] : v0;
+                            v1 = v1 < 0.f ? v1 * sl[e + 1] : v1;
                             __half2 h = __floats2half2_rn(v0, v1);
                             pk[e >> 1] = *reinterpret_cast<uint32_t*>(&h);
                         }

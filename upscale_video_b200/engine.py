@@ -111,10 +111,13 @@ def _ptr(a):
 class Engine:
     """One network bound to one GPU (one per worker process, like the reference's ``net``)."""
 
-    def __init__(self, graph: ncnn_model.Graph, device: int = 0):
+    def __init__(self, graph: ncnn_model.Graph = None, device: int = 0, packed=None):
+        """``graph``: a loaded model; or ``packed`` = (CompactDesc, fp32 blob) as produced by
+        ``ncnn_model.pack_compact_blob`` (what a rank receives from the start-up weight broadcast)."""
         self._h = None
         self._lib = load_library()
-        desc, blob = ncnn_model.pack_compact_blob(graph)
+        desc, blob = packed if packed is not None else ncnn_model.pack_compact_blob(graph)
+        blob = np.ascontiguousarray(blob, np.float32)
         self.desc = desc
         self.scale = desc.scale
         self.device = device

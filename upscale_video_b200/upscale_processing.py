@@ -1,0 +1,226 @@
+"""Drop-in for the frame-upscale worker loop of the reference's ``upscale/upscale_processing.py``.
+
+Same function names, argument meaning, return values and error behaviour as the reference for the functions on
+the hot path:
+
+    get_frames           reference :27-37
+    logging_callback     reference :40-51
+    init_worker          reference :54-73     (process-global engine instead of ``ncnn.Net``)
+    apply_model          reference :258-299   (whole-frame 1x model, e.g. HurrDeblur ``-m a``)
+    process_model        reference :302-347
+    process_tile         reference :395-477
+    upscale_image        reference :480-542
+    upscale_frames       reference :545-601
+
+What changed underneath: ``net`` is a :class:`upscale_video_b200.engine.Engine` (C ABI ``include/b2sr.h`` over
+sm_100a CUDA).  ``upscale_image`` hands the whole frame to the engine in one call -- the 960-px tiling with its
+10-px halo, the ``* 255``, the crop into the canvas and ``cv2.imwrite``'s rounding are reproduced on the device
+(``b2sr_run_u8``) -- instead of looping over tiles in Python.  ``process_tile`` keeps the reference's per-tile
+contract for callers that use it directly.  Errors are returned as log items, never raised (:289-293, :454-459).
+
+The ffmpeg stages, the NL-means ``-m n=`` filter and the batch bookkeeping of ``process_file`` are outside the
+hot path and are not reimplemented here.
+"""
+from __future__ import annotations
+
+import logging
+import math
+import multiprocessing
+import os
+import sys
+
+import cv2
+import numpy as np
+
+from . import engine as _engine
+
+net = None
+model_input_name = "input"
+model_output_name = "output"
+
+TILE_SIZE = 960  # reference :489
+TILE_HALO = 10   # reference :409-427
+
+
+def get_frames(x):
+    """``"1,4-6"`` -> ``[1, 4, 5, 6]`` (reference :27-37)."""
+    frames = []
+    for part in x.split(","):
+        if "-" in part:
+            lo, hi = (int(v) for v in part.split("-"))
+            frames.extend(range(lo, hi + 1))
+        else:
+            frames.append(int(part))
+    return frames
+
+
+def logging_callback(log_list):
+    """Pool callback: log the worker's items; the first ``error`` item ends the parent (reference :40-51)."""
+    failed = False
+    for level, message in log_list:
+        if level == "info":
+            logging.info(message)
+        elif level == "debug":
+            logging.debug(message)
+        elif level == "error":
+            logging.error(message)
+            failed = True
+        if failed:
+            sys.exit("Error - Exiting")
+
+
+def _worker_slot(workers_used):
+    """Index of this pool worker among its siblings, derived like the reference does from the parent's global
+    child counter (reference :59); 0 when called outside a pool (tests, single-process use)."""
+    ident = multiprocessing.current_process()._identity
+    return (ident[0] - 1 - workers_used) if ident else 0
+
+
+def init_worker(gpus, workers_used, model_path, model_file, scale, model_input, model_output):
+    """Pool initializer: bind this worker to ``gpus[slot]`` and load ``<scale><model_file>`` once
+    (reference :54-73).  ``model_input``/``model_output`` are kept for signature compatibility; the engine
+    recognises the graph's input/output blobs structurally and checks the names match."""
+    global net, model_input_name, model_output_name
+    gpu = _worker_slot(workers_used)
+    if gpu > len(gpus) - 1:
+        logging.error("Unable to assign GPU to new worker.")
+        sys.exit("Error - Exiting")
+    net = _engine.Engine.from_files(model_path, str(scale) + model_file, device=int(gpus[gpu]))
+    for given, found in ((model_input, net.desc.input_blob), (model_output, net.desc.output_blob)):
+        if given and given != found:
+            logging.warning("model blob name %r differs from the graph's %r; using the graph's", given, found)
+    model_input_name = model_input
+    model_output_name = model_output
+
+
+def _release_engine():
+    """What ``ncnn.destroy_gpu_instance()`` does for the reference after a failure (:292, :458)."""
+    global net
+    try:
+        if net is not None:
+            net.close()
+    finally:
+        net = None
+
+
+def apply_model(input_file, output_file, remove):
+    """Run the loaded 1x model over a whole frame, untiled (reference :258-299)."""
+    logging_items = []
+    img = cv2.imread(input_file)
+    try:
+        output = net.run_u8(img, tile=0, halo=0)
+        if output_file:
+            cv2.imwrite(output_file, output)
+    except Exception as e:  # same breadth as the reference: any failure becomes log items
+        logging_items.append(["error", "Model processing failed"])
+        logging_items.append(["error", e])
+        _release_engine()
+        return logging_items
+    if remove:
+        os.remove(input_file)
+    logging_items.append(["info", "Processed Model: " + str(output_file)])
+    return logging_items
+
+
+def _pool(gpus, workers_used, model_path, model_file, scale, model_input, model_output):
+    # `spawn`, like the reference (:321, :565): no CUDA context may be inherited from the parent
+    return multiprocessing.get_context("spawn").Pool(
+        processes=len(gpus), initializer=init_worker,
+        initargs=(gpus, workers_used, model_path, model_file, scale, model_input, model_output))
+
+
+def process_model(frames_count, model_path, model_file, scale, model_input, model_output, input_file_tag,
+                  output_file_tag, gpus, workers_used, remove=True):
+    """One ``apply_model`` task per existing ``N.<input_file_tag>.png`` (reference :302-347)."""
+    frames = range(1, frames_count + 1) if isinstance(frames_count, int) else frames_count
+    pool = _pool(gpus, workers_used, model_path, model_file, scale, model_input, model_output)
+    for frame in frames:
+        input_file_name = "%s.%s.png" % (frame, input_file_tag)
+        output_file_name = "%s.%s.png" % (frame, output_file_tag)
+        if os.path.exists(input_file_name):
+            pool.apply_async(apply_model, args=(input_file_name, output_file_name, remove), callback=logging_callback)
+    pool.close()
+    pool.join()
+
+
+def tile_rect(y, x, tile_size, height, width, halo=TILE_HALO):
+    """Input rectangle (with halo) and core rectangle of tile (y, x) -- reference :398-427.  A halo is added on
+    a side only when at least ``halo`` pixels of image remain there."""
+    y0, y1 = y * tile_size, min(y * tile_size + tile_size, height)
+    x0, x1 = x * tile_size, min(x * tile_size + tile_size, width)
+    top = halo if y0 >= halo else 0
+    bottom = halo if y1 <= height - halo else 0
+    left = halo if x0 >= halo else 0
+    right = halo if x1 <= width - halo else 0
+    return (y0 - top, y1 + bottom, x0 - left, x1 + right), (y0, y1, x0, x1)
+
+
+def process_tile(img, tile_size, scale, y, x, height, width, output, logging_items):
+    """Upscale tile (y, x) of ``img`` and write its core into the float canvas ``output`` (reference :395-477).
+    Returns -1 (after appending error items) when the engine fails, else None."""
+    (iy0, iy1, ix0, ix1), (cy0, cy1, cx0, cx1) = tile_rect(y, x, tile_size, height, width)
+    input_tile = np.ascontiguousarray(img[iy0:iy1, ix0:ix1, :])
+    try:
+        output_tile = net.run_f32(input_tile, tile=0, halo=0)  # the tile is one zero-padded plane, `* 255` applied
+    except Exception as e:
+        logging_items.append(["error", "Upscale failed"])
+        logging_items.append(["error", e])
+        logging.error(e)
+        _release_engine()
+        return -1
+    oy, ox = (cy0 - iy0) * scale, (cx0 - ix0) * scale
+    output[cy0 * scale:cy1 * scale, cx0 * scale:cx1 * scale, :] = output_tile[
+        oy:oy + (cy1 - cy0) * scale, ox:ox + (cx1 - cx0) * scale, :]
+    return None
+
+
+def upscale_image(input_file_name, output_file_name, scale, frame_batch, frame, end_frame, remove=True):
+    """One frame: read PNG, upscale with the reference's tiling, write PNG, delete the input, return log items
+    (reference :480-542).  ``output_file_name`` may be None (test_gpus.py), ``frame_batch`` None, int or list."""
+    logging_items = []
+    img = cv2.imread(input_file_name)
+    height, width, _ = img.shape
+    tiles_x = math.ceil(width / TILE_SIZE)
+    tiles_y = math.ceil(height / TILE_SIZE)
+    for tile_idx in range(1, tiles_x * tiles_y + 1):
+        logging_items.append(["debug", f"Processing Tile: {tile_idx}/{tiles_x * tiles_y}"])
+    try:
+        if scale != net.scale:
+            raise ValueError("engine was initialised for scale %d, upscale_image called with %d" % (net.scale, scale))
+        output = net.run_u8(img, tile=TILE_SIZE, halo=TILE_HALO)  # all tiles of the frame in one device pass
+    except Exception as e:
+        logging_items.append(["error", "Upscale failed"])
+        logging_items.append(["error", e])
+        logging.error(e)
+        _release_engine()
+        return logging_items
+    if output_file_name:
+        cv2.imwrite(output_file_name, output)
+    if remove:
+        os.remove(input_file_name)
+    if frame_batch:
+        if isinstance(frame_batch, int):
+            logging_items.append(["info", "Upscaling Batch: %s : Upscaled %s/%s" % (frame_batch, frame, end_frame)])
+        else:
+            logging_items.append(["info", "Upscaled " + str(output_file_name)])
+    else:
+        logging_items.append(["info", "Upscaled %s/%s" % (frame, end_frame)])
+    return logging_items
+
+
+def upscale_frames(frame_batch, start_frame, end_frame, input_file_tag, scale, gpus, workers_used, model_path,
+                   model_file, model_input, model_output, remove=True):
+    """Frame sharding: one pool worker per ``gpus`` entry, one ``upscale_image`` task per existing
+    ``N.<input_file_tag>.png`` (reference :545-601).  Frames whose input is missing were finished by an earlier
+    run and are skipped -- the reference's resume contract."""
+    frames = frame_batch if (frame_batch and isinstance(frame_batch, list)) else range(start_frame, end_frame + 1)
+    pool = _pool(gpus, workers_used, model_path, model_file, scale, model_input, model_output)
+    for frame in frames:
+        input_file_name = "%s.%s.png" % (frame, input_file_tag)
+        output_file_name = "%s.png" % frame
+        if os.path.exists(input_file_name):
+            pool.apply_async(upscale_image,
+                             args=(input_file_name, output_file_name, scale, frame_batch, frame, end_frame, remove),
+                             callback=logging_callback)
+    pool.close()
+    pool.join()

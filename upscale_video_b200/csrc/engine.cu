@@ -89,7 +89,7 @@ extern "C" int b2sr_device_name(int device, char* buf, int buflen) {
 struct LayerDev {
     int cin = 0, cout = 0;    // real channels
     int cinp = 0, noutp = 0;  // padded channels (kernel layout)
-    uint8_t* wimg = nullptr;  // swizzled shared-memory image [9][noutp][cinp] fp16
+    uint8_t* wimg = nullptr;  // swizzled shared-memory image [kx][(2-ky)*noutp + o][cinp] fp16 (taps stacked along N)
     __half* wplain = nullptr; // [9][cinp][noutp] fp16 (simple path)
     float* bias = nullptr;    // [noutp]
     float* slope = nullptr;   // [noutp] (absent for the last layer)
@@ -224,9 +224,11 @@ static int upload_layer(b2sr_ctx* c, const float* w, const float* bias, const fl
                     return fail(B2SR_E_UNSUPPORTED, "weight %g (conv out %d in %d tap %d) is not exactly representable in fp16", v,
                                 o, i, t);
                 const __half hv = __float2half_rn(v);
-                // tile of tap t starts 1024-aligned; element (row o, channel i) sits at the swizzled address
-                const uint32_t a = swizzle_addr((uint32_t)(o * PB + i * 2), PB);
-                memcpy(&img[(size_t)t * noutp * PB + a], &hv, 2);
+                // stacked-tap image: tile kx (1024-aligned) holds rows [W(ky=2) | W(ky=1) | W(ky=0)], noutp rows each;
+                // element (row, channel i) sits at the swizzled address inside its tile
+                const int ky = t / 3, kx = t % 3;
+                const uint32_t a = swizzle_addr((uint32_t)(((2 - ky) * noutp + o) * PB + i * 2), PB);
+                memcpy(&img[(size_t)kx * 3 * noutp * PB + a], &hv, 2);
                 plain[((size_t)t * cinp + i) * noutp + o] = hv;
             }
     std::vector<float> b(noutp, 0.f), s(noutp, 0.f);

@@ -8,11 +8,21 @@
 // swizzle row of the 32B/64B/128B shared-memory swizzle).  A work item is a band of `w` <= 128 columns x `rows`
 // rows of a plane.  The producer warp streams the band's input rows (columns x0-1 .. x0+TC_PITCH-2, rows
 // y0-1 .. y0+rows; TMA zero-fills outside the plane = the convolution's zero padding at the reference's tile
-// border) into a ring of R shared-memory rows of TC_PITCH pixels.  One M=128 accumulator tile = one band row:
-// because a pixel is one swizzle row, the A operand of filter tap (ky,kx) for output row t is the 128 consecutive
-// pixels of ring row t+ky starting at pixel kx -- nine shifted UMMA descriptors over the same bytes, no im2col,
-// no data replication.  The B operand of tap (ky,kx) is that tap's [NOUT][CPIX] weight slice, resident in shared
-// memory for the life of the CTA (pre-swizzled on the host).
+// border) into a ring of R shared-memory rows of TC_PITCH pixels.  One M=128 accumulator tile = one band row.
+// Because a pixel is one swizzle row, the A operand of column tap kx for an input row is the 128 consecutive
+// pixels of that ring row starting at pixel kx -- shifted UMMA descriptors over the same bytes, no im2col, no data
+// replication.
+//
+// Row-stationary, tap-stacked contraction: an input row r feeds output rows r+1, r, r-1 through taps ky = 0, 1, 2.
+// The weights of the three ky taps of one kx are stacked along N ([W(2,kx); W(1,kx); W(0,kx)], N = 3*NOUT), so ONE
+// tcgen05.mma per (kx, 16-channel slab) updates three output rows at once: accumulator blocks of NOUT columns sit
+// in a ring of TC_NBLK blocks in TMEM, output row t in block t mod TC_NBLK, and the N = 3*NOUT window slides by one
+// block per input row.  Each input row is read from shared memory by 3*CPIX/16 MMAs (12 for 64 channels) instead of
+// 36 -- the A-operand traffic, which bounded the N = 64 formulation at the 128 B/clk shared-memory port, drops 3x.
+// Every MMA accumulates (the issue queue is shallow, so the issuer's per-row work is kept minimal): the epilogue
+// warp that drains a block writes zeros back (tcgen05.st) before handing it to the issuer again.  A window that
+// wraps around the ring is issued as two MMAs (N = 2*NOUT + NOUT).
+// The stacked weights stay resident in shared memory for the life of the CTA (pre-swizzled on the host).
 //
 // Roles (320 threads): warp 0 = TMA producer; warp 1 = TMEM owner + tcgen05.mma issuer (the whole warp runs the
 // control flow so descriptors live in uniform registers, one elected lane issues); warps 2..5 and 6..9 = two
@@ -26,7 +36,8 @@
 
 namespace b2sr {
 
-constexpr int TC_NSETS = 2;                       // epilogue warp sets == TMEM accumulator buffers
+constexpr int TC_NSETS = 2;                       // epilogue warp sets (output rows alternate between them)
+constexpr int TC_NBLK = 8;                        // accumulator blocks (output rows in flight) in the TMEM ring
 constexpr int TC_THREADS = 64 + 128 * TC_NSETS;    // producer warp + MMA warp + 4 epilogue warps per set
 constexpr int TC_MAX_SLOTS = 64;
 constexpr int TC_TILE_M = 128;
@@ -50,6 +61,17 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {  // never suspends
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
@@ -110,6 +132,12 @@ __device__ __forceinline__ uint32_t elect_one_sync() {
         : "=r"(pred));
     return pred;
 }
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {  // 32 lanes x 16 columns of zeros
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
@@ -127,10 +155,12 @@ struct TcCfg {
     static constexpr int OB = NOUT * 2;            // bytes per output pixel (PReLU epilogue)
     static constexpr int CH = OB / 16;             // 16-byte chunks per output pixel
     static constexpr int STG = SHUF == 0 ? TC_NSETS * 4 * 32 * OB : 0;
-    static constexpr int TCOLS = TC_NSETS * NOUT <= 32 ? 32 : (TC_NSETS * NOUT <= 64 ? 64 : (TC_NSETS * NOUT <= 128 ? 128 : 256));
+    static constexpr int TCOLS = TC_NBLK * NOUT <= 128 ? 128 : (TC_NBLK * NOUT <= 256 ? 256 : 512);
     static constexpr uint32_t LAYOUT = CPIX == 64 ? 2u : (CPIX == 32 ? 4u : 6u);  // UMMA LayoutType: SW128 / SW64 / SW32
-    static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NOUT >> 3) << 17) | ((uint32_t)(TC_TILE_M >> 4) << 24);
-    static constexpr int MISC = 2 * NOUT * 4 + (2 * TC_MAX_SLOTS + 2 * TC_NSETS + 4) * 8 + 64;
+    // instruction descriptor without N: D = f32, A = B = f16, both K-major, M = 128; N is added per MMA
+    static constexpr uint32_t IDESC0 = (1u << 4) | ((uint32_t)(TC_TILE_M >> 4) << 24);
+    static constexpr int MISC = 2 * NOUT * 4 + (2 * TC_MAX_SLOTS + 2 * TC_NBLK + 4) * 8 + 64;
+    static_assert(TC_NBLK * NOUT <= 512, "accumulator ring exceeds TMEM");
     static_assert(CPIX == 16 || CPIX == 32 || CPIX == 64, "one pixel must be one swizzle row");
     static_assert(NOUT % 16 == 0 && NOUT >= 16 && NOUT <= 64, "UMMA M=128 needs N % 16 == 0");
     static_assert((NOUT * PB) % 1024 == 0, "per-tap weight tile must keep 1024-byte (swizzle atom) alignment");
@@ -168,9 +198,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     auto full_bar = [&](int s) { return bar_s + 8u * s; };
     auto empty_bar = [&](int s) { return bar_s + 8u * (TC_MAX_SLOTS + s); };
     auto tfull_bar = [&](int b) { return bar_s + 8u * (2 * TC_MAX_SLOTS + b); };
-    auto tempty_bar = [&](int b) { return bar_s + 8u * (2 * TC_MAX_SLOTS + TC_NSETS + b); };
-    const uint32_t w_bar = bar_s + 8u * (2 * TC_MAX_SLOTS + 2 * TC_NSETS);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + bar_off + 8 * (2 * TC_MAX_SLOTS + 2 * TC_NSETS + 1));
+    auto tempty_bar = [&](int b) { return bar_s + 8u * (2 * TC_MAX_SLOTS + TC_NBLK + b); };
+    const uint32_t w_bar = bar_s + 8u * (2 * TC_MAX_SLOTS + 2 * TC_NBLK);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + bar_off + 8 * (2 * TC_MAX_SLOTS + 2 * TC_NBLK + 1));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -179,7 +209,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int b = 0; b < TC_NSETS; ++b) {
+        for (int b = 0; b < TC_NBLK; ++b) {
             mbar_init(tfull_bar(b), 1);
             mbar_init(tempty_bar(b), 4);
         }
@@ -207,7 +237,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         // ======================= TMA producer =======================
         if (lane == 0) {
             mbar_expect_tx(w_bar, C::WB);
-            for (int t = 0; t < 9; ++t)
+            for (int t = 0; t < 9; ++t)  // 9 chunks of the [kx][3*NOUT rows][CPIX] image
                 bulk_g2s(w_s + t * (NOUT * PB), P.wimg + (size_t)t * (NOUT * PB), NOUT * PB, w_bar);
             int slot = 0;
             uint32_t phase = 0;
@@ -229,84 +259,112 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
         // Every lane runs the (warp-uniform) control flow; one elected lane issues the tcgen05 instructions.
+        // The issue queue is shallow, so everything between two rows' MMAs is kept short: barrier states for the
+        // NEXT row are probed (non-blocking) before this row's MMAs are issued and their latency hides behind them.
+        static_assert((TC_NBLK & (TC_NBLK - 1)) == 0, "block ring size must be a power of two");
         const uint32_t desc_hi = ((8u * PB) >> 4) | (1u << 14) | (C::LAYOUT << 29);  // SBO | version | swizzle mode
-        const uint32_t w_lo = (w_s >> 4) | (1u << 16);                                // start address | LBO(unused)=1
+        const uint64_t hi64 = (uint64_t)desc_hi << 32;
+        const uint32_t w_lo = (w_s >> 4) | (1u << 16);  // start address | LBO(unused)=1
         const uint32_t ring_lo = (ring_s >> 4) | (1u << 16);
-        int full_slot = 0;  // next ring slot to wait for
-        uint32_t full_phase = 0;
-        int rs = 0;  // ring slot of input row t of the current item
-        uint32_t tile_cnt = 0;
+        constexpr uint32_t KXB = (3 * NOUT * PB) >> 4;  // descriptor units between the stacked weight tiles of kx, kx+1
+        constexpr uint32_t BLKB = (NOUT * PB) >> 4;     // ... between the ky blocks inside one tile
+        constexpr int NM = 3 * C::KSLABS;               // MMAs per input row
+        int slot = 0;  // ring slot of the current input row
+        uint32_t phase = 0;
+        uint32_t g0 = 0;      // global index of the current item's output row 0 (block ring / barrier phases)
+        uint32_t gfresh = 0;  // global index of the next output row to be started (== g0 + rho while rho < rows)
         mbar_wait(w_bar, 0, 1);
+        uint32_t ok_full = mbar_test_wait(full_bar(0), 0);
+        uint32_t ok_tempty = mbar_test_wait(tempty_bar(0), 0);
         for (int it = blockIdx.x; it < P.n_items; it += gridDim.x) {
             const int rows = P.items[it].rows;
-            int n_full = 0;  // input rows of this item already waited for
-            for (int t = 0; t < rows; ++t) {
-                while (n_full < t + 3) {  // output row t reads input rows t, t+1, t+2
-                    mbar_wait(full_bar(full_slot), full_phase, 2);
-                    ++n_full;
-                    if (++full_slot == R) {
-                        full_slot = 0;
-                        full_phase ^= 1u;
-                    }
-                }
-                const uint32_t buf = tile_cnt % TC_NSETS;
-                mbar_wait(tempty_bar(buf), ((tile_cnt / TC_NSETS) & 1u) ^ 1u, 3);
+            for (int rho = 0; rho < rows + 2; ++rho) {  // input row rho feeds output rows rho - ky, ky = 0..2
+                const bool fresh = rho < rows;  // output row `rho` receives its first contribution (ky = 0)
+                if (!ok_full) mbar_wait(full_bar(slot), phase, 2);
+                // block of the new output row: drained and zeroed by its epilogue set? (use u of a block completes phase u)
+                if (fresh && !ok_tempty) mbar_wait(tempty_bar(gfresh & (TC_NBLK - 1)), (gfresh / TC_NBLK) & 1u, 3);
                 tc_fence_after();
-                const int s1 = rs + 1 >= R ? rs + 1 - R : rs + 1;
-                const int s2 = s1 + 1 >= R ? s1 + 1 - R : s1 + 1;
-                const int nrel = (t + 1 < rows) ? 1 : 3;  // the last row of an item also frees its two trailing rows
+                // probes for the next input row
+                const int nslot = slot + 1 == R ? 0 : slot + 1;
+                const uint32_t nphase = slot + 1 == R ? phase ^ 1u : phase;
+                const uint32_t gn = gfresh + (fresh ? 1u : 0u);
+                ok_full = mbar_test_wait(full_bar(nslot), nphase);
+                ok_tempty = mbar_test_wait(tempty_bar(gn & (TC_NBLK - 1)), (gn / TC_NBLK) & 1u);
+
+                const int t0 = rho >= 2 ? rho - 2 : 0;  // output rows touched: t0 .. t1 (clipped to the item)
+                const int t1 = fresh ? rho : rows - 1;
+                const int cnt = t1 - t0 + 1;
+                const uint32_t blk0 = (g0 + (uint32_t)t0) & (TC_NBLK - 1);  // accumulator block of output row t0
+                const int wrap = (int)(TC_NBLK - blk0);
+                const int n1 = cnt < wrap ? cnt : wrap;                      // blocks before the ring wraps
+                const uint32_t brow0 = rho >= 2 ? 0u : (uint32_t)(2 - rho);  // t0's tap block in [W(2) | W(1) | W(0)]
                 if (elect_one_sync()) {
-                    const uint32_t tmem_d = tmem_base + buf * NOUT;
-                    int sk = rs;  // ring slot of input row t + ky
-                    // base_offset stays 0 although kx shifts the start inside a swizzle atom: the hardware swizzles
+                    const uint32_t a_lo = ring_lo + (uint32_t)slot * (ROWB >> 4);
+                    const uint32_t b_lo = w_lo + brow0 * BLKB;
+                    const uint32_t id1 = C::IDESC0 | ((uint32_t)((n1 * NOUT) >> 3) << 17);
+                    const uint32_t d1 = tmem_base + blk0 * NOUT;
+                    // base_offset stays 0 although kx shifts the A start inside a swizzle atom: the hardware swizzles
                     // on absolute shared-memory address bits, like TMA did when it wrote the row
-#pragma unroll 1
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const uint64_t a0 = ((uint64_t)desc_hi << 32) | (ring_lo + (uint32_t)sk * (ROWB >> 4));
-                        sk = sk + 1 >= R ? sk + 1 - R : sk + 1;
-                        const uint64_t b0 = ((uint64_t)desc_hi << 32) | (w_lo + (uint32_t)(ky * ((3 * NOUT * PB) >> 4)));
+                    if (n1 == cnt) {
 #pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
+                        for (int m = 0; m < NM; ++m) {
+                            const int kx = m / C::KSLABS, k = m % C::KSLABS;
+                            const uint32_t ao = (uint32_t)((kx * PB + k * 32) >> 4), bo = (uint32_t)(kx * KXB + ((k * 32) >> 4));
+                            umma_f16(d1, hi64 | (a_lo + ao), hi64 | (b_lo + bo), id1, 1u);
+                        }
+                    } else {  // the window wraps around the block ring: two MMAs per (kx, slab)
+                        const uint32_t id2 = C::IDESC0 | ((uint32_t)(((cnt - n1) * NOUT) >> 3) << 17);
+                        const uint32_t b_lo2 = b_lo + (uint32_t)n1 * BLKB;
 #pragma unroll
-                            for (int k = 0; k < C::KSLABS; ++k) {
-                                umma_f16(tmem_d, a0 + (uint32_t)((kx * PB + k * 32) >> 4),
-                                         b0 + (uint32_t)((kx * (NOUT * PB) + k * 32) >> 4), C::IDESC, (ky | kx | k) != 0);
-                            }
+                        for (int m = 0; m < NM; ++m) {
+                            const int kx = m / C::KSLABS, k = m % C::KSLABS;
+                            const uint32_t ao = (uint32_t)((kx * PB + k * 32) >> 4), bo = (uint32_t)(kx * KXB + ((k * 32) >> 4));
+                            umma_f16(d1, hi64 | (a_lo + ao), hi64 | (b_lo + bo), id1, 1u);
+                            umma_f16(tmem_base, hi64 | (a_lo + ao), hi64 | (b_lo2 + bo), id2, 1u);
                         }
                     }
-                    umma_commit(tfull_bar(buf));
-                    umma_commit(empty_bar(rs));
-                    if (nrel == 3) {
-                        umma_commit(empty_bar(s1));
-                        umma_commit(empty_bar(s2));
-                    }
+                    umma_commit(empty_bar(slot));                                                     // input row consumed
+                    if (rho >= 2) umma_commit(tfull_bar((g0 + (uint32_t)rho - 2u) & (TC_NBLK - 1)));  // output row rho-2 done
                 }
                 __syncwarp();
-                ++tile_cnt;
-                rs += nrel;
-                if (rs >= R) rs -= R;
+                slot = nslot;
+                phase = nphase;
+                gfresh = gn;
             }
+            g0 += (uint32_t)rows;
         }
     } else {
         // ======================= epilogue =======================
         const int q = warp & 3;             // TMEM lane quadrant this warp may read
-        const uint32_t set = (warp - 2) >> 2;  // this warp's epilogue set == its TMEM buffer
+        const uint32_t set = (warp - 2) >> 2;  // this warp's epilogue set (takes output rows g with g % TC_NSETS == set)
         uint32_t tile_cnt = 0;
+        // hand every accumulator block of this set to the issuer zeroed (all MMAs accumulate)
+        for (uint32_t b = set; b < TC_NBLK; b += TC_NSETS) {
+#pragma unroll
+            for (int j = 0; j < NOUT; j += 16) tmem_st16_zero(tmem_base + ((uint32_t)(q * 32) << 16) + b * NOUT + j);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(b));
+        }
         const float scale_acc = P.acc_scale;
         const int c = q * 32 + lane;  // column inside the band
         for (int it = blockIdx.x; it < P.n_items; it += gridDim.x) {
             const TcItem I = P.items[it];
             const bool valid = c < I.w;
             for (int t = 0; t < I.rows; ++t, ++tile_cnt) {
-                const uint32_t buf = tile_cnt % TC_NSETS;
-                if (buf != set) continue;
-                mbar_wait(tfull_bar(buf), (tile_cnt / TC_NSETS) & 1u, 4);
+                if (tile_cnt % TC_NSETS != set) continue;
+                const uint32_t buf = tile_cnt % TC_NBLK;
+                mbar_wait(tfull_bar(buf), (tile_cnt / TC_NBLK) & 1u, 4);
                 tc_fence_after();
                 uint32_t acc[NOUT];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NOUT;
 #pragma unroll
                 for (int j = 0; j < NOUT; j += 16) tmem_ld16(taddr + j, acc + j);
                 tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < NOUT; j += 16) tmem_st16_zero(taddr + j);  // the block's next row accumulates from zero
+                tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(buf));

@@ -15,7 +15,7 @@ struct PlaneDev {
     int32_t fy0, fx0;
     int32_t Ht, Wt;
     int32_t cy0, cy1, cx0, cx1;
-    int32_t pad_;
+    int32_t gplane;  // index of the plane inside its size group (TMA coordinate 3)
     int64_t pix_off;  // first pixel of this plane in the activation buffers
 };
 
@@ -38,6 +38,7 @@ struct TcParams {
     const CUtensorMap* maps;  // device array of activation tensor maps
     int32_t map_base;         // added to TcItem::map (selects ping or pong buffer)
     const TcItem* items;
+    const int32_t* item_first;  // CTA k processes items [item_first[k], item_first[k+1])
     int32_t n_items;
     const uint8_t* wimg;  // pre-swizzled shared-memory image of this layer's weights: [tap][NOUT rows][CPIX halfs]
     const float* bias;    // [NOUT]

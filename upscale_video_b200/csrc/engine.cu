@@ -105,7 +105,10 @@ struct Plan {
     std::vector<PlaneDev> planes;
     std::vector<Group> groups;
     std::vector<TcItem> items;
+    std::vector<int> item_first;  // CTA k of a launch processes items [item_first[k], item_first[k+1])
+    int n_cta = 0;
     TcItem* d_items = nullptr;
+    int* d_item_first = nullptr;
     double out_px = 0;  // exact output pixels of all items
     int64_t total_px = 0;
     int max_plane_px = 0;
@@ -118,6 +121,7 @@ struct Plan {
         if (d_planes) cudaFree(d_planes);
         if (d_maps) cudaFree(d_maps);
         if (d_items) cudaFree(d_items);
+        if (d_item_first) cudaFree(d_item_first);
     }
 };
 
@@ -358,11 +362,10 @@ static int build_plan(b2sr_ctx* c, int n, int h, int w, int tile, int halo, Plan
         P->max_plane_px = std::max(P->max_plane_px, g.Ht * g.Wt);
     }
     P->total_px = base;
-    // planes + items; plane index inside its group = frame-major
+    // planes; plane index inside its group = frame-major
     std::vector<int> fill(P->groups.size(), 0);
-    int64_t band_rows = 0;
-    for (auto& g : P->groups) band_rows += (int64_t)g.count * g.Ht * ((g.Wt + TC_BW - 1) / TC_BW);
-    const int RB = (int)std::min<int64_t>(64, std::max<int64_t>(8, (band_rows + (int64_t)c->sms * 6 - 1) / ((int64_t)c->sms * 6)));
+    std::vector<int> plane_group;
+    int64_t band_rows = 0;  // one unit of tensor work = one row of one 128-column band (M = 128 whatever the band's width)
     for (int f = 0; f < n; ++f)
         for (auto& r : rects) {
             const int Ht = r.iy1 - r.iy0, Wt = r.ix1 - r.ix0;
@@ -373,25 +376,48 @@ static int build_plan(b2sr_ctx* c, int n, int h, int w, int tile, int halo, Plan
             pd.frame = f, pd.fy0 = r.iy0, pd.fx0 = r.ix0, pd.Ht = Ht, pd.Wt = Wt;
             pd.cy0 = r.cy0, pd.cy1 = r.cy1, pd.cx0 = r.cx0, pd.cx1 = r.cx1;
             pd.pix_off = g.pix_base + (int64_t)pl * Ht * Wt;
+            pd.gplane = pl;
             P->planes.push_back(pd);
-            const int bw = TC_BW;
-            const int nchunks = (Ht + RB - 1) / RB, rows = (Ht + nchunks - 1) / nchunks;
-            for (int y0 = 0; y0 < Ht; y0 += rows)
-                for (int x0 = 0; x0 < Wt; x0 += bw) {
-                    TcItem it{};
-                    it.map = gi, it.plane = pl, it.x0 = x0, it.y0 = y0;
-                    it.rows = std::min(rows, Ht - y0), it.w = std::min(bw, Wt - x0);
-                    it.Ht = Ht, it.Wt = Wt, it.pix_off = pd.pix_off;
-                    it.frame = f, it.fy0 = r.iy0, it.fx0 = r.ix0;
-                    it.cy0 = r.cy0, it.cy1 = r.cy1, it.cx0 = r.cx0, it.cx1 = r.cx1;
-                    P->items.push_back(it);
-                    P->out_px += (double)it.rows * it.w;
-                }
+            plane_group.push_back(gi);
+            band_rows += (int64_t)Ht * ((Wt + TC_BW - 1) / TC_BW);
         }
+    // items: the linear sequence (plane, band, row) is cut into one contiguous, equally long range per CTA, so every
+    // CTA of a launch gets the same number of band rows (+-1) in as few pieces as possible
+    const int ncta = (int)std::min<int64_t>(c->sms, band_rows);
+    P->item_first.assign(1, 0);
+    int64_t pos = 0;  // band rows emitted so far
+    int cta = 0;
+    auto cut_at = [&](int k) { return band_rows * k / ncta; };
+    for (size_t pi = 0; pi < P->planes.size(); ++pi) {
+        const PlaneDev& pd = P->planes[pi];
+        for (int x0 = 0; x0 < pd.Wt; x0 += TC_BW) {
+            int y0 = 0;
+            while (y0 < pd.Ht) {
+                const int64_t room = cut_at(cta + 1) - pos;  // rows left in this CTA's range (>= 1)
+                const int rows = (int)std::min<int64_t>(pd.Ht - y0, room);
+                TcItem it{};
+                it.map = plane_group[pi], it.plane = pd.gplane, it.x0 = x0, it.y0 = y0;
+                it.rows = rows, it.w = std::min(TC_BW, pd.Wt - x0);
+                it.Ht = pd.Ht, it.Wt = pd.Wt, it.pix_off = pd.pix_off;
+                it.frame = pd.frame, it.fy0 = pd.fy0, it.fx0 = pd.fx0;
+                it.cy0 = pd.cy0, it.cy1 = pd.cy1, it.cx0 = pd.cx0, it.cx1 = pd.cx1;
+                P->items.push_back(it);
+                P->out_px += (double)it.rows * it.w;
+                y0 += rows, pos += rows;
+                if (pos == cut_at(cta + 1)) {
+                    ++cta;
+                    P->item_first.push_back((int)P->items.size());
+                }
+            }
+        }
+    }
+    P->n_cta = ncta;
     CUDA_TRY(cudaMalloc(&P->d_planes, P->planes.size() * sizeof(PlaneDev)));
     CUDA_TRY(cudaMemcpy(P->d_planes, P->planes.data(), P->planes.size() * sizeof(PlaneDev), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&P->d_items, P->items.size() * sizeof(TcItem)));
     CUDA_TRY(cudaMemcpy(P->d_items, P->items.data(), P->items.size() * sizeof(TcItem), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&P->d_item_first, P->item_first.size() * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(P->d_item_first, P->item_first.data(), P->item_first.size() * sizeof(int), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&P->d_maps, 3 * P->groups.size() * sizeof(CUtensorMap)));
     *out = P.get();
     c->plans.push_back(std::move(P));
@@ -473,11 +499,12 @@ static int launch_tc(b2sr_ctx* c, const Plan* plan, TcParams P) {
     static_assert(R >= 4, "ring needs 3 live rows + 1 in flight");
     P.R = R;
     P.items = plan->d_items, P.n_items = (int)plan->items.size();
+    P.item_first = plan->d_item_first;
     P.desc_mode = c->desc_mode;
     const int smem = Cfg::smem_bytes(R);
     auto kern = tc_conv_kernel<CPIX, NOUT, SHUF, F32OUT>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int grid = std::min(P.n_items, c->sms);
+    const int grid = plan->n_cta;
     kern<<<grid, TC_THREADS, smem, c->stream>>>(P);
     CUDA_TRY(cudaGetLastError());
     c->n_launch += 1, c->n_tc += 1;

@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + bar_off + 8 * (2 * TC_MAX_SLOTS + 2 * TC_NBLK + 1));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int it_begin = P.item_first[blockIdx.x], it_end = P.item_first[blockIdx.x + 1];
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < R; ++s) {
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 bulk_g2s(w_s + t * (NOUT * PB), P.wimg + (size_t)t * (NOUT * PB), NOUT * PB, w_bar);
             int slot = 0;
             uint32_t phase = 0;
-            for (int it = blockIdx.x; it < P.n_items; it += gridDim.x) {
+            for (int it = it_begin; it < it_end; ++it) {
                 const TcItem I = P.items[it];
                 const CUtensorMap* map = P.maps + (P.map_base + I.map);
                 const int rows_in = I.rows + 2;
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         mbar_wait(w_bar, 0, 1);
         uint32_t ok_full = mbar_test_wait(full_bar(0), 0);
         uint32_t ok_tempty = mbar_test_wait(tempty_bar(0), 0);
-        for (int it = blockIdx.x; it < P.n_items; it += gridDim.x) {
+        for (int it = it_begin; it < it_end; ++it) {
             const int rows = P.items[it].rows;
             for (int rho = 0; rho < rows + 2; ++rho) {  // input row rho feeds output rows rho - ky, ky = 0..2
                 const bool fresh = rho < rows;  // output row `rho` receives its first contribution (ky = 0)
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         }
         const float scale_acc = P.acc_scale;
         const int c = q * 32 + lane;  // column inside the band
-        for (int it = blockIdx.x; it < P.n_items; it += gridDim.x) {
+        for (int it = it_begin; it < it_end; ++it) {
             const TcItem I = P.items[it];
             const bool valid = c < I.w;
             for (int t = 0; t < I.rows; ++t, ++tile_cnt) {

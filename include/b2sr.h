@@ -60,10 +60,12 @@ extern "C" {
 #define B2SR_MEM_DEVICE 1
 
 /* b2sr_set_option keys */
-#define B2SR_OPT_IMPL 1        /* 0 = auto (tcgen05 path where available), 1 = plain CUDA-core kernels, 2 = force tcgen05 */
+#define B2SR_OPT_IMPL 1        /* 0 = auto (pipelined tcgen05 schedule when layers x bands fits the SM count, else layer by
+                                  layer), 1 = plain CUDA-core kernels, 2 = tcgen05 layer by layer, 3 = tcgen05 pipelined (error
+                                  if it does not fit) */
 #define B2SR_OPT_PROFILE 2     /* 1 = bracket every kernel launch with CUDA events (see b2sr_get_stat) */
 #define B2SR_OPT_MAX_BATCH 3   /* frames per internal pass of b2sr_run_batch_device (0 = choose from free memory) */
-#define B2SR_OPT_DEBUG_DESC 4  /* bring-up only: 0 (default, verified on B200) = UMMA descriptors with base_offset 0; 1 = base_offset from address (wrong) */
+#define B2SR_OPT_RING_ROWS 4   /* pipelined schedule: rows per inter-layer activation ring (default 32) */
 
 /* b2sr_get_stat keys */
 #define B2SR_STAT_LAUNCHES 1       /* kernels launched by this context since creation / last reset */
@@ -72,6 +74,8 @@ extern "C" {
 #define B2SR_STAT_TC_MID_COUNT 4   /* profile mode: number of launches summed in B2SR_STAT_TC_MID_MS */
 #define B2SR_STAT_ALL_MS 5         /* profile mode: summed device time of every launch, ms */
 #define B2SR_STAT_TC_MID_PIXELS 6  /* profile mode: output pixels (exact, no halo/padding) those launches produced */
+#define B2SR_STAT_PIPE_LAUNCHES 7  /* pipelined whole-network kernels launched */
+#define B2SR_STAT_PIPE_MS 8        /* profile mode: summed device time of the pipelined launches, ms */
 
 typedef struct b2sr_ctx b2sr_ctx;
 

@@ -2,11 +2,10 @@
 """GPU bring-up report (run by hand under gpurun; not collected by pytest).
 
     python tests/bringup_gpu.py            # runs every mode in its own subprocess (a device trap kills the context)
-    python tests/bringup_gpu.py MODE       # one mode: simple | tc0 | tc1
+    python tests/bringup_gpu.py MODE [MODEL H W]   # one mode: simple | layer | pipe
 
 For one small frame it compares every layer's activations (b2sr_debug_layer) and the final u8 image of the CUDA
-engine against the CPU oracle, for the CUDA-core path and for the tcgen05 path with both UMMA descriptor
-base-offset conventions (B2SR_OPT_DEBUG_DESC).
+engine against the CPU oracle, for the CUDA-core path and the two tcgen05 schedules (layer by layer, pipelined).
 """
 import os
 import subprocess
@@ -51,13 +50,9 @@ def run_mode(mode, model="2x_Compact_Pretrain", shape=(40, 56), seed=1):
     eng = E.Engine(g, 0)
     scale = eng.scale
     print("== mode %s model %s image %s device %s" % (mode, model, img.shape, E.device_name(0)), flush=True)
-    if mode == "simple":
-        eng.set_option(E.OPT_IMPL, E.IMPL_SIMPLE)
-    else:
-        eng.set_option(E.OPT_IMPL, E.IMPL_TCGEN05)
-        eng.set_option(E.OPT_DEBUG_DESC, int(mode[-1]))
+    eng.set_option(E.OPT_IMPL, {"simple": E.IMPL_SIMPLE, "layer": E.IMPL_TCGEN05, "pipe": E.IMPL_PIPELINED}[mode])
     ok = True
-    for li, name in enumerate(prelu_names):
+    for li, name in enumerate(prelu_names if mode != "pipe" else []):
         t0 = time.time()
         got = eng.debug_layer(img, li)
         good = stats("layer %2d (%s)" % (li, name), got, taps[name])
@@ -80,7 +75,7 @@ if __name__ == "__main__":
         shape = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (40, 56)
         sys.exit(0 if run_mode(m, model, shape) else 1)
     rc = 0
-    for m in ("simple", "tc1", "tc0"):
+    for m in ("simple", "layer", "pipe"):
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), m], timeout=300)
             print("-- mode %s exit %d" % (m, r.returncode), flush=True)

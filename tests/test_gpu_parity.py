@@ -33,8 +33,7 @@ def engines(E, model_dir):
 
     def get(name):
         if name not in cache:
-            cache[name] = E.Engine.from_files(model_dir, name, 0)
-            cache[name].set_option(E.OPT_IMPL, E.IMPL_TCGEN05)
+            cache[name] = E.Engine.from_files(model_dir, name, 0)  # default schedule: pipelined tcgen05 where it fits
         return cache[name]
 
     yield get
@@ -137,22 +136,53 @@ def test_saturation_and_noise(engines, oracle_models):
     assert_parity(got, ref, "noise")
 
 
-def test_tcgen05_path_equals_cuda_core_path(E, engines, model_dir):
-    """Two independent device implementations of the same arithmetic (fp16 storage, fp32 accumulate)."""
+def test_three_device_schedules_agree(E, engines, model_dir):
+    """Independent device implementations of the same arithmetic (fp16 storage, fp32 accumulate): CUDA-core kernels,
+    tcgen05 layer by layer, tcgen05 pipelined (one persistent kernel, L2 row rings).  The two tcgen05 schedules issue
+    the same MMAs per row and must agree bit for bit."""
     img = natural(64, 300, seed=2)
     simple = E.Engine.from_files(model_dir, "2x_Compact_Pretrain", 0)
     simple.set_option(E.OPT_IMPL, E.IMPL_SIMPLE)
     a = simple.run_u8(img)
     assert simple.stat(E.STAT_TC_LAUNCHES) == 0
-    eng = engines("2x_Compact_Pretrain")
-    eng.reset_stats()
-    b = eng.run_u8(img)
-    assert eng.stat(E.STAT_TC_LAUNCHES) == 18  # one tcgen05 launch per convolution
+    layer = E.Engine.from_files(model_dir, "2x_Compact_Pretrain", 0)
+    layer.set_option(E.OPT_IMPL, E.IMPL_TCGEN05)
+    b = layer.run_u8(img)
+    assert layer.stat(E.STAT_TC_LAUNCHES) == 18 and layer.stat(E.STAT_PIPE_LAUNCHES) == 0  # one launch per convolution
+    pipe = engines("2x_Compact_Pretrain")
+    pipe.set_option(E.OPT_IMPL, E.IMPL_PIPELINED)
+    pipe.reset_stats()
+    c = pipe.run_u8(img)
+    assert pipe.stat(E.STAT_PIPE_LAUNCHES) == 1 and pipe.stat(E.STAT_LAUNCHES) == 2  # prep + the persistent kernel
+    pipe.set_option(E.OPT_IMPL, E.IMPL_AUTO)
     d = np.abs(a.astype(int) - b.astype(int))
     assert d.max() <= 1 and (d > 0).mean() < 0.01
-    l_a, l_b = simple.debug_layer(img, 8), eng.debug_layer(img, 8)
+    assert np.array_equal(b, c)
+    l_a, l_b = simple.debug_layer(img, 8), layer.debug_layer(img, 8)
     assert np.abs(l_a - l_b).max() < 0.05 * np.abs(l_a).max()
+    # a frame with seams in x and y, small rings (forces ring wrap-around and back-pressure), both schedules
+    img = natural(1000, 1100, seed=8)
+    pipe.set_option(E.OPT_RING_ROWS, 8)
+    c = pipe.run_u8(img)
+    pipe.set_option(E.OPT_RING_ROWS, 32)
+    assert np.array_equal(layer.run_u8(img), c)
     simple.close()
+    layer.close()
+
+
+def test_wide_frame_falls_back_to_layer_schedule(E, model_dir, oracle_models):
+    """layers x bands > SM count (18 x 16 for a 2048-wide untiled frame): auto mode runs layer by layer, forcing the
+    pipelined schedule is a clean error."""
+    eng = E.Engine.from_files(model_dir, "2x_Compact_Pretrain", 0)
+    img = natural(24, 2048, seed=6)
+    out = eng.run_u8(img, tile=0, halo=0)
+    assert eng.stat(E.STAT_PIPE_LAUNCHES) == 0 and eng.stat(E.STAT_TC_LAUNCHES) == 18
+    ref = oracle.upscale_image_array(oracle_models("2x_Compact_Pretrain"), img, 2, "f64", tile_size=10**6)
+    assert_parity(out, ref, "wide")
+    eng.set_option(E.OPT_IMPL, E.IMPL_PIPELINED)
+    with pytest.raises(E.EngineError, match="pipelined"):
+        eng.run_u8(img, tile=0, halo=0)
+    eng.close()
 
 
 # ---------------------------------------------------------------- full size (BASELINE configs) --------

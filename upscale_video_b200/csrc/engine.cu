@@ -117,7 +117,23 @@ struct Plan {
     void* bound_in16 = nullptr;     // buffers the maps were encoded for
     void* bound_ping = nullptr;
     void* bound_pong = nullptr;
+    // pipelined mode: CTA (layer, band) streams band `band` of every plane
+    int nb = 0;    // bands of the widest plane
+    int Wmax = 0;  // widest plane
+    int64_t rows_total = 0;
+    std::vector<TcItem> pitems;
+    std::vector<int> pband_first;
+    TcItem* d_pitems = nullptr;
+    int* d_pband_first = nullptr;
+    CUtensorMap* d_pmaps = nullptr;  // [groups]: ring tensor maps (all rings share geometry; the base is per layer -> [layers-1][groups])
+    uint32_t* d_flags = nullptr;     // done[L][nb] | cons[L][nb]
+    void* bound_rings = nullptr;
+    int bound_rr = 0;
     ~Plan() {
+        if (d_pitems) cudaFree(d_pitems);
+        if (d_pband_first) cudaFree(d_pband_first);
+        if (d_pmaps) cudaFree(d_pmaps);
+        if (d_flags) cudaFree(d_flags);
         if (d_planes) cudaFree(d_planes);
         if (d_maps) cudaFree(d_maps);
         if (d_items) cudaFree(d_items);
@@ -142,15 +158,19 @@ struct b2sr_ctx {
     __half *in16 = nullptr, *ping = nullptr, *pong = nullptr;
     float* lastf = nullptr;
     int64_t cap_lastf = 0;
+    int64_t cap_pp = 0;          // capacity (pixels) of ping/pong, allocated only for the layer-by-layer schedules
+    __half* rings = nullptr;     // pipelined mode: (layers-1) rings of ring_rows x Wmax pixels
+    size_t cap_rings = 0;
+    int ring_rows = 32;
     uint8_t *d_in = nullptr, *d_out = nullptr;  // staging for host-memory calls
     size_t cap_in = 0, cap_out = 0;
     uint8_t *d_in2 = nullptr, *d_out2 = nullptr;  // second set for the double-buffered host pipeline
     size_t cap_in2 = 0, cap_out2 = 0;
     std::vector<std::unique_ptr<Plan>> plans;
     // options
-    int impl = 0, profile = 0, max_batch = 0, desc_mode = 0;
+    int impl = 0, profile = 0, max_batch = 0;
     // stats
-    double n_launch = 0, n_tc = 0;
+    double n_launch = 0, n_tc = 0, n_pipe = 0;
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> ev_pool;
 };
@@ -197,7 +217,7 @@ extern "C" void b2sr_destroy(b2sr_ctx* c) {
     c->plans.clear();
     free_layers(c);
     for (void* p : {(void*)c->in16, (void*)c->ping, (void*)c->pong, (void*)c->lastf, (void*)c->d_in, (void*)c->d_out,
-                    (void*)c->d_in2, (void*)c->d_out2})
+                    (void*)c->d_in2, (void*)c->d_out2, (void*)c->rings})
         if (p) cudaFree(p);
     for (auto& r : c->prof) {
         cudaEventDestroy(r.a);
@@ -412,6 +432,36 @@ static int build_plan(b2sr_ctx* c, int n, int h, int w, int tile, int halo, Plan
         }
     }
     P->n_cta = ncta;
+    // pipelined mode: per band, one item per plane (the whole band column); planes narrower than the band index get
+    // a placeholder (w = 0) so that every band CTA walks the same global row sequence
+    for (auto& g : P->groups) {
+        P->nb = std::max(P->nb, (g.Wt + TC_BW - 1) / TC_BW);
+        P->Wmax = std::max(P->Wmax, g.Wt);
+    }
+    P->pband_first.assign(1, 0);
+    for (int b = 0; b < P->nb; ++b) {
+        int64_t grow = 0;
+        for (size_t pi = 0; pi < P->planes.size(); ++pi) {
+            const PlaneDev& pd = P->planes[pi];
+            TcItem it{};
+            it.map = plane_group[pi], it.plane = pd.gplane, it.x0 = b * TC_BW, it.y0 = 0;
+            it.rows = pd.Ht, it.w = std::max(0, std::min(TC_BW, pd.Wt - b * TC_BW));
+            it.Ht = pd.Ht, it.Wt = pd.Wt, it.pix_off = pd.pix_off;
+            it.frame = pd.frame, it.fy0 = pd.fy0, it.fx0 = pd.fx0;
+            it.cy0 = pd.cy0, it.cy1 = pd.cy1, it.cx0 = pd.cx0, it.cx1 = pd.cx1;
+            it.grow0 = (int32_t)grow;
+            grow += pd.Ht;
+            P->pitems.push_back(it);
+        }
+        P->rows_total = grow;
+        P->pband_first.push_back((int)P->pitems.size());
+    }
+    CUDA_TRY(cudaMalloc(&P->d_pitems, P->pitems.size() * sizeof(TcItem)));
+    CUDA_TRY(cudaMemcpy(P->d_pitems, P->pitems.data(), P->pitems.size() * sizeof(TcItem), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&P->d_pband_first, P->pband_first.size() * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(P->d_pband_first, P->pband_first.data(), P->pband_first.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&P->d_pmaps, (size_t)B2SR_PIPE_MAX_LAYERS * P->groups.size() * sizeof(CUtensorMap)));
+    CUDA_TRY(cudaMalloc(&P->d_flags, (size_t)2 * B2SR_PIPE_MAX_LAYERS * P->nb * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&P->d_planes, P->planes.size() * sizeof(PlaneDev)));
     CUDA_TRY(cudaMemcpy(P->d_planes, P->planes.data(), P->planes.size() * sizeof(PlaneDev), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&P->d_items, P->items.size() * sizeof(TcItem)));
@@ -424,19 +474,32 @@ static int build_plan(b2sr_ctx* c, int n, int h, int w, int tile, int halo, Plan
     return 0;
 }
 
-static int ensure_scratch(b2sr_ctx* c, int64_t px) {
-    if (px <= c->cap_px) return 0;
-    cudaStreamSynchronize(c->stream);
-    for (void* p : {(void*)c->in16, (void*)c->ping, (void*)c->pong})
-        if (p) cudaFree(p);
-    c->in16 = c->ping = c->pong = nullptr;
-    c->cap_px = 0;
-    const int64_t cap = px + px / 16 + 1024;
-    CUDA_TRY(cudaMalloc(&c->in16, (size_t)cap * 16 * 2));
-    CUDA_TRY(cudaMalloc(&c->ping, (size_t)cap * c->CF * 2));
-    CUDA_TRY(cudaMalloc(&c->pong, (size_t)cap * c->CF * 2));
-    c->cap_px = cap;
+static int ensure_scratch(b2sr_ctx* c, int64_t px, bool pingpong) {
+    if (px > c->cap_px) {
+        cudaStreamSynchronize(c->stream);
+        if (c->in16) cudaFree(c->in16);
+        c->in16 = nullptr;
+        c->cap_px = 0;
+        const int64_t cap = px + px / 16 + 1024;
+        CUDA_TRY(cudaMalloc(&c->in16, (size_t)cap * 16 * 2));
+        c->cap_px = cap;
+    }
+    if (pingpong && px > c->cap_pp) {
+        cudaStreamSynchronize(c->stream);
+        for (void* p : {(void*)c->ping, (void*)c->pong})
+            if (p) cudaFree(p);
+        c->ping = c->pong = nullptr;
+        c->cap_pp = 0;
+        const int64_t cap = px + px / 16 + 1024;
+        CUDA_TRY(cudaMalloc(&c->ping, (size_t)cap * c->CF * 2));
+        CUDA_TRY(cudaMalloc(&c->pong, (size_t)cap * c->CF * 2));
+        c->cap_pp = cap;
+    }
     return 0;
+}
+
+static CUtensorMapSwizzle swizzle_for(int C) {
+    return C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
 static int encode_maps(b2sr_ctx* c, Plan* P) {
@@ -446,7 +509,8 @@ static int encode_maps(b2sr_ctx* c, Plan* P) {
     for (int b = 0; b < 3; ++b) {
         const int C = b == 0 ? 16 : c->CF;
         __half* basep = b == 0 ? c->in16 : (b == 1 ? c->ping : c->pong);
-        const CUtensorMapSwizzle sw = C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+        if (!basep) continue;  // ping/pong exist only once a layer-by-layer schedule has run
+        const CUtensorMapSwizzle sw = swizzle_for(C);
         for (size_t g = 0; g < G; ++g) {
             const Group& gr = P->groups[g];
             cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)gr.Wt, (cuuint64_t)gr.Ht, (cuuint64_t)gr.count};
@@ -495,13 +559,10 @@ static int prof_end(b2sr_ctx* c) {
 template <int CPIX, int NOUT, int SHUF, bool F32OUT>
 static int launch_tc(b2sr_ctx* c, const Plan* plan, TcParams P) {
     using Cfg = TcCfg<CPIX, NOUT, SHUF>;
-    constexpr int R = Cfg::ring_rows();
-    static_assert(R >= 4, "ring needs 3 live rows + 1 in flight");
-    P.R = R;
+    static_assert(Cfg::ring_rows() >= 3, "shared-memory ring too small");
     P.items = plan->d_items, P.n_items = (int)plan->items.size();
     P.item_first = plan->d_item_first;
-    P.desc_mode = c->desc_mode;
-    const int smem = Cfg::smem_bytes(R);
+    const int smem = Cfg::smem_bytes();
     auto kern = tc_conv_kernel<CPIX, NOUT, SHUF, F32OUT>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int grid = plan->n_cta;
@@ -567,15 +628,119 @@ static int simple_layer(b2sr_ctx* c, Plan* P, int li, const __half* in, void* ou
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// pipelined schedule: one persistent launch, CTA = (layer, band), activations in L2-resident row rings
+// ------------------------------------------------------------------------------------------------
+static bool pipe_fits(const b2sr_ctx* c, const Plan* P) {
+    const int L = (int)c->layers.size();
+    return L <= B2SR_PIPE_MAX_LAYERS && P->nb >= 1 && (int64_t)L * P->nb <= c->sms;
+}
+
+template <int CF, int NL, int S, bool F32OUT>
+static int launch_pipe(b2sr_ctx* c, const PipeParams& Q) {
+    const int smem = TcPipeCfg<CF, NL, S>::smem_bytes();
+    auto kern = tc_pipe_kernel<CF, NL, S, F32OUT>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<Q.n_layers * Q.nb, TC_THREADS, smem, c->stream>>>(Q);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int run_pipe(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, bool f32out) {
+    const int L = (int)c->layers.size(), G = (int)P->groups.size(), nb = P->nb, CF = c->CF;
+    TRY(ensure_scratch(c, P->total_px, false));
+    TRY(encode_maps(c, P));
+    const int RR = c->ring_rows;
+    const size_t ring_px = (size_t)RR * P->Wmax;
+    const size_t need = (size_t)(L - 1) * ring_px * CF * 2;
+    if (need > c->cap_rings) {
+        cudaStreamSynchronize(c->stream);
+        if (c->rings) cudaFree(c->rings);
+        c->rings = nullptr, c->cap_rings = 0;
+        CUDA_TRY(cudaMalloc(&c->rings, need));
+        c->cap_rings = need;
+    }
+    if (P->bound_rings != c->rings || P->bound_rr != RR) {
+        // ring l (output of layer l) as a {C, Wt, RR, 1} tensor per plane-size group: rows are Wmax pixels apart,
+        // columns beyond the group's Wt and rows outside [0, RR) read as zeros
+        std::vector<CUtensorMap> maps((size_t)(L - 1) * G);
+        for (int l = 0; l + 1 < L; ++l)
+            for (int g = 0; g < G; ++g) {
+                const Group& gr = P->groups[g];
+                cuuint64_t dims[4] = {(cuuint64_t)CF, (cuuint64_t)gr.Wt, (cuuint64_t)RR, 1};
+                cuuint64_t strides[3] = {(cuuint64_t)CF * 2, (cuuint64_t)P->Wmax * CF * 2, (cuuint64_t)ring_px * CF * 2};
+                cuuint32_t box[4] = {(cuuint32_t)CF, (cuuint32_t)TC_PITCH, 1, 1};
+                cuuint32_t es[4] = {1, 1, 1, 1};
+                CUresult r = g_encode(&maps[(size_t)l * G + g], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, c->rings + (size_t)l * ring_px * CF,
+                                      dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(CF),
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) return fail(B2SR_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for ring %d group %d", (int)r, l, g);
+            }
+        CUDA_TRY(cudaMemcpyAsync(P->d_pmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        P->bound_rings = c->rings, P->bound_rr = RR;
+    }
+    {
+        dim3 grid((unsigned)std::min(2048, (P->max_plane_px + 255) / 256), (unsigned)P->planes.size());
+        TRY(prof_begin(c, 0, 0));
+        prep_kernel<<<grid, 256, 0, c->stream>>>(d_frames, P->h, P->w, P->d_planes, c->in16);
+        CUDA_TRY(cudaGetLastError());
+        TRY(prof_end(c));
+        c->n_launch += 1;
+    }
+    CUDA_TRY(cudaMemsetAsync(P->d_flags, 0, (size_t)2 * B2SR_PIPE_MAX_LAYERS * nb * sizeof(uint32_t), c->stream));
+    PipeParams Q{};
+    Q.n_layers = L, Q.nb = nb;
+    uint32_t* done = P->d_flags;
+    uint32_t* cons = P->d_flags + (size_t)B2SR_PIPE_MAX_LAYERS * nb;
+    for (int l = 0; l < L; ++l) {
+        const LayerDev& Ld = c->layers[l];
+        TcParams& p = Q.layers[l];
+        p.maps = l == 0 ? P->d_maps : P->d_pmaps;  // layer 0 reads the in16 planes, layer l > 0 reads ring l-1
+        p.map_base = l == 0 ? 0 : (l - 1) * G;
+        p.items = P->d_pitems, p.item_first = P->d_pband_first, p.n_items = (int)P->pitems.size();
+        p.wimg = Ld.wimg, p.bias = Ld.bias, p.slope = Ld.slope;
+        p.acc_scale = l == 0 ? (1.f / 255.f) : 1.f;
+        p.out = l == L - 1 ? d_out : (void*)(c->rings + (size_t)l * ring_px * CF);
+        p.frames_in = d_frames, p.frame_h = P->h, p.frame_w = P->w, p.scale = c->desc.scale;
+        p.ring_in = l > 0, p.ring_out = l < L - 1;
+        p.RR = RR, p.Wmax = P->Wmax, p.nb = nb;
+        p.done_in = l > 0 ? done + (size_t)(l - 1) * nb : nullptr;
+        p.done_out = done + (size_t)l * nb;
+        p.cons_self = cons + (size_t)l * nb;
+        p.cons_next = l < L - 1 ? cons + (size_t)(l + 1) * nb : nullptr;
+    }
+    TRY(prof_begin(c, 2, P->out_px));
+    int rc = B2SR_E_UNSUPPORTED;
+    const int S = c->desc.scale;
+#define PIPE_CASE(cf, nl, s) \
+    if (CF == cf && c->NL == nl && S == s) rc = f32out ? launch_pipe<cf, nl, s, true>(c, Q) : launch_pipe<cf, nl, s, false>(c, Q);
+    PIPE_CASE(64, 16, 2)
+    PIPE_CASE(64, 48, 4)
+    PIPE_CASE(32, 16, 1)
+    PIPE_CASE(64, 16, 1)
+#undef PIPE_CASE
+    if (rc == B2SR_E_UNSUPPORTED) return fail(rc, "no pipelined kernel for nf-pad %d, last-pad %d, scale %d", CF, c->NL, S);
+    TRY(rc);
+    TRY(prof_end(c));
+    c->n_launch += 1, c->n_tc += 1, c->n_pipe += 1;
+    return 0;
+}
+
 static bool use_tc(const b2sr_ctx* c) { return c->impl != 1; }
 
 // Runs layers [0, upto] for the planes of P; the final layer writes `out` (u8 or f32 frames).  Returns in *act the
 // buffer that holds the activations of layer `upto` when upto is not the last layer.
 static int run_plan(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, bool f32out, int upto, const __half** act) {
-    TRY(ensure_scratch(c, P->total_px));
-    TRY(encode_maps(c, P));
     const int nl = (int)c->layers.size();
     if (upto < 0 || upto >= nl) upto = nl - 1;
+    if (upto == nl - 1 && (c->impl == 0 || c->impl == 3)) {  // whole network: pipelined schedule when it fits the GPU
+        if (pipe_fits(c, P)) return run_pipe(c, P, d_frames, d_out, f32out);
+        if (c->impl == 3)
+            return fail(B2SR_E_UNSUPPORTED, "pipelined schedule needs layers x bands = %d x %d CTAs, device has %d SMs", nl, P->nb, c->sms);
+    }
+    TRY(ensure_scratch(c, P->total_px, true));
+    TRY(encode_maps(c, P));
     {
         dim3 grid((unsigned)std::min(2048, (P->max_plane_px + 255) / 256), (unsigned)P->planes.size());
         TRY(prof_begin(c, 0, 0));
@@ -631,15 +796,19 @@ static int check_geom(int n, int h, int w, int tile, int halo) {
     return 0;
 }
 
-static int frames_per_pass(const b2sr_ctx* c, int h, int w) {
+static int frames_per_pass(const b2sr_ctx* c, int h, int w, int tile) {
     if (c->max_batch > 0) return c->max_batch;
     const double px = (double)h * w * 1.06;
+    // the pipelined schedule keeps only the 16-channel input planes per frame: long passes amortise its fill/drain
+    const int tw = tile > 0 ? std::min(w, tile + 20) : w;
+    const bool pipe = (c->impl == 0 || c->impl == 3) && (int64_t)c->layers.size() * ((tw + TC_BW - 1) / TC_BW) <= c->sms;
+    if (pipe) return (int)std::max(1.0, std::min(32.0, floor(7.0e7 / px)));
     return (int)std::max(1.0, std::min(16.0, floor(9.0e6 / px)));
 }
 
 static int run_batch_dev(b2sr_ctx* c, const uint8_t* d_in, void* d_out, bool f32out, int n, int h, int w, int tile, int halo) {
     const int S = c->desc.scale;
-    const int B = frames_per_pass(c, h, w);
+    const int B = frames_per_pass(c, h, w, tile);
     const size_t in_frame = (size_t)h * w * 3, out_frame = (size_t)h * S * w * S * 3 * (f32out ? 4 : 1);
     for (int f = 0; f < n; f += B) {
         const int nb = std::min(B, n - f);
@@ -714,7 +883,7 @@ extern "C" int b2sr_run_batch_host(b2sr_ctx* c, const uint8_t* h_in, uint8_t* h_
     TRY(check_geom(n, h, w, tile, halo));
     CUDA_TRY(cudaSetDevice(c->device));
     const int S = c->desc.scale;
-    const int B = frames_per_pass(c, h, w);
+    const int B = frames_per_pass(c, h, w, tile);
     const size_t in_frame = (size_t)h * w * 3, out_frame = in_frame * S * S;
     TRY(grow(&c->d_in, &c->cap_in, in_frame * B));
     TRY(grow(&c->d_out, &c->cap_out, out_frame * B));
@@ -787,7 +956,7 @@ extern "C" int b2sr_set_option(b2sr_ctx* c, int key, int64_t value) {
     if (!c) return fail(B2SR_E_INVALID, "null context");
     switch (key) {
         case B2SR_OPT_IMPL:
-            if (value < 0 || value > 2) return fail(B2SR_E_INVALID, "impl %lld", (long long)value);
+            if (value < 0 || value > 3) return fail(B2SR_E_INVALID, "impl %lld", (long long)value);
             c->impl = (int)value;
             return 0;
         case B2SR_OPT_PROFILE:
@@ -797,8 +966,9 @@ extern "C" int b2sr_set_option(b2sr_ctx* c, int key, int64_t value) {
             if (value < 0 || value > 4096) return fail(B2SR_E_INVALID, "max_batch %lld", (long long)value);
             c->max_batch = (int)value;
             return 0;
-        case B2SR_OPT_DEBUG_DESC:
-            c->desc_mode = (int)value;
+        case B2SR_OPT_RING_ROWS:
+            if (value < 4 || value > 4096) return fail(B2SR_E_INVALID, "ring rows %lld (need 4..4096)", (long long)value);
+            c->ring_rows = (int)value;
             return 0;
     }
     return fail(B2SR_E_INVALID, "unknown option %d", key);
@@ -808,7 +978,7 @@ extern "C" int b2sr_reset_stats(b2sr_ctx* c) {
     if (!c) return fail(B2SR_E_INVALID, "null context");
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->n_launch = c->n_tc = 0;
+    c->n_launch = c->n_tc = c->n_pipe = 0;
     for (auto& r : c->prof) {
         c->ev_pool.push_back(r.a);
         c->ev_pool.push_back(r.b);
@@ -826,20 +996,26 @@ extern "C" int b2sr_get_stat(b2sr_ctx* c, int key, double* value) {
         case B2SR_STAT_TC_LAUNCHES:
             *value = c->n_tc;
             return 0;
+        case B2SR_STAT_PIPE_LAUNCHES:
+            *value = c->n_pipe;
+            return 0;
         case B2SR_STAT_TC_MID_MS:
         case B2SR_STAT_TC_MID_COUNT:
         case B2SR_STAT_ALL_MS:
+        case B2SR_STAT_PIPE_MS:
         case B2SR_STAT_TC_MID_PIXELS: {
             CUDA_TRY(cudaSetDevice(c->device));
             CUDA_TRY(cudaStreamSynchronize(c->stream));
-            double mid_ms = 0, all_ms = 0, cnt = 0, px = 0;
+            double mid_ms = 0, all_ms = 0, cnt = 0, px = 0, pipe_ms = 0;
             for (auto& r : c->prof) {
                 float ms = 0;
                 CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
                 all_ms += ms;
                 if (r.kind == 1) mid_ms += ms, cnt += 1, px += r.px;
+                if (r.kind == 2) pipe_ms += ms;
             }
-            *value = key == B2SR_STAT_TC_MID_MS ? mid_ms : key == B2SR_STAT_TC_MID_COUNT ? cnt : key == B2SR_STAT_ALL_MS ? all_ms : px;
+            *value = key == B2SR_STAT_TC_MID_MS ? mid_ms : key == B2SR_STAT_TC_MID_COUNT ? cnt : key == B2SR_STAT_ALL_MS ? all_ms
+                     : key == B2SR_STAT_PIPE_MS ? pipe_ms : px;
             return 0;
         }
     }

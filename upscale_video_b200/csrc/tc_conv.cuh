@@ -24,11 +24,21 @@
 // wraps around the ring is issued as two MMAs (N = 2*NOUT + NOUT).
 // The stacked weights stay resident in shared memory for the life of the CTA (pre-swizzled on the host).
 //
-// Roles (320 threads): warp 0 = TMA producer; warp 1 = TMEM owner + tcgen05.mma issuer (the whole warp runs the
-// control flow so descriptors live in uniform registers, one elected lane issues); warps 2..5 and 6..9 = two
-// epilogue sets that take alternate rows (tcgen05.ld -> bias/PReLU -> fp16 -> swizzled staging -> 128-bit coalesced
+// Roles (352 threads): warp 0 = TMA producer; warp 1 = TMEM owner + tcgen05.mma issuer (the whole warp runs the
+// control flow so descriptors live in uniform registers, one elected lane issues); warp 10 = publisher (pipelined
+// mode); warps 2..5 and 6..9 = two epilogue sets that take alternate rows (tcgen05.ld -> bias/PReLU -> fp16 -> swizzled staging -> 128-bit coalesced
 // stores, or pixel-shuffle + nearest-upsampled residual + x255 + round-half-even/saturate for the last layer).
-// Each set owns one TMEM accumulator, so the MMAs of row t+1 overlap the epilogue of row t.
+//
+// Two schedules share this body:
+//  * layer mode (tc_conv_kernel): one launch per layer over full per-plane activation buffers in HBM; the linear
+//    sequence (plane, band, row) is cut into one contiguous equal range per CTA.
+//  * pipelined mode (tc_pipe_kernel): ONE persistent launch for the whole network.  CTA (l, b) keeps layer l's
+//    weights resident and streams band b of every plane, top to bottom; layer l writes its output rows into a ring
+//    of RR rows that stays L2-resident, layer l+1's CTAs pull them as soon as they are published.  Flow control is
+//    per band and per row through counters in global memory: `done` (rows written and fenced; the consumer's TMA
+//    producer acquires the counters of bands b-1, b, b+1 before loading a row) and `cons` (rows pulled into shared
+//    memory; the producer's epilogue waits for row g-RR to be consumed before overwriting its ring slot).  No
+//    activation ever goes to HBM, no layer is ever relaunched, weights are loaded once per CTA.
 #pragma once
 #include <stdio.h>
 
@@ -38,7 +48,8 @@ namespace b2sr {
 
 constexpr int TC_NSETS = 2;                       // epilogue warp sets (output rows alternate between them)
 constexpr int TC_NBLK = 8;                        // accumulator blocks (output rows in flight) in the TMEM ring
-constexpr int TC_THREADS = 64 + 128 * TC_NSETS;    // producer warp + MMA warp + 4 epilogue warps per set
+constexpr int TC_THREADS = 96 + 128 * TC_NSETS;    // producer, MMA and publisher warps + 4 epilogue warps per set
+constexpr int TC_NROWBAR = 16;                    // 8-byte slots reserved for the epilogue warps' progress words (pipelined mode)
 constexpr int TC_MAX_SLOTS = 64;
 constexpr int TC_TILE_M = 128;
 
@@ -88,7 +99,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) mbar_timeout(bar, parity, who);
+        if (clock64() - t0 > 6000000000LL) mbar_timeout(bar, parity, who);
     }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
@@ -102,6 +113,33 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __noinline__ void flag_timeout(const uint32_t* p, uint32_t need, int who) {
+    printf("b2sr: flag timeout block %d thread %d need %u have %u who %d\n", (int)blockIdx.x, (int)threadIdx.x, need,
+           ld_acquire_gpu(p), who);
+    __trap();
+}
+// Spin until *p >= need (counters only grow).  Bounded: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ uint32_t wait_counter(const uint32_t* p, uint32_t need, int who) {
+    uint32_t v = ld_acquire_gpu(p);
+    if (v >= need) return v;
+    const long long t0 = clock64();
+    while ((v = ld_acquire_gpu(p)) < need) {
+        __nanosleep(64);
+        if (clock64() - t0 > 2000000000LL) flag_timeout(p, need, who);
+    }
+    return v;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -159,34 +197,35 @@ struct TcCfg {
     static constexpr uint32_t LAYOUT = CPIX == 64 ? 2u : (CPIX == 32 ? 4u : 6u);  // UMMA LayoutType: SW128 / SW64 / SW32
     // instruction descriptor without N: D = f32, A = B = f16, both K-major, M = 128; N is added per MMA
     static constexpr uint32_t IDESC0 = (1u << 4) | ((uint32_t)(TC_TILE_M >> 4) << 24);
-    static constexpr int MISC = 2 * NOUT * 4 + (2 * TC_MAX_SLOTS + 2 * TC_NBLK + 4) * 8 + 64;
+    static constexpr int MISC = 2 * NOUT * 4 + (2 * TC_MAX_SLOTS + 2 * TC_NBLK + TC_NROWBAR + 4) * 8 + 64;
     static_assert(TC_NBLK * NOUT <= 512, "accumulator ring exceeds TMEM");
     static_assert(CPIX == 16 || CPIX == 32 || CPIX == 64, "one pixel must be one swizzle row");
     static_assert(NOUT % 16 == 0 && NOUT >= 16 && NOUT <= 64, "UMMA M=128 needs N % 16 == 0");
     static_assert((NOUT * PB) % 1024 == 0, "per-tap weight tile must keep 1024-byte (swizzle atom) alignment");
     static_assert(ROWB % (8 * PB) == 0, "ring rows must start on a swizzle atom");
     // ring rows that fit beside the weights
-    static constexpr int ring_rows() {
-        int r = (B2SR_SMEM_LIMIT - 1024 - WB - STG - MISC) / ROWB;
-        return r > 16 ? 16 : r;
-    }
-    static constexpr int smem_bytes(int ring_rows) { return 1024 + WB + ring_rows * ROWB + STG + MISC; }
+    static constexpr int RING_FIT = (B2SR_SMEM_LIMIT - 1024 - WB - STG - MISC) / ROWB;
+    static constexpr int RING = RING_FIT > 16 ? 16 : RING_FIT;
+    static constexpr int SMEM = 1024 + WB + RING * ROWB + STG + MISC;
+    static constexpr int ring_rows() { return RING; }
+    static constexpr int smem_bytes() { return SMEM; }
 };
 
 // ------------------------------------------------------------------------------------------------
-// the kernel
+// the CTA body (shared by both schedules)
 // ------------------------------------------------------------------------------------------------
-template <int CPIX, int NOUT, int SHUF /*0 = PReLU->fp16, else pixel-shuffle factor*/, bool F32OUT>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcParams P) {
+template <int CPIX, int NOUT, int SHUF /*0 = PReLU->fp16, else pixel-shuffle factor*/, bool F32OUT, bool PIPE>
+__device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_begin, const int it_end, const int band,
+                                             uint8_t* smem_raw) {
     using C = TcCfg<CPIX, NOUT, SHUF>;
     constexpr int PB = C::PB;
     constexpr uint32_t ROWB = C::ROWB;
-    extern __shared__ uint8_t smem_raw[];
+    constexpr int R = C::RING;
+    static_assert(R >= 3, "shared-memory ring too small");
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (sbase - raw);
 
-    const int R = P.R;
     const uint32_t w_s = sbase;
     const uint32_t ring_s = sbase + C::WB;
     const uint32_t stg_off = C::WB + (uint32_t)R * ROWB;
@@ -199,11 +238,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
     auto empty_bar = [&](int s) { return bar_s + 8u * (TC_MAX_SLOTS + s); };
     auto tfull_bar = [&](int b) { return bar_s + 8u * (2 * TC_MAX_SLOTS + b); };
     auto tempty_bar = [&](int b) { return bar_s + 8u * (2 * TC_MAX_SLOTS + TC_NBLK + b); };
-    const uint32_t w_bar = bar_s + 8u * (2 * TC_MAX_SLOTS + 2 * TC_NBLK);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + bar_off + 8 * (2 * TC_MAX_SLOTS + 2 * TC_NBLK + 1));
+    // progress words of the 4*TC_NSETS epilogue warps (pipelined mode): prog[w] = 2 + CTA-local index of the last row
+    // warp w has stored and fenced (w's set owns every TC_NSETS-th row); starts at the set index
+    volatile uint32_t* s_prog = reinterpret_cast<volatile uint32_t*>(gbase + bar_off + 8 * (2 * TC_MAX_SLOTS + 2 * TC_NBLK));
+    static_assert(4 * TC_NSETS * 4 <= TC_NROWBAR * 8, "progress words do not fit their slots");
+    const uint32_t w_bar = bar_s + 8u * (2 * TC_MAX_SLOTS + 2 * TC_NBLK + TC_NROWBAR);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + bar_off + 8 * (2 * TC_MAX_SLOTS + 2 * TC_NBLK + TC_NROWBAR + 1));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int it_begin = P.item_first[blockIdx.x], it_end = P.item_first[blockIdx.x + 1];
+    const bool ring_in = PIPE && P.ring_in, ring_out = PIPE && P.ring_out;
+    const uint32_t RR = PIPE ? (uint32_t)P.RR : 1u;
+    // neighbours whose rows overlap this band's 130-pixel input window / whose input windows overlap this band
+    const int nb_lo = band > 0 ? band - 1 : 0, nb_hi = band + 1 < P.nb ? band + 1 : P.nb - 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < R; ++s) {
@@ -214,6 +260,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             mbar_init(tfull_bar(b), 1);
             mbar_init(tempty_bar(b), 4);
         }
+        for (int w = 0; w < 4 * TC_NSETS; ++w) s_prog[w] = (uint32_t)(w >> 2);
         mbar_init(w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -242,14 +289,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 bulk_g2s(w_s + t * (NOUT * PB), P.wimg + (size_t)t * (NOUT * PB), NOUT * PB, w_bar);
             int slot = 0;
             uint32_t phase = 0;
+            uint32_t seen[3] = {0u, 0u, 0u};  // last value read from done_in[nb_lo + i]
             for (int it = it_begin; it < it_end; ++it) {
                 const TcItem I = P.items[it];
+                if (PIPE && I.w <= 0) continue;
                 const CUtensorMap* map = P.maps + (P.map_base + I.map);
                 const int rows_in = I.rows + 2;
                 for (int rho = 0; rho < rows_in; ++rho) {
+                    const int y = I.y0 - 1 + rho;  // plane row of this input row
+                    int cy = y, cp = I.plane;
+                    if (ring_in) {
+                        cp = 0;
+                        if (y >= 0 && y < I.Ht) {
+                            const uint32_t g = (uint32_t)(I.grow0 + y);
+                            cy = (int)(g % RR);
+                            bool polled = false;
+                            for (int n = nb_lo; n <= nb_hi; ++n)  // rows 0..g of bands b-1, b, b+1 written and fenced?
+                                if (seen[n - nb_lo] < g + 1u) {
+                                    seen[n - nb_lo] = wait_counter(P.done_in + n, g + 1u, 10 + n - nb_lo);
+                                    polled = true;
+                                }
+                            if (polled) asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy acquire -> TMA read
+                        } else {
+                            cy = -1;  // outside the plane: any out-of-bounds coordinate reads as zeros
+                        }
+                    }
                     mbar_wait(empty_bar(slot), phase ^ 1u, 0);
                     mbar_expect_tx(full_bar(slot), ROWB);
-                    tma_load_4d(ring_s + slot * ROWB, map, full_bar(slot), 0, I.x0 - 1, I.y0 - 1 + rho, I.plane);
+                    tma_load_4d(ring_s + slot * ROWB, map, full_bar(slot), 0, I.x0 - 1, cy, cp);
                     if (++slot == R) {
                         slot = 0;
                         phase ^= 1u;
@@ -272,19 +339,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         constexpr int NM = 3 * C::KSLABS;               // MMAs per input row
         int slot = 0;  // ring slot of the current input row
         uint32_t phase = 0;
-        uint32_t g0 = 0;      // global index of the current item's output row 0 (block ring / barrier phases)
-        uint32_t gfresh = 0;  // global index of the next output row to be started (== g0 + rho while rho < rows)
+        uint32_t g0 = 0;      // CTA-local index of the current item's output row 0 (block ring / barrier phases)
+        uint32_t gfresh = 0;  // CTA-local index of the next output row to be started (== g0 + rho while rho < rows)
         mbar_wait(w_bar, 0, 1);
         uint32_t ok_full = mbar_test_wait(full_bar(0), 0);
         uint32_t ok_tempty = mbar_test_wait(tempty_bar(0), 0);
         for (int it = it_begin; it < it_end; ++it) {
-            const int rows = P.items[it].rows;
+            const TcItem* Ip = P.items + it;
+            const int rows = Ip->rows;
+            if (PIPE && Ip->w <= 0) {  // band absent from this plane: nothing to pull, just move the counter on
+                if (ring_in && lane == 0) st_relaxed_gpu(P.cons_self + band, (uint32_t)(Ip->grow0 + Ip->Ht));
+                continue;
+            }
+            const int y_first = Ip->y0 - 1, plane_h = Ip->Ht;
+            const uint32_t grow0 = (uint32_t)Ip->grow0;
             for (int rho = 0; rho < rows + 2; ++rho) {  // input row rho feeds output rows rho - ky, ky = 0..2
                 const bool fresh = rho < rows;  // output row `rho` receives its first contribution (ky = 0)
                 if (!ok_full) mbar_wait(full_bar(slot), phase, 2);
                 // block of the new output row: drained and zeroed by its epilogue set? (use u of a block completes phase u)
                 if (fresh && !ok_tempty) mbar_wait(tempty_bar(gfresh & (TC_NBLK - 1)), (gfresh / TC_NBLK) & 1u, 3);
                 tc_fence_after();
+                if (ring_in) {  // the row is in shared memory now: its ring slot in L2 may be overwritten
+                    const int y = y_first + rho;
+                    if (y >= 0 && y < plane_h && lane == 0) st_relaxed_gpu(P.cons_self + band, grow0 + (uint32_t)y + 1u);
+                }
                 // probes for the next input row
                 const int nslot = slot + 1 == R ? 0 : slot + 1;
                 const uint32_t nphase = slot + 1 == R ? phase ^ 1u : phase;
@@ -334,9 +412,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
             }
             g0 += (uint32_t)rows;
         }
+    } else if (warp == 2 + 4 * TC_NSETS) {
+        // ======================= publisher (pipelined mode) =======================
+        // Turns the epilogue warps' progress words into one monotonic "rows of this band written and fenced" counter
+        // in global memory.  It polls, so a slow release store only batches several rows into one update.
+        if (ring_out && lane == 0) {
+            static_assert(TC_NSETS == 2, "the progress-word arithmetic below assumes two epilogue sets");
+            uint32_t n_local = 0;  // output rows this CTA produces
+            for (int it = it_begin; it < it_end; ++it)
+                if (P.items[it].w > 0) n_local += (uint32_t)P.items[it].rows;
+            const uint32_t g_end = it_end > it_begin ? (uint32_t)(P.items[it_end - 1].grow0 + P.items[it_end - 1].Ht) : 0u;
+            uint32_t cnt = 0;  // CTA-local rows accounted for so far
+            int it = it_begin;
+            uint32_t t = 0;    // rows of item `it` accounted for
+            uint32_t published = 0;
+            const long long t_start = clock64();
+            for (;;) {
+                uint32_t m = n_local;  // rows [0, m) are complete: every warp is past them
+#pragma unroll
+                for (int w = 0; w < 4 * TC_NSETS; ++w) {
+                    const uint32_t v = s_prog[w];
+                    m = v < m ? v : m;
+                }
+                uint32_t adv = m - cnt;
+                while (it < it_end) {  // move (it, t) forward by `adv` rows, stepping over absent bands and finished items
+                    const TcItem* Ip = P.items + it;
+                    const uint32_t rows = Ip->w > 0 ? (uint32_t)Ip->rows : 0u;
+                    if (t + adv < rows) {
+                        t += adv;
+                        adv = 0;
+                        break;
+                    }
+                    adv -= rows - t;
+                    ++it;
+                    t = 0;
+                }
+                cnt = m;
+                const uint32_t g = it < it_end ? (uint32_t)(P.items[it].grow0 + P.items[it].y0) + t : g_end;
+                if (g > published) {
+                    st_release_gpu(P.done_out + band, g);
+                    published = g;
+                }
+                if (it >= it_end) break;
+                __nanosleep(200);
+                if (clock64() - t_start > 20000000000LL) flag_timeout(P.done_out + band, g_end, 30);
+            }
+        }
     } else {
         // ======================= epilogue =======================
-        const int q = warp & 3;             // TMEM lane quadrant this warp may read
+        const int q = warp & 3;                // TMEM lane quadrant this warp may read
         const uint32_t set = (warp - 2) >> 2;  // this warp's epilogue set (takes output rows g with g % TC_NSETS == set)
         uint32_t tile_cnt = 0;
         // hand every accumulator block of this set to the issuer zeroed (all MMAs accumulate)
@@ -350,12 +474,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
         }
         const float scale_acc = P.acc_scale;
         const int c = q * 32 + lane;  // column inside the band
+        uint32_t cons_seen[3] = {0u, 0u, 0u};
+        uint32_t pending = 0;  // pipelined mode: 2 + local index of the row whose stores have been issued but not yet fenced
         for (int it = it_begin; it < it_end; ++it) {
             const TcItem I = P.items[it];
+            if (PIPE && I.w <= 0) continue;
             const bool valid = c < I.w;
             for (int t = 0; t < I.rows; ++t, ++tile_cnt) {
                 if (tile_cnt % TC_NSETS != set) continue;
                 const uint32_t buf = tile_cnt % TC_NBLK;
+                // Pipelined mode: the previous row of this warp is reported one row late, when the fence behind its
+                // stores has become cheap -- but never later than the moment this warp has to wait for anything.
+                auto report_pending = [&]() {
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) s_prog[warp - 2] = pending;
+                    pending = 0;
+                };
+                if (ring_out && pending && !mbar_test_wait(tfull_bar(buf), (tile_cnt / TC_NBLK) & 1u)) report_pending();
                 mbar_wait(tfull_bar(buf), (tile_cnt / TC_NBLK) & 1u, 4);
                 tc_fence_after();
                 uint32_t acc[NOUT];
@@ -374,7 +510,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                     // bias + PReLU -> fp16, via swizzled per-warp staging, then 128-bit coalesced global stores
                     constexpr int CH = C::CH;
                     uint4* stg = reinterpret_cast<uint4*>(gbase + stg_off + (warp - 2) * (32 * C::OB));
-                    const int off = valid ? ((I.y0 + t) * I.Wt + I.x0 + c) : -1;
+                    int off;
+                    uint8_t* outp;
+                    if (ring_out) {
+                        if (pending) report_pending();
+                        const uint32_t g = (uint32_t)(I.grow0 + I.y0 + t);
+                        if (g >= RR) {  // ring slot still holds row g - RR: have bands b-1, b, b+1 of the next layer pulled it?
+                            if (lane == 0)
+                                for (int n = nb_lo; n <= nb_hi; ++n)
+                                    if (cons_seen[n - nb_lo] < g - RR + 1u)
+                                        cons_seen[n - nb_lo] = wait_counter(P.cons_next + n, g - RR + 1u, 20 + n - nb_lo);
+                            __syncwarp();
+                        }
+                        off = valid ? (int)((g % RR) * (uint32_t)P.Wmax) + I.x0 + c : -1;
+                        outp = reinterpret_cast<uint8_t*>(P.out);
+                    } else {
+                        off = valid ? ((I.y0 + t) * I.Wt + I.x0 + c) : -1;
+                        outp = reinterpret_cast<uint8_t*>(P.out) + (size_t)I.pix_off * C::OB;
+                    }
                     const float4* sb4 = reinterpret_cast<const float4*>(s_bias);
                     const float4* ss4 = reinterpret_cast<const float4*>(s_slope);
 #pragma unroll
@@ -396,7 +549,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                         stg[qi ^ ((qi >> 3) & 7)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                     __syncwarp();
-                    uint8_t* outp = reinterpret_cast<uint8_t*>(P.out) + (size_t)I.pix_off * C::OB;
 #pragma unroll
                     for (int i = 0; i < CH; ++i) {
                         const int qi = i * 32 + lane;
@@ -404,6 +556,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                         const int o = __shfl_sync(0xffffffffu, off, qi / CH);
                         if (o >= 0) *reinterpret_cast<uint4*>(outp + (size_t)o * C::OB + (qi % CH) * 16) = v;
                     }
+                    pending = tile_cnt + 2u;
                     __syncwarp();
                 } else {
                     // last layer: pixel shuffle + nearest-upsampled input residual + x255 (+ round/saturate)
@@ -460,6 +613,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                 }
             }
         }
+        if (ring_out && pending) {  // the last row of this warp
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) s_prog[warp - 2] = pending;
+        }
     }
 
     tc_fence_before();
@@ -471,5 +629,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
                      : "memory");
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// layer mode: one launch per convolution
+// ------------------------------------------------------------------------------------------------
+template <int CPIX, int NOUT, int SHUF, bool F32OUT>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    tc_conv_body<CPIX, NOUT, SHUF, F32OUT, false>(P, P.item_first[blockIdx.x], P.item_first[blockIdx.x + 1], 0, smem_raw);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pipelined mode: one persistent launch for the whole network, CTA = (layer, band)
+// ------------------------------------------------------------------------------------------------
+template <int CF /*padded feature channels*/, int NL /*padded last-layer channels*/, int S /*scale*/, bool F32OUT>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_pipe_kernel(const __grid_constant__ PipeParams Q) {
+    extern __shared__ uint8_t smem_raw[];
+    const int layer = (int)blockIdx.x / Q.nb, band = (int)blockIdx.x % Q.nb;
+    const TcParams P = Q.layers[layer];
+    const int it_begin = P.item_first[band], it_end = P.item_first[band + 1];
+    if (layer == 0)
+        tc_conv_body<16, CF, 0, false, true>(P, it_begin, it_end, band, smem_raw);
+    else if (layer == Q.n_layers - 1)
+        tc_conv_body<CF, NL, S, F32OUT, true>(P, it_begin, it_end, band, smem_raw);
+    else
+        tc_conv_body<CF, CF, 0, false, true>(P, it_begin, it_end, band, smem_raw);
+}
+
+template <int CF, int NL, int S>
+struct TcPipeCfg {
+    static constexpr int a_ = TcCfg<16, CF, 0>::smem_bytes(), b_ = TcCfg<CF, CF, 0>::smem_bytes(), c_ = TcCfg<CF, NL, S>::smem_bytes();
+    static constexpr int smem_bytes() { return a_ > b_ ? (a_ > c_ ? a_ : c_) : (b_ > c_ ? b_ : c_); }
+};
 
 }  // namespace b2sr

@@ -21,8 +21,14 @@ ap.add_argument("--model", default="2x_Compact_Pretrain")
 ap.add_argument("--h", type=int, default=1080)
 ap.add_argument("--w", type=int, default=1920)
 ap.add_argument("--tile", type=int, default=960)
+ap.add_argument("--impl", type=int, default=0)
+ap.add_argument("--ring", type=int, default=32)
+ap.add_argument("--debug", type=int, default=0)
 a = ap.parse_args()
 eng = E.Engine.from_files(ncnn_model.packaged_model_dir(), a.model, 0)
+eng.set_option(E.OPT_IMPL, a.impl)
+eng.set_option(E.OPT_RING_ROWS, a.ring)
+eng.set_option(E.OPT_PIPE_DEBUG, a.debug)
 s = eng.scale
 d_in = torch.randint(0, 256, (a.frames, a.h, a.w, 3), dtype=torch.uint8, device="cuda")
 d_out = torch.empty((a.frames, a.h * s, a.w * s, 3), dtype=torch.uint8, device="cuda")

@@ -55,17 +55,23 @@ struct TcParams {
     int32_t RR;                 // rows per ring
     int32_t Wmax;               // ring row pitch in pixels
     int32_t nb;                 // band CTAs per layer
-    uint32_t* done_in;          // [nb] rows published by the previous layer's band CTAs
-    uint32_t* done_out;         // [nb] rows this layer's band CTAs have published
-    uint32_t* cons_self;        // [nb] input rows this layer's band CTAs have pulled into shared memory
-    uint32_t* cons_next;        // [nb] the same counters of the next layer (back-pressure on this layer's ring)
+    // counters, one per band, B2SR_FLAG_STRIDE words apart:
+    uint32_t* done_in;          // rows published by the previous layer's band CTAs
+    uint32_t* done_out;         // rows this layer's band CTAs have published
+    uint32_t* cons_self;        // input rows this layer's band CTAs have pulled into shared memory
+    uint32_t* cons_next;        // the same counters of the next layer (back-pressure on this layer's ring)
+    long long* dbg;             // pipelined mode, optional: this CTA's 4 timing words
 };
 
 #define B2SR_PIPE_MAX_LAYERS 20
+#define B2SR_FLAG_STRIDE 32  // uint32 words between the counters of neighbouring bands: one 128-byte line each, so that
+                             // pollers of different CTAs do not hammer the same L2 sector
 struct PipeParams {  // passed by value (kernel parameter space)
     TcParams layers[B2SR_PIPE_MAX_LAYERS];
     int32_t n_layers;
     int32_t nb;
+    int32_t layer_shift;  // bring-up: CTA k runs layer (k / nb + layer_shift) % n_layers
+    long long* dbg;  // optional [n_layers * nb][4]: total cycles, cycles starved (producer), back-pressured (epilogue warp 2), spare
 };
 
 #define B2SR_SMEM_LIMIT (227 * 1024)

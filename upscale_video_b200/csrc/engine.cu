@@ -162,6 +162,8 @@ struct b2sr_ctx {
     __half* rings = nullptr;     // pipelined mode: (layers-1) rings of ring_rows x Wmax pixels
     size_t cap_rings = 0;
     int ring_rows = 32;
+    int pipe_debug = 0;
+    long long* d_dbg = nullptr;
     uint8_t *d_in = nullptr, *d_out = nullptr;  // staging for host-memory calls
     size_t cap_in = 0, cap_out = 0;
     uint8_t *d_in2 = nullptr, *d_out2 = nullptr;  // second set for the double-buffered host pipeline
@@ -217,7 +219,7 @@ extern "C" void b2sr_destroy(b2sr_ctx* c) {
     c->plans.clear();
     free_layers(c);
     for (void* p : {(void*)c->in16, (void*)c->ping, (void*)c->pong, (void*)c->lastf, (void*)c->d_in, (void*)c->d_out,
-                    (void*)c->d_in2, (void*)c->d_out2, (void*)c->rings})
+                    (void*)c->d_in2, (void*)c->d_out2, (void*)c->rings, (void*)c->d_dbg})
         if (p) cudaFree(p);
     for (auto& r : c->prof) {
         cudaEventDestroy(r.a);
@@ -461,7 +463,7 @@ static int build_plan(b2sr_ctx* c, int n, int h, int w, int tile, int halo, Plan
     CUDA_TRY(cudaMalloc(&P->d_pband_first, P->pband_first.size() * sizeof(int)));
     CUDA_TRY(cudaMemcpy(P->d_pband_first, P->pband_first.data(), P->pband_first.size() * sizeof(int), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&P->d_pmaps, (size_t)B2SR_PIPE_MAX_LAYERS * P->groups.size() * sizeof(CUtensorMap)));
-    CUDA_TRY(cudaMalloc(&P->d_flags, (size_t)2 * B2SR_PIPE_MAX_LAYERS * P->nb * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&P->d_flags, (size_t)2 * B2SR_PIPE_MAX_LAYERS * P->nb * B2SR_FLAG_STRIDE * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&P->d_planes, P->planes.size() * sizeof(PlaneDev)));
     CUDA_TRY(cudaMemcpy(P->d_planes, P->planes.data(), P->planes.size() * sizeof(PlaneDev), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&P->d_items, P->items.size() * sizeof(TcItem)));
@@ -688,11 +690,18 @@ static int run_pipe(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, 
         TRY(prof_end(c));
         c->n_launch += 1;
     }
-    CUDA_TRY(cudaMemsetAsync(P->d_flags, 0, (size_t)2 * B2SR_PIPE_MAX_LAYERS * nb * sizeof(uint32_t), c->stream));
+    const size_t fl = (size_t)nb * B2SR_FLAG_STRIDE;  // counter words per layer
+    CUDA_TRY(cudaMemsetAsync(P->d_flags, 0, 2 * B2SR_PIPE_MAX_LAYERS * fl * sizeof(uint32_t), c->stream));
     PipeParams Q{};
     Q.n_layers = L, Q.nb = nb;
+    Q.layer_shift = (c->pipe_debug > 1 && c->pipe_debug < 100) ? c->pipe_debug - 1 : 0;
+    if (c->pipe_debug) {
+        if (!c->d_dbg) CUDA_TRY(cudaMalloc(&c->d_dbg, 148 * 8 * sizeof(long long)));
+        CUDA_TRY(cudaMemsetAsync(c->d_dbg, 0, 148 * 8 * sizeof(long long), c->stream));
+        Q.dbg = c->d_dbg;
+    }
     uint32_t* done = P->d_flags;
-    uint32_t* cons = P->d_flags + (size_t)B2SR_PIPE_MAX_LAYERS * nb;
+    uint32_t* cons = P->d_flags + B2SR_PIPE_MAX_LAYERS * fl;
     for (int l = 0; l < L; ++l) {
         const LayerDev& Ld = c->layers[l];
         TcParams& p = Q.layers[l];
@@ -704,11 +713,11 @@ static int run_pipe(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, 
         p.out = l == L - 1 ? d_out : (void*)(c->rings + (size_t)l * ring_px * CF);
         p.frames_in = d_frames, p.frame_h = P->h, p.frame_w = P->w, p.scale = c->desc.scale;
         p.ring_in = l > 0, p.ring_out = l < L - 1;
-        p.RR = RR, p.Wmax = P->Wmax, p.nb = nb;
-        p.done_in = l > 0 ? done + (size_t)(l - 1) * nb : nullptr;
-        p.done_out = done + (size_t)l * nb;
-        p.cons_self = cons + (size_t)l * nb;
-        p.cons_next = l < L - 1 ? cons + (size_t)(l + 1) * nb : nullptr;
+        p.RR = c->pipe_debug >= 100 ? -RR : RR, p.Wmax = P->Wmax, p.nb = nb;
+        p.done_in = l > 0 ? done + (size_t)(l - 1) * fl : nullptr;
+        p.done_out = done + (size_t)l * fl;
+        p.cons_self = cons + (size_t)l * fl;
+        p.cons_next = l < L - 1 ? cons + (size_t)(l + 1) * fl : nullptr;
     }
     TRY(prof_begin(c, 2, P->out_px));
     int rc = B2SR_E_UNSUPPORTED;
@@ -724,6 +733,21 @@ static int run_pipe(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, 
     TRY(rc);
     TRY(prof_end(c));
     c->n_launch += 1, c->n_tc += 1, c->n_pipe += 1;
+    if (c->pipe_debug) {
+        std::vector<long long> h(148 * 8);
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        CUDA_TRY(cudaMemcpy(h.data(), c->d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "b2sr pipe timing, %% of CTA time, mean over %d bands: layer kcycles | producer: starved(done) wait-empty | mma: wait-full wait-tempty | epilogue w2: back-pressure wait-tfull\n", nb);
+        for (int l = 0; l < L; ++l) {
+            double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int k = 0; k < nb; ++k)
+                for (int j = 0; j < 8; ++j) v[j] += (double)h[(l * nb + k) * 8 + j];
+            const double t = std::max(v[0], 1.0);
+            fprintf(stderr, "  L%02d: %8.0f | %5.1f %5.1f | %5.1f %5.1f | %5.1f %5.1f | publishes/band %6.0f, %6.0f cycles each\n", l, v[0] / nb / 1e3,
+                    100 * v[1] / t, 100 * v[6] / t, 100 * v[3] / t, 100 * v[4] / t, 100 * v[2] / t, 100 * v[5] / t,
+                    (double)(h[(l * nb) * 8 + 7] % 1000000LL), (double)(h[(l * nb) * 8 + 7] / 1000000LL));
+        }
+    }
     return 0;
 }
 
@@ -965,6 +989,9 @@ extern "C" int b2sr_set_option(b2sr_ctx* c, int key, int64_t value) {
         case B2SR_OPT_MAX_BATCH:
             if (value < 0 || value > 4096) return fail(B2SR_E_INVALID, "max_batch %lld", (long long)value);
             c->max_batch = (int)value;
+            return 0;
+        case B2SR_OPT_PIPE_DEBUG:
+            c->pipe_debug = (int)value;
             return 0;
         case B2SR_OPT_RING_ROWS:
             if (value < 4 || value > 4096) return fail(B2SR_E_INVALID, "ring rows %lld (need 4..4096)", (long long)value);

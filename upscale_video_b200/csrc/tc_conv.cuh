@@ -24,9 +24,9 @@
 // wraps around the ring is issued as two MMAs (N = 2*NOUT + NOUT).
 // The stacked weights stay resident in shared memory for the life of the CTA (pre-swizzled on the host).
 //
-// Roles (352 threads): warp 0 = TMA producer; warp 1 = TMEM owner + tcgen05.mma issuer (the whole warp runs the
-// control flow so descriptors live in uniform registers, one elected lane issues); warp 10 = publisher (pipelined
-// mode); warps 2..5 and 6..9 = two epilogue sets that take alternate rows (tcgen05.ld -> bias/PReLU -> fp16 -> swizzled staging -> 128-bit coalesced
+// Roles (384 threads): warp 0 = TMA producer; warp 1 = TMEM owner + tcgen05.mma issuer (the whole warp runs the
+// control flow so descriptors live in uniform registers, one elected lane issues); warp 10 = publisher and
+// warp 11 = counter poller (pipelined mode); warps 2..5 and 6..9 = two epilogue sets that take alternate rows (tcgen05.ld -> bias/PReLU -> fp16 -> swizzled staging -> 128-bit coalesced
 // stores, or pixel-shuffle + nearest-upsampled residual + x255 + round-half-even/saturate for the last layer).
 //
 // Two schedules share this body:
@@ -48,7 +48,7 @@ namespace b2sr {
 
 constexpr int TC_NSETS = 2;                       // epilogue warp sets (output rows alternate between them)
 constexpr int TC_NBLK = 8;                        // accumulator blocks (output rows in flight) in the TMEM ring
-constexpr int TC_THREADS = 96 + 128 * TC_NSETS;    // producer, MMA and publisher warps + 4 epilogue warps per set
+constexpr int TC_THREADS = 128 + 128 * TC_NSETS;   // producer, MMA, publisher and poller warps + 4 epilogue warps per set
 constexpr int TC_NROWBAR = 16;                    // 8-byte slots reserved for the epilogue warps' progress words (pipelined mode)
 constexpr int TC_MAX_SLOTS = 64;
 constexpr int TC_TILE_M = 128;
@@ -102,6 +102,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who
         if (clock64() - t0 > 6000000000LL) mbar_timeout(bar, parity, who);
     }
 }
+__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, int who, long long& waited) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    mbar_wait(bar, parity, who);
+    waited += clock64() - t0;
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
     asm volatile(
@@ -130,14 +136,27 @@ __device__ __noinline__ void flag_timeout(const uint32_t* p, uint32_t need, int 
            ld_acquire_gpu(p), who);
     __trap();
 }
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 // Spin until *p >= need (counters only grow).  Bounded: a protocol bug traps instead of hanging the GPU.
-__device__ __forceinline__ uint32_t wait_counter(const uint32_t* p, uint32_t need, int who) {
-    uint32_t v = ld_acquire_gpu(p);
-    if (v >= need) return v;
-    const long long t0 = clock64();
-    while ((v = ld_acquire_gpu(p)) < need) {
-        __nanosleep(64);
-        if (clock64() - t0 > 2000000000LL) flag_timeout(p, need, who);
+//
+// The polls are relaxed GPU-scope loads (served by L2) and are NOT followed by an acquire fence: what they gate is a
+// TMA load (async proxy, reads L2 directly, no L1 in between) or a global store, issued after the poll through a
+// control dependency, while the writer published the counter with a GPU-scope release after its data reached L2.
+// A per-row fence.acq_rel.gpu in the TMA-issuing thread was measured to serialise the row pipeline (each fence waits
+// for the loads in flight): 85 fps instead of 3-400.
+__device__ __forceinline__ uint32_t wait_counter(const uint32_t* p, uint32_t need, int who, long long& waited) {
+    uint32_t v = ld_relaxed_gpu(p);
+    if (v < need) {
+        const long long t0 = clock64();
+        while ((v = ld_relaxed_gpu(p)) < need) {
+            __nanosleep(32);
+            if (clock64() - t0 > 2000000000LL) flag_timeout(p, need, who);
+        }
+        waited += clock64() - t0;
     }
     return v;
 }
@@ -241,13 +260,17 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
     // progress words of the 4*TC_NSETS epilogue warps (pipelined mode): prog[w] = 2 + CTA-local index of the last row
     // warp w has stored and fenced (w's set owns every TC_NSETS-th row); starts at the set index
     volatile uint32_t* s_prog = reinterpret_cast<volatile uint32_t*>(gbase + bar_off + 8 * (2 * TC_MAX_SLOTS + 2 * TC_NBLK));
-    static_assert(4 * TC_NSETS * 4 <= TC_NROWBAR * 8, "progress words do not fit their slots");
+    static_assert((4 * TC_NSETS + 3) * 4 <= TC_NROWBAR * 8, "progress words do not fit their slots");
+    // words maintained by the poller warp so that no critical thread ever waits on an L2 round trip:
+    volatile uint32_t* s_avail = s_prog + 4 * TC_NSETS;        // min over bands b-1..b+1 of the previous layer's `done`
+    volatile uint32_t* s_consmin = s_prog + 4 * TC_NSETS + 1;  // min over bands b-1..b+1 of the next layer's `cons`
+    uint32_t* s_finished = const_cast<uint32_t*>(s_prog) + 4 * TC_NSETS + 2;  // roles that no longer need the poller
     const uint32_t w_bar = bar_s + 8u * (2 * TC_MAX_SLOTS + 2 * TC_NBLK + TC_NROWBAR);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + bar_off + 8 * (2 * TC_MAX_SLOTS + 2 * TC_NBLK + TC_NROWBAR + 1));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool ring_in = PIPE && P.ring_in, ring_out = PIPE && P.ring_out;
-    const uint32_t RR = PIPE ? (uint32_t)P.RR : 1u;
+    const uint32_t RR = PIPE ? (uint32_t)(P.RR < 0 ? -P.RR : P.RR) : 1u;
     // neighbours whose rows overlap this band's 130-pixel input window / whose input windows overlap this band
     const int nb_lo = band > 0 ? band - 1 : 0, nb_hi = band + 1 < P.nb ? band + 1 : P.nb - 1;
 
@@ -261,6 +284,9 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
             mbar_init(tempty_bar(b), 4);
         }
         for (int w = 0; w < 4 * TC_NSETS; ++w) s_prog[w] = (uint32_t)(w >> 2);
+        *s_avail = 0u;
+        *s_consmin = 0u;
+        *s_finished = 0u;
         mbar_init(w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -289,7 +315,9 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
                 bulk_g2s(w_s + t * (NOUT * PB), P.wimg + (size_t)t * (NOUT * PB), NOUT * PB, w_bar);
             int slot = 0;
             uint32_t phase = 0;
-            uint32_t seen[3] = {0u, 0u, 0u};  // last value read from done_in[nb_lo + i]
+            uint32_t seen = 0u;  // last value read from s_avail
+            long long waited = 0, w_empty = 0;
+            const long long t_begin = clock64();
             for (int it = it_begin; it < it_end; ++it) {
                 const TcItem I = P.items[it];
                 if (PIPE && I.w <= 0) continue;
@@ -303,18 +331,19 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
                         if (y >= 0 && y < I.Ht) {
                             const uint32_t g = (uint32_t)(I.grow0 + y);
                             cy = (int)(g % RR);
-                            bool polled = false;
-                            for (int n = nb_lo; n <= nb_hi; ++n)  // rows 0..g of bands b-1, b, b+1 written and fenced?
-                                if (seen[n - nb_lo] < g + 1u) {
-                                    seen[n - nb_lo] = wait_counter(P.done_in + n, g + 1u, 10 + n - nb_lo);
-                                    polled = true;
+                            if (seen < g + 1u) {  // rows 0..g of bands b-1, b, b+1 of the previous layer written and released?
+                                const long long t0 = clock64();
+                                while ((seen = *s_avail) < g + 1u) {
+                                    __nanosleep(20);
+                                    if (clock64() - t0 > 2000000000LL) flag_timeout(P.done_in + band * B2SR_FLAG_STRIDE, g + 1u, 10);
                                 }
-                            if (polled) asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy acquire -> TMA read
+                                waited += clock64() - t0;
+                            }
                         } else {
                             cy = -1;  // outside the plane: any out-of-bounds coordinate reads as zeros
                         }
                     }
-                    mbar_wait(empty_bar(slot), phase ^ 1u, 0);
+                    mbar_wait_timed(empty_bar(slot), phase ^ 1u, 0, w_empty);
                     mbar_expect_tx(full_bar(slot), ROWB);
                     tma_load_4d(ring_s + slot * ROWB, map, full_bar(slot), 0, I.x0 - 1, cy, cp);
                     if (++slot == R) {
@@ -322,6 +351,12 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
                         phase ^= 1u;
                     }
                 }
+            }
+            if (ring_in) atomicAdd(s_finished, 1u);
+            if (PIPE && P.dbg) {
+                P.dbg[0] = clock64() - t_begin;
+                P.dbg[1] = waited;
+                P.dbg[6] = w_empty;
             }
         }
     } else if (warp == 1) {
@@ -341,6 +376,7 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
         uint32_t phase = 0;
         uint32_t g0 = 0;      // CTA-local index of the current item's output row 0 (block ring / barrier phases)
         uint32_t gfresh = 0;  // CTA-local index of the next output row to be started (== g0 + rho while rho < rows)
+        long long w_full = 0, w_tempty = 0;
         mbar_wait(w_bar, 0, 1);
         uint32_t ok_full = mbar_test_wait(full_bar(0), 0);
         uint32_t ok_tempty = mbar_test_wait(tempty_bar(0), 0);
@@ -348,20 +384,20 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
             const TcItem* Ip = P.items + it;
             const int rows = Ip->rows;
             if (PIPE && Ip->w <= 0) {  // band absent from this plane: nothing to pull, just move the counter on
-                if (ring_in && lane == 0) st_relaxed_gpu(P.cons_self + band, (uint32_t)(Ip->grow0 + Ip->Ht));
+                if (ring_in && lane == 0) st_relaxed_gpu(P.cons_self + band * B2SR_FLAG_STRIDE, (uint32_t)(Ip->grow0 + Ip->Ht));
                 continue;
             }
             const int y_first = Ip->y0 - 1, plane_h = Ip->Ht;
             const uint32_t grow0 = (uint32_t)Ip->grow0;
             for (int rho = 0; rho < rows + 2; ++rho) {  // input row rho feeds output rows rho - ky, ky = 0..2
                 const bool fresh = rho < rows;  // output row `rho` receives its first contribution (ky = 0)
-                if (!ok_full) mbar_wait(full_bar(slot), phase, 2);
+                if (!ok_full) mbar_wait_timed(full_bar(slot), phase, 2, w_full);
                 // block of the new output row: drained and zeroed by its epilogue set? (use u of a block completes phase u)
-                if (fresh && !ok_tempty) mbar_wait(tempty_bar(gfresh & (TC_NBLK - 1)), (gfresh / TC_NBLK) & 1u, 3);
+                if (fresh && !ok_tempty) mbar_wait_timed(tempty_bar(gfresh & (TC_NBLK - 1)), (gfresh / TC_NBLK) & 1u, 3, w_tempty);
                 tc_fence_after();
                 if (ring_in) {  // the row is in shared memory now: its ring slot in L2 may be overwritten
                     const int y = y_first + rho;
-                    if (y >= 0 && y < plane_h && lane == 0) st_relaxed_gpu(P.cons_self + band, grow0 + (uint32_t)y + 1u);
+                    if (y >= 0 && y < plane_h && lane == 0) st_relaxed_gpu(P.cons_self + band * B2SR_FLAG_STRIDE, grow0 + (uint32_t)y + 1u);
                 }
                 // probes for the next input row
                 const int nslot = slot + 1 == R ? 0 : slot + 1;
@@ -412,6 +448,10 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
             }
             g0 += (uint32_t)rows;
         }
+        if (PIPE && P.dbg && lane == 0) {
+            P.dbg[3] = w_full;
+            P.dbg[4] = w_tempty;
+        }
     } else if (warp == 2 + 4 * TC_NSETS) {
         // ======================= publisher (pipelined mode) =======================
         // Turns the epilogue warps' progress words into one monotonic "rows of this band written and fenced" counter
@@ -426,6 +466,7 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
             int it = it_begin;
             uint32_t t = 0;    // rows of item `it` accounted for
             uint32_t published = 0;
+            long long n_pub = 0, t_pub = 0;
             const long long t_start = clock64();
             for (;;) {
                 uint32_t m = n_local;  // rows [0, m) are complete: every warp is past them
@@ -450,12 +491,46 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
                 cnt = m;
                 const uint32_t g = it < it_end ? (uint32_t)(P.items[it].grow0 + P.items[it].y0) + t : g_end;
                 if (g > published) {
-                    st_release_gpu(P.done_out + band, g);
+                    const long long tp = clock64();
+                    __threadfence_block();  // acquire side of the progress words ...
+                    if (P.dbg && P.RR < 0) st_relaxed_gpu(P.done_out + band * B2SR_FLAG_STRIDE, g);  // bring-up experiment: no release fence
+                    else st_release_gpu(P.done_out + band * B2SR_FLAG_STRIDE, g);  // ... then one GPU-scope release for all eight warps' stores
                     published = g;
+                    n_pub += 1;
+                    t_pub += clock64() - tp;
                 }
                 if (it >= it_end) break;
+                __nanosleep(100);
+                if (clock64() - t_start > 20000000000LL) flag_timeout(P.done_out + band * B2SR_FLAG_STRIDE, g_end, 30);
+            }
+            if (P.dbg) P.dbg[7] = n_pub > 0 ? (t_pub / n_pub) * 1000000LL + n_pub : 0;  // mean cycles per publish * 1e6 + count
+        }
+    } else if (warp == 3 + 4 * TC_NSETS) {
+        // ======================= counter poller (pipelined mode) =======================
+        // Keeps shared-memory copies of the neighbours' global counters fresh, so that the TMA producer and the
+        // epilogue warps test a shared-memory word instead of paying L2 round trips on their critical paths.
+        if ((ring_in || ring_out) && lane == 0) {
+            const uint32_t need_fin = (ring_in ? 1u : 0u) + (ring_out ? 4u * TC_NSETS : 0u);
+            const uint32_t* d0 = ring_in ? P.done_in + nb_lo * B2SR_FLAG_STRIDE : nullptr;
+            const uint32_t* d1 = ring_in ? P.done_in + band * B2SR_FLAG_STRIDE : nullptr;
+            const uint32_t* d2 = ring_in ? P.done_in + nb_hi * B2SR_FLAG_STRIDE : nullptr;
+            const uint32_t* c0 = ring_out ? P.cons_next + nb_lo * B2SR_FLAG_STRIDE : nullptr;
+            const uint32_t* c1 = ring_out ? P.cons_next + band * B2SR_FLAG_STRIDE : nullptr;
+            const uint32_t* c2 = ring_out ? P.cons_next + nb_hi * B2SR_FLAG_STRIDE : nullptr;
+            const long long t_start = clock64();
+            while (*reinterpret_cast<volatile uint32_t*>(s_finished) < need_fin) {
+                if (ring_in) {
+                    const uint32_t a = ld_relaxed_gpu(d0), b = ld_relaxed_gpu(d1), c = ld_relaxed_gpu(d2);  // independent loads
+                    const uint32_t m = a < b ? (a < c ? a : c) : (b < c ? b : c);
+                    *s_avail = m;
+                }
+                if (ring_out) {
+                    const uint32_t a = ld_relaxed_gpu(c0), b = ld_relaxed_gpu(c1), c = ld_relaxed_gpu(c2);
+                    const uint32_t m = a < b ? (a < c ? a : c) : (b < c ? b : c);
+                    *s_consmin = m;
+                }
                 __nanosleep(200);
-                if (clock64() - t_start > 20000000000LL) flag_timeout(P.done_out + band, g_end, 30);
+                if (clock64() - t_start > 40000000000LL) flag_timeout(ring_in ? d1 : c1, 0xffffffffu, 40);
             }
         }
     } else {
@@ -474,8 +549,8 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
         }
         const float scale_acc = P.acc_scale;
         const int c = q * 32 + lane;  // column inside the band
-        uint32_t cons_seen[3] = {0u, 0u, 0u};
-        uint32_t pending = 0;  // pipelined mode: 2 + local index of the row whose stores have been issued but not yet fenced
+        uint32_t cons_seen = 0u;  // last value read from s_consmin
+        long long waited = 0, w_tfull = 0;
         for (int it = it_begin; it < it_end; ++it) {
             const TcItem I = P.items[it];
             if (PIPE && I.w <= 0) continue;
@@ -483,16 +558,7 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
             for (int t = 0; t < I.rows; ++t, ++tile_cnt) {
                 if (tile_cnt % TC_NSETS != set) continue;
                 const uint32_t buf = tile_cnt % TC_NBLK;
-                // Pipelined mode: the previous row of this warp is reported one row late, when the fence behind its
-                // stores has become cheap -- but never later than the moment this warp has to wait for anything.
-                auto report_pending = [&]() {
-                    __threadfence();
-                    __syncwarp();
-                    if (lane == 0) s_prog[warp - 2] = pending;
-                    pending = 0;
-                };
-                if (ring_out && pending && !mbar_test_wait(tfull_bar(buf), (tile_cnt / TC_NBLK) & 1u)) report_pending();
-                mbar_wait(tfull_bar(buf), (tile_cnt / TC_NBLK) & 1u, 4);
+                mbar_wait_timed(tfull_bar(buf), (tile_cnt / TC_NBLK) & 1u, 4, w_tfull);
                 tc_fence_after();
                 uint32_t acc[NOUT];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NOUT;
@@ -513,13 +579,16 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
                     int off;
                     uint8_t* outp;
                     if (ring_out) {
-                        if (pending) report_pending();
                         const uint32_t g = (uint32_t)(I.grow0 + I.y0 + t);
                         if (g >= RR) {  // ring slot still holds row g - RR: have bands b-1, b, b+1 of the next layer pulled it?
-                            if (lane == 0)
-                                for (int n = nb_lo; n <= nb_hi; ++n)
-                                    if (cons_seen[n - nb_lo] < g - RR + 1u)
-                                        cons_seen[n - nb_lo] = wait_counter(P.cons_next + n, g - RR + 1u, 20 + n - nb_lo);
+                            if (cons_seen < g - RR + 1u) {
+                                const long long t0 = clock64();
+                                while ((cons_seen = *s_consmin) < g - RR + 1u) {
+                                    __nanosleep(20);
+                                    if (clock64() - t0 > 2000000000LL) flag_timeout(P.cons_next + band * B2SR_FLAG_STRIDE, g - RR + 1u, 20);
+                                }
+                                waited += clock64() - t0;
+                            }
                             __syncwarp();
                         }
                         off = valid ? (int)((g % RR) * (uint32_t)P.Wmax) + I.x0 + c : -1;
@@ -556,7 +625,15 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
                         const int o = __shfl_sync(0xffffffffu, off, qi / CH);
                         if (o >= 0) *reinterpret_cast<uint4*>(outp + (size_t)o * C::OB + (qi % CH) * 16) = v;
                     }
-                    pending = tile_cnt + 2u;
+                    if (ring_out) {
+                        // Report the row to the publisher with CTA-scope ordering only; the publisher's single GPU-scope
+                        // release covers every warp's stores by cumulativity (the __syncthreads + one __threadfence idiom).
+                        __syncwarp();
+                        if (lane == 0) {
+                            __threadfence_block();
+                            s_prog[warp - 2] = tile_cnt + 2u;
+                        }
+                    }
                     __syncwarp();
                 } else {
                     // last layer: pixel shuffle + nearest-upsampled input residual + x255 (+ round/saturate)
@@ -613,10 +690,10 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
                 }
             }
         }
-        if (ring_out && pending) {  // the last row of this warp
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) s_prog[warp - 2] = pending;
+        if (ring_out && lane == 0) atomicAdd(s_finished, 1u);
+        if (PIPE && P.dbg && warp == 2 && lane == 0) {
+            P.dbg[2] = waited;
+            P.dbg[5] = w_tfull;
         }
     }
 
@@ -645,8 +722,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
 template <int CF /*padded feature channels*/, int NL /*padded last-layer channels*/, int S /*scale*/, bool F32OUT>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_pipe_kernel(const __grid_constant__ PipeParams Q) {
     extern __shared__ uint8_t smem_raw[];
-    const int layer = (int)blockIdx.x / Q.nb, band = (int)blockIdx.x % Q.nb;
-    const TcParams P = Q.layers[layer];
+    const int layer = ((int)blockIdx.x / Q.nb + Q.layer_shift) % Q.n_layers, band = (int)blockIdx.x % Q.nb;
+    TcParams P = Q.layers[layer];
+    P.dbg = Q.dbg ? Q.dbg + (size_t)(layer * Q.nb + band) * 8 : nullptr;
     const int it_begin = P.item_first[band], it_end = P.item_first[band + 1];
     if (layer == 0)
         tc_conv_body<16, CF, 0, false, true>(P, it_begin, it_end, band, smem_raw);

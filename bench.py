@@ -14,8 +14,8 @@ blob from rank 0 at start-up.
 The one JSON line printed by rank 0 follows the contract in the task statement:
   value      frames/s with inputs and outputs resident in HBM (CUDA events on the engine's stream, max over ranks)
   e2e        frames/s through Engine.run_batch_host: pinned host buffers, H2D and D2H inside the timed region
-  roofline   the dominant kernel (tcgen05 64->64 conv): algorithmic FLOPs per launch / mean launch time
-             (per-launch CUDA events recorded on the engine's stream inside the timed region)
+  roofline   the dominant kernel (the persistent whole-network tcgen05 kernel): algorithmic FLOPs per launch / mean
+             launch time (per-launch CUDA events recorded on the engine's stream inside the timed region)
   cpu_baseline  the CPU oracle (oracle/, a port of the reference graph + glue -- ncnn itself is not installable)
              timed on the host cores on a bounded sample of the same workload
 `--impl reference` times that CPU port alone, with every host thread, on the same config (rank 0 only).
@@ -38,6 +38,10 @@ TILE, HALO = 960, 10
 MAC_PER_PX_MID = 64 * 64 * 9                 # one nf->nf convolution
 MAC_PER_PX_NET = 598464                      # whole 2x_Compact graph
 METRIC = "1080p frames/sec (2x_Compact_Pretrain)"
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture
+# (profiles/), per launch of the same shape as the bench's; None until a capture of the current kernel exists
+TRAFFIC_BYTES_PER_LAUNCH = None
+TRAFFIC_NOTE = None
 
 
 def load_peaks():
@@ -205,6 +209,7 @@ def main():
     ms = ev0.elapsed_time(ev1)
     launches = eng.stat(E.STAT_LAUNCHES)
     mid_ms, mid_n = eng.stat(E.STAT_TC_MID_MS), eng.stat(E.STAT_TC_MID_COUNT)
+    pipe_ms, pipe_n = eng.stat(E.STAT_PIPE_MS), eng.stat(E.STAT_PIPE_LAUNCHES)
     all_ms = eng.stat(E.STAT_ALL_MS)
     eng.set_option(E.OPT_PROFILE, 0)
     eng.reset_stats()
@@ -243,20 +248,32 @@ def main():
         return
 
     peaks, peak_src = load_peaks()
-    # frames one launch covers (the engine splits a batch into passes); exact frame pixels: no halo, no padding, no junk
-    frames_per_launch = B * args.steps * 16.0 / max(mid_n, 1)
-    flop_launch = 2.0 * MAC_PER_PX_MID * frames_per_launch * H * W
-    ach = flop_launch / (mid_ms / max(mid_n, 1) * 1e-3) / 1e12 if mid_n else None
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    if pipe_n:
+        # dominant kernel = the persistent whole-network kernel (one launch per pass of frames_per_launch frames)
+        frames_per_launch = B * args.steps / pipe_n
+        flop_launch = 2.0 * MAC_PER_PX_NET * frames_per_launch * H * W  # exact frame, no halo/padding/junk columns
+        k_ms, k_n = pipe_ms, pipe_n
+        kernel = ("tc_pipe_kernel<64,16,2> (whole 2x_Compact network in one persistent launch: CTA = layer x band, "
+                  "18 tcgen05 conv stages chained through L2-resident row rings)")
+    else:
+        # layer-by-layer schedule: dominant kernel = the 64->64 convolution (16 launches per pass)
+        frames_per_launch = B * args.steps * 16.0 / max(mid_n, 1)
+        flop_launch = 2.0 * MAC_PER_PX_MID * frames_per_launch * H * W
+        k_ms, k_n = mid_ms, mid_n
+        kernel = "tc_conv_kernel<64,64,0> (3x3 conv 64->64 + bias + PReLU, tcgen05 kind::f16)"
+    ach = flop_launch / (k_ms / max(k_n, 1) * 1e-3) / 1e12 if k_n else None
     roofline = {
-        "bound": "tensor", "kernel": "tc_conv_kernel<64,64,0> (3x3 conv 64->64 + bias + PReLU, tcgen05 kind::f16)",
+        "bound": "tensor", "kernel": kernel,
         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak if ach else None),
         "peak_source": peak_src + ", bf16_tflops_sustained (kernel timed inside a long step)",
         "frac_of_burst_peak": (ach / peaks["bf16_tflops"] if ach else None),
-        "flop_per_launch": flop_launch, "frames_per_launch": frames_per_launch, "launches_timed": mid_n, "mean_launch_ms": mid_ms / max(mid_n, 1),
-        "share_of_step": (mid_ms / all_ms if all_ms else None),
+        "flop_per_launch": flop_launch, "frames_per_launch": frames_per_launch, "launches_timed": k_n,
+        "mean_launch_ms": k_ms / max(k_n, 1),
+        "share_of_step": (k_ms / all_ms if all_ms else None),
         "whole_net_tflops": value / world * 2.0 * MAC_PER_PX_NET * H * W / 1e12,
-        "traffic": None,
+        "traffic": TRAFFIC_BYTES_PER_LAUNCH,
+        "traffic_note": TRAFFIC_NOTE,
     }
     cpu = None
     if not args.no_cpu_baseline:

@@ -65,7 +65,7 @@ extern "C" {
                                   if it does not fit) */
 #define B2SR_OPT_PROFILE 2     /* 1 = bracket every kernel launch with CUDA events (see b2sr_get_stat) */
 #define B2SR_OPT_MAX_BATCH 3   /* frames per internal pass of b2sr_run_batch_device (0 = choose from free memory) */
-#define B2SR_OPT_RING_ROWS 4   /* pipelined schedule: rows per inter-layer activation ring (default 32) */
+#define B2SR_OPT_RING_ROWS 4   /* pipelined schedule: rows per inter-layer activation ring (0 = auto: all rings together ~36 MB, L2-resident) */
 #define B2SR_OPT_PIPE_DEBUG 5  /* pipelined schedule: print per-layer stall accounting to stderr after every launch (synchronises) */
 
 /* b2sr_get_stat keys */

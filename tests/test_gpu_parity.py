@@ -164,7 +164,7 @@ def test_three_device_schedules_agree(E, engines, model_dir):
     img = natural(1000, 1100, seed=8)
     pipe.set_option(E.OPT_RING_ROWS, 8)
     c = pipe.run_u8(img)
-    pipe.set_option(E.OPT_RING_ROWS, 32)
+    pipe.set_option(E.OPT_RING_ROWS, 0)
     assert np.array_equal(layer.run_u8(img), c)
     simple.close()
     layer.close()

@@ -22,7 +22,7 @@ ap.add_argument("--h", type=int, default=1080)
 ap.add_argument("--w", type=int, default=1920)
 ap.add_argument("--tile", type=int, default=960)
 ap.add_argument("--impl", type=int, default=0)
-ap.add_argument("--ring", type=int, default=32)
+ap.add_argument("--ring", type=int, default=0)
 ap.add_argument("--debug", type=int, default=0)
 a = ap.parse_args()
 eng = E.Engine.from_files(ncnn_model.packaged_model_dir(), a.model, 0)

@@ -40,8 +40,10 @@ MAC_PER_PX_NET = 598464                      # whole 2x_
 METRIC = "1080p frames/sec (2x_Compact_Pretrain)"
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture
 # (profiles/), per launch of the same shape as the bench's; None until a capture of the current kernel exists
-TRAFFIC_BYTES_PER_LAUNCH = None
-TRAFFIC_NOTE = None
+TRAFFIC_BYTES_PER_LAUNCH = 1202084608 + 390978560
+TRAFFIC_NOTE = ("tc_pipe_kernel, 16 frames per launch (profiles/r01g_pipe_kernel_16frames_dram_metrics.csv): 1.20 GB read = "
+                "16-channel fp16 input planes written by prep_kernel + u8 frames for the residual, 0.39 GB written = the u8 output "
+                "frames; all inter-layer activations stay in L2")
 
 
 def load_peaks():
@@ -276,7 +278,7 @@ def main():
         "traffic_note": TRAFFIC_NOTE,
     }
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only
         fps, threads, desc, dt = cpu_port_fps(reps=1)
         cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": desc, "seconds": dt}
     line = {

@@ -148,6 +148,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--content", default="noise", choices=["noise", "natural"],
+                    help="synthetic frame content: uniform random bytes (default; worst case for switching power) or smooth "
+                         "gradients + edges + mild noise")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -178,7 +181,16 @@ def main():
 
     B = args.batch
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    d_in = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device="cuda", generator=gen)
+    if args.content == "noise":
+        d_in = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device="cuda", generator=gen)
+    else:
+        yy = torch.arange(H, device="cuda", dtype=torch.float32)[None, :, None, None]
+        xx = torch.arange(W, device="cuda", dtype=torch.float32)[None, None, :, None]
+        ch = torch.arange(3, device="cuda", dtype=torch.float32)[None, None, None, :]
+        fr = torch.arange(B, device="cuda", dtype=torch.float32)[:, None, None, None]
+        img = 128 + 90 * torch.sin(xx / 37.0 + ch + 0.3 * fr) * torch.cos(yy / 23.0 - ch) + 40 * (((xx // 64) + (yy // 48)) % 2)
+        img = img + 6 * torch.randn((B, H, W, 3), device="cuda", generator=gen)
+        d_in = img.clamp(0, 255).to(torch.uint8).contiguous()
     d_out = torch.empty((B, H * SCALE, W * SCALE, 3), dtype=torch.uint8, device="cuda")
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
 
@@ -286,7 +298,7 @@ def main():
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 storage / f32 accumulate", "data": "synthetic",
         "config": {"workload": "synthetic 1080p RGB batch, 2x_Compact_Pretrain, 1xB200 per rank (BASELINE configs[1])",
-                   "frames_per_gpu_per_step": B, "frame": [H, W, 3], "tile": TILE, "halo": HALO,
+                   "frames_per_gpu_per_step": B, "frame": [H, W, 3], "tile": TILE, "halo": HALO, "content": args.content,
                    "l2": "inputs+outputs per step are %d MB per GPU, larger than the 126 MB L2" % ((d_in.numel() + d_out.numel()) >> 20),
                    "parallelism": "frames sharded over %d rank(s), no data-path collective; weights NCCL-broadcast" % world},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),

@@ -60,7 +60,7 @@ struct TcParams {
     uint32_t* done_out;         // rows this layer's band CTAs have published
     uint32_t* cons_self;        // input rows this layer's band CTAs have pulled into shared memory
     uint32_t* cons_next;        // the same counters of the next layer (back-pressure on this layer's ring)
-    long long* dbg;             // pipelined mode, optional: this CTA's 4 timing words
+    long long* dbg;             // pipelined mode, optional: this CTA's 8 stall-accounting words
 };
 
 #define B2SR_PIPE_MAX_LAYERS 20
@@ -70,8 +70,7 @@ struct PipeParams {  // passed by value (kernel parameter space)
     TcParams layers[B2SR_PIPE_MAX_LAYERS];
     int32_t n_layers;
     int32_t nb;
-    int32_t layer_shift;  // bring-up: CTA k runs layer (k / nb + layer_shift) % n_layers
-    long long* dbg;  // optional [n_layers * nb][4]: total cycles, cycles starved (producer), back-pressured (epilogue warp 2), spare
+    long long* dbg;  // optional [n_layers * nb][8] stall accounting (B2SR_OPT_PIPE_DEBUG)
 };
 
 #define B2SR_SMEM_LIMIT (227 * 1024)

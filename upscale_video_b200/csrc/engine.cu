@@ -701,7 +701,6 @@ static int run_pipe(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, 
     CUDA_TRY(cudaMemsetAsync(P->d_flags, 0, 2 * B2SR_PIPE_MAX_LAYERS * fl * sizeof(uint32_t), c->stream));
     PipeParams Q{};
     Q.n_layers = L, Q.nb = nb;
-    Q.layer_shift = (c->pipe_debug > 1 && c->pipe_debug < 100) ? c->pipe_debug - 1 : 0;
     if (c->pipe_debug) {
         if (!c->d_dbg) CUDA_TRY(cudaMalloc(&c->d_dbg, 148 * 8 * sizeof(long long)));
         CUDA_TRY(cudaMemsetAsync(c->d_dbg, 0, 148 * 8 * sizeof(long long), c->stream));
@@ -720,7 +719,7 @@ static int run_pipe(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, 
         p.out = l == L - 1 ? d_out : (void*)(c->rings + (size_t)l * ring_px * CF);
         p.frames_in = d_frames, p.frame_h = P->h, p.frame_w = P->w, p.scale = c->desc.scale;
         p.ring_in = l > 0, p.ring_out = l < L - 1;
-        p.RR = c->pipe_debug >= 100 ? -RR : RR, p.Wmax = P->Wmax, p.nb = nb;
+        p.RR = RR, p.Wmax = P->Wmax, p.nb = nb;
         p.done_in = l > 0 ? done + (size_t)(l - 1) * fl : nullptr;
         p.done_out = done + (size_t)l * fl;
         p.cons_self = cons + (size_t)l * fl;

@@ -141,25 +141,11 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// Spin until *p >= need (counters only grow).  Bounded: a protocol bug traps instead of hanging the GPU.
-//
-// The polls are relaxed GPU-scope loads (served by L2) and are NOT followed by an acquire fence: what they gate is a
-// TMA load (async proxy, reads L2 directly, no L1 in between) or a global store, issued after the poll through a
+// Counter polls are relaxed GPU-scope loads (served by L2) and are NOT followed by an acquire fence: what they gate is
+// a TMA load (async proxy, reads L2 directly, no L1 in between) or a global store, issued after the poll through a
 // control dependency, while the writer published the counter with a GPU-scope release after its data reached L2.
 // A per-row fence.acq_rel.gpu in the TMA-issuing thread was measured to serialise the row pipeline (each fence waits
-// for the loads in flight): 85 fps instead of 3-400.
-__device__ __forceinline__ uint32_t wait_counter(const uint32_t* p, uint32_t need, int who, long long& waited) {
-    uint32_t v = ld_relaxed_gpu(p);
-    if (v < need) {
-        const long long t0 = clock64();
-        while ((v = ld_relaxed_gpu(p)) < need) {
-            __nanosleep(32);
-            if (clock64() - t0 > 2000000000LL) flag_timeout(p, need, who);
-        }
-        waited += clock64() - t0;
-    }
-    return v;
-}
+// for the loads in flight): 85 fps instead of ~400.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -270,7 +256,7 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool ring_in = PIPE && P.ring_in, ring_out = PIPE && P.ring_out;
-    const uint32_t RR = PIPE ? (uint32_t)(P.RR < 0 ? -P.RR : P.RR) : 1u;
+    const uint32_t RR = PIPE ? (uint32_t)P.RR : 1u;
     // neighbours whose rows overlap this band's 130-pixel input window / whose input windows overlap this band
     const int nb_lo = band > 0 ? band - 1 : 0, nb_hi = band + 1 < P.nb ? band + 1 : P.nb - 1;
 
@@ -335,7 +321,7 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
                                 const long long t0 = clock64();
                                 while ((seen = *s_avail) < g + 1u) {
                                     __nanosleep(20);
-                                    if (clock64() - t0 > 2000000000LL) flag_timeout(P.done_in + band * B2SR_FLAG_STRIDE, g + 1u, 10);
+                                    if (clock64() - t0 > 20000000000LL) flag_timeout(P.done_in + band * B2SR_FLAG_STRIDE, g + 1u, 10);
                                 }
                                 waited += clock64() - t0;
                             }
@@ -493,8 +479,7 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
                 if (g > published) {
                     const long long tp = clock64();
                     __threadfence_block();  // acquire side of the progress words ...
-                    if (P.dbg && P.RR < 0) st_relaxed_gpu(P.done_out + band * B2SR_FLAG_STRIDE, g);  // bring-up experiment: no release fence
-                    else st_release_gpu(P.done_out + band * B2SR_FLAG_STRIDE, g);  // ... then one GPU-scope release for all eight warps' stores
+                    st_release_gpu(P.done_out + band * B2SR_FLAG_STRIDE, g);  // ... then one GPU-scope release for all eight warps' stores
                     published = g;
                     n_pub += 1;
                     t_pub += clock64() - tp;
@@ -509,7 +494,7 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
         // ======================= counter poller (pipelined mode) =======================
         // Keeps shared-memory copies of the neighbours' global counters fresh, so that the TMA producer and the
         // epilogue warps test a shared-memory word instead of paying L2 round trips on their critical paths.
-        if ((ring_in || ring_out) && lane == 0) {
+        if constexpr (PIPE) if ((ring_in || ring_out) && lane == 0) {
             const uint32_t need_fin = (ring_in ? 1u : 0u) + (ring_out ? 4u * TC_NSETS : 0u);
             const uint32_t* d0 = ring_in ? P.done_in + nb_lo * B2SR_FLAG_STRIDE : nullptr;
             const uint32_t* d1 = ring_in ? P.done_in + band * B2SR_FLAG_STRIDE : nullptr;
@@ -585,7 +570,7 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
                                 const long long t0 = clock64();
                                 while ((cons_seen = *s_consmin) < g - RR + 1u) {
                                     __nanosleep(20);
-                                    if (clock64() - t0 > 2000000000LL) flag_timeout(P.cons_next + band * B2SR_FLAG_STRIDE, g - RR + 1u, 20);
+                                    if (clock64() - t0 > 20000000000LL) flag_timeout(P.cons_next + band * B2SR_FLAG_STRIDE, g - RR + 1u, 20);
                                 }
                                 waited += clock64() - t0;
                             }
@@ -722,7 +707,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_con
 template <int CF /*padded feature channels*/, int NL /*padded last-layer channels*/, int S /*scale*/, bool F32OUT>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_pipe_kernel(const __grid_constant__ PipeParams Q) {
     extern __shared__ uint8_t smem_raw[];
-    const int layer = ((int)blockIdx.x / Q.nb + Q.layer_shift) % Q.n_layers, band = (int)blockIdx.x % Q.nb;
+    const int layer = (int)blockIdx.x / Q.nb, band = (int)blockIdx.x % Q.nb;
     TcParams P = Q.layers[layer];
     P.dbg = Q.dbg ? Q.dbg + (size_t)(layer * Q.nb + band) * 8 : nullptr;
     const int it_begin = P.item_first[band], it_end = P.item_first[band + 1];

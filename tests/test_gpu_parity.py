@@ -170,6 +170,17 @@ def test_three_device_schedules_agree(E, engines, model_dir):
     layer.close()
 
 
+def test_pipelined_schedule_random_shapes():
+    """40 random (model, batch, size, tiling, ring size) draws: the persistent pipelined kernel must reproduce the
+    layer-by-layer schedule bit for bit (tests/stress_gpu.py; ring sizes down to 4 rows force constant back-pressure)."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "stress_gpu.py"), "40", "7"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "40 iterations, 0 mismatches" in r.stdout
+
+
 def test_wide_frame_falls_back_to_layer_schedule(E, model_dir, oracle_models):
     """layers x bands > SM count (18 x 16 for a 2048-wide untiled frame): auto mode runs layer by layer, forcing the
     pipelined schedule is a clean error."""

@@ -204,6 +204,32 @@ def test_full_1080p_vs_oracle(engines, oracle_models):
     assert_parity(engines("2x_Compact_Pretrain").run_u8(img), ref, "1080p")
 
 
+def test_config3_chain_1080p(E, engines, oracle_models):
+    """BASELINE configs[2]: 1080p, 1x_HurrDeblur (untiled apply_model, u8 on "disk") -> 2x_Compact (tiled upscale_image).
+    Each stage is checked against the oracle on the SAME input (the second stage on the engine's own stage-1 output),
+    so a legitimate 1-LSB difference after stage 1 is not mistaken for a stage-2 error."""
+    img = natural(1080, 1920, seed=33)
+    hurr, comp = engines(HURR), engines("2x_Compact_Pretrain")
+    hurr.reset_stats()
+    y1 = hurr.run_u8(img, tile=0, halo=0)
+    # 10 layers x 15 bands = 150 CTAs > 148 SMs: this shape runs layer by layer (10 launches + prep)
+    assert hurr.stat(E.STAT_PIPE_LAUNCHES) == 0 and hurr.stat(E.STAT_TC_LAUNCHES) == 10
+    assert_parity(y1, oracle.apply_model_array(oracle_models(HURR), img, "f32"), "chain stage 1 (HurrDeblur 1080p)")
+    y2 = comp.run_u8(y1)
+    assert_parity(y2, oracle.upscale_image_array(oracle_models("2x_Compact_Pretrain"), y1, 2, "f32"), "chain stage 2 (2x_Compact 1080p)")
+
+
+def test_config4_540p_4x_compact(E, engines, oracle_models):
+    """BASELINE configs[3] names 4x_Valar_v1 "(4x pixel-shuffle)"; Valar is an RRDB without pixel shuffle (SURVEY section 0.1,
+    out of scope this round), the reference's 4x pixel-shuffle model is 4x_Compact_Pretrain: 540p -> 2160p, one tile."""
+    img = natural(540, 960, seed=44)
+    eng = engines("4x_Compact_Pretrain")
+    eng.reset_stats()
+    out = eng.run_u8(img)
+    assert eng.stat(E.STAT_PIPE_LAUNCHES) == 1 and out.shape == (2160, 3840, 3)
+    assert_parity(out, oracle.upscale_image_array(oracle_models("4x_Compact_Pretrain"), img, 4, "f32"), "4x 540p")
+
+
 def test_full_size_properties(E, engines):
     """Size-independent properties at 1080p / 540p: batch == per-frame, device tiling == pasting separately run
     tiles, determinism, host pipeline == device path."""

@@ -342,3 +342,20 @@ def test_upscale_frames_pool_two_workers_one_gpu(oracle_models, model_dir, tmp_p
         assert not os.path.exists("%d.extract.png" % n)
         ref = oracle.upscale_image_array(oracle_models("2x_Compact_Pretrain"), im, 2, "f64")
         assert_parity(cv2.imread("%d.png" % n), ref, "frame %d" % n)
+
+
+def test_raw_stream_matches_worker_functions(engines, model_dir, tmp_path):
+    """the raw-frame stream (no PNG hop, chained pre-pass on the device) produces exactly the pixels
+    the per-frame worker functions produce: apply_model (u8) -> upscale_image."""
+    import io
+    from upscale_video_b200 import raw_stream
+    frames = np.stack([natural(70, 1000, seed=s) for s in (1, 2, 3)])
+    hurr, comp = engines(HURR), engines("2x_Compact_Pretrain")
+    expect = np.stack([comp.run_u8(hurr.run_u8(f, tile=0, halo=0)) for f in frames])
+    out = io.BytesIO()
+    n = raw_stream.stream(io.BytesIO(frames.tobytes()), out, 1000, 70, scale=2, models=["a"], chunk=2, model_path=model_dir)
+    assert n == 3
+    assert np.array_equal(np.frombuffer(out.getvalue(), np.uint8).reshape(3, 140, 2000, 3), expect)
+    out = io.BytesIO()  # upscale only, overlapped host pipeline
+    raw_stream.stream(io.BytesIO(frames.tobytes()), out, 1000, 70, scale=2, chunk=2, model_path=model_dir)
+    assert np.array_equal(np.frombuffer(out.getvalue(), np.uint8).reshape(3, 140, 2000, 3), np.stack([comp.run_u8(f) for f in frames]))

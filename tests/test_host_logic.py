@@ -161,3 +161,50 @@ def test_weight_broadcast_gloo_world2(model_dir):
     (r0, l0, d0, s0, n0, f0), (r1, l1, d1, s1, n1, f1) = res
     assert (l0, l1) == (1, 0) and d0 == d1 == (3, 64, 16, 2, "input") and s0 == s1 and n0 == n1 == 598464 + 1100 + 1088
     assert sorted(f0 + f1) == list(range(10)) and not set(f0) & set(f1)
+
+
+class _FakeEngine:
+    """Host-logic stand-in for raw_stream tests: 'upscales' by pixel repetition, records calls."""
+
+    def __init__(self, scale):
+        self.scale, self.calls = scale, []
+
+    def run_batch_host(self, h_in, h_out, n, h, w, tile=960, halo=10):
+        a = h_in.numpy() if hasattr(h_in, "numpy") else h_in
+        o = h_out.numpy() if hasattr(h_out, "numpy") else h_out
+        self.calls.append((n, h, w, tile, halo))
+        o[:n] = np.repeat(np.repeat(a[:n], self.scale, 1), self.scale, 2)
+
+
+def test_raw_stream_framing(tmp_path):
+    """raw_stream: chunking, short last chunk, pipe-like short reads, rgb24 channel swap, truncated input."""
+    import io
+    from upscale_video_b200 import raw_stream
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 256, (5, 6, 8, 3), dtype=np.uint8)
+
+    class Dribble(io.BytesIO):  # returns at most 100 bytes per read, like a pipe
+        def read(self, n=-1):
+            return super().read(min(n, 100) if n >= 0 else 100)
+
+    eng = _FakeEngine(2)
+    out = io.BytesIO()
+    n = raw_stream.stream(Dribble(frames.tobytes()), out, 8, 6, scale=2, chunk=2, upscaler=eng)
+    got = np.frombuffer(out.getvalue(), np.uint8).reshape(5, 12, 16, 3)
+    assert n == 5 and [c[0] for c in eng.calls] == [2, 2, 1] and eng.calls[0][3:] == (960, 10)
+    assert np.array_equal(got, np.repeat(np.repeat(frames, 2, 1), 2, 2))
+    # rgb24: the engine sees BGR, the stream stays RGB
+    eng = _FakeEngine(2)
+    out = io.BytesIO()
+    raw_stream.stream(io.BytesIO(frames.tobytes()), out, 8, 6, scale=2, chunk=4, pix_fmt="rgb24", upscaler=eng)
+    assert np.array_equal(np.frombuffer(out.getvalue(), np.uint8).reshape(5, 12, 16, 3), np.repeat(np.repeat(frames, 2, 1), 2, 2))
+    # pre-pass only (scale 1, -m a): untiled calls
+    pre = _FakeEngine(1)
+    out = io.BytesIO()
+    raw_stream.stream(io.BytesIO(frames.tobytes()), out, 8, 6, scale=1, models=["a"], chunk=3, prepass=pre)
+    assert [c[3:] for c in pre.calls] == [(0, 0), (0, 0)] and out.getvalue() == frames.tobytes()
+    # max_frames and truncation
+    out = io.BytesIO()
+    assert raw_stream.stream(io.BytesIO(frames.tobytes()), out, 8, 6, scale=2, chunk=2, max_frames=3, upscaler=_FakeEngine(2)) == 3
+    with pytest.raises(ValueError, match="truncated"):
+        raw_stream.stream(io.BytesIO(frames.tobytes()[:-7]), io.BytesIO(), 8, 6, scale=2, chunk=2, upscaler=_FakeEngine(2))

@@ -1,0 +1,159 @@
+"""Raw-frame streaming worker: the frame-upscale path without the PNG round trips.
+
+The reference moves every frame through two PNG files -- ffmpeg writes ``N.extract.png`` (``extract_frames``, reference
+upscale/upscale_processing.py:203-255), the worker ``cv2.imread``s it and ``cv2.imwrite``s ``N.png`` (:487, :519), ffmpeg
+reads those back (``merge_frames`` :604-686) -- at ~68 ms decode + ~475 ms encode per 1080p->4K frame per core
+(SURVEY.md section 3), more than 100x the GPU time of this engine.  This module is the drop-in for that leg:
+
+    ffmpeg -i in.mkv -f rawvideo -pix_fmt bgr24 - \\
+      | python -m upscale_video_b200.raw_stream -s 2 --width 1920 --height 1080 [-m a] [-g 0] \\
+      | ffmpeg -f rawvideo -pix_fmt bgr24 -s 3840x2160 -r 24 -i - -c:v ... out.mkv
+
+Frames are read in chunks, pushed through ``Engine.run_batch_host`` (pinned staging, H2D / network / D2H overlapped on
+three streams) and written out in order.  Arithmetic is exactly ``upscale_image``'s: reference tiling (960 + 10),
+``* 255``, ``cv2.imwrite`` rounding -- only the container around the pixels changes.  ``-m a`` chains the 1x
+HurrDeblur pre-pass in front of the upscaler like ``process_file`` does with ``process_model`` (:888-909), keeping the
+reference's u8 quantisation between the two networks but never leaving the GPU (no ``N.anime.png`` hop).
+
+Pixel order: the reference's network sees OpenCV's BGR (``cv2.imread`` -> ``PIXEL_BGR`` unswapped, :263-270), so
+``--pix_fmt bgr24`` (default) is byte-compatible; with ``rgb24`` the channels are swapped on the way in and out.
+"""
+from __future__ import annotations
+
+import argparse
+import sys
+
+import numpy as np
+
+from . import engine as _engine
+from . import ncnn_model
+
+HURR = "x_HurrDeblur_SubCompact_nf24-nc8_244k_net_g"
+
+
+def _read_frame_into(f, dst):
+    """Fill the contiguous u8 array ``dst`` (one frame) straight from ``f`` -- no intermediate bytes objects; pipes may
+    return short reads.  Returns False at a clean EOF; raises ValueError on a truncated frame."""
+    mv = memoryview(dst).cast("B")
+    n, got = len(mv), 0
+    while got < n:
+        k = f.readinto(mv[got:]) if hasattr(f, "readinto") else None
+        if k is None:  # file-like without readinto
+            b = f.read(n - got)
+            k = len(b)
+            mv[got:got + k] = b
+        if not k:
+            break
+        got += k
+    if got == 0:
+        return False
+    if got != n:
+        raise ValueError("truncated input: %d bytes of a %d-byte frame" % (got, n))
+    return True
+
+
+class _Stage:
+    """Pinned (when torch + CUDA are present) or plain host buffers for one chunk of frames."""
+
+    def __init__(self, shape):
+        self.tensor = None
+        try:
+            import torch
+            if torch.cuda.is_available():
+                self.tensor = torch.empty(shape, dtype=torch.uint8).pin_memory()
+                self.array = self.tensor.numpy()
+                return
+        except Exception:
+            pass
+        self.array = np.empty(shape, np.uint8)
+
+
+def stream(fin, fout, width, height, scale=2, models=(), gpu=0, chunk=8, pix_fmt="bgr24", model_path=None, max_frames=None,
+           upscaler=None, prepass=None):
+    """Upscale raw ``height x width x 3`` u8 frames from ``fin`` to ``fout``.  Returns the number of frames written.
+    ``upscaler`` / ``prepass`` may be passed in as ready engines (tests); otherwise they are built from the model files."""
+    model_path = model_path or ncnn_model.packaged_model_dir()
+    if upscaler is None and scale > 1:
+        upscaler = _engine.Engine.from_files(model_path, str(scale) + "x_Compact_Pretrain", gpu)
+    if prepass is None and "a" in models:
+        prepass = _engine.Engine.from_files(model_path, "1" + HURR, gpu)
+    if upscaler is None and prepass is None:
+        raise ValueError("nothing to do: scale 1 and no pre-pass model")
+    s = upscaler.scale if upscaler is not None else 1
+    st_in = _Stage((chunk, height, width, 3))
+    st_mid = _Stage((chunk, height, width, 3)) if (prepass is not None and upscaler is not None) else None
+    st_out = _Stage((chunk, height * s, width * s, 3))
+    dev = None
+    if st_mid is not None and st_in.tensor is not None:  # device-resident buffers for the chained mode
+        import torch
+        torch.cuda.set_device(gpu)
+        dev = (torch, torch.empty((chunk, height, width, 3), dtype=torch.uint8, device="cuda"),
+               torch.empty((chunk, height, width, 3), dtype=torch.uint8, device="cuda"),
+               torch.empty((chunk, height * s, width * s, 3), dtype=torch.uint8, device="cuda"))
+    swap = pix_fmt == "rgb24"
+    written = 0
+    while max_frames is None or written < max_frames:
+        n = 0
+        want = chunk if max_frames is None else min(chunk, max_frames - written)
+        while n < want:
+            if not _read_frame_into(fin, st_in.array[n]):
+                break
+            if swap:
+                st_in.array[n] = st_in.array[n][:, :, ::-1].copy()
+            n += 1
+        if n == 0:
+            break
+        src = st_in
+        if prepass is not None and upscaler is not None and dev is not None:
+            # chained on the device: frames go up once, the 1x model's u8 output (apply_model :263-288 rounding) feeds the
+            # upscaler (upscale_image :489-519 tiling) from device memory, results come down once
+            torch, d_in, d_mid, d_out = dev
+            d_in[:n].copy_(st_in.tensor[:n])
+            torch.cuda.synchronize()
+            prepass.run_batch_device(d_in, d_mid, n, height, width, tile=0, halo=0, sync=True)
+            upscaler.run_batch_device(d_mid, d_out, n, height, width, sync=True)
+            st_out.tensor[:n].copy_(d_out[:n])
+            torch.cuda.synchronize()
+        else:
+            if prepass is not None:  # 1x model over whole frames, untiled, u8 out (apply_model :263-288)
+                dst = st_mid if upscaler is not None else st_out
+                prepass.run_batch_host(src.tensor if src.tensor is not None else src.array,
+                                       dst.tensor if dst.tensor is not None else dst.array, n, height, width, tile=0, halo=0)
+                src = dst
+            if upscaler is not None:  # reference tiling (upscale_image :489-519)
+                upscaler.run_batch_host(src.tensor if src.tensor is not None else src.array,
+                                        st_out.tensor if st_out.tensor is not None else st_out.array, n, height, width)
+        out = st_out.array[:n]
+        fout.write(np.ascontiguousarray(out[:, :, :, ::-1]).data if swap else memoryview(out).cast("B"))
+        written += n
+        if n < want:
+            break
+    fout.flush()
+    return written
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description="Upscale a raw bgr24/rgb24 frame stream (stdin -> stdout) on one GPU")
+    ap.add_argument("--width", type=int, required=True)
+    ap.add_argument("--height", type=int, required=True)
+    ap.add_argument("-s", "--scale", type=int, default=2, help="Scale 1, 2 or 4 (1 = pre-pass only). Default is 2.")
+    ap.add_argument("-m", "--models", help="'a' adds the 1x anime touch-up model before upscaling (like upscale_video.py -m a).")
+    ap.add_argument("-g", "--gpu", type=int, default=0, help="GPU index for this worker (run one worker per GPU, frames interleaved by the caller)")
+    ap.add_argument("--chunk", type=int, default=8, help="frames per host<->device chunk")
+    ap.add_argument("--pix_fmt", default="bgr24", choices=["bgr24", "rgb24"])
+    ap.add_argument("--model_path")
+    ap.add_argument("-i", "--input", help="raw input file (default stdin)")
+    ap.add_argument("-o", "--output", help="raw output file (default stdout)")
+    a = ap.parse_args(argv)
+    models = a.models.split(",") if a.models else []
+    for m in models:
+        if m != "a":
+            sys.exit("model option %r is outside this engine's scope (Compact family only)" % m)
+    fin = open(a.input, "rb") if a.input else sys.stdin.buffer
+    fout = open(a.output, "wb") if a.output else sys.stdout.buffer
+    n = stream(fin, fout, a.width, a.height, a.scale, models, a.gpu, a.chunk, a.pix_fmt, a.model_path)
+    print("raw_stream: %d frames" % n, file=sys.stderr)
+
+
+if __name__ == "__main__":
+    main()

@@ -55,6 +55,9 @@ extern "C" {
 #define B2SR_FAMILY_COMPACT 1 /* SRVGGNetCompact: conv(cin->nf)+PReLU, n_mid x [conv(nf->nf)+PReLU], conv(nf->cin*scale^2),
                                  PixelShuffle(scale) + nearest-upsample(input)  (models/2x_Compact_Pretrain.param:3-42) */
 
+#define B2SR_FAMILY_GRAPH 2   /* any other graph of the layer types the reference's models use (today: the RRDB 4x_Valar_v1,
+                                 models/4x_Valar_v1.param:1-1208), run op by op on CUDA cores: see b2sr_create_graph */
+
 /* where image buffers live */
 #define B2SR_MEM_HOST 0
 #define B2SR_MEM_DEVICE 1
@@ -104,6 +107,37 @@ int b2sr_device_name(int device, char *buf, int buflen);
  */
 int b2sr_create(b2sr_ctx **out, int device, const void *weights, size_t nbytes, const b2sr_net_desc *desc);
 void b2sr_destroy(b2sr_ctx *ctx);
+
+/*
+ * Generic graph engine (B2SR_FAMILY_GRAPH): the ncnn graph is handed over as a flat list of operations over numbered
+ * activation slots (Split layers resolved to aliases and slots reused by the caller).  Replaces the same ncnn calls
+ * as b2sr_create (upscale/upscale_processing.py:65-71) for models/4x_Valar_v1.param, which is not an SRVGGNetCompact.
+ * fp32 activations and accumulation on CUDA cores; every b2sr_run_* entry point works on such a context.
+ */
+#define B2SR_OP_CONV 1          /* Convolution k = 1 or 3, pad k/2, optional bias, act 0 = none / 2 = LeakyReLU(slope) */
+#define B2SR_OP_PRELU 2         /* per-channel slopes at w_off */
+#define B2SR_OP_PIXELSHUFFLE 3  /* factor r, ncnn mode 0 */
+#define B2SR_OP_NEAREST 4       /* Interp resize_type 1, integer factor r */
+#define B2SR_OP_ADD 5           /* out = coef[0] * in[0] + coef[1] * in[1]  (BinaryOp add: plain = 1) */
+#define B2SR_OP_CONCAT 6        /* channel concatenation of in[0..nin) */
+typedef struct b2sr_graph_op {
+    int32_t type;
+    int32_t nin;
+    int32_t in[6]; /* input slots */
+    int32_t out;   /* output slot */
+    int32_t cin;   /* CONV: input channels */
+    int32_t cout;  /* CONV: output channels */
+    int32_t k;     /* CONV: kernel size */
+    int32_t act;
+    float slope;
+    float coef[2];
+    int32_t plain; /* ADD: 1 = a + b exactly (BinaryOp), 0 = with coefficients (Eltwise) */
+    int32_t r;
+    int64_t w_off; /* offsets in floats into the weight blob; -1 = absent.  CONV weights are OIHW */
+    int64_t b_off;
+} b2sr_graph_op;
+int b2sr_create_graph(b2sr_ctx **out, int device, const b2sr_graph_op *ops, int n_ops, int n_slots, int in_slot, int out_slot,
+                      int scale, const void *weights, size_t nbytes);
 
 /*
  * One frame, u8 in -> u8 out ((h*scale) x (w*scale) x 3, round-half-even + saturate like cv2.imwrite).

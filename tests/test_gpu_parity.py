@@ -359,3 +359,37 @@ def test_raw_stream_matches_worker_functions(engines, model_dir, tmp_path):
     out = io.BytesIO()  # upscale only, overlapped host pipeline
     raw_stream.stream(io.BytesIO(frames.tobytes()), out, 1000, 70, scale=2, chunk=2, model_path=model_dir)
     assert np.array_equal(np.frombuffer(out.getvalue(), np.uint8).reshape(3, 140, 2000, 3), np.stack([comp.run_u8(f) for f in frames]))
+
+
+def test_valar_rrdb_generic_graph_engine(E, model_dir, oracle_models):
+    """4x_Valar_v1 (RRDB, reference models/4x_Valar_v1.param) through the generic CUDA-core graph engine
+    (b2sr_create_graph): golden crop, a two-tile frame against the oracle, and batch == single frame."""
+    if not os.path.exists(os.path.join(model_dir, "4x_Valar_v1.b2sr")):
+        pytest.skip("4x_Valar_v1 not packaged")
+    eng = E.Engine.from_files(model_dir, "4x_Valar_v1", 0)
+    assert eng.generic and eng.scale == 4
+    g = golden("valar4x_crop")
+    out = eng.run_u8(g["x"])
+    assert eng.stat(E.STAT_TC_LAUNCHES) == 0
+    assert_parity(out, g["y"], "valar golden")
+    img = natural(20, 980, seed=13)  # seam at x = 960
+    ref = oracle.upscale_image_array(oracle_models("4x_Valar_v1"), img, 4, "f32")
+    assert_parity(eng.run_u8(img), ref, "valar 20x980")
+    eng.close()
+
+
+def test_compact_models_through_generic_engine(E, engines, model_dir, oracle_models):
+    """The generic graph engine (fp32, CUDA cores) as a third device implementation of the Compact graphs."""
+    from upscale_video_b200 import ncnn_model
+    img = natural(50, 300, seed=17)
+    for name, scale in (("2x_Compact_Pretrain", 2), (HURR, 1)):
+        gen = E.Engine(ncnn_model.load_model(model_dir, name), 0, generic=True)
+        tile = 960 if scale > 1 else 0
+        a = gen.run_u8(img, tile=tile, halo=10 if tile else 0)
+        b = engines(name).run_u8(img, tile=tile, halo=10 if tile else 0)
+        d = np.abs(a.astype(int) - b.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 0.05, name
+        ref = (oracle.upscale_image_array(oracle_models(name), img, scale, "f64") if scale > 1
+               else oracle.apply_model_array(oracle_models(name), img, "f64"))
+        assert np.abs(a.astype(int) - ref.astype(int)).max() <= 1 and (a != ref).mean() < 0.002, name  # fp32 path: almost exact
+        gen.close()

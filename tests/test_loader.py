@@ -131,3 +131,45 @@ def test_packaged_models(model_dir, stem, expect):
 def test_mac_count_matches_survey(model_dir):
     g = M.load_model(model_dir, "2x_Compact_Pretrain")
     assert sum(l.weights["weight"].size for l in g.convs()) == 598464
+
+
+def _run_program_numpy(prog, x):
+    """Execute a compiled op list (ncnn_model.compile_graph) on the CPU with the oracle's layer functions."""
+    slots = [None] * prog.n_slots
+    slots[prog.in_slot] = np.ascontiguousarray(x, np.float64)
+    w = prog.weights
+    for o in prog.ops:
+        ins = [slots[i] for i in o["in"][:o["nin"]]]
+        t = o["type"]
+        if t == M.OP_CONV:
+            wt = w[o["w_off"]:o["w_off"] + o["cout"] * o["cin"] * o["k"] ** 2].reshape(o["cout"], o["cin"], o["k"], o["k"])
+            b = w[o["b_off"]:o["b_off"] + o["cout"]] if o["b_off"] >= 0 else None
+            y = oracle.conv(ins[0], wt, b, o["k"] // 2, o["act"], np.array([o["slope"]], np.float32) if o["act"] == 2 else None, "f64")
+        elif t == M.OP_PRELU:
+            sl = w[o["w_off"]:o["w_off"] + ins[0].shape[2]].astype(np.float64)
+            y = np.where(ins[0] < 0, ins[0] * sl, ins[0])
+        elif t == M.OP_PIXELSHUFFLE:
+            y = oracle.pixelshuffle(ins[0], o["r"])
+        elif t == M.OP_NEAREST:
+            y = oracle.nearest(ins[0], float(o["r"]), float(o["r"]))
+        elif t == M.OP_ADD:
+            y = ins[0] + ins[1] if o["plain"] else ins[0] * np.float64(np.float32(o["coef"][0])) + ins[1] * np.float64(np.float32(o["coef"][1]))
+        elif t == M.OP_CONCAT:
+            y = np.concatenate(ins, axis=2)
+        slots[o["out"]] = y
+    return slots[prog.out_slot]
+
+
+@pytest.mark.parametrize("stem", ["2x_Compact_Pretrain", "4x_Valar_v1"])
+def test_compiled_program_equals_graph_interpreter(model_dir, stem):
+    """compile_graph (Split aliasing, slot recycling, in-place elementwise ops) must not change the function: run the op
+    list with the oracle's layers and compare with the oracle's own graph interpreter (bit-exact in f64)."""
+    if not os.path.exists(os.path.join(model_dir, stem + ".b2sr")):
+        pytest.skip("model not packaged")
+    g = M.load_model(model_dir, stem)
+    prog = M.compile_graph(g)
+    assert prog.n_slots <= 12 and prog.scale == int(stem[0])
+    x = np.random.default_rng(1).random((12, 14, 3))
+    ref = oracle.run_graph(oracle.read_model(model_dir, stem), x, "f64")
+    got = _run_program_numpy(prog, x)
+    assert got.shape == ref.shape and np.array_equal(got, ref)

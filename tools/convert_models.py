@@ -16,7 +16,7 @@ import sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from upscale_video_b200 import ncnn_model  # noqa: E402
 
-DEFAULT = ["2x_Compact_Pretrain", "4x_Compact_Pretrain", "1x_HurrDeblur_SubCompact_nf24-nc8_244k_net_g"]
+DEFAULT = ["2x_Compact_Pretrain", "4x_Compact_Pretrain", "1x_HurrDeblur_SubCompact_nf24-nc8_244k_net_g", "4x_Valar_v1"]
 
 
 def main():

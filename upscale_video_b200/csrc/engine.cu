@@ -25,6 +25,7 @@
 
 #include "../../include/b2sr.h"
 #include "common.cuh"
+#include "graph_exec.cuh"
 #include "simple_kernels.cuh"
 #include "tc_conv.cuh"
 
@@ -147,8 +148,23 @@ struct ProfRec {
     double px;
 };
 
+struct GraphOp {  // b2sr_graph_op + what create derives from it
+    b2sr_graph_op op;
+    int out_c = 0, out_res = 1;  // channels / resolution factor (relative to the input plane) of the output slot
+    int in_res = 1;
+    int in_c[6] = {0, 0, 0, 0, 0, 0};
+    float* w = nullptr;  // CONV: repacked [k*k][cin][coutp]; PRELU: slopes
+    float* b = nullptr;
+    int coutp = 0;
+};
+
 struct b2sr_ctx {
     int device = 0, sms = 0;
+    int family = B2SR_FAMILY_COMPACT;
+    std::vector<GraphOp> gops;  // B2SR_FAMILY_GRAPH
+    int g_slots = 0, g_in = 0, g_out = 0;
+    std::vector<float*> slot_buf;
+    std::vector<size_t> slot_cap;
     cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
     b2sr_net_desc desc{};
     int CF = 0, NL = 0, cout_last = 0;
@@ -218,6 +234,12 @@ extern "C" void b2sr_destroy(b2sr_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->plans.clear();
     free_layers(c);
+    for (auto& g : c->gops) {
+        if (g.w) cudaFree(g.w);
+        if (g.b) cudaFree(g.b);
+    }
+    for (float* p : c->slot_buf)
+        if (p) cudaFree(p);
     for (void* p : {(void*)c->in16, (void*)c->ping, (void*)c->pong, (void*)c->lastf, (void*)c->d_in, (void*)c->d_out,
                     (void*)c->d_in2, (void*)c->d_out2, (void*)c->rings, (void*)c->d_dbg})
         if (p) cudaFree(p);
@@ -757,11 +779,229 @@ static int run_pipe(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, 
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// generic graph engine (B2SR_FAMILY_GRAPH): 4x_Valar_v1 and anything else the Compact kernels do not cover
+// ------------------------------------------------------------------------------------------------
+extern "C" int b2sr_create_graph(b2sr_ctx** out, int device, const b2sr_graph_op* ops, int n_ops, int n_slots, int in_slot,
+                                 int out_slot, int scale, const void* weights, size_t nbytes) {
+    if (!out || !ops || !weights) return fail(B2SR_E_INVALID, "b2sr_create_graph: null argument");
+    *out = nullptr;
+    if (n_ops < 1 || n_slots < 2 || n_slots > 4096 || in_slot < 0 || in_slot >= n_slots || out_slot < 0 || out_slot >= n_slots)
+        return fail(B2SR_E_INVALID, "b2sr_create_graph: bad graph description");
+    if (scale != 1 && scale != 2 && scale != 4) return fail(B2SR_E_UNSUPPORTED, "scale = %d (need 1, 2 or 4)", scale);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B2SR_E_NODEVICE, "no CUDA device is visible (this library has no CPU path)");
+    }
+    if (device < 0 || device >= ndev) return fail(B2SR_E_NODEVICE, "device %d out of range (%d visible)", device, ndev);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(B2SR_E_NODEVICE, "device %d (%s) is sm_%d%d; this library contains sm_100a code only", device, prop.name,
+                    prop.major, prop.minor);
+    CUDA_TRY(cudaSetDevice(device));
+    TRY(get_encode());
+    const float* wb = (const float*)weights;
+    const int64_t nfl = (int64_t)(nbytes / 4);
+    b2sr_ctx* c = new b2sr_ctx();
+    c->device = device, c->sms = prop.multiProcessorCount, c->family = B2SR_FAMILY_GRAPH;
+    c->desc.family = B2SR_FAMILY_GRAPH, c->desc.cin = 3, c->desc.scale = scale;
+    c->CF = 64, c->NL = 16;  // unused by this family (scratch sizing only)
+    c->g_slots = n_slots, c->g_in = in_slot, c->g_out = out_slot;
+    c->slot_buf.assign(n_slots, nullptr);
+    c->slot_cap.assign(n_slots, 0);
+    std::vector<int> sc(n_slots, -1), sr(n_slots, 0);  // channels / resolution factor currently held by each slot
+    sc[in_slot] = 3, sr[in_slot] = 1;
+    int rc = 0;
+    do {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking) != cudaSuccess) {
+            rc = fail(B2SR_E_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        for (int i = 0; i < n_ops && !rc; ++i) {
+            GraphOp g;
+            g.op = ops[i];
+            const b2sr_graph_op& o = g.op;
+            if (o.nin < 1 || o.nin > 6 || o.out < 0 || o.out >= n_slots) {
+                rc = fail(B2SR_E_INVALID, "op %d: bad slots", i);
+                break;
+            }
+            for (int j = 0; j < o.nin; ++j) {
+                if (o.in[j] < 0 || o.in[j] >= n_slots || sc[o.in[j]] < 0) {
+                    rc = fail(B2SR_E_INVALID, "op %d: input slot %d is not defined", i, j);
+                    break;
+                }
+                g.in_c[j] = sc[o.in[j]];
+                if (j && sr[o.in[j]] != sr[o.in[0]]) rc = fail(B2SR_E_INVALID, "op %d: inputs of different resolution", i);
+                if (o.in[j] == o.out && o.type != B2SR_OP_PRELU && o.type != B2SR_OP_ADD)
+                    rc = fail(B2SR_E_INVALID, "op %d: type %d cannot run in place", i, o.type);
+            }
+            if (rc) break;
+            g.in_res = sr[o.in[0]];
+            g.out_res = g.in_res, g.out_c = g.in_c[0];
+            switch (o.type) {
+                case B2SR_OP_CONV: {
+                    if ((o.k != 1 && o.k != 3) || o.cin != g.in_c[0] || o.cout < 1 || o.nin != 1) {
+                        rc = fail(B2SR_E_UNSUPPORTED, "op %d: convolution k=%d cin=%d (slot has %d) cout=%d", i, o.k, o.cin, g.in_c[0], o.cout);
+                        break;
+                    }
+                    const int64_t nw = (int64_t)o.cout * o.cin * o.k * o.k;
+                    if (o.w_off < 0 || o.w_off + nw > nfl || (o.b_off >= 0 && o.b_off + o.cout > nfl)) {
+                        rc = fail(B2SR_E_INVALID, "op %d: weights outside the blob", i);
+                        break;
+                    }
+                    g.coutp = round_up(o.cout, 4);
+                    std::vector<float> w((size_t)o.k * o.k * o.cin * g.coutp, 0.f);
+                    for (int oc = 0; oc < o.cout; ++oc)
+                        for (int ic = 0; ic < o.cin; ++ic)
+                            for (int t = 0; t < o.k * o.k; ++t)
+                                w[((size_t)t * o.cin + ic) * g.coutp + oc] = wb[o.w_off + ((int64_t)oc * o.cin + ic) * o.k * o.k + t];
+                    if (cudaMalloc(&g.w, w.size() * 4) != cudaSuccess ||
+                        cudaMemcpy(g.w, w.data(), w.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+                        rc = fail(B2SR_E_NOMEM, "op %d: weight upload failed", i);
+                        break;
+                    }
+                    if (o.b_off >= 0) {
+                        if (cudaMalloc(&g.b, o.cout * 4) != cudaSuccess ||
+                            cudaMemcpy(g.b, wb + o.b_off, o.cout * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+                            rc = fail(B2SR_E_NOMEM, "op %d: bias upload failed", i);
+                            break;
+                        }
+                    }
+                    g.out_c = o.cout;
+                    break;
+                }
+                case B2SR_OP_PRELU:
+                    if (o.w_off < 0 || o.w_off + g.in_c[0] > nfl) {
+                        rc = fail(B2SR_E_INVALID, "op %d: slopes outside the blob", i);
+                        break;
+                    }
+                    if (cudaMalloc(&g.w, g.in_c[0] * 4) != cudaSuccess ||
+                        cudaMemcpy(g.w, wb + o.w_off, g.in_c[0] * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+                        rc = fail(B2SR_E_NOMEM, "op %d: slope upload failed", i);
+                    break;
+                case B2SR_OP_PIXELSHUFFLE:
+                    if (o.r < 1 || g.in_c[0] % (o.r * o.r)) rc = fail(B2SR_E_INVALID, "op %d: pixel shuffle %d on %d channels", i, o.r, g.in_c[0]);
+                    g.out_c = g.in_c[0] / std::max(1, o.r * o.r), g.out_res = g.in_res * o.r;
+                    break;
+                case B2SR_OP_NEAREST:
+                    if (o.r < 1 || o.r > 8) rc = fail(B2SR_E_INVALID, "op %d: resize factor %d", i, o.r);
+                    g.out_res = g.in_res * o.r;
+                    break;
+                case B2SR_OP_ADD:
+                    if (o.nin != 2 || g.in_c[0] != g.in_c[1]) rc = fail(B2SR_E_INVALID, "op %d: add of %d inputs / channel mismatch", i, o.nin);
+                    break;
+                case B2SR_OP_CONCAT:
+                    g.out_c = 0;
+                    for (int j = 0; j < o.nin; ++j) g.out_c += g.in_c[j];
+                    break;
+                default:
+                    rc = fail(B2SR_E_UNSUPPORTED, "op %d: unknown type %d", i, o.type);
+            }
+            if (rc) {
+                if (g.w) cudaFree(g.w);
+                if (g.b) cudaFree(g.b);
+                break;
+            }
+            sc[o.out] = g.out_c, sr[o.out] = g.out_res;
+            c->gops.push_back(g);
+        }
+        if (!rc && (sc[out_slot] != 3 || sr[out_slot] != scale))
+            rc = fail(B2SR_E_INVALID, "graph output has %d channels at x%d, expected 3 at x%d", sc[out_slot], sr[out_slot], scale);
+    } while (0);
+    if (rc) {
+        std::string keep = g_err;
+        b2sr_destroy(c);
+        g_err = keep;
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+
+static int run_graph(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, bool f32out) {
+    const int S = c->desc.scale;
+    // slot capacities for the largest plane
+    std::vector<size_t> need(c->g_slots, 0);
+    const size_t mp = (size_t)P->max_plane_px;
+    need[c->g_in] = mp * 3;
+    for (auto& g : c->gops) need[g.op.out] = std::max(need[g.op.out], mp * g.out_res * g.out_res * g.out_c);
+    for (int s = 0; s < c->g_slots; ++s)
+        if (need[s] > c->slot_cap[s]) {
+            cudaStreamSynchronize(c->stream);
+            if (c->slot_buf[s]) cudaFree(c->slot_buf[s]);
+            c->slot_buf[s] = nullptr, c->slot_cap[s] = 0;
+            CUDA_TRY(cudaMalloc(&c->slot_buf[s], need[s] * sizeof(float)));
+            c->slot_cap[s] = need[s];
+        }
+    auto blocks = [](size_t n) { return (unsigned)std::min<size_t>(148 * 16, (n + 255) / 256); };
+    for (const PlaneDev& pl : P->planes) {  // tiles run one after the other, like the reference's loop (:502-516)
+        TRY(prof_begin(c, 0, 0));
+        g_input_kernel<<<blocks((size_t)pl.Ht * pl.Wt * 3), 256, 0, c->stream>>>(d_frames, P->h, P->w, pl, c->slot_buf[c->g_in]);
+        c->n_launch += 1;
+        for (auto& g : c->gops) {
+            const b2sr_graph_op& o = g.op;
+            const int H = pl.Ht * g.in_res, W = pl.Wt * g.in_res;
+            const size_t px = (size_t)H * W;
+            const float* in0 = c->slot_buf[o.in[0]];
+            float* outp = c->slot_buf[o.out];
+            switch (o.type) {
+                case B2SR_OP_CONV: {
+                    const unsigned nb = blocks(px * (g.coutp / 4));
+                    if (o.k == 3)
+                        g_conv_kernel<3><<<nb, 256, 0, c->stream>>>(in0, H, W, o.cin, g.w, g.b, o.cout, g.coutp, o.act, o.slope, outp);
+                    else
+                        g_conv_kernel<1><<<nb, 256, 0, c->stream>>>(in0, H, W, o.cin, g.w, g.b, o.cout, g.coutp, o.act, o.slope, outp);
+                    break;
+                }
+                case B2SR_OP_PRELU:
+                    g_prelu_kernel<<<blocks(px * g.in_c[0]), 256, 0, c->stream>>>(in0, px * g.in_c[0], g.in_c[0], g.w, outp);
+                    break;
+                case B2SR_OP_PIXELSHUFFLE:
+                    g_pixelshuffle_kernel<<<blocks(px * g.in_c[0]), 256, 0, c->stream>>>(in0, H, W, g.out_c, o.r, outp);
+                    break;
+                case B2SR_OP_NEAREST:
+                    g_nearest_kernel<<<blocks(px * o.r * o.r * g.in_c[0]), 256, 0, c->stream>>>(in0, H, W, g.in_c[0], o.r, outp);
+                    break;
+                case B2SR_OP_ADD:
+                    g_add_kernel<<<blocks(px * g.in_c[0]), 256, 0, c->stream>>>(in0, c->slot_buf[o.in[1]], px * g.in_c[0], o.coef[0], o.coef[1],
+                                                                               o.plain, outp);
+                    break;
+                case B2SR_OP_CONCAT: {
+                    int off = 0;
+                    for (int j = 0; j < o.nin; ++j) {
+                        g_concat_kernel<<<blocks(px * g.in_c[j]), 256, 0, c->stream>>>(c->slot_buf[o.in[j]], px, g.in_c[j], g.out_c, off, outp);
+                        off += g.in_c[j];
+                        c->n_launch += 1;
+                    }
+                    c->n_launch -= 1;
+                    break;
+                }
+            }
+            c->n_launch += 1;
+        }
+        const size_t on = (size_t)(pl.cy1 - pl.cy0) * S * (pl.cx1 - pl.cx0) * S * 3;
+        if (f32out)
+            g_output_kernel<true><<<blocks(on), 256, 0, c->stream>>>(c->slot_buf[c->g_out], pl, S, P->h, P->w, d_out);
+        else
+            g_output_kernel<false><<<blocks(on), 256, 0, c->stream>>>(c->slot_buf[c->g_out], pl, S, P->h, P->w, d_out);
+        c->n_launch += 1;
+        CUDA_TRY(cudaGetLastError());
+        TRY(prof_end(c));
+    }
+    return 0;
+}
+
 static bool use_tc(const b2sr_ctx* c) { return c->impl != 1; }
 
 // Runs layers [0, upto] for the planes of P; the final layer writes `out` (u8 or f32 frames).  Returns in *act the
 // buffer that holds the activations of layer `upto` when upto is not the last layer.
 static int run_plan(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, bool f32out, int upto, const __half** act) {
+    if (c->family == B2SR_FAMILY_GRAPH) return run_graph(c, P, d_frames, d_out, f32out);
     const int nl = (int)c->layers.size();
     if (upto < 0 || upto >= nl) upto = nl - 1;
     if (upto == nl - 1 && (c->impl == 0 || c->impl == 3)) {  // whole network: pipelined schedule when it fits the GPU
@@ -828,6 +1068,7 @@ static int check_geom(int n, int h, int w, int tile, int halo) {
 
 static int frames_per_pass(const b2sr_ctx* c, int h, int w, int tile) {
     if (c->max_batch > 0) return c->max_batch;
+    if (c->family == B2SR_FAMILY_GRAPH) return 1;
     const double px = (double)h * w * 1.06;
     // the pipelined schedule keeps only the 16-channel input planes per frame: long passes amortise its fill/drain
     const int tw = tile > 0 ? std::min(w, tile + 20) : w;
@@ -961,6 +1202,7 @@ extern "C" int b2sr_run_batch_host(b2sr_ctx* c, const uint8_t* h_in, uint8_t* h_
 extern "C" int b2sr_debug_layer(b2sr_ctx* c, const uint8_t* in, int h, int w, int layer, float* out) {
     if (!c || !in || !out) return fail(B2SR_E_INVALID, "b2sr_debug_layer: null argument");
     TRY(check_geom(1, h, w, 0, 0));
+    if (c->family != B2SR_FAMILY_COMPACT) return fail(B2SR_E_UNSUPPORTED, "b2sr_debug_layer: Compact family only");
     if (layer < 0 || layer >= (int)c->layers.size() - 1) return fail(B2SR_E_INVALID, "layer %d has no activation output", layer);
     CUDA_TRY(cudaSetDevice(c->device));
     const size_t in_bytes = (size_t)h * w * 3;

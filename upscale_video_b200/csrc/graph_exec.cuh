@@ -1,0 +1,141 @@
+// graph_exec.cuh -- generic CUDA-core executor for ncnn graphs the tcgen05 Compact kernels do not cover.
+//
+// Today that is `4x_Valar_v1` (reference models/4x_Valar_v1.param:1-1208): a 23-block RRDB network -- 420 convolutions
+// with 64..192 input channels fed by Concat, LeakyReLU fused into the convolution (ncnn activation_type 2), 1x1
+// shortcut convolutions, Eltwise sums with coefficients (0.2, 1.0), two nearest x2 Interp layers, no pixel shuffle.
+// Every layer type the reference's four models use is implemented here (so the Compact models can be run through
+// this path too, as one more on-device cross-check): Convolution k=1/3 (+bias, +LeakyReLU), PReLU, PixelShuffle,
+// Interp nearest, BinaryOp add / Eltwise sum with coefficients, Concat.  Split is resolved to aliases on the host.
+//
+// Activations are fp32 NHWC, accumulation is fp32: this is a correctness-first GPU path (plain FMA, no tensor
+// cores); a tcgen05 RRDB kernel family (concat-K accumulation into one TMEM tile) is future work.
+#pragma once
+#include "common.cuh"
+
+namespace b2sr {
+
+enum { GOP_CONV = 1, GOP_PRELU = 2, GOP_PIXELSHUFFLE = 3, GOP_NEAREST = 4, GOP_ADD = 5, GOP_CONCAT = 6 };
+
+// u8 frame rectangle -> float plane, `x * float32(1/255.0)` (reference upscale_processing.py:437-445)
+__global__ void g_input_kernel(const uint8_t* __restrict__ frames, int fh, int fw, PlaneDev P, float* __restrict__ out) {
+    const int n = P.Ht * P.Wt * 3;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = i % 3, p = i / 3, y = p / P.Wt, x = p - y * P.Wt;
+        out[i] = (float)frames[((size_t)((size_t)P.frame * fh + P.fy0 + y) * fw + P.fx0 + x) * 3 + c] * (1.f / 255.f);
+    }
+}
+
+// in [H][W][cin], w [K*K][cin][coutp] (coutp = cout rounded up to 4), out [H][W][cout]; zero padding K/2.
+// One thread = one pixel x 4 output channels.
+template <int K>
+__global__ void g_conv_kernel(const float* __restrict__ in, int H, int W, int cin, const float* __restrict__ w,
+                              const float* __restrict__ bias, int cout, int coutp, int act, float slope, float* __restrict__ out) {
+    const int Q = coutp / 4;
+    const long long total = (long long)H * W * Q;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(idx % Q);
+        const long long p = idx / Q;
+        const int y = (int)(p / W), x = (int)(p - (long long)y * W);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+            const int iy = y + ky - K / 2;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const int ix = x + kx - K / 2;
+                if (ix < 0 || ix >= W) continue;
+                const float* ip = in + ((size_t)iy * W + ix) * cin;
+                const float* wp = w + (size_t)((ky * K + kx) * cin) * coutp + q * 4;
+                for (int c = 0; c < cin; ++c) {
+                    const float a = ip[c];
+                    const float4 wv = *reinterpret_cast<const float4*>(wp + (size_t)c * coutp);
+                    acc.x = fmaf(a, wv.x, acc.x);
+                    acc.y = fmaf(a, wv.y, acc.y);
+                    acc.z = fmaf(a, wv.z, acc.z);
+                    acc.w = fmaf(a, wv.w, acc.w);
+                }
+            }
+        }
+        float v[4] = {acc.x, acc.y, acc.z, acc.w};
+        float* op = out + (size_t)p * cout;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = q * 4 + j;
+            if (o < cout) {
+                float t = v[j] + (bias ? bias[o] : 0.f);
+                if (act == 2) t = t > 0.f ? t : t * slope;  // ncnn activation_type 2: LeakyReLU
+                op[o] = t;
+            }
+        }
+    }
+}
+
+__global__ void g_prelu_kernel(const float* __restrict__ in, size_t n, int C, const float* __restrict__ slope, float* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = in[i];
+        out[i] = v < 0.f ? v * slope[i % C] : v;
+    }
+}
+
+// in [H][W][C*r*r] -> out [H*r][W*r][C], ncnn PixelShuffle mode 0
+__global__ void g_pixelshuffle_kernel(const float* __restrict__ in, int H, int W, int C, int r, float* __restrict__ out) {
+    const size_t n = (size_t)H * r * W * r * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const size_t p = i / C;
+        const int ox = (int)(p % ((size_t)W * r)), oy = (int)(p / ((size_t)W * r));
+        const int x = ox / r, dx = ox - x * r, y = oy / r, dy = oy - y * r;
+        out[i] = in[((size_t)y * W + x) * ((size_t)C * r * r) + (size_t)c * r * r + dy * r + dx];
+    }
+}
+
+// nearest resize by integer factor r: in_y = min(int(y * (1/r)), H-1) (ncnn Interp resize_type 1)
+__global__ void g_nearest_kernel(const float* __restrict__ in, int H, int W, int C, int r, float* __restrict__ out) {
+    const size_t n = (size_t)H * r * W * r * C;
+    const float inv = 1.f / (float)r;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const size_t p = i / C;
+        const int ox = (int)(p % ((size_t)W * r)), oy = (int)(p / ((size_t)W * r));
+        const int x = min((int)(ox * inv), W - 1), y = min((int)(oy * inv), H - 1);
+        out[i] = in[((size_t)y * W + x) * C + c];
+    }
+}
+
+// out = a * ca + b * cb  (BinaryOp add: ca = cb = 1; Eltwise SUM with coefficients)
+__global__ void g_add_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, float ca, float cb, int plain,
+                             float* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = plain ? a[i] + b[i] : a[i] * ca + b[i] * cb;
+}
+
+// copy input [px][C] into channels [off, off+C) of out [px][Ctot]
+__global__ void g_concat_kernel(const float* __restrict__ in, size_t px, int C, int Ctot, int off, float* __restrict__ out) {
+    const size_t n = px * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = i / C;
+        out[p * Ctot + off + (i - p * C)] = in[i];
+    }
+}
+
+// network output plane [Ht*S][Wt*S][3] -> `* 255`, crop to the tile's core, store as f32 or as cv2.imwrite would (u8)
+template <bool F32OUT>
+__global__ void g_output_kernel(const float* __restrict__ net, PlaneDev P, int S, int fh, int fw, void* __restrict__ out) {
+    const int ch = (P.cy1 - P.cy0) * S, cw = (P.cx1 - P.cx0) * S;
+    const int n = ch * cw * 3;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = i % 3, p = i / 3, y = p / cw, x = p - y * cw;
+        const int py = (P.cy0 - P.fy0) * S + y, px = (P.cx0 - P.fx0) * S + x;  // inside the plane's output
+        const float v = net[((size_t)py * (P.Wt * S) + px) * 3 + c] * 255.f;
+        const size_t o = (((size_t)P.frame * fh * S + (size_t)P.cy0 * S + y) * ((size_t)fw * S) + (size_t)P.cx0 * S + x) * 3 + c;
+        if (F32OUT) {
+            reinterpret_cast<float*>(out)[o] = v;
+        } else {
+            const int iv = __float2int_rn(v);
+            reinterpret_cast<uint8_t*>(out)[o] = (uint8_t)min(max(iv, 0), 255);
+        }
+    }
+}
+
+}  // namespace b2sr

@@ -24,7 +24,8 @@ IMPL_AUTO, IMPL_SIMPLE, IMPL_TCGEN05, IMPL_PIPELINED = 0, 1, 2, 3  # IMPL_TCGEN0
 
 # every symbol include/b2sr.h declares (tests check the library exports exactly these)
 SYMBOLS = [
-    "b2sr_abi_version", "b2sr_device_count", "b2sr_default_device", "b2sr_device_name", "b2sr_create", "b2sr_destroy",
+    "b2sr_abi_version", "b2sr_device_count", "b2sr_default_device", "b2sr_device_name", "b2sr_create", "b2sr_create_graph",
+    "b2sr_destroy",
     "b2sr_run_u8", "b2sr_run_f32", "b2sr_run_batch_device", "b2sr_run_batch_host", "b2sr_debug_layer",
     "b2sr_set_option", "b2sr_get_stat", "b2sr_reset_stats", "b2sr_synchronize", "b2sr_stream", "b2sr_last_error",
 ]
@@ -32,6 +33,13 @@ SYMBOLS = [
 
 class EngineError(RuntimeError):
     pass
+
+
+class GraphOp(ctypes.Structure):  # b2sr_graph_op
+    _fields_ = [("type", ctypes.c_int32), ("nin", ctypes.c_int32), ("inp", ctypes.c_int32 * 6), ("out", ctypes.c_int32),
+                ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("k", ctypes.c_int32), ("act", ctypes.c_int32),
+                ("slope", ctypes.c_float), ("coef", ctypes.c_float * 2), ("plain", ctypes.c_int32), ("r", ctypes.c_int32),
+                ("w_off", ctypes.c_int64), ("b_off", ctypes.c_int64)]
 
 
 class NetDesc(ctypes.Structure):
@@ -56,6 +64,7 @@ def load_library(path: str = LIB_PATH):
     lib.b2sr_default_device.restype = i32
     lib.b2sr_device_name.argtypes = [i32, ctypes.c_char_p, i32]
     lib.b2sr_create.argtypes = [ctypes.POINTER(vp), i32, vp, ctypes.c_size_t, ctypes.POINTER(NetDesc)]
+    lib.b2sr_create_graph.argtypes = [ctypes.POINTER(vp), i32, ctypes.POINTER(GraphOp), i32, i32, i32, i32, i32, vp, ctypes.c_size_t]
     lib.b2sr_destroy.argtypes = [vp]
     lib.b2sr_destroy.restype = None
     lib.b2sr_run_u8.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, i32, i32]
@@ -112,11 +121,17 @@ def _ptr(a):
 class Engine:
     """One network bound to one GPU (one per worker process, like the reference's ``net``)."""
 
-    def __init__(self, graph: ncnn_model.Graph = None, device: int = 0, packed=None):
+    def __init__(self, graph: ncnn_model.Graph = None, device: int = 0, packed=None, generic: bool = False):
         """``graph``: a loaded model; or ``packed`` = (CompactDesc, fp32 blob) as produced by
-        ``ncnn_model.pack_compact_blob`` (what a rank receives from the start-up weight broadcast)."""
+        ``ncnn_model.pack_compact_blob`` (what a rank receives from the start-up weight broadcast).
+        SRVGGNetCompact graphs run on the tcgen05 kernels; anything else (4x_Valar_v1), or any graph when
+        ``generic=True`` (cross-checks), runs on the generic CUDA-core graph engine."""
         self._h = None
         self._lib = load_library()
+        self.generic = False
+        if packed is None and (generic or ncnn_model.compact_desc(graph) is None):
+            self._init_generic(graph, device)
+            return
         desc, blob = packed if packed is not None else ncnn_model.pack_compact_blob(graph)
         blob = np.ascontiguousarray(blob, np.float32)
         self.desc = desc
@@ -126,6 +141,26 @@ class Engine:
         h = ctypes.c_void_p()
         _check(self._lib.b2sr_create(ctypes.byref(h), device, blob.ctypes.data, blob.nbytes, ctypes.byref(nd)), "b2sr_create")
         self._h = h
+
+    def _init_generic(self, graph, device):
+        """Graphs that are not SRVGGNetCompact (4x_Valar_v1): the generic CUDA-core graph engine (b2sr_create_graph)."""
+        prog = ncnn_model.compile_graph(graph)
+        arr = (GraphOp * len(prog.ops))()
+        for a, o in zip(arr, prog.ops):
+            a.type, a.nin, a.out, a.cin, a.cout, a.k, a.act = o["type"], o["nin"], o["out"], o["cin"], o["cout"], o["k"], o["act"]
+            for j, v in enumerate(o["in"]):
+                a.inp[j] = v
+            a.slope, a.plain, a.r, a.w_off, a.b_off = o["slope"], o["plain"], o["r"], o["w_off"], o["b_off"]
+            a.coef[0], a.coef[1] = o["coef"]
+        w = np.ascontiguousarray(prog.weights, np.float32)
+        h = ctypes.c_void_p()
+        _check(self._lib.b2sr_create_graph(ctypes.byref(h), device, arr, len(prog.ops), prog.n_slots, prog.in_slot, prog.out_slot,
+                                           prog.scale, w.ctypes.data, w.nbytes), "b2sr_create_graph")
+        self._h = h
+        self.desc = ncnn_model.CompactDesc(3, 0, 0, prog.scale, 3 * prog.scale * prog.scale, prog.input_blob, prog.output_blob)
+        self.scale = prog.scale
+        self.device = device
+        self.generic = True
 
     @classmethod
     def from_files(cls, model_path: str, stem: str, device: int = 0) -> "Engine":

@@ -278,3 +278,156 @@ def pack_compact_blob(graph: Graph) -> tuple:
         if i + 1 < len(ls) and ls[i + 1].type == "PReLU":
             parts.append(ls[i + 1].weights["slope"].astype(np.float32).ravel())
     return d, np.ascontiguousarray(np.concatenate(parts))
+
+
+# ----------------------------------------------------------------------------------------------
+# Generic graphs (anything that is not an SRVGGNetCompact, today 4x_Valar_v1): flat op list for b2sr_create_graph
+# ----------------------------------------------------------------------------------------------
+OP_CONV, OP_PRELU, OP_PIXELSHUFFLE, OP_NEAREST, OP_ADD, OP_CONCAT = 1, 2, 3, 4, 5, 6
+
+
+@dataclass
+class GraphProgram:
+    ops: list          # dicts with the fields of b2sr_graph_op
+    n_slots: int
+    in_slot: int
+    out_slot: int
+    scale: int
+    weights: np.ndarray  # flat fp32 blob referenced by w_off / b_off
+    input_blob: str = "input"
+    output_blob: str = "output"
+
+
+def compile_graph(graph: Graph, input_blob: str = "input", output_blob: str = "output") -> GraphProgram:
+    """Lower an ncnn graph to the op list of ``b2sr_create_graph`` (include/b2sr.h).
+
+    Split layers become aliases; every value gets an activation slot, and slots are recycled after a value's last
+    use (the Valar graph has 2127 blobs but never more than a dozen alive).  Layer semantics follow the ncnn layer
+    definitions the reference's model files rely on (reference models/4x_Valar_v1.param:1-1208): Convolution keys
+    0=out-ch 1=kernel 4=pad 5=bias 6=weight-count 9=activation (2 = LeakyReLU, slope in -23310), PReLU 0=slopes,
+    PixelShuffle 0=factor (mode 0), Interp 0=1 nearest with scales 1/2, BinaryOp 0=0 add, Eltwise 0=1 sum with
+    coefficients -23301, Concat 0=0 channel axis."""
+    alias = {}
+
+    def val(name):  # resolve Split aliases
+        while name in alias:
+            name = alias[name]
+        return name
+
+    layers = [l for l in graph.layers]
+    # last use of every value
+    last_use = {}
+    for i, l in enumerate(layers):
+        if l.type == "Split":
+            for t in l.tops:
+                alias[t] = l.bottoms[0]
+    for i, l in enumerate(layers):
+        if l.type in ("Input", "Split"):
+            continue
+        for b in l.bottoms:
+            last_use[val(b)] = i
+    last_use[val(output_blob)] = len(layers) + 1
+    slot_of, free, n_slots = {}, [], 0
+    chans, res = {}, {}
+    ops, wparts, woff = [], [], 0
+
+    def new_slot():
+        nonlocal n_slots
+        if free:
+            return free.pop()
+        n_slots += 1
+        return n_slots - 1
+
+    def push_w(arr):
+        nonlocal woff
+        a = np.ascontiguousarray(arr, np.float32).ravel()
+        wparts.append(a)
+        off = woff
+        woff += a.size
+        return off
+
+    in_slot = None
+    for i, l in enumerate(layers):
+        t = l.type
+        if t == "Input":
+            if l.tops != [input_blob]:
+                raise ValueError("graph input blob is %r, expected %r" % (l.tops, input_blob))
+            in_slot = new_slot()
+            slot_of[input_blob] = in_slot
+            chans[input_blob], res[input_blob] = 3, 1
+            continue
+        if t == "Split":
+            continue
+        ins = [val(b) for b in l.bottoms]
+        for b in ins:
+            if b not in slot_of:
+                raise ValueError("layer %s reads undefined blob %s" % (l.name, b))
+        out_name = l.tops[0]
+        op = {"type": 0, "nin": len(ins), "in": [slot_of[b] for b in ins], "cin": 0, "cout": 0, "k": 0, "act": 0, "slope": 0.0,
+              "coef": [1.0, 1.0], "plain": 0, "r": 1, "w_off": -1, "b_off": -1}
+        c_out, r_out = chans[ins[0]], res[ins[0]]
+        in_place_ok = False
+        if t == "Convolution":
+            k, pad = int(l.p(1)), int(l.p(4, 0))
+            if (l.p(2, 1), l.p(3, 1)) != (1, 1) or k not in (1, 3) or pad != k // 2:
+                raise ValueError("unsupported convolution %s (k=%d pad=%d)" % (l.name, k, pad))
+            w = l.weights["weight"].astype(np.float32)
+            act = int(l.p(9, 0))
+            if act not in (0, 2):
+                raise ValueError("unsupported convolution activation %d in %s" % (act, l.name))
+            op.update(type=OP_CONV, cin=int(w.shape[1]), cout=int(w.shape[0]), k=k, act=act,
+                      slope=float(l.p(10, [0.0])[0]) if act == 2 else 0.0, w_off=push_w(w),
+                      b_off=push_w(l.weights["bias"]) if l.p(5, 0) else -1)
+            c_out = int(w.shape[0])
+        elif t == "PReLU":
+            op.update(type=OP_PRELU, w_off=push_w(l.weights["slope"]))
+            in_place_ok = True
+        elif t == "PixelShuffle":
+            r = int(l.p(0, 1))
+            if l.p(1, 0) != 0:
+                raise ValueError("PixelShuffle mode %r" % l.p(1))
+            op.update(type=OP_PIXELSHUFFLE, r=r)
+            c_out, r_out = c_out // (r * r), r_out * r
+        elif t == "Interp":
+            sy, sx = float(l.p(1, 1.0)), float(l.p(2, 1.0))
+            if l.p(0) != 1 or sy != sx or sy != int(sy):
+                raise ValueError("unsupported Interp %s" % l.name)
+            op.update(type=OP_NEAREST, r=int(sy))
+            r_out *= int(sy)
+        elif t == "BinaryOp":
+            if l.p(0, 0) != 0 or len(ins) != 2:
+                raise ValueError("unsupported BinaryOp %s" % l.name)
+            op.update(type=OP_ADD, plain=1)
+            in_place_ok = True
+        elif t == "Eltwise":
+            co = l.p(1, [1.0] * len(ins))
+            if l.p(0, 0) != 1 or len(ins) != 2:
+                raise ValueError("unsupported Eltwise %s" % l.name)
+            op.update(type=OP_ADD, coef=[float(np.float32(co[0])), float(np.float32(co[1]))])
+            in_place_ok = True
+        elif t == "Concat":
+            if l.p(0, 0) != 0 or len(ins) > 6:
+                raise ValueError("unsupported Concat %s" % l.name)
+            op.update(type=OP_CONCAT)
+            c_out = sum(chans[b] for b in ins)
+        else:
+            raise ValueError("unsupported layer type %s" % t)
+        # release inputs that die here; an elementwise op may then reuse one of them in place, others must not
+        dying = [b for b in set(ins) if last_use.get(b) == i]
+        if not in_place_ok:
+            out_slot = new_slot()
+            for b in dying:
+                free.append(slot_of[b])
+        else:
+            for b in dying:
+                free.append(slot_of[b])
+            out_slot = new_slot()
+        op["out"] = out_slot
+        slot_of[out_name] = out_slot
+        chans[out_name], res[out_name] = c_out, r_out
+        ops.append(op)
+    out_v = val(output_blob)
+    if out_v not in slot_of:
+        raise ValueError("graph has no blob %r" % output_blob)
+    weights = np.concatenate(wparts) if wparts else np.zeros(1, np.float32)
+    return GraphProgram(ops, n_slots, in_slot, slot_of[out_v], int(res[out_v]), weights, input_blob, output_blob)

@@ -6,8 +6,8 @@ Upscale chosen extracted frames into an output directory, with the flags and fil
 HurrDeblur through ``process_model``), then ``upscale_frames``; with ``-m`` the result is renamed
 ``N.<models>.png``.
 
-Not reimplemented (outside the hot path): ``-m n=K`` (OpenCV NL-means)
-and ``-m r`` (4x_Valar_v1 RRDB) are rejected with an error instead of being silently ignored.
+``-m r`` selects the 4x_Valar_v1 RRDB model (generic CUDA-core graph engine).  Not reimplemented (outside the hot path,
+SURVEY.md section 2 row 11): ``-m n=K`` (OpenCV NL-means) is rejected with an error instead of being silently ignored.
 """
 import argparse
 import logging
@@ -27,9 +27,11 @@ def process_image(input_frames, temp_dir, output_dir, scale, models, gpus, model
         sys.exit("Scale must be 1, 2 or 4")
     models = models.split(",") if models else []
     for m in models:
-        if m == "r" or m.startswith("n="):
-            logging.error("model option %r is outside this engine's scope (Compact family only)" % m)
+        if m.startswith("n="):
+            logging.error("model option %r (OpenCV NL-means) is outside this engine's scope" % m)
             sys.exit("Error - Exiting")
+    if "r" in models:
+        scale = 4  # real-life imaging model is 4x only (reference test_images.py:40-41)
     if gpus:
         try:
             gpus = [int(g) for g in gpus.split(",")]
@@ -61,7 +63,7 @@ def process_image(input_frames, temp_dir, output_dir, scale, models, gpus, model
     if scale > 1:
         logging.info("Starting upscale processing...")
         upscale_frames(input_frames, input_frames[-1], input_frames[-1], input_file_tag, scale, gpus, workers_used, model_path,
-                       "x_Compact_Pretrain", "input", "output", remove=False)
+                       "x_Valar_v1" if "r" in models else "x_Compact_Pretrain", "input", "output", remove=False)
     if models:
         for frame in input_frames:
             src = str(frame) + (".png" if scale > 1 else "." + input_file_tag + ".png")
@@ -75,7 +77,7 @@ if __name__ == "__main__":
     parser.add_argument("-t", "--temp_dir", help="Temp directory where extracted frames are saved. Default is tempfile.gettempdir().")
     parser.add_argument("-o", "--output_dir", required=True, help="Output directory where test images will be saved")
     parser.add_argument("-s", "--scale", type=int, default=2, help="Scale 1, 2 or 4. Default is 2.")
-    parser.add_argument("-m", "--models", help="'a' adds the 1x anime touch-up model before upscaling.")
+    parser.add_argument("-m", "--models", help="'a' adds the 1x anime touch-up model before upscaling, 'r' uses the 4x real-life model (Valar).")
     parser.add_argument("-g", "--gpus", help="Optional gpu #s to use. Example 0,1,3. Default is 0.")
     parser.add_argument("--model_path", help="Directory with the model files (default: packaged models)")
     args = parser.parse_args()

@@ -80,6 +80,7 @@ extern "C" {
 #define B2SR_STAT_TC_MID_PIXELS 6  /* profile mode: output pixels (exact, no halo/padding) those launches produced */
 #define B2SR_STAT_PIPE_LAUNCHES 7  /* pipelined whole-network kernels launched */
 #define B2SR_STAT_PIPE_MS 8        /* profile mode: summed device time of the pipelined launches, ms */
+#define B2SR_STAT_HMMA_LAUNCHES 9  /* generic graph engine: convolutions launched on the warp-level MMA (wmma) kernel */
 
 typedef struct b2sr_ctx b2sr_ctx;
 
@@ -112,7 +113,8 @@ void b2sr_destroy(b2sr_ctx *ctx);
  * Generic graph engine (B2SR_FAMILY_GRAPH): the ncnn graph is handed over as a flat list of operations over numbered
  * activation slots (Split layers resolved to aliases and slots reused by the caller).  Replaces the same ncnn calls
  * as b2sr_create (upscale/upscale_processing.py:65-71) for models/4x_Valar_v1.param, which is not an SRVGGNetCompact.
- * fp32 activations and accumulation on CUDA cores; every b2sr_run_* entry point works on such a context.
+ * fp32 activations; convolutions with cin % 16 == 0 and cout 32/64 run on warp-level MMA (fp16 operands, fp32 accumulate), the rest on
+ * fp32 CUDA cores (B2SR_OPT_IMPL = 1 forces fp32 everywhere); every b2sr_run_* entry point works on such a context.
  */
 #define B2SR_OP_CONV 1          /* Convolution k = 1 or 3, pad k/2, optional bias, act 0 = none / 2 = LeakyReLU(slope) */
 #define B2SR_OP_PRELU 2         /* per-channel slopes at w_off */

@@ -51,12 +51,12 @@ def natural(h, w, seed=0):
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
-def assert_parity(got, ref, what=""):
+def assert_parity(got, ref, what="", max_mismatch=MAX_MISMATCH):
     assert got.shape == ref.shape and got.dtype == np.uint8, what
     d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
     assert d.max() <= MAX_LSB, "%s: max |diff| = %d LSB at %s" % (what, d.max(), np.unravel_index(d.argmax(), d.shape))
     # the fraction bound is only meaningful on images with enough values (a 1x1 frame has 12)
-    assert (d > 0).sum() <= max(2, MAX_MISMATCH * d.size), "%s: %.2f%% of values differ" % (what, 100 * (d > 0).mean())
+    assert (d > 0).sum() <= max(2, max_mismatch * d.size), "%s: %.2f%% of values differ" % (what, 100 * (d > 0).mean())
 
 
 # ---------------------------------------------------------------- goldens ----------------------------
@@ -369,12 +369,21 @@ def test_valar_rrdb_generic_graph_engine(E, model_dir, oracle_models):
     eng = E.Engine.from_files(model_dir, "4x_Valar_v1", 0)
     assert eng.generic and eng.scale == 4
     g = golden("valar4x_crop")
+    # default: RRDB convolutions on warp-level MMA with fp16 operands.  420 convolutions deep and without an input
+    # residual, ~5 % of the u8 values land on the other side of a rounding boundary (same figure as a CPU emulation of
+    # fp16 activation rounding); never more than 1 LSB.
     out = eng.run_u8(g["x"])
-    assert eng.stat(E.STAT_TC_LAUNCHES) == 0
-    assert_parity(out, g["y"], "valar golden")
+    assert eng.stat(E.STAT_TC_LAUNCHES) == 0 and eng.stat(E.STAT_HMMA_LAUNCHES) >= 400
+    assert_parity(out, g["y"], "valar golden (hmma)", max_mismatch=0.09)
     img = natural(20, 980, seed=13)  # seam at x = 960
     ref = oracle.upscale_image_array(oracle_models("4x_Valar_v1"), img, 4, "f32")
-    assert_parity(eng.run_u8(img), ref, "valar 20x980")
+    assert_parity(eng.run_u8(img), ref, "valar 20x980 (hmma)", max_mismatch=0.09)
+    # fp32 CUDA-core kernels everywhere: essentially exact
+    eng.set_option(E.OPT_IMPL, E.IMPL_SIMPLE)
+    eng.reset_stats()
+    out32 = eng.run_u8(g["x"])
+    assert eng.stat(E.STAT_HMMA_LAUNCHES) == 0
+    assert_parity(out32, g["y"], "valar golden (fp32)", max_mismatch=0.005)
     eng.close()
 
 
@@ -384,6 +393,7 @@ def test_compact_models_through_generic_engine(E, engines, model_dir, oracle_mod
     img = natural(50, 300, seed=17)
     for name, scale in (("2x_Compact_Pretrain", 2), (HURR, 1)):
         gen = E.Engine(ncnn_model.load_model(model_dir, name), 0, generic=True)
+        gen.set_option(E.OPT_IMPL, E.IMPL_SIMPLE)  # fp32 CUDA-core kernels (the default would use HMMA for the 64->64 convolutions)
         tile = 960 if scale > 1 else 0
         a = gen.run_u8(img, tile=tile, halo=10 if tile else 0)
         b = engines(name).run_u8(img, tile=tile, halo=10 if tile else 0)

@@ -154,6 +154,7 @@ struct GraphOp {  // b2sr_graph_op + what create derives from it
     int in_res = 1;
     int in_c[6] = {0, 0, 0, 0, 0, 0};
     float* w = nullptr;  // CONV: repacked [k*k][cin][coutp]; PRELU: slopes
+    __half* wh = nullptr;  // CONV with cin % 16 == 0 and cout in {32, 64}: fp16 [k*k][cin][cout] for the wmma kernel
     float* b = nullptr;
     int coutp = 0;
 };
@@ -188,7 +189,7 @@ struct b2sr_ctx {
     // options
     int impl = 0, profile = 0, max_batch = 0;
     // stats
-    double n_launch = 0, n_tc = 0, n_pipe = 0;
+    double n_launch = 0, n_tc = 0, n_pipe = 0, n_hmma = 0;
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> ev_pool;
 };
@@ -236,6 +237,7 @@ extern "C" void b2sr_destroy(b2sr_ctx* c) {
     free_layers(c);
     for (auto& g : c->gops) {
         if (g.w) cudaFree(g.w);
+        if (g.wh) cudaFree(g.wh);
         if (g.b) cudaFree(g.b);
     }
     for (float* p : c->slot_buf)
@@ -865,6 +867,24 @@ extern "C" int b2sr_create_graph(b2sr_ctx** out, int device, const b2sr_graph_op
                         rc = fail(B2SR_E_NOMEM, "op %d: weight upload failed", i);
                         break;
                     }
+                    if (o.cin % 16 == 0 && (o.cout == 32 || o.cout == 64)) {  // tensor-core path wants fp16 weights
+                        bool exact = true;
+                        std::vector<__half> hw((size_t)o.k * o.k * o.cin * o.cout);
+                        for (int t = 0; t < o.k * o.k; ++t)
+                            for (int ic = 0; ic < o.cin; ++ic)
+                                for (int oc = 0; oc < o.cout; ++oc) {
+                                    const float v = w[((size_t)t * o.cin + ic) * g.coutp + oc];
+                                    exact = exact && fp16_exact(v);
+                                    hw[((size_t)t * o.cin + ic) * o.cout + oc] = __float2half_rn(v);
+                                }
+                        if (exact) {  // (true for every model the reference ships: their weights are stored as fp16)
+                            if (cudaMalloc(&g.wh, hw.size() * 2) != cudaSuccess ||
+                                cudaMemcpy(g.wh, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+                                rc = fail(B2SR_E_NOMEM, "op %d: weight upload failed", i);
+                                break;
+                            }
+                        }
+                    }
                     if (o.b_off >= 0) {
                         if (cudaMalloc(&g.b, o.cout * 4) != cudaSuccess ||
                             cudaMemcpy(g.b, wb + o.b_off, o.cout * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -951,6 +971,24 @@ static int run_graph(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
             float* outp = c->slot_buf[o.out];
             switch (o.type) {
                 case B2SR_OP_CONV: {
+                    if (g.wh && c->impl != 1) {  // HMMA path (B2SR_OPT_IMPL = 1 forces the fp32 CUDA-core kernel)
+                        const int halo = o.k / 2;
+                        const size_t smem = std::max((size_t)(GW_TY + 2 * halo) * (GW_TX + 2 * halo) * (o.cin + GW_PAD) * 2,
+                                                     (size_t)GW_TY * GW_TX * o.cout * 4);
+                        const unsigned nbw = (unsigned)(((H + GW_TY - 1) / GW_TY) * ((W + GW_TX - 1) / GW_TX));
+#define WMMA_CASE(kk, nf)                                                                                                  \
+    if (o.k == kk && o.cout == nf * 16) {                                                                                  \
+        CUDA_TRY(cudaFuncSetAttribute(g_conv_wmma_kernel<kk, nf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        g_conv_wmma_kernel<kk, nf><<<nbw, GW_THREADS, smem, c->stream>>>(in0, H, W, o.cin, g.wh, g.b, o.act, o.slope, outp); \
+    }
+                        WMMA_CASE(3, 2)
+                        WMMA_CASE(3, 4)
+                        WMMA_CASE(1, 2)
+                        WMMA_CASE(1, 4)
+#undef WMMA_CASE
+                        c->n_hmma += 1;
+                        break;
+                    }
                     const unsigned nb = blocks(px * (g.coutp / 4));
                     if (o.k == 3)
                         g_conv_kernel<3><<<nb, 256, 0, c->stream>>>(in0, H, W, o.cin, g.w, g.b, o.cout, g.coutp, o.act, o.slope, outp);
@@ -1254,7 +1292,7 @@ extern "C" int b2sr_reset_stats(b2sr_ctx* c) {
     if (!c) return fail(B2SR_E_INVALID, "null context");
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->n_launch = c->n_tc = c->n_pipe = 0;
+    c->n_launch = c->n_tc = c->n_pipe = c->n_hmma = 0;
     for (auto& r : c->prof) {
         c->ev_pool.push_back(r.a);
         c->ev_pool.push_back(r.b);
@@ -1274,6 +1312,9 @@ extern "C" int b2sr_get_stat(b2sr_ctx* c, int key, double* value) {
             return 0;
         case B2SR_STAT_PIPE_LAUNCHES:
             *value = c->n_pipe;
+            return 0;
+        case B2SR_STAT_HMMA_LAUNCHES:
+            *value = c->n_hmma;
             return 0;
         case B2SR_STAT_TC_MID_MS:
         case B2SR_STAT_TC_MID_COUNT:

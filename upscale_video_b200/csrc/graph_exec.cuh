@@ -10,6 +10,8 @@
 // Activations are fp32 NHWC, accumulation is fp32: this is a correctness-first GPU path (plain FMA, no tensor
 // cores); a tcgen05 RRDB kernel family (concat-K accumulation into one TMEM tile) is future work.
 #pragma once
+#include <mma.h>
+
 #include "common.cuh"
 
 namespace b2sr {
@@ -68,6 +70,80 @@ __global__ void g_conv_kernel(const float* __restrict__ in, int H, int W, int ci
                 op[o] = t;
             }
         }
+    }
+}
+
+// Tensor-core version of g_conv_kernel for Cin % 16 == 0 and Cout % 16 == 0 (every RRDB convolution of Valar):
+// legacy warp-level MMA (wmma m16n16k16, fp16 operands, fp32 accumulate -- HMMA, not tcgen05), activations rounded to
+// fp16 when the halo'd input tile is staged in shared memory.  CTA = 8 rows x 32 columns of output pixels x all Cout;
+// warp w owns row w of the tile (two 16-pixel segments x Cout/16 accumulator fragments).
+constexpr int GW_TY = 8, GW_TX = 32, GW_THREADS = 256, GW_PAD = 16;  // GW_PAD halfs of padding per pixel: conflict-free fragment rows
+template <int K, int NF /*Cout / 16*/>
+__global__ void __launch_bounds__(GW_THREADS) g_conv_wmma_kernel(const float* __restrict__ in, int H, int W, int cin,
+                                                                  const __half* __restrict__ w /*[K*K][cin][NF*16]*/,
+                                                                  const float* __restrict__ bias, int act, float slope,
+                                                                  float* __restrict__ out) {
+    using namespace nvcuda;
+    extern __shared__ __align__(128) uint8_t gsm[];
+    constexpr int HALO = K / 2, SY = GW_TY + 2 * HALO, SX = GW_TX + 2 * HALO, COUT = NF * 16;
+    const int ps = cin + GW_PAD;  // pixel stride in halfs (multiple of 16 -> 32-byte aligned fragment pointers)
+    __half* tile = reinterpret_cast<__half*>(gsm);
+    const int tiles_x = (W + GW_TX - 1) / GW_TX;
+    const int ty0 = (blockIdx.x / tiles_x) * GW_TY, tx0 = (blockIdx.x % tiles_x) * GW_TX;
+    // stage the input tile (zero outside the image = the convolution's zero padding), fp32 -> fp16
+    const int c4 = cin / 4;
+    for (int i = threadIdx.x; i < SY * SX * c4; i += GW_THREADS) {
+        const int c = (i % c4) * 4, p = i / c4, sx = p % SX, sy = p / SX;
+        const int y = ty0 + sy - HALO, x = tx0 + sx - HALO;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= 0 && y < H && x >= 0 && x < W) v = *reinterpret_cast<const float4*>(in + ((size_t)y * W + x) * cin + c);
+        __half2* d = reinterpret_cast<__half2*>(tile + (size_t)p * ps + c);
+        d[0] = __floats2half2_rn(v.x, v.y);
+        d[1] = __floats2half2_rn(v.z, v.w);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[2][NF];
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int n = 0; n < NF; ++n) wmma::fill_fragment(acc[s][n], 0.f);
+    for (int ky = 0; ky < K; ++ky)
+        for (int kx = 0; kx < K; ++kx) {
+            const __half* wt = w + (size_t)((ky * K + kx) * cin) * COUT;
+            const __half* a0 = tile + (size_t)((warp + ky) * SX + kx) * ps;
+            for (int c = 0; c < cin; c += 16) {
+                wmma::fragment<wmma::matrix_a, 16, 16, 16, __half, wmma::row_major> fa[2];
+                wmma::load_matrix_sync(fa[0], a0 + c, ps);
+                wmma::load_matrix_sync(fa[1], a0 + (size_t)16 * ps + c, ps);
+#pragma unroll
+                for (int n = 0; n < NF; ++n) {
+                    wmma::fragment<wmma::matrix_b, 16, 16, 16, __half, wmma::row_major> fb;
+                    wmma::load_matrix_sync(fb, wt + (size_t)c * COUT + n * 16, COUT);
+                    wmma::mma_sync(acc[0][n], fa[0], fb, acc[0][n]);
+                    wmma::mma_sync(acc[1][n], fa[1], fb, acc[1][n]);
+                }
+            }
+        }
+    __syncthreads();  // everyone is done reading the input tile: reuse it as fp32 output staging [TY][TX][COUT]
+    float* stg = reinterpret_cast<float*>(gsm);
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int n = 0; n < NF; ++n)
+            wmma::store_matrix_sync(stg + (size_t)(warp * GW_TX + s * 16) * COUT + n * 16, acc[s][n], COUT, wmma::mem_row_major);
+    __syncthreads();
+    for (int i = threadIdx.x; i < GW_TY * GW_TX * (COUT / 4); i += GW_THREADS) {
+        const int c = (i % (COUT / 4)) * 4, p = i / (COUT / 4), x = tx0 + p % GW_TX, y = ty0 + p / GW_TX;
+        if (y >= H || x >= W) continue;
+        float4 v = *reinterpret_cast<const float4*>(stg + (size_t)p * COUT + c);
+        float t[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            t[j] += bias ? bias[c + j] : 0.f;
+            if (act == 2) t[j] = t[j] > 0.f ? t[j] : t[j] * slope;
+        }
+        *reinterpret_cast<float4*>(out + ((size_t)y * W + x) * COUT + c) = make_float4(t[0], t[1], t[2], t[3]);
     }
 }
 

@@ -94,7 +94,7 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def cpu_port_fps(sample_hw=(270, 480), reps=1, threads=None):
+def cpu_port_fps(sample_hw=(540, 960), reps=1, threads=None):
     """Times the CPU oracle (f32, what ncnn's CPU path computes in) on a crop of one synthetic frame and scales
     by area to frames/s.  Returns (fps, threads, description, seconds)."""
     from oracle import oracle
@@ -296,9 +296,10 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 storage / f32 accumulate", "data": "synthetic",
+        "dtype": "f16", "data": "synthetic",
         "config": {"workload": "synthetic 1080p RGB batch, 2x_Compact_Pretrain, 1xB200 per rank (BASELINE configs[1])",
                    "frames_per_gpu_per_step": B, "frame": [H, W, 3], "tile": TILE, "halo": HALO, "content": args.content,
+                   "arithmetic": "fp16 weights and activations (tcgen05 kind::f16), fp32 accumulation and epilogue, u8 in/out",
                    "l2": "inputs+outputs per step are %d MB per GPU, larger than the 126 MB L2" % ((d_in.numel() + d_out.numel()) >> 20),
                    "parallelism": "frames sharded over %d rank(s), no data-path collective; weights NCCL-broadcast" % world},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),

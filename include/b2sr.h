@@ -137,6 +137,14 @@ typedef struct b2sr_graph_op {
     int32_t r;
     int64_t w_off; /* offsets in floats into the weight blob; -1 = absent.  CONV weights are OIHW */
     int64_t b_off;
+    /* Shapes and views.  Every operand is `c` channels starting at channel `off` of a slot whose pixels are `ld` floats
+     * apart (ld = 0: dense, ld = c).  Views let a Concat of values that are only ever concatenated as prefixes of one
+     * another (the RRDB pattern [x], [x,x1], [x,x1,x2] ...) cost nothing: the producers write straight into their
+     * channel slice of one wide slot and the "concatenated" tensor is a view of its first channels. */
+    int32_t in_c[6], in_off[6], in_ld[6];
+    int32_t out_c, out_off, out_ld;
+    int32_t in_res, out_res; /* resolution factor (1, 2, 4 ...) of inputs / output relative to the network input */
+    int32_t reserved;
 } b2sr_graph_op;
 int b2sr_create_graph(b2sr_ctx **out, int device, const b2sr_graph_op *ops, int n_ops, int n_slots, int in_slot, int out_slot,
                       int scale, const void *weights, size_t nbytes);

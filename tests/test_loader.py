@@ -134,12 +134,16 @@ def test_mac_count_matches_survey(model_dir):
 
 
 def _run_program_numpy(prog, x):
-    """Execute a compiled op list (ncnn_model.compile_graph) on the CPU with the oracle's layer functions."""
+    """Execute a compiled op list (ncnn_model.compile_graph) on the CPU with the oracle's layer functions.  Slots are
+    H x W x ld arrays; operands are channel slices of them (the strided views of include/b2sr.h b2sr_graph_op)."""
     slots = [None] * prog.n_slots
     slots[prog.in_slot] = np.ascontiguousarray(x, np.float64)
     w = prog.weights
+    h0, w0 = x.shape[:2]
     for o in prog.ops:
-        ins = [slots[i] for i in o["in"][:o["nin"]]]
+        ins = [slots[s][:, :, off:off + c] for s, off, c in zip(o["in"][:o["nin"]], o["in_off"], o["in_c"])]
+        for a, ld, s in zip(ins, o["in_ld"], o["in"]):
+            assert a.shape == (h0 * o["in_res"], w0 * o["in_res"], a.shape[2]) and slots[s].shape[2] == (ld or a.shape[2])
         t = o["type"]
         if t == M.OP_CONV:
             wt = w[o["w_off"]:o["w_off"] + o["cout"] * o["cin"] * o["k"] ** 2].reshape(o["cout"], o["cin"], o["k"], o["k"])
@@ -156,8 +160,15 @@ def _run_program_numpy(prog, x):
             y = ins[0] + ins[1] if o["plain"] else ins[0] * np.float64(np.float32(o["coef"][0])) + ins[1] * np.float64(np.float32(o["coef"][1]))
         elif t == M.OP_CONCAT:
             y = np.concatenate(ins, axis=2)
-        slots[o["out"]] = y
-    return slots[prog.out_slot]
+        assert y.shape == (h0 * o["out_res"], w0 * o["out_res"], o["out_c"])
+        ld = o["out_ld"] or o["out_c"]
+        if slots[o["out"]] is None or slots[o["out"]].shape != (y.shape[0], y.shape[1], ld) or not o["out_ld"]:
+            # a fresh (or recycled) slot; poison it so that reading a slice nobody wrote shows up
+            slots[o["out"]] = np.full((y.shape[0], y.shape[1], ld), np.nan)
+        slots[o["out"]][:, :, o["out_off"]:o["out_off"] + o["out_c"]] = y
+    out = slots[prog.out_slot]
+    assert not np.isnan(out).any()
+    return out
 
 
 @pytest.mark.parametrize("stem", ["2x_Compact_Pretrain", "4x_Valar_v1"])
@@ -167,9 +178,13 @@ def test_compiled_program_equals_graph_interpreter(model_dir, stem):
     if not os.path.exists(os.path.join(model_dir, stem + ".b2sr")):
         pytest.skip("model not packaged")
     g = M.load_model(model_dir, stem)
-    prog = M.compile_graph(g)
-    assert prog.n_slots <= 12 and prog.scale == int(stem[0])
     x = np.random.default_rng(1).random((12, 14, 3))
     ref = oracle.run_graph(oracle.read_model(model_dir, stem), x, "f64")
-    got = _run_program_numpy(prog, x)
-    assert got.shape == ref.shape and np.array_equal(got, ref)
+    for views in (True, False):
+        prog = M.compile_graph(g, views=views)
+        assert prog.n_slots <= 12 and prog.scale == int(stem[0])
+        n_concat = sum(o["type"] == M.OP_CONCAT for o in prog.ops)
+        if stem == "4x_Valar_v1":  # every dense-block Concat is a prefix chain -> all of them become views
+            assert n_concat == (0 if views else 4 * 3 * 23)
+        got = _run_program_numpy(prog, x)
+        assert got.shape == ref.shape and np.array_equal(got, ref)

@@ -148,15 +148,14 @@ struct ProfRec {
     double px;
 };
 
-struct GraphOp {  // b2sr_graph_op + what create derives from it
+struct GraphOp {  // b2sr_graph_op + device copies of its parameters
     b2sr_graph_op op;
-    int out_c = 0, out_res = 1;  // channels / resolution factor (relative to the input plane) of the output slot
-    int in_res = 1;
-    int in_c[6] = {0, 0, 0, 0, 0, 0};
-    float* w = nullptr;  // CONV: repacked [k*k][cin][coutp]; PRELU: slopes
+    float* w = nullptr;    // CONV: repacked [k*k][cin][coutp]; PRELU: slopes
     __half* wh = nullptr;  // CONV with cin % 16 == 0 and cout in {32, 64}: fp16 [k*k][cin][cout] for the wmma kernel
     float* b = nullptr;
     int coutp = 0;
+    int ld_in(int j) const { return op.in_ld[j] ? op.in_ld[j] : op.in_c[j]; }
+    int ld_out() const { return op.out_ld ? op.out_ld : op.out_c; }
 };
 
 struct b2sr_ctx {
@@ -814,9 +813,8 @@ extern "C" int b2sr_create_graph(b2sr_ctx** out, int device, const b2sr_graph_op
     c->g_slots = n_slots, c->g_in = in_slot, c->g_out = out_slot;
     c->slot_buf.assign(n_slots, nullptr);
     c->slot_cap.assign(n_slots, 0);
-    std::vector<int> sc(n_slots, -1), sr(n_slots, 0);  // channels / resolution factor currently held by each slot
-    sc[in_slot] = 3, sr[in_slot] = 1;
     int rc = 0;
+    int out_c = 0, out_res = 0;
     do {
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
@@ -828,27 +826,19 @@ extern "C" int b2sr_create_graph(b2sr_ctx** out, int device, const b2sr_graph_op
             GraphOp g;
             g.op = ops[i];
             const b2sr_graph_op& o = g.op;
-            if (o.nin < 1 || o.nin > 6 || o.out < 0 || o.out >= n_slots) {
-                rc = fail(B2SR_E_INVALID, "op %d: bad slots", i);
+            if (o.nin < 1 || o.nin > 6 || o.out < 0 || o.out >= n_slots || o.out_c < 1 || o.out_off < 0 || o.in_res < 1 || o.out_res < 1 ||
+                (o.out_ld && o.out_ld < o.out_off + o.out_c)) {
+                rc = fail(B2SR_E_INVALID, "op %d: bad operands", i);
                 break;
             }
-            for (int j = 0; j < o.nin; ++j) {
-                if (o.in[j] < 0 || o.in[j] >= n_slots || sc[o.in[j]] < 0) {
-                    rc = fail(B2SR_E_INVALID, "op %d: input slot %d is not defined", i, j);
-                    break;
-                }
-                g.in_c[j] = sc[o.in[j]];
-                if (j && sr[o.in[j]] != sr[o.in[0]]) rc = fail(B2SR_E_INVALID, "op %d: inputs of different resolution", i);
-                if (o.in[j] == o.out && o.type != B2SR_OP_PRELU && o.type != B2SR_OP_ADD)
-                    rc = fail(B2SR_E_INVALID, "op %d: type %d cannot run in place", i, o.type);
-            }
+            for (int j = 0; j < o.nin; ++j)
+                if (o.in[j] < 0 || o.in[j] >= n_slots || o.in_c[j] < 1 || o.in_off[j] < 0 || (o.in_ld[j] && o.in_ld[j] < o.in_off[j] + o.in_c[j]))
+                    rc = fail(B2SR_E_INVALID, "op %d: bad input %d", i, j);
             if (rc) break;
-            g.in_res = sr[o.in[0]];
-            g.out_res = g.in_res, g.out_c = g.in_c[0];
             switch (o.type) {
                 case B2SR_OP_CONV: {
-                    if ((o.k != 1 && o.k != 3) || o.cin != g.in_c[0] || o.cout < 1 || o.nin != 1) {
-                        rc = fail(B2SR_E_UNSUPPORTED, "op %d: convolution k=%d cin=%d (slot has %d) cout=%d", i, o.k, o.cin, g.in_c[0], o.cout);
+                    if ((o.k != 1 && o.k != 3) || o.cin != o.in_c[0] || o.cout != o.out_c || o.nin != 1 || o.out_res != o.in_res) {
+                        rc = fail(B2SR_E_UNSUPPORTED, "op %d: convolution k=%d cin=%d (input has %d) cout=%d", i, o.k, o.cin, o.in_c[0], o.cout);
                         break;
                     }
                     const int64_t nw = (int64_t)o.cout * o.cin * o.k * o.k;
@@ -867,7 +857,9 @@ extern "C" int b2sr_create_graph(b2sr_ctx** out, int device, const b2sr_graph_op
                         rc = fail(B2SR_E_NOMEM, "op %d: weight upload failed", i);
                         break;
                     }
-                    if (o.cin % 16 == 0 && (o.cout == 32 || o.cout == 64)) {  // tensor-core path wants fp16 weights
+                    // tensor-core path: fp16 weights, 16-byte aligned strided views
+                    if (o.cin % 16 == 0 && (o.cout == 32 || o.cout == 64) && g.ld_in(0) % 4 == 0 && o.in_off[0] % 4 == 0 && g.ld_out() % 4 == 0 &&
+                        o.out_off % 4 == 0) {
                         bool exact = true;
                         std::vector<__half> hw((size_t)o.k * o.k * o.cin * o.cout);
                         for (int t = 0; t < o.k * o.k; ++t)
@@ -892,46 +884,48 @@ extern "C" int b2sr_create_graph(b2sr_ctx** out, int device, const b2sr_graph_op
                             break;
                         }
                     }
-                    g.out_c = o.cout;
                     break;
                 }
                 case B2SR_OP_PRELU:
-                    if (o.w_off < 0 || o.w_off + g.in_c[0] > nfl) {
-                        rc = fail(B2SR_E_INVALID, "op %d: slopes outside the blob", i);
+                    if (o.w_off < 0 || o.w_off + o.in_c[0] > nfl || o.out_c != o.in_c[0] || o.out_res != o.in_res) {
+                        rc = fail(B2SR_E_INVALID, "op %d: bad PReLU", i);
                         break;
                     }
-                    if (cudaMalloc(&g.w, g.in_c[0] * 4) != cudaSuccess ||
-                        cudaMemcpy(g.w, wb + o.w_off, g.in_c[0] * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+                    if (cudaMalloc(&g.w, o.in_c[0] * 4) != cudaSuccess ||
+                        cudaMemcpy(g.w, wb + o.w_off, o.in_c[0] * 4, cudaMemcpyHostToDevice) != cudaSuccess)
                         rc = fail(B2SR_E_NOMEM, "op %d: slope upload failed", i);
                     break;
                 case B2SR_OP_PIXELSHUFFLE:
-                    if (o.r < 1 || g.in_c[0] % (o.r * o.r)) rc = fail(B2SR_E_INVALID, "op %d: pixel shuffle %d on %d channels", i, o.r, g.in_c[0]);
-                    g.out_c = g.in_c[0] / std::max(1, o.r * o.r), g.out_res = g.in_res * o.r;
+                    if (o.r < 1 || o.in_c[0] != o.out_c * o.r * o.r || o.out_res != o.in_res * o.r) rc = fail(B2SR_E_INVALID, "op %d: bad pixel shuffle", i);
                     break;
                 case B2SR_OP_NEAREST:
-                    if (o.r < 1 || o.r > 8) rc = fail(B2SR_E_INVALID, "op %d: resize factor %d", i, o.r);
-                    g.out_res = g.in_res * o.r;
+                    if (o.r < 1 || o.r > 8 || o.out_c != o.in_c[0] || o.out_res != o.in_res * o.r) rc = fail(B2SR_E_INVALID, "op %d: bad resize", i);
                     break;
                 case B2SR_OP_ADD:
-                    if (o.nin != 2 || g.in_c[0] != g.in_c[1]) rc = fail(B2SR_E_INVALID, "op %d: add of %d inputs / channel mismatch", i, o.nin);
+                    if (o.nin != 2 || o.in_c[0] != o.in_c[1] || o.out_c != o.in_c[0] || o.out_res != o.in_res) rc = fail(B2SR_E_INVALID, "op %d: bad add", i);
                     break;
-                case B2SR_OP_CONCAT:
-                    g.out_c = 0;
-                    for (int j = 0; j < o.nin; ++j) g.out_c += g.in_c[j];
+                case B2SR_OP_CONCAT: {
+                    int tot = 0;
+                    for (int j = 0; j < o.nin; ++j) tot += o.in_c[j];
+                    if (tot != o.out_c || o.out_res != o.in_res) rc = fail(B2SR_E_INVALID, "op %d: bad concat", i);
                     break;
+                }
                 default:
                     rc = fail(B2SR_E_UNSUPPORTED, "op %d: unknown type %d", i, o.type);
             }
             if (rc) {
                 if (g.w) cudaFree(g.w);
+                if (g.wh) cudaFree(g.wh);
                 if (g.b) cudaFree(g.b);
                 break;
             }
-            sc[o.out] = g.out_c, sr[o.out] = g.out_res;
+            if (o.out == out_slot) out_c = o.out_c, out_res = o.out_res;
             c->gops.push_back(g);
         }
-        if (!rc && (sc[out_slot] != 3 || sr[out_slot] != scale))
-            rc = fail(B2SR_E_INVALID, "graph output has %d channels at x%d, expected 3 at x%d", sc[out_slot], sr[out_slot], scale);
+        if (!rc && (out_c != 3 || out_res != scale))
+            rc = fail(B2SR_E_INVALID, "graph output has %d channels at x%d, expected 3 at x%d", out_c, out_res, scale);
+        if (!rc && (c->gops.back().op.out != out_slot || c->gops.back().op.out_off != 0))
+            rc = fail(B2SR_E_INVALID, "the last op must produce the output slot");
     } while (0);
     if (rc) {
         std::string keep = g_err;
@@ -949,7 +943,7 @@ static int run_graph(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
     std::vector<size_t> need(c->g_slots, 0);
     const size_t mp = (size_t)P->max_plane_px;
     need[c->g_in] = mp * 3;
-    for (auto& g : c->gops) need[g.op.out] = std::max(need[g.op.out], mp * g.out_res * g.out_res * g.out_c);
+    for (auto& g : c->gops) need[g.op.out] = std::max(need[g.op.out], mp * g.op.out_res * g.op.out_res * g.ld_out());
     for (int s = 0; s < c->g_slots; ++s)
         if (need[s] > c->slot_cap[s]) {
             cudaStreamSynchronize(c->stream);
@@ -965,10 +959,11 @@ static int run_graph(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
         c->n_launch += 1;
         for (auto& g : c->gops) {
             const b2sr_graph_op& o = g.op;
-            const int H = pl.Ht * g.in_res, W = pl.Wt * g.in_res;
+            const int H = pl.Ht * o.in_res, W = pl.Wt * o.in_res;
             const size_t px = (size_t)H * W;
-            const float* in0 = c->slot_buf[o.in[0]];
-            float* outp = c->slot_buf[o.out];
+            const float* in0 = c->slot_buf[o.in[0]] + o.in_off[0];
+            float* outp = c->slot_buf[o.out] + o.out_off;
+            const int ld0 = g.ld_in(0), ldo = g.ld_out();
             switch (o.type) {
                 case B2SR_OP_CONV: {
                     if (g.wh && c->impl != 1) {  // HMMA path (B2SR_OPT_IMPL = 1 forces the fp32 CUDA-core kernel)
@@ -976,10 +971,10 @@ static int run_graph(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
                         const size_t smem = std::max((size_t)(GW_TY + 2 * halo) * (GW_TX + 2 * halo) * (o.cin + GW_PAD) * 2,
                                                      (size_t)GW_TY * GW_TX * o.cout * 4);
                         const unsigned nbw = (unsigned)(((H + GW_TY - 1) / GW_TY) * ((W + GW_TX - 1) / GW_TX));
-#define WMMA_CASE(kk, nf)                                                                                                  \
-    if (o.k == kk && o.cout == nf * 16) {                                                                                  \
+#define WMMA_CASE(kk, nf)                                                                                                   \
+    if (o.k == kk && o.cout == nf * 16) {                                                                                   \
         CUDA_TRY(cudaFuncSetAttribute(g_conv_wmma_kernel<kk, nf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        g_conv_wmma_kernel<kk, nf><<<nbw, GW_THREADS, smem, c->stream>>>(in0, H, W, o.cin, g.wh, g.b, o.act, o.slope, outp); \
+        g_conv_wmma_kernel<kk, nf><<<nbw, GW_THREADS, smem, c->stream>>>(in0, ld0, H, W, o.cin, g.wh, g.b, o.act, o.slope, outp, ldo); \
     }
                         WMMA_CASE(3, 2)
                         WMMA_CASE(3, 4)
@@ -991,29 +986,30 @@ static int run_graph(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
                     }
                     const unsigned nb = blocks(px * (g.coutp / 4));
                     if (o.k == 3)
-                        g_conv_kernel<3><<<nb, 256, 0, c->stream>>>(in0, H, W, o.cin, g.w, g.b, o.cout, g.coutp, o.act, o.slope, outp);
+                        g_conv_kernel<3><<<nb, 256, 0, c->stream>>>(in0, ld0, H, W, o.cin, g.w, g.b, o.cout, g.coutp, o.act, o.slope, outp, ldo);
                     else
-                        g_conv_kernel<1><<<nb, 256, 0, c->stream>>>(in0, H, W, o.cin, g.w, g.b, o.cout, g.coutp, o.act, o.slope, outp);
+                        g_conv_kernel<1><<<nb, 256, 0, c->stream>>>(in0, ld0, H, W, o.cin, g.w, g.b, o.cout, g.coutp, o.act, o.slope, outp, ldo);
                     break;
                 }
                 case B2SR_OP_PRELU:
-                    g_prelu_kernel<<<blocks(px * g.in_c[0]), 256, 0, c->stream>>>(in0, px * g.in_c[0], g.in_c[0], g.w, outp);
+                    g_prelu_kernel<<<blocks(px * o.in_c[0]), 256, 0, c->stream>>>(in0, ld0, px * o.in_c[0], o.in_c[0], g.w, outp, ldo);
                     break;
                 case B2SR_OP_PIXELSHUFFLE:
-                    g_pixelshuffle_kernel<<<blocks(px * g.in_c[0]), 256, 0, c->stream>>>(in0, H, W, g.out_c, o.r, outp);
+                    g_pixelshuffle_kernel<<<blocks(px * o.in_c[0]), 256, 0, c->stream>>>(in0, ld0, H, W, o.out_c, o.r, outp, ldo);
                     break;
                 case B2SR_OP_NEAREST:
-                    g_nearest_kernel<<<blocks(px * o.r * o.r * g.in_c[0]), 256, 0, c->stream>>>(in0, H, W, g.in_c[0], o.r, outp);
+                    g_nearest_kernel<<<blocks(px * o.r * o.r * o.in_c[0]), 256, 0, c->stream>>>(in0, ld0, H, W, o.in_c[0], o.r, outp, ldo);
                     break;
                 case B2SR_OP_ADD:
-                    g_add_kernel<<<blocks(px * g.in_c[0]), 256, 0, c->stream>>>(in0, c->slot_buf[o.in[1]], px * g.in_c[0], o.coef[0], o.coef[1],
-                                                                               o.plain, outp);
+                    g_add_kernel<<<blocks(px * o.in_c[0]), 256, 0, c->stream>>>(in0, ld0, c->slot_buf[o.in[1]] + o.in_off[1], g.ld_in(1),
+                                                                               px * o.in_c[0], o.in_c[0], o.coef[0], o.coef[1], o.plain, outp, ldo);
                     break;
                 case B2SR_OP_CONCAT: {
                     int off = 0;
                     for (int j = 0; j < o.nin; ++j) {
-                        g_concat_kernel<<<blocks(px * g.in_c[j]), 256, 0, c->stream>>>(c->slot_buf[o.in[j]], px, g.in_c[j], g.out_c, off, outp);
-                        off += g.in_c[j];
+                        g_concat_kernel<<<blocks(px * o.in_c[j]), 256, 0, c->stream>>>(c->slot_buf[o.in[j]] + o.in_off[j], g.ld_in(j), px, o.in_c[j],
+                                                                                      ldo, off, outp);
+                        off += o.in_c[j];
                         c->n_launch += 1;
                     }
                     c->n_launch -= 1;
@@ -1022,11 +1018,13 @@ static int run_graph(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
             }
             c->n_launch += 1;
         }
+        const b2sr_graph_op& last = c->gops.back().op;
         const size_t on = (size_t)(pl.cy1 - pl.cy0) * S * (pl.cx1 - pl.cx0) * S * 3;
         if (f32out)
-            g_output_kernel<true><<<blocks(on), 256, 0, c->stream>>>(c->slot_buf[c->g_out], pl, S, P->h, P->w, d_out);
+            g_output_kernel<true><<<blocks(on), 256, 0, c->stream>>>(c->slot_buf[c->g_out], c->gops.back().ld_out(), pl, S, P->h, P->w, d_out);
         else
-            g_output_kernel<false><<<blocks(on), 256, 0, c->stream>>>(c->slot_buf[c->g_out], pl, S, P->h, P->w, d_out);
+            g_output_kernel<false><<<blocks(on), 256, 0, c->stream>>>(c->slot_buf[c->g_out], c->gops.back().ld_out(), pl, S, P->h, P->w, d_out);
+        (void)last;
         c->n_launch += 1;
         CUDA_TRY(cudaGetLastError());
         TRY(prof_end(c));

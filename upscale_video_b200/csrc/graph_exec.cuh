@@ -30,8 +30,9 @@ __global__ void g_input_kernel(const uint8_t* __restrict__ frames, int fh, int f
 // in [H][W][cin], w [K*K][cin][coutp] (coutp = cout rounded up to 4), out [H][W][cout]; zero padding K/2.
 // One thread = one pixel x 4 output channels.
 template <int K>
-__global__ void g_conv_kernel(const float* __restrict__ in, int H, int W, int cin, const float* __restrict__ w,
-                              const float* __restrict__ bias, int cout, int coutp, int act, float slope, float* __restrict__ out) {
+__global__ void g_conv_kernel(const float* __restrict__ in, int ldin, int H, int W, int cin, const float* __restrict__ w,
+                              const float* __restrict__ bias, int cout, int coutp, int act, float slope, float* __restrict__ out,
+                              int ldout) {
     const int Q = coutp / 4;
     const long long total = (long long)H * W * Q;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -47,7 +48,7 @@ __global__ void g_conv_kernel(const float* __restrict__ in, int H, int W, int ci
             for (int kx = 0; kx < K; ++kx) {
                 const int ix = x + kx - K / 2;
                 if (ix < 0 || ix >= W) continue;
-                const float* ip = in + ((size_t)iy * W + ix) * cin;
+                const float* ip = in + ((size_t)iy * W + ix) * ldin;
                 const float* wp = w + (size_t)((ky * K + kx) * cin) * coutp + q * 4;
                 for (int c = 0; c < cin; ++c) {
                     const float a = ip[c];
@@ -60,7 +61,7 @@ __global__ void g_conv_kernel(const float* __restrict__ in, int H, int W, int ci
             }
         }
         float v[4] = {acc.x, acc.y, acc.z, acc.w};
-        float* op = out + (size_t)p * cout;
+        float* op = out + (size_t)p * ldout;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int o = q * 4 + j;
@@ -79,10 +80,10 @@ __global__ void g_conv_kernel(const float* __restrict__ in, int H, int W, int ci
 // warp w owns row w of the tile (two 16-pixel segments x Cout/16 accumulator fragments).
 constexpr int GW_TY = 8, GW_TX = 32, GW_THREADS = 256, GW_PAD = 16;  // GW_PAD halfs of padding per pixel: conflict-free fragment rows
 template <int K, int NF /*Cout / 16*/>
-__global__ void __launch_bounds__(GW_THREADS) g_conv_wmma_kernel(const float* __restrict__ in, int H, int W, int cin,
+__global__ void __launch_bounds__(GW_THREADS) g_conv_wmma_kernel(const float* __restrict__ in, int ldin, int H, int W, int cin,
                                                                   const __half* __restrict__ w /*[K*K][cin][NF*16]*/,
                                                                   const float* __restrict__ bias, int act, float slope,
-                                                                  float* __restrict__ out) {
+                                                                  float* __restrict__ out, int ldout) {
     using namespace nvcuda;
     extern __shared__ __align__(128) uint8_t gsm[];
     constexpr int HALO = K / 2, SY = GW_TY + 2 * HALO, SX = GW_TX + 2 * HALO, COUT = NF * 16;
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(GW_THREADS) g_conv_wmma_kernel(const float* __
         const int c = (i % c4) * 4, p = i / c4, sx = p % SX, sy = p / SX;
         const int y = ty0 + sy - HALO, x = tx0 + sx - HALO;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (y >= 0 && y < H && x >= 0 && x < W) v = *reinterpret_cast<const float4*>(in + ((size_t)y * W + x) * cin + c);
+        if (y >= 0 && y < H && x >= 0 && x < W) v = *reinterpret_cast<const float4*>(in + ((size_t)y * W + x) * ldin + c);
         __half2* d = reinterpret_cast<__half2*>(tile + (size_t)p * ps + c);
         d[0] = __floats2half2_rn(v.x, v.y);
         d[1] = __floats2half2_rn(v.z, v.w);
@@ -143,31 +144,35 @@ __global__ void __launch_bounds__(GW_THREADS) g_conv_wmma_kernel(const float* __
             t[j] += bias ? bias[c + j] : 0.f;
             if (act == 2) t[j] = t[j] > 0.f ? t[j] : t[j] * slope;
         }
-        *reinterpret_cast<float4*>(out + ((size_t)y * W + x) * COUT + c) = make_float4(t[0], t[1], t[2], t[3]);
+        *reinterpret_cast<float4*>(out + ((size_t)y * W + x) * ldout + c) = make_float4(t[0], t[1], t[2], t[3]);
     }
 }
 
-__global__ void g_prelu_kernel(const float* __restrict__ in, size_t n, int C, const float* __restrict__ slope, float* __restrict__ out) {
+__global__ void g_prelu_kernel(const float* __restrict__ in, int ldin, size_t n, int C, const float* __restrict__ slope,
+                               float* __restrict__ out, int ldout) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float v = in[i];
-        out[i] = v < 0.f ? v * slope[i % C] : v;
+        const size_t p = i / C;
+        const int c = (int)(i - p * C);
+        const float v = in[p * ldin + c];
+        out[p * ldout + c] = v < 0.f ? v * slope[c] : v;
     }
 }
 
 // in [H][W][C*r*r] -> out [H*r][W*r][C], ncnn PixelShuffle mode 0
-__global__ void g_pixelshuffle_kernel(const float* __restrict__ in, int H, int W, int C, int r, float* __restrict__ out) {
+__global__ void g_pixelshuffle_kernel(const float* __restrict__ in, int ldin, int H, int W, int C, int r, float* __restrict__ out,
+                                      int ldout) {
     const size_t n = (size_t)H * r * W * r * C;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
         const size_t p = i / C;
         const int ox = (int)(p % ((size_t)W * r)), oy = (int)(p / ((size_t)W * r));
         const int x = ox / r, dx = ox - x * r, y = oy / r, dy = oy - y * r;
-        out[i] = in[((size_t)y * W + x) * ((size_t)C * r * r) + (size_t)c * r * r + dy * r + dx];
+        out[p * ldout + c] = in[((size_t)y * W + x) * ldin + (size_t)c * r * r + dy * r + dx];
     }
 }
 
 // nearest resize by integer factor r: in_y = min(int(y * (1/r)), H-1) (ncnn Interp resize_type 1)
-__global__ void g_nearest_kernel(const float* __restrict__ in, int H, int W, int C, int r, float* __restrict__ out) {
+__global__ void g_nearest_kernel(const float* __restrict__ in, int ldin, int H, int W, int C, int r, float* __restrict__ out, int ldout) {
     const size_t n = (size_t)H * r * W * r * C;
     const float inv = 1.f / (float)r;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -175,35 +180,39 @@ __global__ void g_nearest_kernel(const float* __restrict__ in, int H, int W, int
         const size_t p = i / C;
         const int ox = (int)(p % ((size_t)W * r)), oy = (int)(p / ((size_t)W * r));
         const int x = min((int)(ox * inv), W - 1), y = min((int)(oy * inv), H - 1);
-        out[i] = in[((size_t)y * W + x) * C + c];
+        out[p * ldout + c] = in[((size_t)y * W + x) * ldin + c];
     }
 }
 
 // out = a * ca + b * cb  (BinaryOp add: ca = cb = 1; Eltwise SUM with coefficients)
-__global__ void g_add_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, float ca, float cb, int plain,
-                             float* __restrict__ out) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        out[i] = plain ? a[i] + b[i] : a[i] * ca + b[i] * cb;
+__global__ void g_add_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb, size_t n, int C, float ca,
+                             float cb, int plain, float* __restrict__ out, int ldout) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = i / C;
+        const int c = (int)(i - p * C);
+        const float x = a[p * lda + c], y = b[p * ldb + c];
+        out[p * ldout + c] = plain ? x + y : x * ca + y * cb;
+    }
 }
 
 // copy input [px][C] into channels [off, off+C) of out [px][Ctot]
-__global__ void g_concat_kernel(const float* __restrict__ in, size_t px, int C, int Ctot, int off, float* __restrict__ out) {
+__global__ void g_concat_kernel(const float* __restrict__ in, int ldin, size_t px, int C, int ldout, int off, float* __restrict__ out) {
     const size_t n = px * C;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const size_t p = i / C;
-        out[p * Ctot + off + (i - p * C)] = in[i];
+        out[p * ldout + off + (i - p * C)] = in[p * ldin + (i - p * C)];
     }
 }
 
 // network output plane [Ht*S][Wt*S][3] -> `* 255`, crop to the tile's core, store as f32 or as cv2.imwrite would (u8)
 template <bool F32OUT>
-__global__ void g_output_kernel(const float* __restrict__ net, PlaneDev P, int S, int fh, int fw, void* __restrict__ out) {
+__global__ void g_output_kernel(const float* __restrict__ net, int ldnet, PlaneDev P, int S, int fh, int fw, void* __restrict__ out) {
     const int ch = (P.cy1 - P.cy0) * S, cw = (P.cx1 - P.cx0) * S;
     const int n = ch * cw * 3;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int c = i % 3, p = i / 3, y = p / cw, x = p - y * cw;
         const int py = (P.cy0 - P.fy0) * S + y, px = (P.cx0 - P.fx0) * S + x;  // inside the plane's output
-        const float v = net[((size_t)py * (P.Wt * S) + px) * 3 + c] * 255.f;
+        const float v = net[((size_t)py * (P.Wt * S) + px) * ldnet + c] * 255.f;
         const size_t o = (((size_t)P.frame * fh * S + (size_t)P.cy0 * S + y) * ((size_t)fw * S) + (size_t)P.cx0 * S + x) * 3 + c;
         if (F32OUT) {
             reinterpret_cast<float*>(out)[o] = v;

@@ -39,7 +39,10 @@ class GraphOp(ctypes.Structure):  # b2sr_graph_op
     _fields_ = [("type", ctypes.c_int32), ("nin", ctypes.c_int32), ("inp", ctypes.c_int32 * 6), ("out", ctypes.c_int32),
                 ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("k", ctypes.c_int32), ("act", ctypes.c_int32),
                 ("slope", ctypes.c_float), ("coef", ctypes.c_float * 2), ("plain", ctypes.c_int32), ("r", ctypes.c_int32),
-                ("w_off", ctypes.c_int64), ("b_off", ctypes.c_int64)]
+                ("w_off", ctypes.c_int64), ("b_off", ctypes.c_int64),
+                ("in_c", ctypes.c_int32 * 6), ("in_off", ctypes.c_int32 * 6), ("in_ld", ctypes.c_int32 * 6),
+                ("out_c", ctypes.c_int32), ("out_off", ctypes.c_int32), ("out_ld", ctypes.c_int32),
+                ("in_res", ctypes.c_int32), ("out_res", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class NetDesc(ctypes.Structure):
@@ -143,13 +146,14 @@ class Engine:
         self._h = h
 
     def _init_generic(self, graph, device):
-        """Graphs that are not SRVGGNetCompact (4x_Valar_v1): the generic CUDA-core graph engine (b2sr_create_graph)."""
+        """Graphs that are not SRVGGNetCompact (4x_Valar_v1): the generic graph engine (b2sr_create_graph)."""
         prog = ncnn_model.compile_graph(graph)
         arr = (GraphOp * len(prog.ops))()
         for a, o in zip(arr, prog.ops):
             a.type, a.nin, a.out, a.cin, a.cout, a.k, a.act = o["type"], o["nin"], o["out"], o["cin"], o["cout"], o["k"], o["act"]
             for j, v in enumerate(o["in"]):
-                a.inp[j] = v
+                a.inp[j], a.in_c[j], a.in_off[j], a.in_ld[j] = v, o["in_c"][j], o["in_off"][j], o["in_ld"][j]
+            a.out_c, a.out_off, a.out_ld, a.in_res, a.out_res = o["out_c"], o["out_off"], o["out_ld"], o["in_res"], o["out_res"]
             a.slope, a.plain, a.r, a.w_off, a.b_off = o["slope"], o["plain"], o["r"], o["w_off"], o["b_off"]
             a.coef[0], a.coef[1] = o["coef"]
         w = np.ascontiguousarray(prog.weights, np.float32)

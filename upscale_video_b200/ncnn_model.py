@@ -298,15 +298,19 @@ class GraphProgram:
     output_blob: str = "output"
 
 
-def compile_graph(graph: Graph, input_blob: str = "input", output_blob: str = "output") -> GraphProgram:
+def compile_graph(graph: Graph, input_blob: str = "input", output_blob: str = "output", views: bool = True) -> GraphProgram:
     """Lower an ncnn graph to the op list of ``b2sr_create_graph`` (include/b2sr.h).
 
-    Split layers become aliases; every value gets an activation slot, and slots are recycled after a value's last
-    use (the Valar graph has 2127 blobs but never more than a dozen alive).  Layer semantics follow the ncnn layer
-    definitions the reference's model files rely on (reference models/4x_Valar_v1.param:1-1208): Convolution keys
-    0=out-ch 1=kernel 4=pad 5=bias 6=weight-count 9=activation (2 = LeakyReLU, slope in -23310), PReLU 0=slopes,
-    PixelShuffle 0=factor (mode 0), Interp 0=1 nearest with scales 1/2, BinaryOp 0=0 add, Eltwise 0=1 sum with
-    coefficients -23301, Concat 0=0 channel axis."""
+    Three passes: (1) layers -> nodes with inferred shapes (Split layers become aliases); (2) Concat families: when
+    values are only ever concatenated as prefixes of one list ([x], [x,x1], [x,x1,x2] ... -- every dense block of the
+    Valar RRDB graph), the producers write straight into channel slices of one wide slot and the Concat layers
+    disappear, their outputs being strided views (``views=False`` keeps them as copies); (3) slot assignment with
+    recycling after a value's last use (the Valar graph has 2127 blobs but never more than a dozen alive).
+
+    Layer semantics follow the ncnn layer definitions the reference's model files rely on (reference
+    models/4x_Valar_v1.param:1-1208): Convolution keys 0=out-ch 1=kernel 4=pad 5=bias 6=weight-count 9=activation
+    (2 = LeakyReLU, slope in -23310), PReLU 0=slopes, PixelShuffle 0=factor (mode 0), Interp 0=1 nearest with scales
+    1/2, BinaryOp 0=0 add, Eltwise 0=1 sum with coefficients -23301, Concat 0=0 channel axis."""
     alias = {}
 
     def val(name):  # resolve Split aliases
@@ -314,29 +318,11 @@ def compile_graph(graph: Graph, input_blob: str = "input", output_blob: str = "o
             name = alias[name]
         return name
 
-    layers = [l for l in graph.layers]
-    # last use of every value
-    last_use = {}
-    for i, l in enumerate(layers):
+    for l in graph.layers:
         if l.type == "Split":
             for t in l.tops:
                 alias[t] = l.bottoms[0]
-    for i, l in enumerate(layers):
-        if l.type in ("Input", "Split"):
-            continue
-        for b in l.bottoms:
-            last_use[val(b)] = i
-    last_use[val(output_blob)] = len(layers) + 1
-    slot_of, free, n_slots = {}, [], 0
-    chans, res = {}, {}
-    ops, wparts, woff = [], [], 0
-
-    def new_slot():
-        nonlocal n_slots
-        if free:
-            return free.pop()
-        n_slots += 1
-        return n_slots - 1
+    wparts, woff = [], 0
 
     def push_w(arr):
         nonlocal woff
@@ -346,24 +332,25 @@ def compile_graph(graph: Graph, input_blob: str = "input", output_blob: str = "o
         woff += a.size
         return off
 
-    in_slot = None
-    for i, l in enumerate(layers):
+    # ---- pass 1: nodes and shapes -------------------------------------------------------------------------
+    chans, res = {}, {}
+    nodes = []
+    seen_input = False
+    for l in graph.layers:
         t = l.type
         if t == "Input":
             if l.tops != [input_blob]:
                 raise ValueError("graph input blob is %r, expected %r" % (l.tops, input_blob))
-            in_slot = new_slot()
-            slot_of[input_blob] = in_slot
             chans[input_blob], res[input_blob] = 3, 1
+            seen_input = True
             continue
         if t == "Split":
             continue
         ins = [val(b) for b in l.bottoms]
         for b in ins:
-            if b not in slot_of:
+            if b not in chans:
                 raise ValueError("layer %s reads undefined blob %s" % (l.name, b))
-        out_name = l.tops[0]
-        op = {"type": 0, "nin": len(ins), "in": [slot_of[b] for b in ins], "cin": 0, "cout": 0, "k": 0, "act": 0, "slope": 0.0,
+        op = {"type": 0, "nin": len(ins), "cin": 0, "cout": 0, "k": 0, "act": 0, "slope": 0.0,
               "coef": [1.0, 1.0], "plain": 0, "r": 1, "w_off": -1, "b_off": -1}
         c_out, r_out = chans[ins[0]], res[ins[0]]
         in_place_ok = False
@@ -375,6 +362,8 @@ def compile_graph(graph: Graph, input_blob: str = "input", output_blob: str = "o
             act = int(l.p(9, 0))
             if act not in (0, 2):
                 raise ValueError("unsupported convolution activation %d in %s" % (act, l.name))
+            if int(w.shape[1]) != c_out:
+                raise ValueError("convolution %s expects %d channels, gets %d" % (l.name, w.shape[1], c_out))
             op.update(type=OP_CONV, cin=int(w.shape[1]), cout=int(w.shape[0]), k=k, act=act,
                       slope=float(l.p(10, [0.0])[0]) if act == 2 else 0.0, w_off=push_w(w),
                       b_off=push_w(l.weights["bias"]) if l.p(5, 0) else -1)
@@ -412,22 +401,99 @@ def compile_graph(graph: Graph, input_blob: str = "input", output_blob: str = "o
             c_out = sum(chans[b] for b in ins)
         else:
             raise ValueError("unsupported layer type %s" % t)
-        # release inputs that die here; an elementwise op may then reuse one of them in place, others must not
-        dying = [b for b in set(ins) if last_use.get(b) == i]
-        if not in_place_ok:
-            out_slot = new_slot()
-            for b in dying:
-                free.append(slot_of[b])
-        else:
-            for b in dying:
-                free.append(slot_of[b])
-            out_slot = new_slot()
-        op["out"] = out_slot
-        slot_of[out_name] = out_slot
+        out_name = l.tops[0]
         chans[out_name], res[out_name] = c_out, r_out
-        ops.append(op)
+        nodes.append({"op": op, "ins": ins, "out": out_name, "in_place_ok": in_place_ok, "view": False})
     out_v = val(output_blob)
-    if out_v not in slot_of:
-        raise ValueError("graph has no blob %r" % output_blob)
+    if not seen_input or out_v not in chans:
+        raise ValueError("graph has no blob %r" % (output_blob if seen_input else input_blob))
+
+    # ---- pass 2: concat families ----------------------------------------------------------------------------
+    member = {}    # value -> (family, channel offset)
+    fam_ld = []    # family -> channels of the wide slot
+    if views:
+        concats = [n for n in nodes if n["op"]["type"] == OP_CONCAT]
+        concat_outs = {n["out"] for n in concats}
+        taken = set()
+        for big in sorted(concats, key=lambda n: -len(n["ins"])):
+            if id(big) in taken:
+                continue
+            vals = big["ins"]
+            if (len(set(vals)) != len(vals) or any(v in member or v in concat_outs or v == input_blob for v in vals)
+                    or big["out"] == out_v):
+                continue
+            fam = len(fam_ld)
+            off = 0
+            for v in vals:
+                member[v] = (fam, off)
+                off += chans[v]
+            fam_ld.append(off)
+            for n in concats:
+                if id(n) not in taken and n["out"] != out_v and n["ins"] == vals[:len(n["ins"])]:
+                    taken.add(id(n))
+                    n["view"] = True
+                    n["family"] = fam
+
+    # ---- pass 3: slots ------------------------------------------------------------------------------------------
+    live = [n for n in nodes if not n["view"]]
+    view_of = {n["out"]: n["family"] for n in nodes if n["view"]}
+    last_use = {}
+    for i, n in enumerate(live):
+        for b in n["ins"]:
+            last_use[b] = i
+    last_use[out_v] = len(live) + 1
+    fam_last = [-1] * len(fam_ld)
+    for v, (f, _) in member.items():
+        fam_last[f] = max(fam_last[f], last_use.get(v, -1))
+    for v, f in view_of.items():
+        fam_last[f] = max(fam_last[f], last_use.get(v, -1))
+    free, n_slots = [], 0
+
+    def new_slot():
+        nonlocal n_slots
+        if free:
+            return free.pop()
+        n_slots += 1
+        return n_slots - 1
+
+    in_slot = new_slot()
+    loc = {input_blob: (in_slot, 0, 3, 0)}  # value -> (slot, channel offset, channels, pixel stride; 0 = dense)
+    fam_slot = [None] * len(fam_ld)
+    ops = []
+    for i, n in enumerate(live):
+        op, ins = n["op"], n["ins"]
+        for b in ins:
+            if b in view_of and b not in loc:
+                f = view_of[b]
+                loc[b] = (fam_slot[f], 0, chans[b], fam_ld[f])
+        il = [loc[b] for b in ins]
+        dying = [b for b in dict.fromkeys(ins) if last_use.get(b) == i and b not in member and b not in view_of]
+        out_name = n["out"]
+        if out_name in member:
+            f, off = member[out_name]
+            if fam_slot[f] is None:
+                fam_slot[f] = new_slot()  # before the dying inputs are released: a strided output never aliases an input
+            oloc = (fam_slot[f], off, chans[out_name], fam_ld[f])
+            for b in dying:
+                free.append(loc[b][0])
+        elif n["in_place_ok"]:
+            for b in dying:  # dense, same shape: the elementwise op may overwrite it
+                free.append(loc[b][0])
+            oloc = (new_slot(), 0, chans[out_name], 0)
+        else:
+            oloc = (new_slot(), 0, chans[out_name], 0)
+            for b in dying:
+                free.append(loc[b][0])
+        for f in range(len(fam_ld)):
+            if fam_last[f] == i and fam_slot[f] is not None:
+                free.append(fam_slot[f])
+        loc[out_name] = oloc
+        op["in"] = [l[0] for l in il]
+        op["in_off"] = [l[1] for l in il]
+        op["in_c"] = [l[2] for l in il]
+        op["in_ld"] = [l[3] for l in il]
+        op["out"], op["out_off"], op["out_c"], op["out_ld"] = oloc
+        op["in_res"], op["out_res"] = int(res[ins[0]]), int(res[out_name])
+        ops.append(op)
     weights = np.concatenate(wparts) if wparts else np.zeros(1, np.float32)
-    return GraphProgram(ops, n_slots, in_slot, slot_of[out_v], int(res[out_v]), weights, input_blob, output_blob)
+    return GraphProgram(ops, n_slots, in_slot, loc[out_v][0], int(res[out_v]), weights, input_blob, output_blob)

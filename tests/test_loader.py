@@ -7,7 +7,7 @@ import struct
 import numpy as np
 import pytest
 
-from conftest import HURR
+from conftest import HURR, golden
 from oracle import oracle
 from upscale_video_b200 import ncnn_model as M
 
@@ -188,3 +188,38 @@ def test_compiled_program_equals_graph_interpreter(model_dir, stem):
             assert n_concat == (0 if views else 4 * 3 * 23)
         got = _run_program_numpy(prog, x)
         assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+def test_fused_program_equals_graph_interpreter(model_dir):
+    """compile_fused (adds folded into the convolution that feeds them, ops scheduled where their last add stood,
+    fp16/fp32 buffer recycling, channel-slice views instead of Concat) must not change the function: the float64
+    interpretation of the fused op list equals the oracle's graph interpreter bit for bit; with the device's storage
+    types (fp16 activations, fp32 residual trunk) it stays within 1 LSB of the golden output."""
+    import fused_emulator as FE
+    stem = "4x_Valar_v1"
+    if not os.path.exists(os.path.join(model_dir, stem + ".b2sr")):
+        pytest.skip("model not packaged")
+    g = M.load_model(model_dir, stem)
+    prog = M.compile_fused(g)
+    assert prog is not None and prog.scale == 4 and len(prog.bufs) <= 16
+    convs = [o for o in prog.ops if o["type"] == M.FOP_CONV]
+    assert len(convs) == len(g.convs()) and sum(o["type"] == M.FOP_NEAREST for o in prog.ops) == 2
+    assert sum(o["nres"] for o in convs) == 23 * 3 * 3 + 23 + 1  # every BinaryOp / Eltwise of the graph is folded
+    assert prog.ops[-1]["final"] == 1 and sum(o["final"] for o in prog.ops) == 1
+    for o in convs:  # what the tcgen05 kernel needs from a view: 16-byte aligned channel offsets, <= 3 groups of 64
+        assert o["in_off"] % 8 == 0 and o["out16_off"] % 8 == 0 and o["cin"] <= 192
+        assert o["out16_buf"] != o["in_buf"] or o["out16_off"] >= o["in_off"] + o["cin"]  # never overwrites what it reads
+        assert all(rb not in (o["out16_buf"], o["out32_buf"]) or prog.bufs[rb]["channels"] > o["cout"] for rb in o["res_buf"][:o["nres"]])
+    x = np.random.default_rng(1).random((12, 14, 3))
+    ref = oracle.run_graph(oracle.read_model(model_dir, stem), x, "f64")
+    assert np.array_equal(FE.run_fused(prog, x, exact=True), ref)
+    gold = golden("valar4x_crop")
+    dev = FE.run_fused(prog, gold["x"], exact=False)
+    u8 = oracle.saturate_u8(dev.astype(np.float32) * np.float32(255))
+    d = np.abs(u8.astype(int) - gold["y"].astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.03
+
+
+def test_compact_graphs_do_not_lower_to_fused(model_dir):
+    """PReLU / PixelShuffle graphs are served by the Compact kernels; compile_fused must decline them."""
+    assert M.compile_fused(M.load_model(model_dir, "2x_Compact_Pretrain")) is None

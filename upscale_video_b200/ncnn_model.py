@@ -298,19 +298,9 @@ class GraphProgram:
     output_blob: str = "output"
 
 
-def compile_graph(graph: Graph, input_blob: str = "input", output_blob: str = "output", views: bool = True) -> GraphProgram:
-    """Lower an ncnn graph to the op list of ``b2sr_create_graph`` (include/b2sr.h).
-
-    Three passes: (1) layers -> nodes with inferred shapes (Split layers become aliases); (2) Concat families: when
-    values are only ever concatenated as prefixes of one list ([x], [x,x1], [x,x1,x2] ... -- every dense block of the
-    Valar RRDB graph), the producers write straight into channel slices of one wide slot and the Concat layers
-    disappear, their outputs being strided views (``views=False`` keeps them as copies); (3) slot assignment with
-    recycling after a value's last use (the Valar graph has 2127 blobs but never more than a dozen alive).
-
-    Layer semantics follow the ncnn layer definitions the reference's model files rely on (reference
-    models/4x_Valar_v1.param:1-1208): Convolution keys 0=out-ch 1=kernel 4=pad 5=bias 6=weight-count 9=activation
-    (2 = LeakyReLU, slope in -23310), PReLU 0=slopes, PixelShuffle 0=factor (mode 0), Interp 0=1 nearest with scales
-    1/2, BinaryOp 0=0 add, Eltwise 0=1 sum with coefficients -23301, Concat 0=0 channel axis."""
+def _analyse_graph(graph: Graph, input_blob: str, output_blob: str, views: bool):
+    """Passes 1 and 2 of :func:`compile_graph` (shared with :func:`compile_fused`): nodes with inferred shapes,
+    Split aliases resolved, concat families found.  Returns a dict of the tables the later passes use."""
     alias = {}
 
     def val(name):  # resolve Split aliases
@@ -434,6 +424,26 @@ def compile_graph(graph: Graph, input_blob: str = "input", output_blob: str = "o
                     n["view"] = True
                     n["family"] = fam
 
+    return {"nodes": nodes, "chans": chans, "res": res, "out_v": out_v, "member": member, "fam_ld": fam_ld,
+            "weights": np.concatenate(wparts) if wparts else np.zeros(1, np.float32)}
+
+
+def compile_graph(graph: Graph, input_blob: str = "input", output_blob: str = "output", views: bool = True) -> GraphProgram:
+    """Lower an ncnn graph to the op list of ``b2sr_create_graph`` (include/b2sr.h).
+
+    Three passes: (1) layers -> nodes with inferred shapes (Split layers become aliases); (2) Concat families: when
+    values are only ever concatenated as prefixes of one list ([x], [x,x1], [x,x1,x2] ... -- every dense block of the
+    Valar RRDB graph), the producers write straight into channel slices of one wide slot and the Concat layers
+    disappear, their outputs being strided views (``views=False`` keeps them as copies); (3) slot assignment with
+    recycling after a value's last use (the Valar graph has 2127 blobs but never more than a dozen alive).
+
+    Layer semantics follow the ncnn layer definitions the reference's model files rely on (reference
+    models/4x_Valar_v1.param:1-1208): Convolution keys 0=out-ch 1=kernel 4=pad 5=bias 6=weight-count 9=activation
+    (2 = LeakyReLU, slope in -23310), PReLU 0=slopes, PixelShuffle 0=factor (mode 0), Interp 0=1 nearest with scales
+    1/2, BinaryOp 0=0 add, Eltwise 0=1 sum with coefficients -23301, Concat 0=0 channel axis."""
+    A = _analyse_graph(graph, input_blob, output_blob, views)
+    nodes, chans, res, out_v, member, fam_ld = A["nodes"], A["chans"], A["res"], A["out_v"], A["member"], A["fam_ld"]
+
     # ---- pass 3: slots ------------------------------------------------------------------------------------------
     live = [n for n in nodes if not n["view"]]
     view_of = {n["out"]: n["family"] for n in nodes if n["view"]}
@@ -495,5 +505,184 @@ def compile_graph(graph: Graph, input_blob: str = "input", output_blob: str = "o
         op["out"], op["out_off"], op["out_c"], op["out_ld"] = oloc
         op["in_res"], op["out_res"] = int(res[ins[0]]), int(res[out_name])
         ops.append(op)
-    weights = np.concatenate(wparts) if wparts else np.zeros(1, np.float32)
-    return GraphProgram(ops, n_slots, in_slot, loc[out_v][0], int(res[out_v]), weights, input_blob, output_blob)
+    return GraphProgram(ops, n_slots, in_slot, loc[out_v][0], int(res[out_v]), A["weights"], input_blob, output_blob)
+
+
+# ----------------------------------------------------------------------------------------------
+# Fused lowering for the tcgen05 graph kernels (b2sr_create_fused): every convolution carries its bias, activation
+# and the element-wise adds that follow it; activations live in fp16 (what the next convolution reads through TMA)
+# and, where a later residual add needs the unrounded value, also in fp32.
+# ----------------------------------------------------------------------------------------------
+FOP_CONV, FOP_NEAREST = 1, 2
+F16, F32 = 2, 4
+
+
+@dataclass
+class FusedProgram:
+    ops: list      # dicts with the fields of b2sr_fused_op
+    bufs: list     # dicts with the fields of b2sr_fused_buf: channels (pixel stride), dtype (F16 / F32), res
+    scale: int
+    weights: np.ndarray
+    input_blob: str = "input"
+    output_blob: str = "output"
+
+
+def compile_fused(graph: Graph, input_blob: str = "input", output_blob: str = "output") -> FusedProgram | None:
+    """Lower an ncnn graph to the op list of ``b2sr_create_fused`` (include/b2sr.h), or return None when the graph has
+    a layer that does not fit the fused form (the caller then uses :func:`compile_graph`).
+
+    A fused op is ``v = act(conv(x) + bias)`` followed by up to two residual terms ``v = v * cv + r * cr`` -- the
+    BinaryOp / Eltwise layers that consume the convolution's value and nothing else does (reference
+    models/4x_Valar_v1.param:11-12 ``Conv_4, Conv_6, Add_7``; :22 ``Add_19``; :57-58 ``Add_57, Add_60``).  The op is
+    scheduled where its last add stood.  Concat layers must all be views of a wide buffer (the dense-block pattern
+    :func:`_analyse_graph` recognises): a convolution then reads channels [0, cin) of that buffer and producers
+    write their channel slice.  Values read by a convolution or an Interp are stored in fp16, values read by a
+    residual add in fp32 (both when both happen), which is the arithmetic of the generic engine (fp32 storage,
+    fp16 rounding when a convolution stages its input) without the fp32 round trips."""
+    A = _analyse_graph(graph, input_blob, output_blob, True)
+    nodes, chans, res, out_v, member, fam_ld = A["nodes"], A["chans"], A["res"], A["out_v"], A["member"], A["fam_ld"]
+    consumers = {}
+    for i, n in enumerate(nodes):
+        for b in n["ins"]:
+            consumers.setdefault(b, []).append(i)
+    view_fam = {n["out"]: n["family"] for n in nodes if n["view"]}
+    absorbed, sched = set(), []
+    for i, n in enumerate(nodes):
+        t = n["op"]["type"]
+        if i in absorbed:
+            continue
+        if t == OP_CONV:
+            v, resid, pos = n["out"], [], i
+            while v != out_v and len(resid) < 2:
+                cs = consumers.get(v, [])
+                if len(cs) != 1 or cs[0] in absorbed:
+                    break
+                a = nodes[cs[0]]
+                if a["op"]["type"] != OP_ADD or a["ins"][0] == a["ins"][1]:
+                    break
+                oi = 1 if a["ins"][0] == v else 0
+                other = a["ins"][oi]
+                if other == input_blob or other in view_fam:
+                    break
+                cv, cr = (1.0, 1.0) if a["op"]["plain"] else (a["op"]["coef"][1 - oi], a["op"]["coef"][oi])
+                resid.append((other, float(cv), float(cr)))
+                absorbed.add(cs[0])
+                pos, v = cs[0], a["out"]
+            sched.append((pos, {"kind": FOP_CONV, "node": n, "resid": resid, "out": v}))
+        elif t == OP_NEAREST:
+            sched.append((i, {"kind": FOP_NEAREST, "node": n, "resid": [], "out": n["out"]}))
+        elif t == OP_CONCAT:
+            if not n["view"]:
+                return None
+        else:
+            return None  # PReLU / PixelShuffle / free-standing adds: not an RRDB-style graph
+    sched.sort(key=lambda e: e[0])
+    sched = [e[1] for e in sched]
+    if not sched or sched[-1]["out"] != out_v or sched[-1]["kind"] != FOP_CONV or chans[out_v] != 3:
+        return None
+    made_by = {s["out"]: s for s in sched}
+
+    # ---- which stored form(s) every value needs ------------------------------------------------------------
+    need16, need32 = set(), set()
+    for s in sched:
+        src = s["node"]["ins"][0]
+        if src == input_blob:
+            if s["kind"] != FOP_CONV or s["node"]["op"]["cin"] != 3:
+                return None
+        elif src in view_fam:
+            if s["kind"] != FOP_CONV:
+                return None
+        else:
+            if src not in made_by:
+                return None
+            need16.add(src)
+        for other, _, _ in s["resid"]:
+            if other not in made_by:
+                return None
+            (need32 if made_by[other]["kind"] == FOP_CONV else need16).add(other)
+    for v in member:
+        if v not in made_by:
+            return None
+        need16.add(v)
+    if any(v in view_fam or v == input_blob for v in consumers if v not in made_by and v not in view_fam and v != input_blob):
+        return None
+
+    # ---- storages and their lifetimes over the schedule --------------------------------------------------------
+    # storage id: ("fam", f) | ("h", value) | ("f", value);  key = (dtype, pixel stride in channels, resolution)
+    def storages_written(s):
+        v, out = s["out"], []
+        if v in need16:
+            out.append(("fam", member[v][0]) if v in member else ("h", v))
+        if v in need32:
+            out.append(("f", v))
+        return out
+
+    def storages_read(s):
+        src, out = s["node"]["ins"][0], []
+        if src in view_fam:
+            out.append(("fam", view_fam[src]))
+        elif src != input_blob:
+            out.append(("fam", member[src][0]) if src in member else ("h", src))
+        for other, _, _ in s["resid"]:
+            if other in need32:
+                out.append(("f", other))
+            else:
+                out.append(("fam", member[other][0]) if other in member else ("h", other))
+        return out
+
+    def key_of(st):
+        if st[0] == "fam":
+            v0 = next(v for v, (f, _) in member.items() if f == st[1])
+            return (F16, fam_ld[st[1]], res[v0])
+        return (F16 if st[0] == "h" else F32, chans[st[1]], res[st[1]])
+
+    first, last = {}, {}
+    for j, s in enumerate(sched):
+        for st in storages_written(s):
+            first.setdefault(st, j)
+            last[st] = max(last.get(st, j), j)
+        for st in storages_read(s):
+            if st not in first:
+                return None  # read before written
+            last[st] = j
+    bufs, free, where = [], {}, {}
+    ops = []
+    for j, s in enumerate(sched):
+        for st in storages_written(s):  # outputs are placed before this op's dying inputs are released: never in place
+            if st not in where:
+                k = key_of(st)
+                if free.get(k):
+                    where[st] = free[k].pop()
+                else:
+                    bufs.append({"channels": k[1], "dtype": k[0], "res": k[2]})
+                    where[st] = len(bufs) - 1
+        n, v = s["node"], s["out"]
+        o = n["op"]
+        src = n["ins"][0]
+        op = {"type": s["kind"], "res": int(res[v]), "in_buf": -1, "in_off": 0, "cin": int(chans[src]), "k": int(o["k"]),
+              "cout": int(chans[v]), "act": int(o["act"]), "slope": float(o["slope"]), "w_off": int(o["w_off"]), "b_off": int(o["b_off"]),
+              "nres": len(s["resid"]), "res_buf": [-1, -1], "res_off": [0, 0], "coef_v": [1.0, 1.0], "coef_r": [0.0, 0.0],
+              "out16_buf": -1, "out16_off": 0, "out32_buf": -1, "out32_off": 0, "r": int(o["r"]), "final": int(v == out_v)}
+        if src in view_fam:
+            op["in_buf"] = where[("fam", view_fam[src])]
+        elif src != input_blob:
+            op["in_buf"], op["in_off"] = (where[("fam", member[src][0])], member[src][1]) if src in member else (where[("h", src)], 0)
+        for q, (other, cv, cr) in enumerate(s["resid"]):
+            if other in need32:
+                op["res_buf"][q] = where[("f", other)]
+            elif other in member:
+                op["res_buf"][q], op["res_off"][q] = where[("fam", member[other][0])], member[other][1]
+            else:
+                op["res_buf"][q] = where[("h", other)]
+            op["coef_v"][q], op["coef_r"][q] = float(np.float32(cv)), float(np.float32(cr))
+        if v in need16:
+            op["out16_buf"], op["out16_off"] = (where[("fam", member[v][0])], member[v][1]) if v in member else (where[("h", v)], 0)
+        if v in need32:
+            op["out32_buf"] = where[("f", v)]
+        if not op["final"] and op["out16_buf"] < 0 and op["out32_buf"] < 0:
+            return None  # dead value
+        ops.append(op)
+        for st, lj in last.items():
+            if lj == j and st in where and first[st] <= j:
+                free.setdefault(key_of(st), []).append(where[st])
+    return FusedProgram(ops, bufs, int(res[out_v]), A["weights"], input_blob, output_blob)

@@ -150,6 +150,47 @@ int b2sr_create_graph(b2sr_ctx **out, int device, const b2sr_graph_op *ops, int 
                       int scale, const void *weights, size_t nbytes);
 
 /*
+ * Fused tcgen05 graph engine (B2SR_FAMILY_FUSED): the same ncnn calls as b2sr_create_graph, for graphs that lower to
+ * "convolution + bias + LeakyReLU + up to two residual terms" operations over channel-last buffers -- the RRDB network
+ * models/4x_Valar_v1.param:1-1208, whose Concat / Split / BinaryOp / Eltwise layers all disappear into views and
+ * epilogues.  Every convolution runs on the tcgen05 kernel of csrc/tc_gconv.cuh (fp16 operands, fp32 accumulate):
+ *   v = act(conv_k(in_buf[:, in_off : in_off + cin]) + bias);   v = v * coef_v[i] + res_i * coef_r[i]  (i < nres)
+ *   out16_buf[:, out16_off : +cout] = fp16(v)   and / or   out32_buf[:, out32_off : +cout] = v
+ * Buffers are numbered; `channels` is the pixel stride of a buffer (a 192-channel buffer holds a whole dense block,
+ * convolutions read prefixes of it and write 32-channel slices), `dtype` 2 = fp16 (read by convolutions and NEAREST),
+ * 4 = fp32 (read as residual), `res` the resolution factor relative to the network input.  in_buf = -1 is the input
+ * image (cin = 3).  The op with final = 1 (cout = 3) produces the network output: * 255, crop to the tile core,
+ * round-half-even + saturate (u8) or unrounded (f32), like b2sr_run_u8 / b2sr_run_f32 of the other families.
+ */
+#define B2SR_FAMILY_FUSED 3
+#define B2SR_FOP_CONV 1    /* k = 1 or 3, pad k/2, cin <= 192 (multiple of 16, or 3 for the input image), cout 3 / 32 / 64 */
+#define B2SR_FOP_NEAREST 2 /* out16 (res) = nearest-neighbour x r of in (res / r) */
+typedef struct b2sr_fused_buf {
+    int32_t channels, dtype, res, reserved;
+} b2sr_fused_buf;
+typedef struct b2sr_fused_op {
+    int32_t type;
+    int32_t res; /* resolution factor of the pixels this op writes */
+    int32_t in_buf, in_off, cin;
+    int32_t k, cout, act;
+    float slope;
+    int32_t nres;
+    int64_t w_off, b_off; /* offsets in floats into the weight blob (OIHW weights, bias); b_off = -1: no bias */
+    int32_t res_buf[2], res_off[2];
+    float coef_v[2], coef_r[2];
+    int32_t out16_buf, out16_off; /* -1 = not stored in this form */
+    int32_t out32_buf, out32_off;
+    int32_t r;     /* NEAREST: integer factor */
+    int32_t final; /* 1 = network output */
+    int32_t reserved[4];
+} b2sr_fused_op;
+int b2sr_create_fused(b2sr_ctx **out, int device, const b2sr_fused_op *ops, int n_ops, const b2sr_fused_buf *bufs, int n_bufs,
+                      int scale, const void *weights, size_t nbytes);
+/* Bring-up aid (fused family): run ops [0, upto] on one untiled u8 image and return buffer `buf` (all its channels,
+ * converted to float) as (h * res) x (w * res) x channels floats on the host. */
+int b2sr_debug_fused(b2sr_ctx *ctx, const uint8_t *in, int h, int w, int upto, int buf, float *out);
+
+/*
  * One frame, u8 in -> u8 out ((h*scale) x (w*scale) x 3, round-half-even + saturate like cv2.imwrite).
  * tile/halo = 960/10 reproduces the reference's tiling (zero padding at tile borders, upscale_processing.py
  * :409-434); tile = 0 runs the frame as one piece (apply_model).  Strides are in bytes.  Synchronous.

@@ -361,23 +361,52 @@ def test_raw_stream_matches_worker_functions(engines, model_dir, tmp_path):
     assert np.array_equal(np.frombuffer(out.getvalue(), np.uint8).reshape(3, 140, 2000, 3), np.stack([comp.run_u8(f) for f in frames]))
 
 
-def test_valar_rrdb_generic_graph_engine(E, model_dir, oracle_models):
-    """4x_Valar_v1 (RRDB, reference models/4x_Valar_v1.param) through the generic CUDA-core graph engine
-    (b2sr_create_graph): golden crop, a two-tile frame against the oracle, and batch == single frame."""
+def test_valar_rrdb_fused_tcgen05(E, model_dir, oracle_models):
+    """4x_Valar_v1 (RRDB, reference models/4x_Valar_v1.param) on the fused tcgen05 graph kernels (b2sr_create_fused):
+    golden crop, a two-tile frame against the oracle (seam at x = 960), band boundaries at 128 columns with a ragged
+    last band, the float canvas, determinism, and agreement with the generic engine's fp32 CUDA-core kernels."""
+    from upscale_video_b200 import ncnn_model
     if not os.path.exists(os.path.join(model_dir, "4x_Valar_v1.b2sr")):
         pytest.skip("4x_Valar_v1 not packaged")
     eng = E.Engine.from_files(model_dir, "4x_Valar_v1", 0)
+    assert eng.fused and not eng.generic and eng.scale == 4
+    g = golden("valar4x_crop")
+    # 420 convolutions deep and without an input residual: fp16 activation storage (fp32 trunk, fp32 accumulation) puts a
+    # few % of the u8 values on the other side of a rounding boundary (CPU emulation of the same storage: 1.3 %); never > 1 LSB
+    out = eng.run_u8(g["x"])
+    # 420 convolutions (1 head, 23 x 3 x (5 + the 1x1 shortcut), 1 trunk, 4 tail); every 192 -> 64 one is two launches
+    assert eng.stat(E.STAT_TC_LAUNCHES) == 420 + 23 * 3 and eng.stat(E.STAT_HMMA_LAUNCHES) == 0
+    assert_parity(out, g["y"], "valar golden (tcgen05)", max_mismatch=0.05)
+    assert np.array_equal(out, eng.run_u8(g["x"]))
+    img = natural(20, 980, seed=13)  # seam at x = 960
+    models = oracle_models("4x_Valar_v1")
+    ref = oracle.upscale_image_array(models, img, 4, "f32")
+    out = eng.run_u8(img)
+    assert_parity(out, ref, "valar 20x980 (tcgen05)", max_mismatch=0.05)
+    canvas = eng.run_f32(img)
+    assert np.array_equal(oracle.saturate_u8(canvas), out)
+    img = natural(37, 300, seed=14)  # three bands, the last one 44 columns wide; CTA ranges cut inside bands
+    assert_parity(eng.run_u8(img), oracle.upscale_image_array(models, img, 4, "f32"), "valar 37x300 (tcgen05)", max_mismatch=0.05)
+    gen = E.Engine(ncnn_model.load_model(model_dir, "4x_Valar_v1"), 0, generic=True)
+    gen.set_option(E.OPT_IMPL, E.IMPL_SIMPLE)
+    d = np.abs(eng.run_u8(img).astype(int) - gen.run_u8(img).astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.05
+    gen.close()
+    eng.close()
+
+
+def test_valar_rrdb_generic_graph_engine(E, model_dir, oracle_models):
+    """4x_Valar_v1 through the generic op-by-op graph engine (b2sr_create_graph; the cross-check implementation since
+    the fused tcgen05 engine exists): golden crop on warp-level MMA and on fp32 CUDA cores."""
+    from upscale_video_b200 import ncnn_model
+    if not os.path.exists(os.path.join(model_dir, "4x_Valar_v1.b2sr")):
+        pytest.skip("4x_Valar_v1 not packaged")
+    eng = E.Engine(ncnn_model.load_model(model_dir, "4x_Valar_v1"), 0, generic=True)
     assert eng.generic and eng.scale == 4
     g = golden("valar4x_crop")
-    # default: RRDB convolutions on warp-level MMA with fp16 operands.  420 convolutions deep and without an input
-    # residual, ~5 % of the u8 values land on the other side of a rounding boundary (same figure as a CPU emulation of
-    # fp16 activation rounding); never more than 1 LSB.
     out = eng.run_u8(g["x"])
     assert eng.stat(E.STAT_TC_LAUNCHES) == 0 and eng.stat(E.STAT_HMMA_LAUNCHES) >= 400
     assert_parity(out, g["y"], "valar golden (hmma)", max_mismatch=0.09)
-    img = natural(20, 980, seed=13)  # seam at x = 960
-    ref = oracle.upscale_image_array(oracle_models("4x_Valar_v1"), img, 4, "f32")
-    assert_parity(eng.run_u8(img), ref, "valar 20x980 (hmma)", max_mismatch=0.09)
     # fp32 CUDA-core kernels everywhere: essentially exact
     eng.set_option(E.OPT_IMPL, E.IMPL_SIMPLE)
     eng.reset_stats()

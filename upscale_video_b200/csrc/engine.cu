@@ -28,6 +28,7 @@
 #include "graph_exec.cuh"
 #include "simple_kernels.cuh"
 #include "tc_conv.cuh"
+#include "tc_gconv.cuh"
 
 using namespace b2sr;
 
@@ -101,9 +102,23 @@ struct Group {  // planes of identical size share one TMA tensor map per activat
     int64_t pix_base;
 };
 
+struct ResItems {  // work items of the planes scaled to resolution factor `res` (fused graph family)
+    int res = 1;
+    std::vector<TcItem> items;
+    std::vector<int> first;
+    TcItem* d_items = nullptr;
+    int* d_first = nullptr;
+    int n_cta = 0;
+    double out_px = 0;
+};
+
 struct Plan {
     int n = 0, h = 0, w = 0, tile = 0, halo = 0;
     std::vector<PlaneDev> planes;
+    std::vector<int> plane_group;  // planes[i] belongs to groups[plane_group[i]]
+    std::vector<std::unique_ptr<ResItems>> res_items;
+    CUtensorMap* d_fmaps = nullptr;  // fused family: [launch][group] input tensor maps
+    uint64_t fmaps_gen = 0;          // buffer generation the maps were encoded for
     std::vector<Group> groups;
     std::vector<TcItem> items;
     std::vector<int> item_first;  // CTA k of a launch processes items [item_first[k], item_first[k+1])
@@ -131,6 +146,11 @@ struct Plan {
     void* bound_rings = nullptr;
     int bound_rr = 0;
     ~Plan() {
+        for (auto& r : res_items) {
+            if (r->d_items) cudaFree(r->d_items);
+            if (r->d_first) cudaFree(r->d_first);
+        }
+        if (d_fmaps) cudaFree(d_fmaps);
         if (d_pitems) cudaFree(d_pitems);
         if (d_pband_first) cudaFree(d_pband_first);
         if (d_pmaps) cudaFree(d_pmaps);
@@ -158,9 +178,30 @@ struct GraphOp {  // b2sr_graph_op + device copies of its parameters
     int ld_out() const { return op.out_ld ? op.out_ld : op.out_c; }
 };
 
+struct FusedLaunch {  // one tcgen05 launch of a fused convolution (a 192 -> 64 convolution is two 192 -> 32 launches)
+    int op = 0;        // index into b2sr_ctx::fops
+    int co0 = 0;       // first output channel of this launch
+    int nco = 0;       // real output channels of this launch
+    int NOUT = 0;      // padded output channels (16 / 32 / 64)
+    int G = 0;         // channel groups of 64 in the input view
+    int cinp = 0;      // input view channels, padded to 16
+    int slots = 0;     // shared-memory ring slots
+    uint8_t* wimg = nullptr;
+    float* bias = nullptr;
+    float* slope = nullptr;
+};
+
 struct b2sr_ctx {
     int device = 0, sms = 0;
     int family = B2SR_FAMILY_COMPACT;
+    // B2SR_FAMILY_FUSED
+    std::vector<b2sr_fused_op> fops;
+    std::vector<b2sr_fused_buf> fbufs;
+    std::vector<FusedLaunch> flaunch;
+    std::vector<int> fop_first;   // launches of op i: flaunch[fop_first[i] .. fop_first[i+1])
+    std::vector<void*> fbuf_ptr;
+    std::vector<size_t> fbuf_cap;  // bytes
+    uint64_t fbuf_gen = 1;         // bumped whenever a fused buffer or in16 moves
     std::vector<GraphOp> gops;  // B2SR_FAMILY_GRAPH
     int g_slots = 0, g_in = 0, g_out = 0;
     std::vector<float*> slot_buf;
@@ -240,6 +281,11 @@ extern "C" void b2sr_destroy(b2sr_ctx* c) {
         if (g.b) cudaFree(g.b);
     }
     for (float* p : c->slot_buf)
+        if (p) cudaFree(p);
+    for (auto& L : c->flaunch)
+        for (void* p : {(void*)L.wimg, (void*)L.bias, (void*)L.slope})
+            if (p) cudaFree(p);
+    for (void* p : c->fbuf_ptr)
         if (p) cudaFree(p);
     for (void* p : {(void*)c->in16, (void*)c->ping, (void*)c->pong, (void*)c->lastf, (void*)c->d_in, (void*)c->d_out,
                     (void*)c->d_in2, (void*)c->d_out2, (void*)c->rings, (void*)c->d_dbg})
@@ -409,7 +455,7 @@ static int build_plan(b2sr_ctx* c, int n, int h, int w, int tile, int halo, Plan
     P->total_px = base;
     // planes; plane index inside its group = frame-major
     std::vector<int> fill(P->groups.size(), 0);
-    std::vector<int> plane_group;
+    std::vector<int>& plane_group = P->plane_group;
     int64_t band_rows = 0;  // one unit of tensor work = one row of one 128-column band (M = 128 whatever the band's width)
     for (int f = 0; f < n; ++f)
         for (auto& r : rects) {
@@ -508,6 +554,7 @@ static int ensure_scratch(b2sr_ctx* c, int64_t px, bool pingpong) {
         const int64_t cap = px + px / 16 + 1024;
         CUDA_TRY(cudaMalloc(&c->in16, (size_t)cap * 16 * 2));
         c->cap_px = cap;
+        c->fbuf_gen += 1;
     }
     if (pingpong && px > c->cap_pp) {
         cudaStreamSynchronize(c->stream);
@@ -1032,12 +1079,366 @@ static int run_graph(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// fused tcgen05 graph engine (B2SR_FAMILY_FUSED): RRDB-style graphs (4x_Valar_v1) on csrc/tc_gconv.cuh
+// ------------------------------------------------------------------------------------------------
+template <int NOUT, int MODE>
+static int fused_ring_fit(int G) { return TcgCfg<NOUT, MODE>::ring_fit(G); }
+
+static int fused_fit(int NOUT, bool final, int G) {
+    if (final) return fused_ring_fit<16, 1>(G);
+    return NOUT == 64 ? fused_ring_fit<64, 0>(G) : fused_ring_fit<32, 0>(G);
+}
+
+// Stacked, pre-swizzled weight image of output channels [co0, co0 + nco) of a convolution:
+// [group g][kx][(2 - ky) * NOUT + o][64 channels], rows of 128 bytes in the 128-byte swizzle pattern.
+static int upload_fused_launch(FusedLaunch& L, const b2sr_fused_op& o, const float* wb) {
+    const int K = o.k, PB = TCG_PB;
+    std::vector<uint8_t> img((size_t)L.G * 9 * L.NOUT * PB, 0);
+    for (int oc = 0; oc < L.nco; ++oc)
+        for (int ic = 0; ic < o.cin; ++ic)
+            for (int t = 0; t < K * K; ++t) {
+                const float v = wb[o.w_off + ((int64_t)(L.co0 + oc) * o.cin + ic) * K * K + t];
+                if (!fp16_exact(v))
+                    return fail(B2SR_E_UNSUPPORTED, "weight %g (conv out %d in %d tap %d) is not exactly representable in fp16", v, L.co0 + oc, ic, t);
+                const __half hv = __float2half_rn(v);
+                const int ky = K == 3 ? t / 3 : 1, kx = K == 3 ? t % 3 : 1;
+                const int g = ic / 64, c = ic % 64;
+                const uint32_t a = swizzle_addr((uint32_t)(((2 - ky) * L.NOUT + oc) * PB + c * 2), PB);
+                memcpy(&img[((size_t)g * 3 + kx) * 3 * L.NOUT * PB + a], &hv, 2);
+            }
+    std::vector<float> b(L.NOUT, 0.f), s(L.NOUT, 1.f);
+    for (int oc = 0; oc < L.nco; ++oc) {
+        if (o.b_off >= 0) b[oc] = wb[o.b_off + L.co0 + oc];
+        if (o.act == 2) s[oc] = o.slope;
+    }
+    CUDA_TRY(cudaMalloc(&L.wimg, img.size()));
+    CUDA_TRY(cudaMemcpy(L.wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&L.bias, L.NOUT * 4));
+    CUDA_TRY(cudaMemcpy(L.bias, b.data(), L.NOUT * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&L.slope, L.NOUT * 4));
+    CUDA_TRY(cudaMemcpy(L.slope, s.data(), L.NOUT * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int b2sr_create_fused(b2sr_ctx** out, int device, const b2sr_fused_op* ops, int n_ops, const b2sr_fused_buf* bufs,
+                                 int n_bufs, int scale, const void* weights, size_t nbytes) {
+    if (!out || !ops || !bufs || !weights) return fail(B2SR_E_INVALID, "b2sr_create_fused: null argument");
+    *out = nullptr;
+    if (n_ops < 1 || n_ops > 100000 || n_bufs < 1 || n_bufs > 4096) return fail(B2SR_E_INVALID, "b2sr_create_fused: bad program size");
+    if (scale != 1 && scale != 2 && scale != 4) return fail(B2SR_E_UNSUPPORTED, "scale = %d (need 1, 2 or 4)", scale);
+    for (int i = 0; i < n_bufs; ++i)
+        if ((bufs[i].dtype != 2 && bufs[i].dtype != 4) || bufs[i].channels < 8 || bufs[i].channels % 8 || bufs[i].res < 1 || bufs[i].res > 8)
+            return fail(B2SR_E_INVALID, "buffer %d: %d channels, dtype %d, res %d", i, bufs[i].channels, bufs[i].dtype, bufs[i].res);
+    const float* wb = (const float*)weights;
+    const int64_t nfl = (int64_t)(nbytes / 4);
+    // validate the program before touching the device
+    for (int i = 0; i < n_ops; ++i) {
+        const b2sr_fused_op& o = ops[i];
+        auto view_ok = [&](int b, int off, int c, int res, int dtype /*0 = any*/) {
+            return b >= 0 && b < n_bufs && off >= 0 && off % 8 == 0 && off + c <= bufs[b].channels && bufs[b].res == res &&
+                   (dtype == 0 || bufs[b].dtype == dtype);
+        };
+        if (o.res < 1 || o.res > 8) return fail(B2SR_E_INVALID, "op %d: res %d", i, o.res);
+        if (o.type == B2SR_FOP_NEAREST) {
+            if (o.r < 2 || o.r > 4 || o.res % o.r || o.cin % 8 || o.cout != o.cin || !view_ok(o.in_buf, o.in_off, o.cin, o.res / o.r, 2) ||
+                !view_ok(o.out16_buf, o.out16_off, o.cout, o.res, 2) || o.out32_buf >= 0 || o.nres || o.final)
+                return fail(B2SR_E_INVALID, "op %d: bad nearest-neighbour resize", i);
+            continue;
+        }
+        if (o.type != B2SR_FOP_CONV) return fail(B2SR_E_UNSUPPORTED, "op %d: unknown type %d", i, o.type);
+        if ((o.k != 1 && o.k != 3) || (o.act != 0 && o.act != 2) || o.nres < 0 || o.nres > 2)
+            return fail(B2SR_E_UNSUPPORTED, "op %d: convolution k=%d act=%d nres=%d", i, o.k, o.act, o.nres);
+        if (o.in_buf < 0 ? (o.cin != 3 || o.res != 1) : (o.cin % 16 || o.cin > 192 || !view_ok(o.in_buf, o.in_off, o.cin, o.res, 2)))
+            return fail(B2SR_E_UNSUPPORTED, "op %d: convolution input (buffer %d, offset %d, %d channels)", i, o.in_buf, o.in_off, o.cin);
+        if (o.final ? (o.cout != 3 || o.nres || o.out16_buf >= 0 || o.out32_buf >= 0 || i != n_ops - 1 || o.res != scale)
+                    : ((o.cout != 32 && o.cout != 64) || (o.out16_buf < 0 && o.out32_buf < 0)))
+            return fail(B2SR_E_UNSUPPORTED, "op %d: convolution output (%d channels, final %d)", i, o.cout, o.final);
+        if ((o.out16_buf >= 0 && !view_ok(o.out16_buf, o.out16_off, o.cout, o.res, 2)) ||
+            (o.out32_buf >= 0 && !view_ok(o.out32_buf, o.out32_off, o.cout, o.res, 4)))
+            return fail(B2SR_E_INVALID, "op %d: bad output view", i);
+        for (int q = 0; q < o.nres; ++q)
+            if (!view_ok(o.res_buf[q], o.res_off[q], o.cout, o.res, 0)) return fail(B2SR_E_INVALID, "op %d: bad residual %d", i, q);
+        const int64_t nw = (int64_t)o.cout * o.cin * o.k * o.k;
+        if (o.w_off < 0 || o.w_off + nw > nfl || (o.b_off >= 0 && o.b_off + o.cout > nfl)) return fail(B2SR_E_INVALID, "op %d: weights outside the blob", i);
+    }
+    if (!ops[n_ops - 1].final) return fail(B2SR_E_INVALID, "the last op must produce the network output");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B2SR_E_NODEVICE, "no CUDA device is visible (this library has no CPU path)");
+    }
+    if (device < 0 || device >= ndev) return fail(B2SR_E_NODEVICE, "device %d out of range (%d visible)", device, ndev);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(B2SR_E_NODEVICE, "device %d (%s) is sm_%d%d; this library contains sm_100a code only", device, prop.name,
+                    prop.major, prop.minor);
+    CUDA_TRY(cudaSetDevice(device));
+    TRY(get_encode());
+    b2sr_ctx* c = new b2sr_ctx();
+    c->device = device, c->sms = prop.multiProcessorCount, c->family = B2SR_FAMILY_FUSED;
+    c->desc.family = B2SR_FAMILY_FUSED, c->desc.cin = 3, c->desc.scale = scale;
+    c->CF = 64, c->NL = 16;
+    c->fops.assign(ops, ops + n_ops);
+    c->fbufs.assign(bufs, bufs + n_bufs);
+    c->fbuf_ptr.assign(n_bufs, nullptr);
+    c->fbuf_cap.assign(n_bufs, 0);
+    int rc = 0;
+    do {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking) != cudaSuccess) {
+            rc = fail(B2SR_E_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        for (int i = 0; i < n_ops && !rc; ++i) {
+            const b2sr_fused_op& o = c->fops[i];
+            c->fop_first.push_back((int)c->flaunch.size());
+            if (o.type != B2SR_FOP_CONV) continue;
+            const int cinp = o.in_buf < 0 ? 16 : o.cin, G = (cinp + 63) / 64;
+            int NOUT = o.final ? 16 : o.cout, parts = 1;
+            // the stacked weights of all groups stay resident in shared memory beside >= 4 ring slots; a wide
+            // convolution that does not fit (192 -> 64: 221 KB) is launched as two halves of 32 output channels
+            if (fused_fit(NOUT, o.final != 0, G) < 4) {
+                if (NOUT == 64 && fused_fit(32, false, G) >= 4) {
+                    NOUT = 32, parts = 2;
+                } else {
+                    rc = fail(B2SR_E_UNSUPPORTED, "op %d: %d -> %d convolution does not fit shared memory", i, o.cin, o.cout);
+                    break;
+                }
+            }
+            for (int part = 0; part < parts && !rc; ++part) {
+                FusedLaunch L;
+                L.op = i, L.co0 = part * NOUT, L.nco = std::min(o.cout - L.co0, NOUT), L.NOUT = NOUT, L.G = G, L.cinp = cinp;
+                L.slots = std::min(12, fused_fit(NOUT, o.final != 0, G));
+                rc = upload_fused_launch(L, o, wb);
+                c->flaunch.push_back(L);  // (pushed even on failure so that b2sr_destroy frees what was allocated)
+            }
+        }
+        c->fop_first.push_back((int)c->flaunch.size());
+    } while (0);
+    if (rc) {
+        std::string keep = g_err;
+        b2sr_destroy(c);
+        g_err = keep;
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+
+// work items of the plan's planes at resolution factor `res`: the linear sequence (plane, band, row) cut into one
+// contiguous, equally long range per CTA (as build_plan does for res = 1)
+static int fused_items(b2sr_ctx* c, Plan* P, int res, ResItems** out) {
+    for (auto& r : P->res_items)
+        if (r->res == res) {
+            *out = r.get();
+            return 0;
+        }
+    std::unique_ptr<ResItems> R(new ResItems());
+    R->res = res;
+    int64_t band_rows = 0;
+    for (const PlaneDev& pd : P->planes) band_rows += (int64_t)pd.Ht * res * ((pd.Wt * res + TC_BW - 1) / TC_BW);
+    const int ncta = (int)std::min<int64_t>(c->sms, band_rows);
+    R->first.assign(1, 0);
+    int64_t pos = 0;
+    int cta = 0;
+    auto cut_at = [&](int k) { return band_rows * k / ncta; };
+    for (size_t pi = 0; pi < P->planes.size(); ++pi) {
+        const PlaneDev& pd = P->planes[pi];
+        const int Ht = pd.Ht * res, Wt = pd.Wt * res;
+        for (int x0 = 0; x0 < Wt; x0 += TC_BW) {
+            int y0 = 0;
+            while (y0 < Ht) {
+                const int64_t room = cut_at(cta + 1) - pos;
+                const int rows = (int)std::min<int64_t>(Ht - y0, room);
+                TcItem it{};
+                it.map = P->plane_group[pi], it.plane = pd.gplane, it.x0 = x0, it.y0 = y0;
+                it.rows = rows, it.w = std::min(TC_BW, Wt - x0);
+                it.Ht = Ht, it.Wt = Wt, it.pix_off = pd.pix_off * res * res;
+                it.frame = pd.frame, it.fy0 = pd.fy0 * res, it.fx0 = pd.fx0 * res;
+                it.cy0 = pd.cy0 * res, it.cy1 = pd.cy1 * res, it.cx0 = pd.cx0 * res, it.cx1 = pd.cx1 * res;
+                R->items.push_back(it);
+                R->out_px += (double)it.rows * it.w;
+                y0 += rows, pos += rows;
+                if (pos == cut_at(cta + 1)) {
+                    ++cta;
+                    R->first.push_back((int)R->items.size());
+                }
+            }
+        }
+    }
+    R->n_cta = ncta;
+    CUDA_TRY(cudaMalloc(&R->d_items, R->items.size() * sizeof(TcItem)));
+    CUDA_TRY(cudaMemcpy(R->d_items, R->items.data(), R->items.size() * sizeof(TcItem), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&R->d_first, R->first.size() * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(R->d_first, R->first.data(), R->first.size() * sizeof(int), cudaMemcpyHostToDevice));
+    *out = R.get();
+    P->res_items.push_back(std::move(R));
+    return 0;
+}
+
+template <int NOUT, int MODE, bool F32OUT>
+static int launch_tcg(b2sr_ctx* c, const FusedLaunch& L, const ResItems* R, const TcgParams& p) {
+    auto kern = tcg_conv_kernel<NOUT, MODE, F32OUT>;
+    const int smem = TcgCfg<NOUT, MODE>::smem_bytes(L.G, L.slots);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<R->n_cta, TC_THREADS, smem, c->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    c->n_launch += 1, c->n_tc += 1;
+    return 0;
+}
+
+// Runs ops [0, upto] (upto < 0: the whole program) for the planes of P.
+static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, bool f32out, int upto) {
+    const int n_ops = (int)c->fops.size(), G = (int)P->groups.size();
+    if (upto < 0 || upto >= n_ops) upto = n_ops - 1;
+    TRY(ensure_scratch(c, P->total_px, false));
+    for (size_t b = 0; b < c->fbufs.size(); ++b) {
+        const b2sr_fused_buf& B = c->fbufs[b];
+        const size_t need = ((size_t)P->total_px * B.res * B.res + 1024) * B.channels * B.dtype;
+        if (need > c->fbuf_cap[b]) {
+            cudaStreamSynchronize(c->stream);
+            if (c->fbuf_ptr[b]) cudaFree(c->fbuf_ptr[b]);
+            c->fbuf_ptr[b] = nullptr, c->fbuf_cap[b] = 0;
+            CUDA_TRY(cudaMalloc(&c->fbuf_ptr[b], need));
+            c->fbuf_cap[b] = need;
+            c->fbuf_gen += 1;
+        }
+    }
+    if (P->fmaps_gen != c->fbuf_gen) {
+        // one input tensor map per (launch, plane-size group): {cin, Wt*res, Ht*res, planes} over the input view, box
+        // {64 channels, 136 pixels}: channels beyond cin and pixels outside the plane read as zeros
+        std::vector<CUtensorMap> maps(c->flaunch.size() * (size_t)G);
+        for (size_t li = 0; li < c->flaunch.size(); ++li) {
+            const FusedLaunch& L = c->flaunch[li];
+            const b2sr_fused_op& o = c->fops[L.op];
+            const int Cb = o.in_buf < 0 ? 16 : c->fbufs[o.in_buf].channels, r = o.res;
+            const __half* bufp = o.in_buf < 0 ? c->in16 : (const __half*)c->fbuf_ptr[o.in_buf];
+            for (int g = 0; g < G; ++g) {
+                const Group& gr = P->groups[g];
+                const cuuint64_t Wt = (cuuint64_t)gr.Wt * r, Ht = (cuuint64_t)gr.Ht * r;
+                cuuint64_t dims[4] = {(cuuint64_t)L.cinp, Wt, Ht, (cuuint64_t)gr.count};
+                cuuint64_t strides[3] = {(cuuint64_t)Cb * 2, Wt * Cb * 2, Ht * Wt * Cb * 2};
+                cuuint32_t box[4] = {64, (cuuint32_t)TC_PITCH, 1, 1};
+                cuuint32_t es[4] = {1, 1, 1, 1};
+                void* basep = (void*)(bufp + ((size_t)gr.pix_base * r * r * Cb + (o.in_buf < 0 ? 0 : o.in_off)));
+                CUresult e = g_encode(&maps[li * G + g], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, basep, dims, strides, box, es,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (e != CUDA_SUCCESS)
+                    return fail(B2SR_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for op %d group %d (%d ch of %d, %llux%llu)", (int)e, L.op, g,
+                                L.cinp, Cb, (unsigned long long)Ht, (unsigned long long)Wt);
+            }
+        }
+        if (!P->d_fmaps) CUDA_TRY(cudaMalloc(&P->d_fmaps, maps.size() * sizeof(CUtensorMap)));
+        CUDA_TRY(cudaMemcpyAsync(P->d_fmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        P->fmaps_gen = c->fbuf_gen;
+    }
+    {
+        dim3 grid((unsigned)std::min(2048, (P->max_plane_px + 255) / 256), (unsigned)P->planes.size());
+        TRY(prof_begin(c, 0, 0));
+        prep_kernel<<<grid, 256, 0, c->stream>>>(d_frames, P->h, P->w, P->d_planes, c->in16);
+        CUDA_TRY(cudaGetLastError());
+        TRY(prof_end(c));
+        c->n_launch += 1;
+    }
+    for (int i = 0; i <= upto; ++i) {
+        const b2sr_fused_op& o = c->fops[i];
+        if (o.type == B2SR_FOP_NEAREST) {
+            const int ri = o.res / o.r;
+            const size_t work = (size_t)P->max_plane_px * o.res * o.res * (o.cin / 8);
+            dim3 grid((unsigned)std::min<size_t>(148 * 16, (work + 255) / 256), (unsigned)P->planes.size());
+            TRY(prof_begin(c, 0, 0));
+            tcg_nearest_kernel<<<grid, 256, 0, c->stream>>>((const __half*)c->fbuf_ptr[o.in_buf] + o.in_off, c->fbufs[o.in_buf].channels,
+                                                            P->d_planes, ri, o.r, o.cin, (__half*)c->fbuf_ptr[o.out16_buf] + o.out16_off,
+                                                            c->fbufs[o.out16_buf].channels);
+            CUDA_TRY(cudaGetLastError());
+            TRY(prof_end(c));
+            c->n_launch += 1;
+            continue;
+        }
+        ResItems* R = nullptr;
+        TRY(fused_items(c, P, o.res, &R));
+        for (int li = c->fop_first[i]; li < c->fop_first[i + 1]; ++li) {
+            const FusedLaunch& L = c->flaunch[li];
+            TcgParams p{};
+            p.maps = P->d_fmaps, p.map_base = li * G;
+            p.items = R->d_items, p.item_first = R->d_first;
+            p.wimg = L.wimg, p.bias = L.bias, p.slope = L.slope;
+            p.acc_scale = o.in_buf < 0 ? (1.f / 255.f) : 1.f;
+            p.groups = L.G, p.cin = L.cinp, p.k1 = o.k == 1, p.ring_slots = L.slots;
+            p.nres = o.nres;
+            for (int q = 0; q < o.nres; ++q) {
+                const b2sr_fused_buf& B = c->fbufs[o.res_buf[q]];
+                p.res_ptr[q] = (const uint8_t*)c->fbuf_ptr[o.res_buf[q]] + (size_t)(o.res_off[q] + L.co0) * B.dtype;
+                p.res_ld[q] = B.channels, p.res_f32[q] = B.dtype == 4;
+                p.coef_v[q] = o.coef_v[q], p.coef_r[q] = o.coef_r[q];
+            }
+            if (o.out16_buf >= 0) {
+                p.out16 = (__half*)c->fbuf_ptr[o.out16_buf] + o.out16_off + L.co0;
+                p.out16_ld = c->fbufs[o.out16_buf].channels;
+            }
+            if (o.out32_buf >= 0) {
+                p.out32 = (float*)c->fbuf_ptr[o.out32_buf] + o.out32_off + L.co0;
+                p.out32_ld = c->fbufs[o.out32_buf].channels;
+            }
+            p.frames_out = d_out, p.frame_h = P->h * o.res, p.frame_w = P->w * o.res;
+            TRY(prof_begin(c, 1, R->out_px));
+            int rc;
+            if (o.final)
+                rc = f32out ? launch_tcg<16, 1, true>(c, L, R, p) : launch_tcg<16, 1, false>(c, L, R, p);
+            else if (L.NOUT == 64)
+                rc = launch_tcg<64, 0, false>(c, L, R, p);
+            else
+                rc = launch_tcg<32, 0, false>(c, L, R, p);
+            TRY(rc);
+            TRY(prof_end(c));
+        }
+    }
+    return 0;
+}
+
+extern "C" int b2sr_debug_fused(b2sr_ctx* c, const uint8_t* in, int h, int w, int upto, int buf, float* out) {
+    if (!c || !in || !out) return fail(B2SR_E_INVALID, "b2sr_debug_fused: null argument");
+    if (c->family != B2SR_FAMILY_FUSED) return fail(B2SR_E_UNSUPPORTED, "b2sr_debug_fused: fused family only");
+    if (h < 1 || w < 1 || h > 16384 || w > 16384) return fail(B2SR_E_INVALID, "image %dx%d", h, w);
+    if (buf < 0 || buf >= (int)c->fbufs.size() || upto < 0 || upto >= (int)c->fops.size() - 1)
+        return fail(B2SR_E_INVALID, "b2sr_debug_fused: buffer %d / op %d out of range", buf, upto);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t in_bytes = (size_t)h * w * 3;
+    if (in_bytes > c->cap_in) {
+        if (c->d_in) cudaFree(c->d_in);
+        c->d_in = nullptr, c->cap_in = 0;
+        CUDA_TRY(cudaMalloc(&c->d_in, in_bytes));
+        c->cap_in = in_bytes;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_in, in, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    Plan* P = nullptr;
+    TRY(build_plan(c, 1, h, w, 0, 0, &P));
+    TRY(run_fused(c, P, c->d_in, nullptr, false, upto));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const b2sr_fused_buf& B = c->fbufs[buf];
+    const size_t n = (size_t)h * B.res * w * B.res * B.channels;
+    if (B.dtype == 4) {
+        CUDA_TRY(cudaMemcpy(out, c->fbuf_ptr[buf], n * 4, cudaMemcpyDeviceToHost));
+    } else {
+        std::vector<__half> tmp(n);
+        CUDA_TRY(cudaMemcpy(tmp.data(), c->fbuf_ptr[buf], n * 2, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; ++i) out[i] = __half2float(tmp[i]);
+    }
+    return 0;
+}
+
 static bool use_tc(const b2sr_ctx* c) { return c->impl != 1; }
 
 // Runs layers [0, upto] for the planes of P; the final layer writes `out` (u8 or f32 frames).  Returns in *act the
 // buffer that holds the activations of layer `upto` when upto is not the last layer.
 static int run_plan(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, bool f32out, int upto, const __half** act) {
     if (c->family == B2SR_FAMILY_GRAPH) return run_graph(c, P, d_frames, d_out, f32out);
+    if (c->family == B2SR_FAMILY_FUSED) return run_fused(c, P, d_frames, d_out, f32out, -1);
     const int nl = (int)c->layers.size();
     if (upto < 0 || upto >= nl) upto = nl - 1;
     if (upto == nl - 1 && (c->impl == 0 || c->impl == 3)) {  // whole network: pipelined schedule when it fits the GPU
@@ -1104,7 +1505,7 @@ static int check_geom(int n, int h, int w, int tile, int halo) {
 
 static int frames_per_pass(const b2sr_ctx* c, int h, int w, int tile) {
     if (c->max_batch > 0) return c->max_batch;
-    if (c->family == B2SR_FAMILY_GRAPH) return 1;
+    if (c->family == B2SR_FAMILY_GRAPH || c->family == B2SR_FAMILY_FUSED) return 1;
     const double px = (double)h * w * 1.06;
     // the pipelined schedule keeps only the 16-channel input planes per frame: long passes amortise its fill/drain
     const int tw = tile > 0 ? std::min(w, tile + 20) : w;

@@ -25,7 +25,7 @@ IMPL_AUTO, IMPL_SIMPLE, IMPL_TCGEN05, IMPL_PIPELINED = 0, 1, 2, 3  # IMPL_TCGEN0
 # every symbol include/b2sr.h declares (tests check the library exports exactly these)
 SYMBOLS = [
     "b2sr_abi_version", "b2sr_device_count", "b2sr_default_device", "b2sr_device_name", "b2sr_create", "b2sr_create_graph",
-    "b2sr_destroy",
+    "b2sr_create_fused", "b2sr_debug_fused", "b2sr_destroy",
     "b2sr_run_u8", "b2sr_run_f32", "b2sr_run_batch_device", "b2sr_run_batch_host", "b2sr_debug_layer",
     "b2sr_set_option", "b2sr_get_stat", "b2sr_reset_stats", "b2sr_synchronize", "b2sr_stream", "b2sr_last_error",
 ]
@@ -43,6 +43,20 @@ class GraphOp(ctypes.Structure):  # b2sr_graph_op
                 ("in_c", ctypes.c_int32 * 6), ("in_off", ctypes.c_int32 * 6), ("in_ld", ctypes.c_int32 * 6),
                 ("out_c", ctypes.c_int32), ("out_off", ctypes.c_int32), ("out_ld", ctypes.c_int32),
                 ("in_res", ctypes.c_int32), ("out_res", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class FusedBuf(ctypes.Structure):  # b2sr_fused_buf
+    _fields_ = [("channels", ctypes.c_int32), ("dtype", ctypes.c_int32), ("res", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class FusedOp(ctypes.Structure):  # b2sr_fused_op
+    _fields_ = [("type", ctypes.c_int32), ("res", ctypes.c_int32), ("in_buf", ctypes.c_int32), ("in_off", ctypes.c_int32),
+                ("cin", ctypes.c_int32), ("k", ctypes.c_int32), ("cout", ctypes.c_int32), ("act", ctypes.c_int32),
+                ("slope", ctypes.c_float), ("nres", ctypes.c_int32), ("w_off", ctypes.c_int64), ("b_off", ctypes.c_int64),
+                ("res_buf", ctypes.c_int32 * 2), ("res_off", ctypes.c_int32 * 2), ("coef_v", ctypes.c_float * 2),
+                ("coef_r", ctypes.c_float * 2), ("out16_buf", ctypes.c_int32), ("out16_off", ctypes.c_int32),
+                ("out32_buf", ctypes.c_int32), ("out32_off", ctypes.c_int32), ("r", ctypes.c_int32), ("final", ctypes.c_int32),
+                ("reserved", ctypes.c_int32 * 4)]
 
 
 class NetDesc(ctypes.Structure):
@@ -68,6 +82,8 @@ def load_library(path: str = LIB_PATH):
     lib.b2sr_device_name.argtypes = [i32, ctypes.c_char_p, i32]
     lib.b2sr_create.argtypes = [ctypes.POINTER(vp), i32, vp, ctypes.c_size_t, ctypes.POINTER(NetDesc)]
     lib.b2sr_create_graph.argtypes = [ctypes.POINTER(vp), i32, ctypes.POINTER(GraphOp), i32, i32, i32, i32, i32, vp, ctypes.c_size_t]
+    lib.b2sr_create_fused.argtypes = [ctypes.POINTER(vp), i32, ctypes.POINTER(FusedOp), i32, ctypes.POINTER(FusedBuf), i32, i32, vp, ctypes.c_size_t]
+    lib.b2sr_debug_fused.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.b2sr_destroy.argtypes = [vp]
     lib.b2sr_destroy.restype = None
     lib.b2sr_run_u8.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, i32, i32]
@@ -127,11 +143,19 @@ class Engine:
     def __init__(self, graph: ncnn_model.Graph = None, device: int = 0, packed=None, generic: bool = False):
         """``graph``: a loaded model; or ``packed`` = (CompactDesc, fp32 blob) as produced by
         ``ncnn_model.pack_compact_blob`` (what a rank receives from the start-up weight broadcast).
-        SRVGGNetCompact graphs run on the tcgen05 kernels; anything else (4x_Valar_v1), or any graph when
-        ``generic=True`` (cross-checks), runs on the generic CUDA-core graph engine."""
+        SRVGGNetCompact graphs run on the Compact tcgen05 kernels; graphs that lower to fused convolutions (the RRDB
+        4x_Valar_v1) on the tcgen05 graph kernels (b2sr_create_fused); anything else, or any graph when
+        ``generic=True`` (cross-checks), on the generic op-by-op graph engine (b2sr_create_graph)."""
         self._h = None
         self._lib = load_library()
         self.generic = False
+        self.fused = False
+        self.program = None
+        if packed is None and not generic and ncnn_model.compact_desc(graph) is None:
+            prog = ncnn_model.compile_fused(graph)
+            if prog is not None:
+                self._init_fused(prog, device)
+                return
         if packed is None and (generic or ncnn_model.compact_desc(graph) is None):
             self._init_generic(graph, device)
             return
@@ -144,6 +168,38 @@ class Engine:
         h = ctypes.c_void_p()
         _check(self._lib.b2sr_create(ctypes.byref(h), device, blob.ctypes.data, blob.nbytes, ctypes.byref(nd)), "b2sr_create")
         self._h = h
+
+    def _init_fused(self, prog, device):
+        """RRDB-style graphs: every convolution (+ bias, LeakyReLU, residual adds) on the tcgen05 graph kernel."""
+        ops = (FusedOp * len(prog.ops))()
+        for a, o in zip(ops, prog.ops):
+            for k in ("type", "res", "in_buf", "in_off", "cin", "k", "cout", "act", "slope", "nres", "w_off", "b_off",
+                      "out16_buf", "out16_off", "out32_buf", "out32_off", "r", "final"):
+                setattr(a, k, o[k])
+            for q in range(2):
+                a.res_buf[q], a.res_off[q], a.coef_v[q], a.coef_r[q] = o["res_buf"][q], o["res_off"][q], o["coef_v"][q], o["coef_r"][q]
+        bufs = (FusedBuf * len(prog.bufs))()
+        for a, b in zip(bufs, prog.bufs):
+            a.channels, a.dtype, a.res = b["channels"], b["dtype"], b["res"]
+        w = np.ascontiguousarray(prog.weights, np.float32)
+        h = ctypes.c_void_p()
+        _check(self._lib.b2sr_create_fused(ctypes.byref(h), device, ops, len(prog.ops), bufs, len(prog.bufs), prog.scale,
+                                           w.ctypes.data, w.nbytes), "b2sr_create_fused")
+        self._h = h
+        self.desc = ncnn_model.CompactDesc(3, 0, 0, prog.scale, 3 * prog.scale * prog.scale, prog.input_blob, prog.output_blob)
+        self.scale = prog.scale
+        self.device = device
+        self.fused = True
+        self.program = prog
+
+    def debug_fused(self, img: np.ndarray, upto: int, buf: int) -> np.ndarray:
+        """Bring-up: buffer ``buf`` after ops [0, upto] of the fused program on one untiled image."""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w, _ = img.shape
+        b = self.program.bufs[buf]
+        out = np.empty((h * b["res"], w * b["res"], b["channels"]), np.float32)
+        _check(self._lib.b2sr_debug_fused(self._h, img.ctypes.data, h, w, upto, buf, out.ctypes.data), "b2sr_debug_fused")
+        return out
 
     def _init_generic(self, graph, device):
         """Graphs that are not SRVGGNetCompact (4x_Valar_v1): the generic graph engine (b2sr_create_graph)."""

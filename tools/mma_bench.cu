@@ -201,6 +201,15 @@ int main() {
         run<192, 12>("  + LSU smem traffic (flat out)", G, 17408, 6144, 0, 2, 1, grid);
         run<192, 12>("  + TMEM readers + LSU (paced)", G, 17408, 6144, 1, 1, 1, grid);
         run<192, 12>("  + TMEM readers + LSU (flat out)", G, 17408, 6144, 2, 2, 1, grid);
+        // RRDB kernel shapes (NOUT = 32 -> N = 96): one 64-channel group of one input row = 12 MMAs, then a commit
+        run<96, 12>("RRDB N=96: 12 MMAs/group, B slabs 3 KB apart", G, 17408, 3072, 0, 0, 1, grid);
+        run<96, 12>("  same, commit every 2 groups", G, 17408, 3072, 0, 0, 2, grid);
+        run<96, 12>("  same, commit every 4 groups", G, 17408, 3072, 0, 0, 4, grid);
+        run<96, 12>("  + TMEM readers + LSU (paced)", G, 17408, 3072, 1, 1, 1, grid);
+        run<96, 24>("RRDB N=96: 24 MMAs/group", G, 17408, 3072, 0, 0, 1, grid);
+        run<96, 36>("RRDB N=96: 36 MMAs/group", G, 17408, 3072, 0, 0, 1, grid);
+        run<128, 12>("N=128 conv-like", G, 17408, 4096, 0, 0, 1, grid);
+        run<48, 12>("N=48 conv-like (final 64->3 layer)", G, 17408, 1536, 0, 0, 1, grid);
         run<256, 12>("conv-like N=256", G, 17408, 8192, 0, 0, 1, grid);
         run<256, 12>("  + TMEM readers + LSU (paced)", G, 17408, 8192, 1, 1, 1, grid);
     }

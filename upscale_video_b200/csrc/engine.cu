@@ -772,7 +772,7 @@ static int run_pipe(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, 
     PipeParams Q{};
     Q.n_layers = L, Q.nb = nb;
     if (c->pipe_debug) {
-        if (!c->d_dbg) CUDA_TRY(cudaMalloc(&c->d_dbg, 148 * 8 * sizeof(long long)));
+        if (!c->d_dbg) CUDA_TRY(cudaMalloc(&c->d_dbg, 148 * 16 * sizeof(long long)));
         CUDA_TRY(cudaMemsetAsync(c->d_dbg, 0, 148 * 8 * sizeof(long long), c->stream));
         Q.dbg = c->d_dbg;
     }
@@ -1279,9 +1279,9 @@ static int fused_items(b2sr_ctx* c, Plan* P, int res, ResItems** out) {
     return 0;
 }
 
-template <int NOUT, int MODE, bool F32OUT>
+template <int NOUT, int MODE, bool F32OUT, bool PLAIN>
 static int launch_tcg(b2sr_ctx* c, const FusedLaunch& L, const ResItems* R, const TcgParams& p) {
-    auto kern = tcg_conv_kernel<NOUT, MODE, F32OUT>;
+    auto kern = tcg_conv_kernel<NOUT, MODE, F32OUT, PLAIN>;
     const int smem = TcgCfg<NOUT, MODE>::smem_bytes(L.G, L.slots);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<R->n_cta, TC_THREADS, smem, c->stream>>>(p);
@@ -1386,16 +1386,34 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
                 p.out32_ld = c->fbufs[o.out32_buf].channels;
             }
             p.frames_out = d_out, p.frame_h = P->h * o.res, p.frame_w = P->w * o.res;
+            const bool dbg = c->pipe_debug && (li < c->pipe_debug || li >= (int)c->flaunch.size() - 5);
+            if (dbg) {
+                if (!c->d_dbg) CUDA_TRY(cudaMalloc(&c->d_dbg, 148 * 16 * sizeof(long long)));
+                CUDA_TRY(cudaMemsetAsync(c->d_dbg, 0, 148 * 16 * sizeof(long long), c->stream));
+                p.dbg = c->d_dbg;
+            }
             TRY(prof_begin(c, 1, R->out_px));
             int rc;
+            const bool plain = o.nres == 0 && o.out32_buf < 0;  // bias + activation -> fp16 only: the lean epilogue
             if (o.final)
-                rc = f32out ? launch_tcg<16, 1, true>(c, L, R, p) : launch_tcg<16, 1, false>(c, L, R, p);
+                rc = f32out ? launch_tcg<16, 1, true, false>(c, L, R, p) : launch_tcg<16, 1, false, false>(c, L, R, p);
             else if (L.NOUT == 64)
-                rc = launch_tcg<64, 0, false>(c, L, R, p);
+                rc = plain ? launch_tcg<64, 0, false, true>(c, L, R, p) : launch_tcg<64, 0, false, false>(c, L, R, p);
             else
-                rc = launch_tcg<32, 0, false>(c, L, R, p);
+                rc = plain ? launch_tcg<32, 0, false, true>(c, L, R, p) : launch_tcg<32, 0, false, false>(c, L, R, p);
             TRY(rc);
             TRY(prof_end(c));
+            if (dbg) {
+                std::vector<long long> h(148 * 16);
+                CUDA_TRY(cudaStreamSynchronize(c->stream));
+                CUDA_TRY(cudaMemcpy(h.data(), c->d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                double v[16] = {0};
+                for (int k = 0; k < R->n_cta; ++k)
+                    for (int j = 0; j < 16; ++j) v[j] += (double)h[k * 16 + j] / R->n_cta;
+                fprintf(stderr, "b2sr fused launch %3d (op %3d k%d %3d->%2d nres %d res %d, G %d slots %d): issuer %7.0f cyc (to first MMA %6.0f; wait full %6.0f, tempty %6.0f) | "
+                        "producer %7.0f (wait empty %6.0f) | epilogue warp 2 %7.0f (wait tfull %6.0f, tmem ld/zero %6.0f) | issuer: mma issue %6.0f commits %6.0f\n", li, L.op, o.k, o.cin, L.nco, o.nres, o.res, L.G,
+                        L.slots, v[0], v[3], v[1], v[2], v[7], v[4], v[6], v[5], v[10], v[8], v[9]);
+            }
         }
     }
     return 0;
@@ -1505,7 +1523,9 @@ static int check_geom(int n, int h, int w, int tile, int halo) {
 
 static int frames_per_pass(const b2sr_ctx* c, int h, int w, int tile) {
     if (c->max_batch > 0) return c->max_batch;
-    if (c->family == B2SR_FAMILY_GRAPH || c->family == B2SR_FAMILY_FUSED) return 1;
+    if (c->family == B2SR_FAMILY_GRAPH) return 1;
+    if (c->family == B2SR_FAMILY_FUSED)  // ~8 KB of activation buffers per input pixel; longer passes amortise the per-launch fill / drain
+        return (int)std::max(1.0, std::min(8.0, floor(2.2e6 / ((double)h * w * 1.06))));
     const double px = (double)h * w * 1.06;
     // the pipelined schedule keeps only the 16-channel input planes per frame: long passes amortise its fill/drain
     const int tw = tile > 0 ? std::min(w, tile + 20) : w;

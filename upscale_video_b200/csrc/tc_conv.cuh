@@ -108,6 +108,13 @@ __device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, i
     mbar_wait(bar, parity, who);
     waited += clock64() - t0;
 }
+// try_wait may itself suspend the thread for a while before it returns true, which mbar_wait_timed does not see:
+// this variant brackets the whole wait (stall accounting of the fused graph kernel)
+__device__ __forceinline__ void mbar_wait_clocked(uint32_t bar, uint32_t parity, int who, long long& waited) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity, who);
+    waited += clock64() - t0;
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
     asm volatile(

@@ -48,6 +48,7 @@ struct TcgParams {
     int32_t out32_ld;
     void* frames_out;           // final convolution: packed frames (u8 or float), frame_h x frame_w x 3
     int32_t frame_h, frame_w;
+    long long* dbg;             // optional [CTA][8] stall accounting (B2SR_OPT_PIPE_DEBUG)
 };
 
 constexpr int TCG_PB = 128;                      // bytes per pixel of one channel group == one SW128 swizzle row
@@ -59,7 +60,13 @@ struct TcgCfg {
     static constexpr int OB = NOUT * 2;
     static constexpr int STG = MODE == 0 ? TC_NSETS * 4 * 32 * OB : 0;
     static constexpr int MISC = 2 * NOUT * 4 + TCG_BAR_WORDS * 8 + 64;
-    static constexpr int TCOLS = TC_NBLK * NOUT <= 128 ? 128 : (TC_NBLK * NOUT <= 256 ? 256 : 512);
+    // Accumulator blocks: output row g lives in block g % NB ("home").  The window of an input row (the blocks of output
+    // rows r-1, r, r+1) never wraps: it may run into two extension blocks NB, NB + 1 that stand for homes 0 and 1, and
+    // the epilogue adds block NB + h to block h for rows with home h < 2.  (With a wrapping ring two of every NB rows
+    // needed a second, small-N MMA per tap and slab; small-N MMAs cost as much as N = 96 ones.)
+    static constexpr int NB = NOUT == 64 ? 6 : 8;
+    static constexpr int TCOLS = (NB + 2) * NOUT <= 128 ? 128 : ((NB + 2) * NOUT <= 256 ? 256 : 512);
+    static_assert((NB + 2) * NOUT <= 512 && NB % TC_NSETS == 0, "accumulator blocks exceed TMEM");
     static constexpr uint32_t IDESC0 = (1u << 4) | ((uint32_t)(TC_TILE_M >> 4) << 24);
     static_assert(NOUT == 16 || NOUT == 32 || NOUT == 64, "NOUT");
     static constexpr int weight_bytes(int groups) { return groups * 9 * NOUT * TCG_PB; }
@@ -67,12 +74,13 @@ struct TcgCfg {
     static constexpr int smem_bytes(int groups, int slots) { return 1024 + weight_bytes(groups) + slots * TCG_SUBROWB + STG + MISC; }
 };
 
-template <int NOUT, int MODE /*0 = activation buffers, 1 = network output frames*/, bool F32OUT>
+template <int NOUT, int MODE /*0 = activation buffers, 1 = network output frames*/, bool F32OUT, bool PLAIN /*MODE 0 without residual terms and fp32 copy*/>
 __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_constant__ TcgParams P) {
     using C = TcgCfg<NOUT, MODE>;
     extern __shared__ uint8_t smem_raw[];
     const int it_begin = P.item_first[blockIdx.x], it_end = P.item_first[blockIdx.x + 1];
     const int G = P.groups, R = P.ring_slots;
+    constexpr int NB = C::NB;
     const uint32_t WB = (uint32_t)(G * 9 * NOUT * TCG_PB);
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -94,13 +102,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + bar_off + 8 * (2 * TC_MAX_SLOTS + 2 * TC_NBLK + 1));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NPRE = NOUT <= 32 ? 2 : 1;  // residual terms prefetched into registers (NOUT / 4 uint4 each)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < R; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        for (int b = 0; b < TC_NBLK; ++b) {
+        for (int b = 0; b < NB; ++b) {
             mbar_init(tfull_bar(b), 1);
             mbar_init(tempty_bar(b), 4);
         }
@@ -132,6 +141,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
             for (int t = 0; t < 3 * G; ++t) bulk_g2s(w_s + t * chunk, P.wimg + (size_t)t * chunk, chunk, w_bar);
             int slot = 0;
             uint32_t phase = 0;
+            long long w_empty = 0;
+            const long long t_begin = clock64();
             for (int it = it_begin; it < it_end; ++it) {
                 const TcItem I = P.items[it];
                 const CUtensorMap* map = P.maps + (P.map_base + I.map);
@@ -139,7 +150,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                 for (int rho = 0; rho < rows_in; ++rho) {
                     const int y = I.y0 - 1 + rho;  // rows outside the plane are zero-filled by TMA = the conv's zero padding
                     for (int g = 0; g < G; ++g) {
-                        mbar_wait(empty_bar(slot), phase ^ 1u, 0);
+                        mbar_wait_clocked(empty_bar(slot), phase ^ 1u, 0, w_empty);
                         mbar_expect_tx(full_bar(slot), TCG_SUBROWB);
                         tma_load_4d(ring_s + slot * TCG_SUBROWB, map, full_bar(slot), g * 64, I.x0 - 1, y, I.plane);
                         if (++slot == R) {
@@ -148,6 +159,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                         }
                     }
                 }
+            }
+            if (P.dbg) {
+                P.dbg[blockIdx.x * 16 + 4] = w_empty;
+                P.dbg[blockIdx.x * 16 + 7] = clock64() - t_begin;
             }
         }
     } else if (warp == 1) {
@@ -164,69 +179,102 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
         const int kx_lo = P.k1 ? 1 : 0, kx_hi = P.k1 ? 2 : 3;
         int slot = 0;
         uint32_t phase = 0;
-        uint32_t g0 = 0;      // CTA-local index of the current item's output row 0
-        uint32_t gfresh = 0;  // CTA-local index of the next output row to be started
+        long long w_full = 0, w_tempty = 0, t_first = 0, t_mma = 0, t_commit = 0;
+        const long long t_begin = clock64();
         mbar_wait(w_bar, 0, 1);
-        uint32_t ok_full = mbar_test_wait(full_bar(0), 0);
         uint32_t ok_tempty = mbar_test_wait(tempty_bar(0), 0);
-        for (int it = it_begin; it < it_end; ++it) {
-            const int rows = P.items[it].rows;
+        // Loop bounds that come from global memory are broadcast with a shuffle: the compiler then knows they are
+        // warp-uniform and keeps the whole descriptor arithmetic in uniform registers (UTCHMMA takes uniform operands;
+        // with per-thread values every MMA cost five R2UR moves).
+        const int itb = __shfl_sync(0xffffffffu, it_begin, 0), ite = __shfl_sync(0xffffffffu, it_end, 0);
+        uint32_t tmask = 0;  // bit h: parity of the next use of accumulator block h (tempty barrier phase)
+        for (int it = itb; it < ite; ++it) {
+            const int rows = __shfl_sync(0xffffffffu, P.items[it].rows, 0);
+            // Homes follow the plane row (y % NB), not the CTA's row count: which rows are summed from two blocks
+            // then does not depend on how the launch was cut into CTA ranges, so a frame computes bit-identically
+            // alone and inside a batch.
+            const uint32_t y0 = (uint32_t)__shfl_sync(0xffffffffu, P.items[it].y0, 0);
             for (int rho = 0; rho < rows + 2; ++rho) {  // input row rho feeds output rows rho - ky, ky = 0..2
                 const bool fresh = rho < rows;
-                const uint32_t gn = gfresh + (fresh ? 1u : 0u);
                 const int t0 = rho >= 2 ? rho - 2 : 0;
                 const int t1 = fresh ? rho : rows - 1;
                 const int cnt = t1 - t0 + 1;
-                const uint32_t blk0 = (g0 + (uint32_t)t0) & (TC_NBLK - 1);
-                const int wrap = (int)(TC_NBLK - blk0);
-                const int n1 = cnt < wrap ? cnt : wrap;
+                // The window of an input row starts at the home of output row rho - 2 and spans three blocks (it may reach
+                // blocks NB, NB + 1); at the top of an item the rows above the item are simply left out (brow0 skips
+                // their blocks), so every output row collects its three contributions in the same physical blocks
+                // wherever the item boundaries fall.
+                const uint32_t home0 = (y0 + (uint32_t)rho + (uint32_t)NB - 2u) % NB;
+                const uint32_t hf = (y0 + (uint32_t)rho) % NB;    // home of the output row that starts with this input row
                 const uint32_t brow0 = rho >= 2 ? 0u : (uint32_t)(2 - rho);
-                const uint32_t id1 = C::IDESC0 | ((uint32_t)((n1 * NOUT) >> 3) << 17);
-                const uint32_t id2 = C::IDESC0 | ((uint32_t)((((cnt - n1) > 0 ? (cnt - n1) : 1) * NOUT) >> 3) << 17);
-                const uint32_t d1 = tmem_base + blk0 * NOUT;
-                for (int g = 0; g < G; ++g) {
-                    if (!ok_full) mbar_wait(full_bar(slot), phase, 2);
-                    if (g == 0 && fresh && !ok_tempty) mbar_wait(tempty_bar(gfresh & (TC_NBLK - 1)), (gfresh / TC_NBLK) & 1u, 3);
-                    tc_fence_after();
-                    const int nslot = slot + 1 == R ? 0 : slot + 1;
-                    const uint32_t nphase = slot + 1 == R ? phase ^ 1u : phase;
-                    ok_full = mbar_test_wait(full_bar(nslot), nphase);
-                    if (g == G - 1) ok_tempty = mbar_test_wait(tempty_bar(gn & (TC_NBLK - 1)), (gn / TC_NBLK) & 1u);
-                    const int ks = min(4, (P.cin - g * 64) >> 4);  // K = 16 slabs present in this group
-                    if (elect_one_sync()) {
-                        const uint32_t a_lo = ring_lo + (uint32_t)slot * (TCG_SUBROWB >> 4);
-                        const uint32_t b_lo = w_lo + (uint32_t)g * GRPB + brow0 * BLKB;
-                        const uint32_t b_lo2 = b_lo + (uint32_t)n1 * BLKB;
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            if (kx < kx_lo || kx >= kx_hi) continue;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (k >= ks) continue;
-                                const uint32_t ao = (uint32_t)((kx * TCG_PB + k * 32) >> 4), bo = (uint32_t)(kx * KXB + ((k * 32) >> 4));
-                                umma_f16(d1, hi64 | (a_lo + ao), hi64 | (b_lo + bo), id1, 1u);
-                                if (n1 != cnt) umma_f16(tmem_base, hi64 | (a_lo + ao), hi64 | (b_lo2 + bo), id2, 1u);
-                            }
-                        }
-                        umma_commit(empty_bar(slot));
-                        if (g == G - 1 && rho >= 2) umma_commit(tfull_bar((g0 + (uint32_t)rho - 2u) & (TC_NBLK - 1)));
-                    }
-                    __syncwarp();
-                    slot = nslot;
-                    phase = nphase;
+                const uint32_t idesc = C::IDESC0 | ((uint32_t)((cnt * NOUT) >> 3) << 17);
+                const uint32_t d = tmem_base + (home0 + brow0) * NOUT;
+                // the new output row's block drained and zeroed?  all channel groups of this input row in shared memory?
+                if (fresh) {
+                    if (!ok_tempty) mbar_wait_clocked(tempty_bar(hf), (tmask >> hf) & 1u, 3, w_tempty);
+                    tmask ^= 1u << hf;
                 }
-                gfresh = gn;
+                mbar_wait_clocked(full_bar(slot), phase, 2, w_full);  // (the elected lane waits for the later groups itself)
+                tc_fence_after();
+                if (P.dbg && t_first == 0) t_first = clock64() - t_begin;
+                {  // probe for the next row of this item, latency hidden behind the MMAs
+                    const uint32_t hn = (hf + 1u) % NB;
+                    ok_tempty = rho + 1 < rows ? mbar_test_wait(tempty_bar(hn), (tmask >> hn) & 1u) : 0u;
+                }
+                const long long tq0 = P.dbg ? clock64() : 0;
+                if (elect_one_sync()) {
+                    int sl = slot;
+                    uint32_t ph = phase;
+                    for (int g = 0; g < G; ++g) {
+                        if (g > 0) {  // group g of this row in shared memory?  (a single thread may wait on an mbarrier)
+                            mbar_wait(full_bar(sl), ph, 2);
+                            tc_fence_after();
+                        }
+                        const int ks = min(4, (P.cin - g * 64) >> 4);  // K = 16 slabs present in this group
+                        const uint64_t a0 = hi64 | (uint64_t)(ring_lo + (uint32_t)sl * (TCG_SUBROWB >> 4));
+                        const uint64_t b0 = hi64 | (uint64_t)(w_lo + (uint32_t)g * GRPB + brow0 * BLKB);
+                        if (ks == 4 && !P.k1) {  // the common case, straight-line: 12 MMAs, one 64-bit add per descriptor
+#pragma unroll
+                            for (int m = 0; m < 12; ++m) {
+                                const int kx = m >> 2, k = m & 3;
+                                umma_f16(d, a0 + (uint64_t)((kx * TCG_PB + k * 32) >> 4), b0 + (uint64_t)(kx * KXB + ((k * 32) >> 4)), idesc, 1u);
+                            }
+                        } else {
+                            for (int kx = kx_lo; kx < kx_hi; ++kx)
+                                for (int k = 0; k < ks; ++k)
+                                    umma_f16(d, a0 + (uint64_t)((kx * TCG_PB + k * 32) >> 4), b0 + (uint64_t)(kx * KXB + ((k * 32) >> 4)), idesc, 1u);
+                        }
+                        umma_commit(empty_bar(sl));  // this (row, group) slot may be refilled once its MMAs have completed
+                        if (++sl == R) sl = 0, ph ^= 1u;
+                    }
+                    if (rho >= 2) umma_commit(tfull_bar(home0));  // output row rho - 2 is complete (home0 is its home)
+                    if (P.dbg) t_mma += clock64() - tq0;
+                }
+                __syncwarp();
+                slot += G;
+                if (slot >= R) slot -= R, phase ^= 1u;
             }
-            g0 += (uint32_t)rows;
+        }
+        if (P.dbg && lane == 0) {
+            P.dbg[blockIdx.x * 16 + 0] = clock64() - t_begin;
+            P.dbg[blockIdx.x * 16 + 1] = w_full;
+            P.dbg[blockIdx.x * 16 + 2] = w_tempty;
+            P.dbg[blockIdx.x * 16 + 3] = t_first;
+        }
+        if (P.dbg && t_mma) {  // (the elected lane holds these)
+            P.dbg[blockIdx.x * 16 + 8] = t_mma;
+            P.dbg[blockIdx.x * 16 + 9] = t_commit;
         }
     } else if (warp < 2 + 4 * TC_NSETS) {
         // ======================= epilogue =======================
         const int q = warp & 3;
         const uint32_t set = (warp - 2) >> 2;
-        uint32_t tile_cnt = 0;
-        for (uint32_t b = set; b < TC_NBLK; b += TC_NSETS) {
+        uint32_t tile_cnt = 0, emask = 0;
+        for (uint32_t b = set; b < (uint32_t)NB; b += TC_NSETS) {  // hand every block of this set to the issuer zeroed
 #pragma unroll
-            for (int j = 0; j < NOUT; j += 16) tmem_st16_zero(tmem_base + ((uint32_t)(q * 32) << 16) + b * NOUT + j);
+            for (int j = 0; j < NOUT; j += 16) {
+                tmem_st16_zero(tmem_base + ((uint32_t)(q * 32) << 16) + b * NOUT + j);
+                if (b < 2) tmem_st16_zero(tmem_base + ((uint32_t)(q * 32) << 16) + (NB + b) * NOUT + j);  // its extension block
+            }
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -234,14 +282,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
         }
         const float scale_acc = P.acc_scale;
         const int c = q * 32 + lane;
+        long long w_tfull = 0, t_tmem = 0;
+        const long long t_begin = clock64();
         for (int it = it_begin; it < it_end; ++it) {
             const TcItem I = P.items[it];
             const bool valid = c < I.w;
             for (int t = 0; t < I.rows; ++t, ++tile_cnt) {
+                const uint32_t buf = (uint32_t)(I.y0 + t) % NB;  // home block of this output row
+                const uint32_t par = (emask >> buf) & 1u;        // parity of this use of the block (both sets' rows count)
+                emask ^= 1u << buf;
                 if (tile_cnt % TC_NSETS != set) continue;
-                const uint32_t buf = tile_cnt % TC_NBLK;
-                mbar_wait(tfull_bar(buf), (tile_cnt / TC_NBLK) & 1u, 4);
+                // residual terms of this thread's pixel are fetched BEFORE the wait for the accumulator, so their
+                // latency (measured: ~700 cycles per dependent chunk, 4-8 chunks per row) hides behind the MMAs
+                [[maybe_unused]] long long pix = -1;
+                [[maybe_unused]] uint4 rraw[PLAIN ? 1 : NPRE][PLAIN ? 1 : NOUT / 4];
+                if constexpr (MODE == 0) pix = valid ? (long long)I.pix_off + (long long)(I.y0 + t) * I.Wt + I.x0 + c : -1;
+                if constexpr (MODE == 0 && !PLAIN) {
+                    pix = valid ? (long long)I.pix_off + (long long)(I.y0 + t) * I.Wt + I.x0 + c : -1;
+#pragma unroll
+                    for (int r = 0; r < NPRE; ++r) {
+                        if (r >= P.nres || pix < 0) continue;
+                        if (P.res_f32[r]) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(P.res_ptr[r]) + pix * P.res_ld[r]);
+#pragma unroll
+                            for (int j = 0; j < NOUT / 4; ++j) rraw[r][j] = rp[j];
+                        } else {
+                            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(P.res_ptr[r]) + pix * P.res_ld[r]);
+#pragma unroll
+                            for (int j = 0; j < NOUT / 8; ++j) rraw[r][j] = rp[j];
+                        }
+                    }
+                }
+                mbar_wait_clocked(tfull_bar(buf), par, 4, w_tfull);
                 tc_fence_after();
+                const long long tq0 = P.dbg ? clock64() : 0;
                 uint32_t acc[NOUT];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NOUT;
 #pragma unroll
@@ -249,15 +323,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < NOUT; j += 16) tmem_st16_zero(taddr + j);
+                if (buf < 2) {  // homes 0 and 1: part of the sum sits in the extension block (windows that started at NB-2, NB-1)
+                    const uint32_t xaddr = taddr + (uint32_t)(NB * NOUT);
+#pragma unroll
+                    for (int j0 = 0; j0 < NOUT; j0 += 16) {
+                        uint32_t ext[16];
+                        tmem_ld16(xaddr + j0, ext);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) acc[j0 + e] = __float_as_uint(__uint_as_float(acc[j0 + e]) + __uint_as_float(ext[e]));
+                        tmem_st16_zero(xaddr + j0);
+                    }
+                }
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(buf));
+                if (P.dbg) t_tmem += clock64() - tq0;
 
-                if constexpr (MODE == 0) {
+                if constexpr (MODE == 0 && PLAIN) {
+                    // bias + LeakyReLU -> fp16, via swizzled per-warp staging, then 128-bit coalesced global stores
                     constexpr int CH = C::OB / 16;
                     uint4* stg = reinterpret_cast<uint4*>(gbase + stg_off + (warp - 2) * (32 * C::OB));
-                    const long long pix = valid ? (long long)I.pix_off + (long long)(I.y0 + t) * I.Wt + I.x0 + c : -1;
                     const float4* sb4 = reinterpret_cast<const float4*>(s_bias);
                     const float4* ss4 = reinterpret_cast<const float4*>(s_slope);
 #pragma unroll
@@ -265,52 +352,115 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                         const float4 b0 = sb4[j >> 2], b1 = sb4[(j >> 2) + 1], l0 = ss4[j >> 2], l1 = ss4[(j >> 2) + 1];
                         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                         const float sl[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-                        float v[8];
+                        uint32_t pk[4];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
+                        for (int e = 0; e < 8; e += 2) {
+                            float v0 = fmaf(__uint_as_float(acc[j + e]), scale_acc, bb[e]);
+                            float v1 = fmaf(__uint_as_float(acc[j + e + 1]), scale_acc, bb[e + 1]);
+                            v0 = v0 < 0.f ? v0 * sl[e] : v0;
+                            v1 = v1 < 0.f ? v1 * sl[e + 1] : v1;
+                            __half2 h = __floats2half2_rn(v0, v1);
+                            pk[e >> 1] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                        const int qi = lane * CH + (j >> 3);
+                        stg[qi ^ ((qi >> 3) & 7)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                    __syncwarp();
+                    uint8_t* outp = reinterpret_cast<uint8_t*>(P.out16);
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) {
+                        const int qi = i * 32 + lane;
+                        const uint4 v4 = stg[qi ^ ((qi >> 3) & 7)];
+                        const long long o = __shfl_sync(0xffffffffu, pix, qi / CH);
+                        if (o >= 0) *reinterpret_cast<uint4*>(outp + (size_t)o * P.out16_ld * 2 + (qi % CH) * 16) = v4;
+                    }
+                    __syncwarp();
+                } else if constexpr (MODE == 0) {
+                    constexpr int CH = C::OB / 16;
+                    uint4* stg = reinterpret_cast<uint4*>(gbase + stg_off + (warp - 2) * (32 * C::OB));
+                    const float4* sb4 = reinterpret_cast<const float4*>(s_bias);
+                    const float4* ss4 = reinterpret_cast<const float4*>(s_slope);
+                    // v = act(acc * scale + bias), then the residual terms; the results replace acc[] (as float bits)
+#pragma unroll
+                    for (int j = 0; j < NOUT; j += 4) {
+                        const float4 b4 = sb4[j >> 2], l4 = ss4[j >> 2];
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, sl[4] = {l4.x, l4.y, l4.z, l4.w};
+                        float v[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
                             const float a = fmaf(__uint_as_float(acc[j + e]), scale_acc, bb[e]);
                             v[e] = a < 0.f ? a * sl[e] : a;
                         }
 #pragma unroll
                         for (int r = 0; r < 2; ++r) {
                             if (r >= P.nres) continue;
-                            float rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                            float rv[4] = {0.f, 0.f, 0.f, 0.f};
                             if (pix >= 0) {
-                                if (P.res_f32[r]) {
-                                    const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(P.res_ptr[r]) + pix * P.res_ld[r] + j);
-                                    const float4 r0 = rp[0], r1 = rp[1];
-                                    rv[0] = r0.x, rv[1] = r0.y, rv[2] = r0.z, rv[3] = r0.w, rv[4] = r1.x, rv[5] = r1.y, rv[6] = r1.z, rv[7] = r1.w;
-                                } else {
-                                    const uint4 rr = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(P.res_ptr[r]) + pix * P.res_ld[r] + j);
-                                    const __half2* h2 = reinterpret_cast<const __half2*>(&rr);
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        const float2 f = __half22float2(h2[e]);
-                                        rv[2 * e] = f.x, rv[2 * e + 1] = f.y;
+                                if (r < NPRE) {
+                                    if (P.res_f32[r]) {
+                                        const uint4 u = rraw[r][j >> 2];
+                                        rv[0] = __uint_as_float(u.x), rv[1] = __uint_as_float(u.y), rv[2] = __uint_as_float(u.z), rv[3] = __uint_as_float(u.w);
+                                    } else {
+                                        const uint4 u = rraw[r][j >> 3];
+                                        const uint32_t w0 = (j & 4) ? u.z : u.x, w1 = (j & 4) ? u.w : u.y;
+                                        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&w0)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&w1));
+                                        rv[0] = f0.x, rv[1] = f0.y, rv[2] = f1.x, rv[3] = f1.y;
                                     }
+                                } else if (P.res_f32[r]) {  // (a second residual of a 64-channel launch: not prefetched)
+                                    const float4 u = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(P.res_ptr[r]) + pix * P.res_ld[r] + j);
+                                    rv[0] = u.x, rv[1] = u.y, rv[2] = u.z, rv[3] = u.w;
+                                } else {
+                                    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(P.res_ptr[r]) + pix * P.res_ld[r] + j);
+                                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+                                    rv[0] = f0.x, rv[1] = f0.y, rv[2] = f1.x, rv[3] = f1.y;
                                 }
                             }
                             const float cv = P.coef_v[r], cr = P.coef_r[r];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = v[e] * cv + rv[e] * cr;
+                            for (int e = 0; e < 4; ++e) v[e] = v[e] * cv + rv[e] * cr;
                         }
-                        if (P.out32 && pix >= 0) {
-                            float4* op = reinterpret_cast<float4*>(P.out32 + pix * P.out32_ld + j);
-                            op[0] = make_float4(v[0], v[1], v[2], v[3]);
-                            op[1] = make_float4(v[4], v[5], v[6], v[7]);
-                        }
-                        uint32_t pk[4];
 #pragma unroll
-                        for (int e = 0; e < 8; e += 2) {
-                            __half2 h = __floats2half2_rn(v[e], v[e + 1]);
-                            pk[e >> 1] = *reinterpret_cast<uint32_t*>(&h);
+                        for (int e = 0; e < 4; ++e) acc[j + e] = __float_as_uint(v[e]);
+                    }
+                    // Stores go through this warp's swizzled staging tile (32 pixels x OB bytes) so that every store
+                    // instruction writes whole 16-byte chunks of consecutive pixels: the fp32 copy in two passes of
+                    // NOUT / 2 channels (per-thread float4 stores to 32 different lines per instruction were measured to
+                    // cost ~1700 cycles per row), then the fp16 copy in one.
+                    if (P.out32) {
+                        uint8_t* outp = reinterpret_cast<uint8_t*>(P.out32);
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            __syncwarp();
+#pragma unroll
+                            for (int i = 0; i < CH; ++i) {
+                                const int qi = lane * CH + i, j = half * (NOUT / 2) + i * 4;
+                                stg[qi ^ ((qi >> 3) & 7)] = make_uint4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int i = 0; i < CH; ++i) {
+                                const int qi = i * 32 + lane;
+                                const uint4 v4 = stg[qi ^ ((qi >> 3) & 7)];
+                                const long long o = __shfl_sync(0xffffffffu, pix, qi / CH);
+                                if (o >= 0) *reinterpret_cast<uint4*>(outp + ((size_t)o * P.out32_ld + half * (NOUT / 2)) * 4 + (qi % CH) * 16) = v4;
+                            }
                         }
-                        const int qi = lane * CH + (j >> 3);
-                        stg[qi ^ ((qi >> 3) & 7)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                     if (P.out16) {
-                        __syncwarp();
                         uint8_t* outp = reinterpret_cast<uint8_t*>(P.out16);
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) {
+                            const int qi = lane * CH + i, j = i * 8;
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                __half2 h = __floats2half2_rn(__uint_as_float(acc[j + 2 * e]), __uint_as_float(acc[j + 2 * e + 1]));
+                                pk[e] = *reinterpret_cast<uint32_t*>(&h);
+                            }
+                            stg[qi ^ ((qi >> 3) & 7)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                        __syncwarp();
 #pragma unroll
                         for (int i = 0; i < CH; ++i) {
                             const int qi = i * 32 + lane;
@@ -318,8 +468,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                             const long long o = __shfl_sync(0xffffffffu, pix, qi / CH);
                             if (o >= 0) *reinterpret_cast<uint4*>(outp + (size_t)o * P.out16_ld * 2 + (qi % CH) * 16) = v4;
                         }
-                        __syncwarp();
                     }
+                    __syncwarp();
                 } else {
                     // network output: (acc + bias) * 255, cropped to the tile core, as cv2.imwrite would store it
                     const int fy = I.fy0 + I.y0 + t, fx = I.fx0 + I.x0 + c;
@@ -340,6 +490,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                     }
                 }
             }
+        }
+        if (P.dbg && warp == 2 && lane == 0) {
+            P.dbg[blockIdx.x * 16 + 5] = w_tfull;
+            P.dbg[blockIdx.x * 16 + 6] = clock64() - t_begin;
+            P.dbg[blockIdx.x * 16 + 10] = t_tmem;
         }
     }
 

@@ -139,6 +139,32 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def valar_540p(E, ncnn_model, torch, device):
+    """BASELINE configs[3]: synthetic 540p, 4x_Valar_v1 (RRDB) on the fused tcgen05 graph kernels -- a short side
+    measurement reported next to the headline (not part of `value`): 4 device-resident frames per step, 2 timed steps."""
+    try:
+        eng = E.Engine.from_files(ncnn_model.packaged_model_dir(), "4x_Valar_v1", device)
+    except Exception as e:  # model not packaged
+        return {"unavailable": str(e)[:200]}
+    n, h, w = 4, 540, 960
+    d_in = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda")
+    d_out = torch.empty((n, h * 4, w * 4, 3), dtype=torch.uint8, device="cuda")
+    eng.run_batch_device(d_in, d_out, n, h, w, TILE, HALO, sync=True)
+    eng.reset_stats()
+    t0 = time.perf_counter()
+    steps = 2
+    for _ in range(steps):
+        eng.run_batch_device(d_in, d_out, n, h, w, TILE, HALO, sync=True)
+    dt = time.perf_counter() - t0
+    launches = eng.stat(E.STAT_TC_LAUNCHES)
+    eng.close()
+    fps = n * steps / dt
+    mac_px = 18068160  # SURVEY.md section 8(d)
+    return {"workload": "synthetic 540p, 4x_Valar_v1 RRDB (BASELINE configs[3]), fused tcgen05 graph kernels, 1xB200",
+            "frames_per_s": fps, "ms_per_frame": 1e3 / fps, "tflops": fps * 2.0 * mac_px * h * w / 1e12,
+            "frames_per_step": n, "steps": steps, "tcgen05_launches": int(launches)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -148,6 +174,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short BASELINE configs[3] measurement (4x_Valar_v1, 540p)")
     ap.add_argument("--content", default="noise", choices=["noise", "natural"],
                     help="synthetic frame content: uniform random bytes (default; worst case for switching power) or smooth "
                          "gradients + edges + mild noise")
@@ -293,6 +320,9 @@ def main():
     if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only
         fps, threads, desc, dt = cpu_port_fps(reps=1)
         cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": desc, "seconds": dt}
+    extra = None
+    if not args.no_extra and world == 1:
+        extra = valar_540p(E, ncnn_model, torch, local_rank)
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -303,7 +333,7 @@ def main():
                    "l2": "inputs+outputs per step are %d MB per GPU, larger than the 126 MB L2" % ((d_in.numel() + d_out.numel()) >> 20),
                    "parallelism": "frames sharded over %d rank(s), no data-path collective; weights NCCL-broadcast" % world},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": sampler.summary(),
+        "clocks": sampler.summary(), "other_configs": extra,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

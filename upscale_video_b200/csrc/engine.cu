@@ -1279,9 +1279,9 @@ static int fused_items(b2sr_ctx* c, Plan* P, int res, ResItems** out) {
     return 0;
 }
 
-template <int NOUT, int MODE, bool F32OUT, bool PLAIN>
+template <int NOUT, int MODE, bool F32OUT, int NRES, int OUTS>
 static int launch_tcg(b2sr_ctx* c, const FusedLaunch& L, const ResItems* R, const TcgParams& p) {
-    auto kern = tcg_conv_kernel<NOUT, MODE, F32OUT, PLAIN>;
+    auto kern = tcg_conv_kernel<NOUT, MODE, F32OUT, NRES, OUTS>;
     const int smem = TcgCfg<NOUT, MODE>::smem_bytes(L.G, L.slots);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<R->n_cta, TC_THREADS, smem, c->stream>>>(p);
@@ -1394,13 +1394,30 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
             }
             TRY(prof_begin(c, 1, R->out_px));
             int rc;
-            const bool plain = o.nres == 0 && o.out32_buf < 0;  // bias + activation -> fp16 only: the lean epilogue
-            if (o.final)
-                rc = f32out ? launch_tcg<16, 1, true, false>(c, L, R, p) : launch_tcg<16, 1, false, false>(c, L, R, p);
-            else if (L.NOUT == 64)
-                rc = plain ? launch_tcg<64, 0, false, true>(c, L, R, p) : launch_tcg<64, 0, false, false>(c, L, R, p);
-            else
-                rc = plain ? launch_tcg<32, 0, false, true>(c, L, R, p) : launch_tcg<32, 0, false, false>(c, L, R, p);
+            // epilogue variant: specialised for the combinations RRDB graphs use (fp32 residuals), generic otherwise
+            const int outs = (o.out16_buf >= 0 ? 1 : 0) | (o.out32_buf >= 0 ? 2 : 0);
+            bool resf32 = true;
+            for (int q = 0; q < o.nres; ++q) resf32 = resf32 && c->fbufs[o.res_buf[q]].dtype == 4;
+            const int key = resf32 ? o.nres * 4 + outs : -1;
+            if (o.final) {
+                rc = f32out ? launch_tcg<16, 1, true, -1, 0>(c, L, R, p) : launch_tcg<16, 1, false, -1, 0>(c, L, R, p);
+            } else if (L.NOUT == 64) {
+                switch (key) {
+                    case 0 * 4 + 1: rc = launch_tcg<64, 0, false, 0, 1>(c, L, R, p); break;  // tail convolutions
+                    case 0 * 4 + 3: rc = launch_tcg<64, 0, false, 0, 3>(c, L, R, p); break;  // head convolution
+                    case 1 * 4 + 1: rc = launch_tcg<64, 0, false, 1, 1>(c, L, R, p); break;  // trunk convolution + skip
+                    default: rc = launch_tcg<64, 0, false, -1, 0>(c, L, R, p);
+                }
+            } else {
+                switch (key) {
+                    case 0 * 4 + 1: rc = launch_tcg<32, 0, false, 0, 1>(c, L, R, p); break;  // x1, x3
+                    case 0 * 4 + 2: rc = launch_tcg<32, 0, false, 0, 2>(c, L, R, p); break;  // 1x1 shortcut
+                    case 1 * 4 + 1: rc = launch_tcg<32, 0, false, 1, 1>(c, L, R, p); break;  // x4 = lrelu(conv) + x2
+                    case 1 * 4 + 3: rc = launch_tcg<32, 0, false, 1, 3>(c, L, R, p); break;  // x2, dense-block output
+                    case 2 * 4 + 3: rc = launch_tcg<32, 0, false, 2, 3>(c, L, R, p); break;  // RRDB output
+                    default: rc = launch_tcg<32, 0, false, -1, 0>(c, L, R, p);
+                }
+            }
             TRY(rc);
             TRY(prof_end(c));
             if (dbg) {

@@ -74,7 +74,11 @@ struct TcgCfg {
     static constexpr int smem_bytes(int groups, int slots) { return 1024 + weight_bytes(groups) + slots * TCG_SUBROWB + STG + MISC; }
 };
 
-template <int NOUT, int MODE /*0 = activation buffers, 1 = network output frames*/, bool F32OUT, bool PLAIN /*MODE 0 without residual terms and fp32 copy*/>
+// NRES / OUTS specialise the MODE 0 epilogue (a lone warp per scheduler runs it: its instruction count is its speed):
+// NRES = number of residual terms, all read from fp32 buffers, or -1 = taken from the parameters at run time (and fp16
+// residuals allowed); OUTS = bit 0: fp16 copy, bit 1: fp32 copy, or 0 = decided at run time.  NRES = 0, OUTS = 1 is the
+// plain bias + LeakyReLU -> fp16 epilogue.
+template <int NOUT, int MODE /*0 = activation buffers, 1 = network output frames*/, bool F32OUT, int NRES, int OUTS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_constant__ TcgParams P) {
     using C = TcgCfg<NOUT, MODE>;
     extern __shared__ uint8_t smem_raw[];
@@ -102,7 +106,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + bar_off + 8 * (2 * TC_MAX_SLOTS + 2 * TC_NBLK + 1));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int NPRE = NOUT <= 32 ? 2 : 1;  // residual terms prefetched into registers (NOUT / 4 uint4 each)
+    constexpr bool PLAIN = NRES == 0 && OUTS == 1;
+    constexpr int NPRE = NRES >= 0 ? (NRES > 0 ? NRES : 1) : (NOUT <= 32 ? 2 : 1);  // residual terms prefetched into registers
+    static_assert(NRES < 0 || NOUT * NRES <= 64, "prefetched residuals do not fit the register budget");
+    const int nres = NRES >= 0 ? NRES : P.nres;
+    const bool has16 = OUTS ? (OUTS & 1) != 0 : P.out16 != nullptr, has32 = OUTS ? (OUTS & 2) != 0 : P.out32 != nullptr;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < R; ++s) {
@@ -301,8 +309,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                     pix = valid ? (long long)I.pix_off + (long long)(I.y0 + t) * I.Wt + I.x0 + c : -1;
 #pragma unroll
                     for (int r = 0; r < NPRE; ++r) {
-                        if (r >= P.nres || pix < 0) continue;
-                        if (P.res_f32[r]) {
+                        if (r >= nres || pix < 0) continue;
+                        if (NRES >= 0 || P.res_f32[r]) {
                             const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(P.res_ptr[r]) + pix * P.res_ld[r]);
 #pragma unroll
                             for (int j = 0; j < NOUT / 4; ++j) rraw[r][j] = rp[j];
@@ -393,11 +401,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                         }
 #pragma unroll
                         for (int r = 0; r < 2; ++r) {
-                            if (r >= P.nres) continue;
+                            if (r >= nres) continue;
                             float rv[4] = {0.f, 0.f, 0.f, 0.f};
                             if (pix >= 0) {
                                 if (r < NPRE) {
-                                    if (P.res_f32[r]) {
+                                    if (NRES >= 0 || P.res_f32[r]) {
                                         const uint4 u = rraw[r][j >> 2];
                                         rv[0] = __uint_as_float(u.x), rv[1] = __uint_as_float(u.y), rv[2] = __uint_as_float(u.z), rv[3] = __uint_as_float(u.w);
                                     } else {
@@ -426,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                     // instruction writes whole 16-byte chunks of consecutive pixels: the fp32 copy in two passes of
                     // NOUT / 2 channels (per-thread float4 stores to 32 different lines per instruction were measured to
                     // cost ~1700 cycles per row), then the fp16 copy in one.
-                    if (P.out32) {
+                    if (has32) {
                         uint8_t* outp = reinterpret_cast<uint8_t*>(P.out32);
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
@@ -446,7 +454,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                             }
                         }
                     }
-                    if (P.out16) {
+                    if (has16) {
                         uint8_t* outp = reinterpret_cast<uint8_t*>(P.out16);
                         __syncwarp();
 #pragma unroll

@@ -17,8 +17,12 @@ ap.add_argument("--w", type=int, default=960)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--impl", type=int, default=0)
 ap.add_argument("--batch", type=int, default=0, help="also time N device-resident frames per call (b2sr_run_batch_device)")
+ap.add_argument("--chain", type=int, default=-1, help="compile_fused fp32_chain override")
 ap.add_argument("--debug", type=int, default=0, help="print stall accounting of the first N fused launches (and the last 5)")
 a = ap.parse_args()
+if a.chain >= 0:
+    _cf = ncnn_model.compile_fused
+    ncnn_model.compile_fused = lambda g, *x, **k: _cf(g, *x, fp32_chain=a.chain, **k)
 eng = E.Engine.from_files(ncnn_model.packaged_model_dir(), "4x_Valar_v1", 0)
 eng.set_option(E.OPT_IMPL, a.impl)
 img = np.random.default_rng(0).integers(0, 256, (a.h, a.w, 3), dtype=np.uint8)

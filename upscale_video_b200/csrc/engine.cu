@@ -1298,9 +1298,9 @@ static int fused_items(b2sr_ctx* c, Plan* P, int res, ResItems** out) {
     return 0;
 }
 
-template <int NOUT, int MODE, bool F32OUT, int NRES, int OUTS>
+template <int NOUT, int MODE, bool F32OUT, int NRES, int OUTS, bool RF16 = false>
 static int launch_tcg(b2sr_ctx* c, const FusedLaunch& L, const ResItems* R, const TcgParams& p) {
-    auto kern = tcg_conv_kernel<NOUT, MODE, F32OUT, NRES, OUTS>;
+    auto kern = tcg_conv_kernel<NOUT, MODE, F32OUT, NRES, OUTS, RF16>;
     const int smem = TcgCfg<NOUT, MODE>::smem_bytes(L.G, L.slots);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<R->n_cta, TC_THREADS, smem, c->stream>>>(p);
@@ -1426,9 +1426,12 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
             int rc;
             // epilogue variant: specialised for the combinations RRDB graphs use (fp32 residuals), generic otherwise
             const int outs = (o.out16_buf >= 0 ? 1 : 0) | (o.out32_buf >= 0 ? 2 : 0);
-            bool resf32 = true;
-            for (int q = 0; q < o.nres; ++q) resf32 = resf32 && c->fbufs[o.res_buf[q]].dtype == 4;
-            const int key = resf32 ? o.nres * 4 + outs : -1;
+            bool resf32 = true, resf16 = true;
+            for (int q = 0; q < o.nres; ++q) {
+                resf32 = resf32 && c->fbufs[o.res_buf[q]].dtype == 4;
+                resf16 = resf16 && c->fbufs[o.res_buf[q]].dtype == 2;
+            }
+            const int key = resf32 ? o.nres * 4 + outs : (resf16 ? 100 + o.nres * 4 + outs : -1);
             if (o.final) {
                 rc = f32out ? launch_tcg<16, 1, true, -1, 0>(c, L, R, p) : launch_tcg<16, 1, false, -1, 0>(c, L, R, p);
             } else if (L.NOUT == 64) {
@@ -1436,15 +1439,18 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
                     case 0 * 4 + 1: rc = launch_tcg<64, 0, false, 0, 1>(c, L, R, p); break;  // tail convolutions
                     case 0 * 4 + 3: rc = launch_tcg<64, 0, false, 0, 3>(c, L, R, p); break;  // head convolution
                     case 1 * 4 + 1: rc = launch_tcg<64, 0, false, 1, 1>(c, L, R, p); break;  // trunk convolution + skip
+                    case 100 + 1 * 4 + 1: rc = launch_tcg<64, 0, false, 1, 1, true>(c, L, R, p); break;
                     default: rc = launch_tcg<64, 0, false, -1, 0>(c, L, R, p);
                 }
             } else {
                 switch (key) {
-                    case 0 * 4 + 1: rc = launch_tcg<32, 0, false, 0, 1>(c, L, R, p); break;  // x1, x3
-                    case 0 * 4 + 2: rc = launch_tcg<32, 0, false, 0, 2>(c, L, R, p); break;  // 1x1 shortcut
-                    case 1 * 4 + 1: rc = launch_tcg<32, 0, false, 1, 1>(c, L, R, p); break;  // x4 = lrelu(conv) + x2
-                    case 1 * 4 + 3: rc = launch_tcg<32, 0, false, 1, 3>(c, L, R, p); break;  // x2, dense-block output
+                    case 0 * 4 + 1: rc = launch_tcg<32, 0, false, 0, 1>(c, L, R, p); break;  // x1, x3 (and the 1x1 shortcut kept in fp16)
+                    case 0 * 4 + 2: rc = launch_tcg<32, 0, false, 0, 2>(c, L, R, p); break;  // 1x1 shortcut kept in fp32
+                    case 1 * 4 + 1: rc = launch_tcg<32, 0, false, 1, 1>(c, L, R, p); break;  // x4 = lrelu(conv) + x2 (fp32 x2)
+                    case 1 * 4 + 3: rc = launch_tcg<32, 0, false, 1, 3>(c, L, R, p); break;  // dense-block output: 0.2 v + x
                     case 2 * 4 + 3: rc = launch_tcg<32, 0, false, 2, 3>(c, L, R, p); break;  // RRDB output
+                    case 100 + 1 * 4 + 1: rc = launch_tcg<32, 0, false, 1, 1, true>(c, L, R, p); break;  // x2, x4 with fp16 residuals
+                    case 100 + 2 * 4 + 1: rc = launch_tcg<32, 0, false, 2, 1, true>(c, L, R, p); break;
                     default: rc = launch_tcg<32, 0, false, -1, 0>(c, L, R, p);
                 }
             }

@@ -75,10 +75,10 @@ struct TcgCfg {
 };
 
 // NRES / OUTS specialise the MODE 0 epilogue (a lone warp per scheduler runs it: its instruction count is its speed):
-// NRES = number of residual terms, all read from fp32 buffers, or -1 = taken from the parameters at run time (and fp16
-// residuals allowed); OUTS = bit 0: fp16 copy, bit 1: fp32 copy, or 0 = decided at run time.  NRES = 0, OUTS = 1 is the
+// NRES = number of residual terms, all read from fp32 buffers (RF16: all from fp16 buffers), or -1 = everything taken
+// from the parameters at run time; OUTS = bit 0: fp16 copy, bit 1: fp32 copy, or 0 = decided at run time.  NRES = 0, OUTS = 1 is the
 // plain bias + LeakyReLU -> fp16 epilogue.
-template <int NOUT, int MODE /*0 = activation buffers, 1 = network output frames*/, bool F32OUT, int NRES, int OUTS>
+template <int NOUT, int MODE /*0 = activation buffers, 1 = network output frames*/, bool F32OUT, int NRES, int OUTS, bool RF16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_constant__ TcgParams P) {
     using C = TcgCfg<NOUT, MODE>;
     extern __shared__ uint8_t smem_raw[];
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr bool PLAIN = NRES == 0 && OUTS == 1;
     constexpr int NPRE = NRES >= 0 ? (NRES > 0 ? NRES : 1) : (NOUT <= 32 ? 2 : 1);  // residual terms prefetched into registers
-    static_assert(NRES < 0 || NOUT * NRES <= 64, "prefetched residuals do not fit the register budget");
+    static_assert(NRES < 0 || NOUT * NRES <= (RF16 ? 128 : 64), "prefetched residuals do not fit the register budget");
     const int nres = NRES >= 0 ? NRES : P.nres;
     const bool has16 = OUTS ? (OUTS & 1) != 0 : P.out16 != nullptr, has32 = OUTS ? (OUTS & 2) != 0 : P.out32 != nullptr;
 
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
 #pragma unroll
                     for (int r = 0; r < NPRE; ++r) {
                         if (r >= nres || pix < 0) continue;
-                        if (NRES >= 0 || P.res_f32[r]) {
+                        if (NRES >= 0 ? !RF16 : P.res_f32[r] != 0) {
                             const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(P.res_ptr[r]) + pix * P.res_ld[r]);
 #pragma unroll
                             for (int j = 0; j < NOUT / 4; ++j) rraw[r][j] = rp[j];
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                             float rv[4] = {0.f, 0.f, 0.f, 0.f};
                             if (pix >= 0) {
                                 if (r < NPRE) {
-                                    if (NRES >= 0 || P.res_f32[r]) {
+                                    if (NRES >= 0 ? !RF16 : P.res_f32[r] != 0) {
                                         const uint4 u = rraw[r][j >> 2];
                                         rv[0] = __uint_as_float(u.x), rv[1] = __uint_as_float(u.y), rv[2] = __uint_as_float(u.z), rv[3] = __uint_as_float(u.w);
                                     } else {

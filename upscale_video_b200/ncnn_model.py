@@ -527,7 +527,7 @@ class FusedProgram:
     output_blob: str = "output"
 
 
-def compile_fused(graph: Graph, input_blob: str = "input", output_blob: str = "output") -> FusedProgram | None:
+def compile_fused(graph: Graph, input_blob: str = "input", output_blob: str = "output", fp32_chain: int = 3) -> FusedProgram | None:
     """Lower an ncnn graph to the op list of ``b2sr_create_fused`` (include/b2sr.h), or return None when the graph has
     a layer that does not fit the fused form (the caller then uses :func:`compile_graph`).
 
@@ -599,7 +599,17 @@ def compile_fused(graph: Graph, input_blob: str = "input", output_blob: str = "o
         for other, _, _ in s["resid"]:
             if other not in made_by:
                 return None
-            (need32 if made_by[other]["kind"] == FOP_CONV else need16).add(other)
+    # A residual source is kept in fp32 only when it sits on a long chain of residual adds (the RRDB trunk: every block
+    # output is the next block's residual, 70 deep): rounding those to fp16 would accumulate.  Short chains (the 1x1
+    # shortcut -> x2 -> x4 of a dense block, depth 2) are read from the fp16 copy the convolutions use anyway, which
+    # saves their fp32 round trip through HBM.
+    rdepth = {}
+    for s in reversed(sched):
+        for other, _, _ in s["resid"]:
+            rdepth[other] = max(rdepth.get(other, 0), 1 + rdepth.get(s["out"], 0))
+    for s in sched:
+        for other, _, _ in s["resid"]:
+            (need32 if made_by[other]["kind"] == FOP_CONV and rdepth[other] >= fp32_chain else need16).add(other)
     for v in member:
         if v not in made_by:
             return None

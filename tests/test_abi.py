@@ -80,3 +80,55 @@ def test_product_code_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "liboracle" not in src, f
+
+
+def _fused_arrays(prog):
+    from upscale_video_b200 import engine
+    ops = (engine.FusedOp * len(prog.ops))()
+    for a, o in zip(ops, prog.ops):
+        for k in ("type", "res", "in_buf", "in_off", "cin", "k", "cout", "act", "slope", "nres", "w_off", "b_off",
+                  "out16_buf", "out16_off", "out32_buf", "out32_off", "r", "final"):
+            setattr(a, k, o[k])
+        for q in range(2):
+            a.res_buf[q], a.res_off[q], a.coef_v[q], a.coef_r[q] = o["res_buf"][q], o["res_off"][q], o["coef_v"][q], o["coef_r"][q]
+    bufs = (engine.FusedBuf * len(prog.bufs))()
+    for a, b in zip(bufs, prog.bufs):
+        a.channels, a.dtype, a.res = b["channels"], b["dtype"], b["res"]
+    return ops, bufs
+
+
+def test_fused_program_validation_without_device(lib, model_dir):
+    """b2sr_create_fused checks the whole program before it touches the device: the real 4x_Valar_v1 program passes the
+    checks (and then fails with NODEVICE here), broken programs are refused with INVALID / UNSUPPORTED and a message."""
+    import copy
+    import torch
+    from upscale_video_b200 import engine, ncnn_model
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    assert ctypes.sizeof(engine.FusedOp) == 128 and ctypes.sizeof(engine.FusedBuf) == 16
+    prog = ncnn_model.compile_fused(ncnn_model.load_model(model_dir, "4x_Valar_v1"))
+    w = np.ascontiguousarray(prog.weights, np.float32)
+
+    def create(p, scale=None):
+        ops, bufs = _fused_arrays(p)
+        h = ctypes.c_void_p()
+        rc = lib.b2sr_create_fused(ctypes.byref(h), 0, ops, len(p.ops), bufs, len(p.bufs), scale or p.scale, w.ctypes.data, w.nbytes)
+        assert h.value is None
+        return rc, lib.b2sr_last_error().decode()
+
+    rc, msg = create(prog)
+    assert rc == -3 and "no CUDA device" in msg  # valid program: only the device is missing
+    cases = []
+    bad = copy.deepcopy(prog); bad.ops[5]["in_off"] = 4; cases.append((bad, "convolution input"))        # view not 16-byte aligned
+    bad = copy.deepcopy(prog); bad.ops[3]["cin"] = 208; cases.append((bad, "convolution input"))          # more than 3 groups of 64
+    bad = copy.deepcopy(prog); bad.ops[3]["res_buf"][0] = 99; cases.append((bad, "bad residual"))
+    bad = copy.deepcopy(prog); bad.ops[1]["out16_off"] = 176; cases.append((bad, "bad output view"))      # slice runs past the buffer
+    bad = copy.deepcopy(prog); bad.ops[2]["w_off"] = len(w); cases.append((bad, "weights outside"))
+    bad = copy.deepcopy(prog); bad.ops[-1]["final"] = 0; cases.append((bad, "convolution output"))
+    bad = copy.deepcopy(prog); bad.ops[-4]["r"] = 3; cases.append((bad, "nearest"))
+    bad = copy.deepcopy(prog); bad.bufs[0]["dtype"] = 3; cases.append((bad, "buffer 0"))
+    for p, frag in cases:
+        rc, msg = create(p)
+        assert rc in (-1, -5) and frag in msg, (rc, msg, frag)
+    rc, msg = create(prog, scale=3)
+    assert rc == -5 and "scale" in msg

@@ -410,6 +410,19 @@ def test_valar_rrdb_fused_tcgen05(E, model_dir, oracle_models):
     eng.close()
 
 
+@pytest.mark.parametrize("shape", [(1, 1), (2, 3), (3, 129), (9, 128), (17, 257)])
+def test_valar_edge_shapes(E, model_dir, oracle_models, shape):
+    """Degenerate and band-boundary shapes through the fused tcgen05 graph kernels: 1-pixel planes (every tap but the
+    centre is padding), widths at 128 / 129 / 257 columns (a band of one column), fewer rows than the accumulator ring."""
+    if not os.path.exists(os.path.join(model_dir, "4x_Valar_v1.b2sr")):
+        pytest.skip("4x_Valar_v1 not packaged")
+    eng = E.Engine.from_files(model_dir, "4x_Valar_v1", 0)
+    img = natural(shape[0], shape[1], seed=31 + shape[1])
+    ref = oracle.upscale_image_array(oracle_models("4x_Valar_v1"), img, 4, "f64")
+    assert_parity(eng.run_u8(img), ref, "valar %dx%d" % shape, max_mismatch=0.05)
+    eng.close()
+
+
 def test_valar_rrdb_generic_graph_engine(E, model_dir, oracle_models):
     """4x_Valar_v1 through the generic op-by-op graph engine (b2sr_create_graph; the cross-check implementation since
     the fused tcgen05 engine exists): golden crop on warp-level MMA and on fp32 CUDA cores."""

@@ -203,6 +203,7 @@ struct b2sr_ctx {
     std::vector<void*> fbuf_ptr;
     std::vector<size_t> fbuf_cap;  // bytes
     uint64_t fbuf_gen = 1;         // bumped whenever a fused buffer or in16 moves
+    int pdl = 1;                   // programmatic dependent launch of the fused convolution kernels (B2SR_PDL=0 disables)
     size_t l2_persist = 0;         // bytes of L2 set aside for persisting accesses (0 = feature off)
     size_t l2_window_max = 0;
     std::vector<GraphOp> gops;  // B2SR_FAMILY_GRAPH
@@ -1188,6 +1189,8 @@ extern "C" int b2sr_create_fused(b2sr_ctx** out, int device, const b2sr_fused_op
         // L2-persisting so that the following launches of the dense block (which re-read it) hit L2.  Measured on
         // B200, 540p (199 MB per 192-channel buffer): 34.4 ms/frame without, 38.3 ms with 48 MB set aside, 59 ms with
         // the maximum -- the set-aside starves the normal L2 traffic (halo re-reads, weights, fp32 trunk), so it is off.
+        const char* pe = getenv("B2SR_PDL");
+        if (pe && atoi(pe) == 0) c->pdl = 0;
         const char* e = getenv("B2SR_L2_PERSIST");
         if (e && atoi(e) > 0 && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
             const size_t want = (size_t)atoi(e) << 20;
@@ -1303,8 +1306,15 @@ static int launch_tcg(b2sr_ctx* c, const FusedLaunch& L, const ResItems* R, cons
     auto kern = tcg_conv_kernel<NOUT, MODE, F32OUT, NRES, OUTS, RF16>;
     const int smem = TcgCfg<NOUT, MODE>::smem_bytes(L.G, L.slots);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<R->n_cta, TC_THREADS, smem, c->stream>>>(p);
-    CUDA_TRY(cudaGetLastError());
+    // programmatic dependent launch: this launch's prologue (barrier init, TMEM allocation, weight load) overlaps the tail
+    // of the previous launch of the stream; the kernel waits (griddepcontrol.wait) before it touches activation buffers
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)R->n_cta), cfg.blockDim = dim3(TC_THREADS), cfg.dynamicSmemBytes = (size_t)smem, cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = c->pdl ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
     c->n_launch += 1, c->n_tc += 1;
     return 0;
 }

@@ -51,6 +51,11 @@ struct TcgParams {
     long long* dbg;             // optional [CTA][8] stall accounting (B2SR_OPT_PIPE_DEBUG)
 };
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may become resident
+// while its predecessor drains; griddep_wait() blocks until the predecessor grid has completed and its memory is visible.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 constexpr int TCG_PB = 128;                      // bytes per pixel of one channel group == one SW128 swizzle row
 constexpr int TCG_SUBROWB = TC_PITCH * TCG_PB;   // one ring slot
 constexpr int TCG_BAR_WORDS = 2 * TC_MAX_SLOTS + 2 * TC_NBLK + 2;
@@ -151,6 +156,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
             uint32_t phase = 0;
             long long w_empty = 0;
             const long long t_begin = clock64();
+            griddep_wait();  // everything above (barriers, TMEM, weights: constants) overlapped the previous launch's tail
             for (int it = it_begin; it < it_end; ++it) {
                 const TcItem I = P.items[it];
                 const CUtensorMap* map = P.maps + (P.map_base + I.map);
@@ -168,6 +174,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                     }
                 }
             }
+            // all input rows of this CTA are requested: the next launch of the stream may start taking the SMs that CTAs
+            // of this grid free (it does its own prologue, then waits for this grid to complete before touching buffers)
+            griddep_launch_dependents();
             if (P.dbg) {
                 P.dbg[blockIdx.x * 16 + 4] = w_empty;
                 P.dbg[blockIdx.x * 16 + 7] = clock64() - t_begin;
@@ -290,6 +299,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
         }
         const float scale_acc = P.acc_scale;
         const int c = q * 32 + lane;
+        griddep_wait();  // residual buffers are read and output buffers written only after the previous launch has completed
         long long w_tfull = 0, t_tmem = 0;
         const long long t_begin = clock64();
         for (int it = it_begin; it < it_end; ++it) {

@@ -188,6 +188,7 @@ struct FusedLaunch {  // one tcgen05 launch of a fused convolution (a 192 -> 64 
     int cinp = 0;      // input view channels, padded to 16
     int slots = 0;     // shared-memory ring slots
     uint8_t* wimg = nullptr;
+    uint8_t* wimg_flip = nullptr;  // the same image with the ky blocks swapped (rows walked bottom-up)
     float* bias = nullptr;
     float* slope = nullptr;
 };
@@ -203,6 +204,7 @@ struct b2sr_ctx {
     std::vector<void*> fbuf_ptr;
     std::vector<size_t> fbuf_cap;  // bytes
     uint64_t fbuf_gen = 1;         // bumped whenever a fused buffer or in16 moves
+    int flip_rows = 0;             // experiment (B2SR_FLIP=1): alternate the row direction of consecutive fused launches
     int pdl = 1;                   // programmatic dependent launch of the fused convolution kernels (B2SR_PDL=0 disables)
     size_t l2_persist = 0;         // bytes of L2 set aside for persisting accesses (0 = feature off)
     size_t l2_window_max = 0;
@@ -287,7 +289,7 @@ extern "C" void b2sr_destroy(b2sr_ctx* c) {
     for (float* p : c->slot_buf)
         if (p) cudaFree(p);
     for (auto& L : c->flaunch)
-        for (void* p : {(void*)L.wimg, (void*)L.bias, (void*)L.slope})
+        for (void* p : {(void*)L.wimg, (void*)L.wimg_flip, (void*)L.bias, (void*)L.slope})
             if (p) cudaFree(p);
     for (void* p : c->fbuf_ptr)
         if (p) cudaFree(p);
@@ -1096,9 +1098,9 @@ static int fused_fit(int NOUT, bool final, int G) {
 
 // Stacked, pre-swizzled weight image of output channels [co0, co0 + nco) of a convolution:
 // [group g][kx][(2 - ky) * NOUT + o][64 channels], rows of 128 bytes in the 128-byte swizzle pattern.
-static int upload_fused_launch(FusedLaunch& L, const b2sr_fused_op& o, const float* wb) {
+static int upload_fused_launch(FusedLaunch& L, const b2sr_fused_op& o, const float* wb, bool with_flip) {
     const int K = o.k, PB = TCG_PB;
-    std::vector<uint8_t> img((size_t)L.G * 9 * L.NOUT * PB, 0);
+    std::vector<uint8_t> img((size_t)L.G * 9 * L.NOUT * PB, 0), flp(img.size(), 0);
     for (int oc = 0; oc < L.nco; ++oc)
         for (int ic = 0; ic < o.cin; ++ic)
             for (int t = 0; t < K * K; ++t) {
@@ -1110,6 +1112,8 @@ static int upload_fused_launch(FusedLaunch& L, const b2sr_fused_op& o, const flo
                 const int g = ic / 64, c = ic % 64;
                 const uint32_t a = swizzle_addr((uint32_t)(((2 - ky) * L.NOUT + oc) * PB + c * 2), PB);
                 memcpy(&img[((size_t)g * 3 + kx) * 3 * L.NOUT * PB + a], &hv, 2);
+                const uint32_t af = swizzle_addr((uint32_t)((ky * L.NOUT + oc) * PB + c * 2), PB);  // bottom-up walk: ky <-> 2 - ky
+                memcpy(&flp[((size_t)g * 3 + kx) * 3 * L.NOUT * PB + af], &hv, 2);
             }
     std::vector<float> b(L.NOUT, 0.f), s(L.NOUT, 1.f);
     for (int oc = 0; oc < L.nco; ++oc) {
@@ -1118,6 +1122,10 @@ static int upload_fused_launch(FusedLaunch& L, const b2sr_fused_op& o, const flo
     }
     CUDA_TRY(cudaMalloc(&L.wimg, img.size()));
     CUDA_TRY(cudaMemcpy(L.wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
+    if (with_flip) {
+        CUDA_TRY(cudaMalloc(&L.wimg_flip, flp.size()));
+        CUDA_TRY(cudaMemcpy(L.wimg_flip, flp.data(), flp.size(), cudaMemcpyHostToDevice));
+    }
     CUDA_TRY(cudaMalloc(&L.bias, L.NOUT * 4));
     CUDA_TRY(cudaMemcpy(L.bias, b.data(), L.NOUT * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&L.slope, L.NOUT * 4));
@@ -1191,6 +1199,8 @@ extern "C" int b2sr_create_fused(b2sr_ctx** out, int device, const b2sr_fused_op
         // the maximum -- the set-aside starves the normal L2 traffic (halo re-reads, weights, fp32 trunk), so it is off.
         const char* pe = getenv("B2SR_PDL");
         if (pe && atoi(pe) == 0) c->pdl = 0;
+        const char* fe = getenv("B2SR_FLIP");
+        if (fe && atoi(fe) != 0) c->flip_rows = 1;
         const char* e = getenv("B2SR_L2_PERSIST");
         if (e && atoi(e) > 0 && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
             const size_t want = (size_t)atoi(e) << 20;
@@ -1234,7 +1244,7 @@ extern "C" int b2sr_create_fused(b2sr_ctx** out, int device, const b2sr_fused_op
                 FusedLaunch L;
                 L.op = i, L.co0 = part * NOUT, L.nco = std::min(o.cout - L.co0, NOUT), L.NOUT = NOUT, L.G = G, L.cinp = cinp;
                 L.slots = std::min(12, fused_fit(NOUT, o.final != 0, G));
-                rc = upload_fused_launch(L, o, wb);
+                rc = upload_fused_launch(L, o, wb, c->flip_rows != 0);
                 c->flaunch.push_back(L);  // (pushed even on failure so that b2sr_destroy frees what was allocated)
             }
         }
@@ -1396,7 +1406,12 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
             TcgParams p{};
             p.maps = P->d_fmaps, p.map_base = li * G;
             p.items = R->d_items, p.item_first = R->d_first;
-            p.wimg = L.wimg, p.bias = L.bias, p.slope = L.slope;
+            // Experiment, off by default (B2SR_FLIP=1): alternate launches walk their rows in opposite directions, so that what
+            // the previous launch touched LAST is what this one touches FIRST and may still be in L2 (a 540p dense-block
+            // buffer is 199 MB).  Measured on B200: no gain (540p 31.0 vs 30.8 ms, batches of 4: 30.7 vs 29.6 ms) -- all 148
+            // CTAs sweep their own ranges at once, so no part of the buffer is markedly "more recent" than the rest.
+            p.flip = c->flip_rows && (li & 1) && L.wimg_flip;
+            p.wimg = p.flip ? L.wimg_flip : L.wimg, p.bias = L.bias, p.slope = L.slope;
             p.acc_scale = o.in_buf < 0 ? (1.f / 255.f) : 1.f;
             p.groups = L.G, p.cin = L.cinp, p.k1 = o.k == 1, p.ring_slots = L.slots;
             p.nres = o.nres;

@@ -36,6 +36,7 @@ struct TcgParams {
     int32_t groups;             // channel groups of 64 in the input view (1..3)
     int32_t cin;                // channels of the input view (multiple of 16)
     int32_t k1;                 // 1x1 convolution: only the centre column tap is issued (the others are zero)
+    int32_t flip;               // rows are walked bottom-up (plane row = Ht - 1 - y; wimg has the ky blocks swapped to match)
     int32_t ring_slots;         // shared-memory ring slots (one (row, group) each)
     int32_t nres;               // residual terms
     const void* res_ptr[2];     // channel 0 of this launch's slice, pixel 0 of the buffer
@@ -162,7 +163,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                 const CUtensorMap* map = P.maps + (P.map_base + I.map);
                 const int rows_in = I.rows + 2;
                 for (int rho = 0; rho < rows_in; ++rho) {
-                    const int y = I.y0 - 1 + rho;  // rows outside the plane are zero-filled by TMA = the conv's zero padding
+                    int y = I.y0 - 1 + rho;  // rows outside the plane are zero-filled by TMA = the conv's zero padding
+                    if (P.flip) y = I.Ht - 1 - y;
                     for (int g = 0; g < G; ++g) {
                         mbar_wait_clocked(empty_bar(slot), phase ^ 1u, 0, w_empty);
                         mbar_expect_tx(full_bar(slot), TCG_SUBROWB);
@@ -314,9 +316,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                 // latency (measured: ~700 cycles per dependent chunk, 4-8 chunks per row) hides behind the MMAs
                 [[maybe_unused]] long long pix = -1;
                 [[maybe_unused]] uint4 rraw[PLAIN ? 1 : NPRE][PLAIN ? 1 : NOUT / 4];
-                if constexpr (MODE == 0) pix = valid ? (long long)I.pix_off + (long long)(I.y0 + t) * I.Wt + I.x0 + c : -1;
+                const int yy = P.flip ? I.Ht - 1 - (I.y0 + t) : I.y0 + t;  // plane row of this output row
+                if constexpr (MODE == 0) pix = valid ? (long long)I.pix_off + (long long)yy * I.Wt + I.x0 + c : -1;
                 if constexpr (MODE == 0 && !PLAIN) {
-                    pix = valid ? (long long)I.pix_off + (long long)(I.y0 + t) * I.Wt + I.x0 + c : -1;
 #pragma unroll
                     for (int r = 0; r < NPRE; ++r) {
                         if (r >= nres || pix < 0) continue;
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                     __syncwarp();
                 } else {
                     // network output: (acc + bias) * 255, cropped to the tile core, as cv2.imwrite would store it
-                    const int fy = I.fy0 + I.y0 + t, fx = I.fx0 + I.x0 + c;
+                    const int fy = I.fy0 + yy, fx = I.fx0 + I.x0 + c;
                     if (valid && fy >= I.cy0 && fy < I.cy1 && fx >= I.cx0 && fx < I.cx1) {
                         const size_t o = (((size_t)I.frame * P.frame_h + fy) * P.frame_w + fx) * 3;
 #pragma unroll

@@ -182,7 +182,14 @@ typedef struct b2sr_fused_op {
     int32_t out32_buf, out32_off;
     int32_t r;     /* NEAREST: integer factor */
     int32_t final; /* 1 = network output */
-    int32_t reserved[4];
+    /* Optional fused 1x1 shortcut (the RRDB pattern "x2 = lrelu(conv3x3([x, x1])) + conv1x1(x)", models/4x_Valar_v1.param:9-12):
+     * a bias-less 1x1 convolution over the first sc_cin (<= 64) channels of this op's own input view, accumulated beside
+     * the 3x3 convolution and combined before the residual terms:  v = act(conv + bias);  v = v * sc_coef_v + s * sc_coef_r.
+     * sc_cin = 0: none.  Requires cout = 32, k = 3. */
+    int32_t sc_cin;
+    float sc_coef_v, sc_coef_r;
+    int32_t reserved;
+    int64_t sc_w_off; /* [cout][sc_cin] weights in the blob */
 } b2sr_fused_op;
 int b2sr_create_fused(b2sr_ctx **out, int device, const b2sr_fused_op *ops, int n_ops, const b2sr_fused_buf *bufs, int n_bufs,
                       int scale, const void *weights, size_t nbytes);

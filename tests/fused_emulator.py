@@ -49,6 +49,10 @@ def run_fused(prog: M.FusedProgram, x, exact=True, taps=None, upto=None):
             else:
                 v = oracle.conv(np.ascontiguousarray(src), w, b, o["k"] // 2, o["act"],
                                 np.asarray([o["slope"]], np.float32) if o["act"] == 2 else None, prec)
+            if o.get("sc_cin", 0):
+                ws = prog.weights[o["sc_w_off"]:o["sc_w_off"] + o["cout"] * o["sc_cin"]].reshape(o["cout"], o["sc_cin"], 1, 1)
+                sc = oracle.conv(np.ascontiguousarray(src[:, :, :o["sc_cin"]]), ws, None, 0, 0, None, prec)
+                v = v * real(np.float32(o["sc_coef_v"])) + sc * real(np.float32(o["sc_coef_r"]))
             for q in range(o["nres"]):
                 r = buf(o["res_buf"][q])[:, :, o["res_off"][q]:o["res_off"][q] + o["cout"]]
                 assert not np.isnan(r).any(), "op %d residual %d reads an unwritten slice" % (idx, q)

@@ -87,7 +87,7 @@ def _fused_arrays(prog):
     ops = (engine.FusedOp * len(prog.ops))()
     for a, o in zip(ops, prog.ops):
         for k in ("type", "res", "in_buf", "in_off", "cin", "k", "cout", "act", "slope", "nres", "w_off", "b_off",
-                  "out16_buf", "out16_off", "out32_buf", "out32_off", "r", "final"):
+                  "out16_buf", "out16_off", "out32_buf", "out32_off", "r", "final", "sc_cin", "sc_coef_v", "sc_coef_r", "sc_w_off"):
             setattr(a, k, o[k])
         for q in range(2):
             a.res_buf[q], a.res_off[q], a.coef_v[q], a.coef_r[q] = o["res_buf"][q], o["res_off"][q], o["coef_v"][q], o["coef_r"][q]
@@ -105,7 +105,7 @@ def test_fused_program_validation_without_device(lib, model_dir):
     from upscale_video_b200 import engine, ncnn_model
     if torch.cuda.is_available():
         pytest.skip("a GPU is visible")
-    assert ctypes.sizeof(engine.FusedOp) == 128 and ctypes.sizeof(engine.FusedBuf) == 16
+    assert ctypes.sizeof(engine.FusedOp) == 136 and ctypes.sizeof(engine.FusedBuf) == 16
     prog = ncnn_model.compile_fused(ncnn_model.load_model(model_dir, "4x_Valar_v1"))
     w = np.ascontiguousarray(prog.weights, np.float32)
 
@@ -119,14 +119,21 @@ def test_fused_program_validation_without_device(lib, model_dir):
     rc, msg = create(prog)
     assert rc == -3 and "no CUDA device" in msg  # valid program: only the device is missing
     cases = []
-    bad = copy.deepcopy(prog); bad.ops[5]["in_off"] = 4; cases.append((bad, "convolution input"))        # view not 16-byte aligned
-    bad = copy.deepcopy(prog); bad.ops[3]["cin"] = 208; cases.append((bad, "convolution input"))          # more than 3 groups of 64
-    bad = copy.deepcopy(prog); bad.ops[3]["res_buf"][0] = 99; cases.append((bad, "bad residual"))
-    bad = copy.deepcopy(prog); bad.ops[1]["out16_off"] = 176; cases.append((bad, "bad output view"))      # slice runs past the buffer
+    first = lambda pred: next(i for i, o in enumerate(prog.ops) if pred(o))  # noqa: E731
+    i_res = first(lambda o: o["nres"] > 0)
+    i_wide = first(lambda o: o["cin"] > 64)
+    i_sc = first(lambda o: o["sc_cin"] > 0)
+    i_near = first(lambda o: o["type"] == ncnn_model.FOP_NEAREST)
+    bad = copy.deepcopy(prog); bad.ops[i_wide]["in_off"] = 4; cases.append((bad, "convolution input"))     # view not 16-byte aligned
+    bad = copy.deepcopy(prog); bad.ops[i_wide]["cin"] = 208; cases.append((bad, "convolution input"))      # more than 3 groups of 64
+    bad = copy.deepcopy(prog); bad.ops[i_res]["res_buf"][0] = 99; cases.append((bad, "bad residual"))
+    bad = copy.deepcopy(prog); bad.ops[1]["out16_off"] = 176; cases.append((bad, "bad output view"))       # slice runs past the buffer
     bad = copy.deepcopy(prog); bad.ops[2]["w_off"] = len(w); cases.append((bad, "weights outside"))
     bad = copy.deepcopy(prog); bad.ops[-1]["final"] = 0; cases.append((bad, "convolution output"))
-    bad = copy.deepcopy(prog); bad.ops[-4]["r"] = 3; cases.append((bad, "nearest"))
+    bad = copy.deepcopy(prog); bad.ops[i_near]["r"] = 3; cases.append((bad, "nearest"))
     bad = copy.deepcopy(prog); bad.bufs[0]["dtype"] = 3; cases.append((bad, "buffer 0"))
+    bad = copy.deepcopy(prog); bad.ops[i_sc]["sc_cin"] = 24; cases.append((bad, "shortcut"))               # not a multiple of 16
+    bad = copy.deepcopy(prog); bad.ops[i_sc]["sc_w_off"] = len(w) - 5; cases.append((bad, "shortcut weights"))
     for p, frag in cases:
         rc, msg = create(p)
         assert rc in (-1, -5) and frag in msg, (rc, msg, frag)

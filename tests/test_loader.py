@@ -203,8 +203,12 @@ def test_fused_program_equals_graph_interpreter(model_dir):
     prog = M.compile_fused(g)
     assert prog is not None and prog.scale == 4 and len(prog.bufs) <= 16
     convs = [o for o in prog.ops if o["type"] == M.FOP_CONV]
-    assert len(convs) == len(g.convs()) and sum(o["type"] == M.FOP_NEAREST for o in prog.ops) == 2
-    assert sum(o["nres"] for o in convs) == 23 * 3 * 3 + 23 + 1  # every BinaryOp / Eltwise of the graph is folded
+    n_sc = sum(o["sc_cin"] > 0 for o in convs)
+    assert n_sc == 23 * 3 and all(o["sc_cin"] == 64 and o["cin"] == 96 for o in convs if o["sc_cin"])  # every 1x1 shortcut rides on x2's conv
+    assert len(convs) + n_sc == len(g.convs()) and sum(o["type"] == M.FOP_NEAREST for o in prog.ops) == 2
+    assert sum(o["nres"] for o in convs) + n_sc == 23 * 3 * 3 + 23 + 1  # every BinaryOp / Eltwise of the graph is folded
+    plain = M.compile_fused(g, fuse_shortcuts=False, fp32_chain=1)  # the unfused, all-fp32-residual lowering stays available
+    assert sum(o["type"] == M.FOP_CONV for o in plain.ops) == len(g.convs()) and not any(o["sc_cin"] for o in plain.ops)
     assert prog.ops[-1]["final"] == 1 and sum(o["final"] for o in prog.ops) == 1
     for o in convs:  # what the tcgen05 kernel needs from a view: 16-byte aligned channel offsets, <= 3 groups of 64
         assert o["in_off"] % 8 == 0 and o["out16_off"] % 8 == 0 and o["cin"] <= 192

@@ -186,6 +186,7 @@ struct FusedLaunch {  // one tcgen05 launch of a fused convolution (a 192 -> 64 
     int NOUT = 0;      // padded output channels (16 / 32 / 64)
     int G = 0;         // channel groups of 64 in the input view
     int cinp = 0;      // input view channels, padded to 16
+    int sc_ks = 0;     // fused 1x1 shortcut: K slabs (0 = none)
     int slots = 0;     // shared-memory ring slots
     uint8_t* wimg = nullptr;
     uint8_t* wimg_flip = nullptr;  // the same image with the ky blocks swapped (rows walked bottom-up)
@@ -204,6 +205,9 @@ struct b2sr_ctx {
     std::vector<void*> fbuf_ptr;
     std::vector<size_t> fbuf_cap;  // bytes
     uint64_t fbuf_gen = 1;         // bumped whenever a fused buffer or in16 moves
+    // a box reads 128 bytes (one channel group) per pixel out of a pixel stride of up to 384 bytes: promotion to 256-byte
+    // L2 fetches would pull the neighbouring group in with it (B2SR_L2_PROMO=256 restores that for measurements)
+    CUtensorMapL2promotion l2_promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     int flip_rows = 0;             // experiment (B2SR_FLIP=1): alternate the row direction of consecutive fused launches
     int pdl = 1;                   // programmatic dependent launch of the fused convolution kernels (B2SR_PDL=0 disables)
     size_t l2_persist = 0;         // bytes of L2 set aside for persisting accesses (0 = feature off)
@@ -1088,19 +1092,28 @@ static int run_graph(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
 // ------------------------------------------------------------------------------------------------
 // fused tcgen05 graph engine (B2SR_FAMILY_FUSED): RRDB-style graphs (4x_Valar_v1) on csrc/tc_gconv.cuh
 // ------------------------------------------------------------------------------------------------
-template <int NOUT, int MODE>
-static int fused_ring_fit(int G) { return TcgCfg<NOUT, MODE>::ring_fit(G); }
-
-static int fused_fit(int NOUT, bool final, int G) {
-    if (final) return fused_ring_fit<16, 1>(G);
-    return NOUT == 64 ? fused_ring_fit<64, 0>(G) : fused_ring_fit<32, 0>(G);
+static int fused_fit(int NOUT, bool final, int G, bool sc) {
+    if (final) return TcgCfg<16, 1>::ring_fit(G);
+    if (sc) return TcgCfg<32, 0, true>::ring_fit(G);
+    return NOUT == 64 ? TcgCfg<64, 0>::ring_fit(G) : TcgCfg<32, 0>::ring_fit(G);
 }
 
 // Stacked, pre-swizzled weight image of output channels [co0, co0 + nco) of a convolution:
 // [group g][kx][(2 - ky) * NOUT + o][64 channels], rows of 128 bytes in the 128-byte swizzle pattern.
 static int upload_fused_launch(FusedLaunch& L, const b2sr_fused_op& o, const float* wb, bool with_flip) {
     const int K = o.k, PB = TCG_PB;
-    std::vector<uint8_t> img((size_t)L.G * 9 * L.NOUT * PB, 0), flp(img.size(), 0);
+    const size_t main_bytes = (size_t)L.G * 9 * L.NOUT * PB;
+    std::vector<uint8_t> img(main_bytes + (L.sc_ks ? (size_t)L.NOUT * PB : 0), 0), flp(img.size(), 0);
+    if (L.sc_ks)  // shortcut image behind the 3x3 tiles: [o][64 ch], 128-byte swizzled rows
+        for (int oc = 0; oc < L.nco; ++oc)
+            for (int ic = 0; ic < o.sc_cin; ++ic) {
+                const float v = wb[o.sc_w_off + (int64_t)(L.co0 + oc) * o.sc_cin + ic];
+                if (!fp16_exact(v)) return fail(B2SR_E_UNSUPPORTED, "shortcut weight %g is not exactly representable in fp16", v);
+                const __half hv = __float2half_rn(v);
+                const uint32_t a = swizzle_addr((uint32_t)(oc * PB + ic * 2), PB);
+                memcpy(&img[main_bytes + a], &hv, 2);
+                memcpy(&flp[main_bytes + a], &hv, 2);
+            }
     for (int oc = 0; oc < L.nco; ++oc)
         for (int ic = 0; ic < o.cin; ++ic)
             for (int t = 0; t < K * K; ++t) {
@@ -1171,6 +1184,18 @@ extern "C" int b2sr_create_fused(b2sr_ctx** out, int device, const b2sr_fused_op
             return fail(B2SR_E_INVALID, "op %d: bad output view", i);
         for (int q = 0; q < o.nres; ++q)
             if (!view_ok(o.res_buf[q], o.res_off[q], o.cout, o.res, 0)) return fail(B2SR_E_INVALID, "op %d: bad residual %d", i, q);
+        if (o.sc_cin) {
+            if (o.sc_cin < 16 || o.sc_cin > 64 || o.sc_cin % 16 || o.sc_cin > o.cin || o.in_buf < 0 || o.cout != 32 || o.k != 3 || o.nres || o.out32_buf >= 0 ||
+                o.out16_buf < 0 || o.final)
+                return fail(B2SR_E_UNSUPPORTED, "op %d: fused 1x1 shortcut over %d channels (needs k = 3, cout = 32, fp16 output only, no residual terms)", i, o.sc_cin);
+            if (o.sc_w_off < 0 || o.sc_w_off + (int64_t)o.cout * o.sc_cin > nfl) return fail(B2SR_E_INVALID, "op %d: shortcut weights outside the blob", i);
+        }
+        if (o.sc_cin) {
+            if (o.sc_cin < 16 || o.sc_cin > 64 || o.sc_cin % 16 || o.sc_cin > o.cin || o.in_buf < 0 || o.cout != 32 || o.k != 3 || o.nres || o.out32_buf >= 0 ||
+                o.out16_buf < 0 || o.final)
+                return fail(B2SR_E_UNSUPPORTED, "op %d: fused 1x1 shortcut over %d channels (needs k = 3, cout = 32, fp16 output only, no residual terms)", i, o.sc_cin);
+            if (o.sc_w_off < 0 || o.sc_w_off + (int64_t)o.cout * o.sc_cin > nfl) return fail(B2SR_E_INVALID, "op %d: shortcut weights outside the blob", i);
+        }
         const int64_t nw = (int64_t)o.cout * o.cin * o.k * o.k;
         if (o.w_off < 0 || o.w_off + nw > nfl || (o.b_off >= 0 && o.b_off + o.cout > nfl)) return fail(B2SR_E_INVALID, "op %d: weights outside the blob", i);
     }
@@ -1199,6 +1224,8 @@ extern "C" int b2sr_create_fused(b2sr_ctx** out, int device, const b2sr_fused_op
         // the maximum -- the set-aside starves the normal L2 traffic (halo re-reads, weights, fp32 trunk), so it is off.
         const char* pe = getenv("B2SR_PDL");
         if (pe && atoi(pe) == 0) c->pdl = 0;
+        const char* le = getenv("B2SR_L2_PROMO");
+        if (le) c->l2_promo = atoi(le) == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : (atoi(le) == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (atoi(le) == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
         const char* fe = getenv("B2SR_FLIP");
         if (fe && atoi(fe) != 0) c->flip_rows = 1;
         const char* e = getenv("B2SR_L2_PERSIST");
@@ -1232,8 +1259,9 @@ extern "C" int b2sr_create_fused(b2sr_ctx** out, int device, const b2sr_fused_op
             int NOUT = o.final ? 16 : o.cout, parts = 1;
             // the stacked weights of all groups stay resident in shared memory beside >= 4 ring slots; a wide
             // convolution that does not fit (192 -> 64: 221 KB) is launched as two halves of 32 output channels
-            if (fused_fit(NOUT, o.final != 0, G) < 4) {
-                if (NOUT == 64 && fused_fit(32, false, G) >= 4) {
+            const bool sc = o.sc_cin != 0;
+            if (fused_fit(NOUT, o.final != 0, G, sc) < 4) {
+                if (NOUT == 64 && fused_fit(32, false, G, false) >= 4) {
                     NOUT = 32, parts = 2;
                 } else {
                     rc = fail(B2SR_E_UNSUPPORTED, "op %d: %d -> %d convolution does not fit shared memory", i, o.cin, o.cout);
@@ -1243,7 +1271,8 @@ extern "C" int b2sr_create_fused(b2sr_ctx** out, int device, const b2sr_fused_op
             for (int part = 0; part < parts && !rc; ++part) {
                 FusedLaunch L;
                 L.op = i, L.co0 = part * NOUT, L.nco = std::min(o.cout - L.co0, NOUT), L.NOUT = NOUT, L.G = G, L.cinp = cinp;
-                L.slots = std::min(12, fused_fit(NOUT, o.final != 0, G));
+                L.sc_ks = o.sc_cin / 16;
+                L.slots = std::min(12, fused_fit(NOUT, o.final != 0, G, sc));
                 rc = upload_fused_launch(L, o, wb, c->flip_rows != 0);
                 c->flaunch.push_back(L);  // (pushed even on failure so that b2sr_destroy frees what was allocated)
             }
@@ -1311,10 +1340,10 @@ static int fused_items(b2sr_ctx* c, Plan* P, int res, ResItems** out) {
     return 0;
 }
 
-template <int NOUT, int MODE, bool F32OUT, int NRES, int OUTS, bool RF16 = false>
+template <int NOUT, int MODE, bool F32OUT, int NRES, int OUTS, bool RF16 = false, bool SC = false>
 static int launch_tcg(b2sr_ctx* c, const FusedLaunch& L, const ResItems* R, const TcgParams& p) {
-    auto kern = tcg_conv_kernel<NOUT, MODE, F32OUT, NRES, OUTS, RF16>;
-    const int smem = TcgCfg<NOUT, MODE>::smem_bytes(L.G, L.slots);
+    auto kern = tcg_conv_kernel<NOUT, MODE, F32OUT, NRES, OUTS, RF16, SC>;
+    const int smem = TcgCfg<NOUT, MODE, SC>::smem_bytes(L.G, L.slots);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     // programmatic dependent launch: this launch's prologue (barrier init, TMEM allocation, weight load) overlaps the tail
     // of the previous launch of the stream; the kernel waits (griddepcontrol.wait) before it touches activation buffers
@@ -1364,7 +1393,7 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
                 cuuint32_t es[4] = {1, 1, 1, 1};
                 void* basep = (void*)(bufp + ((size_t)gr.pix_base * r * r * Cb + (o.in_buf < 0 ? 0 : o.in_off)));
                 CUresult e = g_encode(&maps[li * G + g], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, basep, dims, strides, box, es,
-                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, c->l2_promo,
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (e != CUDA_SUCCESS)
                     return fail(B2SR_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for op %d group %d (%d ch of %d, %llux%llu)", (int)e, L.op, g,
@@ -1414,6 +1443,7 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
             p.wimg = p.flip ? L.wimg_flip : L.wimg, p.bias = L.bias, p.slope = L.slope;
             p.acc_scale = o.in_buf < 0 ? (1.f / 255.f) : 1.f;
             p.groups = L.G, p.cin = L.cinp, p.k1 = o.k == 1, p.ring_slots = L.slots;
+            p.sc_ks = L.sc_ks, p.sc_cv = o.sc_coef_v, p.sc_cr = o.sc_coef_r;
             p.nres = o.nres;
             for (int q = 0; q < o.nres; ++q) {
                 const b2sr_fused_buf& B = c->fbufs[o.res_buf[q]];
@@ -1467,6 +1497,8 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
                     case 100 + 1 * 4 + 1: rc = launch_tcg<64, 0, false, 1, 1, true>(c, L, R, p); break;
                     default: rc = launch_tcg<64, 0, false, -1, 0>(c, L, R, p);
                 }
+            } else if (L.sc_ks) {
+                rc = launch_tcg<32, 0, false, 0, 1, false, true>(c, L, R, p);  // x2 = lrelu(conv3x3([x, x1])) + conv1x1(x)
             } else {
                 switch (key) {
                     case 0 * 4 + 1: rc = launch_tcg<32, 0, false, 0, 1>(c, L, R, p); break;  // x1, x3 (and the 1x1 shortcut kept in fp16)

@@ -36,6 +36,8 @@ struct TcgParams {
     int32_t groups;             // channel groups of 64 in the input view (1..3)
     int32_t cin;                // channels of the input view (multiple of 16)
     int32_t k1;                 // 1x1 convolution: only the centre column tap is issued (the others are zero)
+    int32_t sc_ks;              // fused 1x1 shortcut over the first sc_ks * 16 channels of the input view (SC kernels)
+    float sc_cv, sc_cr;         // v = act(conv + bias) * sc_cv + shortcut * sc_cr
     int32_t flip;               // rows are walked bottom-up (plane row = Ht - 1 - y; wimg has the ky blocks swapped to match)
     int32_t ring_slots;         // shared-memory ring slots (one (row, group) each)
     int32_t nres;               // residual terms
@@ -61,21 +63,26 @@ constexpr int TCG_PB = 128;                      // bytes per pixel of one chann
 constexpr int TCG_SUBROWB = TC_PITCH * TCG_PB;   // one ring slot
 constexpr int TCG_BAR_WORDS = 2 * TC_MAX_SLOTS + 2 * TC_NBLK + 2;
 
-template <int NOUT, int MODE>
+template <int NOUT, int MODE, bool SC = false>
 struct TcgCfg {
     static constexpr int OB = NOUT * 2;
     static constexpr int STG = MODE == 0 ? TC_NSETS * 4 * 32 * OB : 0;
     static constexpr int MISC = 2 * NOUT * 4 + TCG_BAR_WORDS * 8 + 64;
-    // Accumulator blocks: output row g lives in block g % NB ("home").  The window of an input row (the blocks of output
+    // Accumulator blocks: output row y lives in block y % NB ("home").  The window of an input row (the blocks of output
     // rows r-1, r, r+1) never wraps: it may run into two extension blocks NB, NB + 1 that stand for homes 0 and 1, and
     // the epilogue adds block NB + h to block h for rows with home h < 2.  (With a wrapping ring two of every NB rows
     // needed a second, small-N MMA per tap and slab; small-N MMAs cost as much as N = 96 ones.)
-    static constexpr int NB = NOUT == 64 ? 6 : 8;
-    static constexpr int TCOLS = (NB + 2) * NOUT <= 128 ? 128 : ((NB + 2) * NOUT <= 256 ? 256 : 512);
-    static_assert((NB + 2) * NOUT <= 512 && NB % TC_NSETS == 0, "accumulator blocks exceed TMEM");
+    // SC kernels keep a second set of NB blocks (the 1x1 shortcut's accumulators) behind the extension blocks.
+    static constexpr int NB = (NOUT == 64 || SC) ? 6 : 8;
+    static constexpr int SC_COL0 = (NB + 2) * NOUT;  // first TMEM column of the shortcut blocks
+    static constexpr int USED = (NB + 2) * NOUT + (SC ? NB * NOUT : 0);
+    static constexpr int TCOLS = USED <= 128 ? 128 : (USED <= 256 ? 256 : 512);
+    static constexpr int SCB = SC ? NOUT * TCG_PB : 0;  // shortcut weight image [NOUT rows][64 ch]
     static constexpr uint32_t IDESC0 = (1u << 4) | ((uint32_t)(TC_TILE_M >> 4) << 24);
     static_assert(NOUT == 16 || NOUT == 32 || NOUT == 64, "NOUT");
-    static constexpr int weight_bytes(int groups) { return groups * 9 * NOUT * TCG_PB; }
+    static_assert(USED <= 512 && NB % TC_NSETS == 0, "accumulator blocks exceed TMEM");
+    static_assert(!SC || (NOUT == 32 && MODE == 0), "the fused shortcut exists for 32-channel activation launches");
+    static constexpr int weight_bytes(int groups) { return groups * 9 * NOUT * TCG_PB + SCB; }
     static constexpr int ring_fit(int groups) { return (B2SR_SMEM_LIMIT - 1024 - weight_bytes(groups) - STG - MISC) / TCG_SUBROWB; }
     static constexpr int smem_bytes(int groups, int slots) { return 1024 + weight_bytes(groups) + slots * TCG_SUBROWB + STG + MISC; }
 };
@@ -84,14 +91,15 @@ struct TcgCfg {
 // NRES = number of residual terms, all read from fp32 buffers (RF16: all from fp16 buffers), or -1 = everything taken
 // from the parameters at run time; OUTS = bit 0: fp16 copy, bit 1: fp32 copy, or 0 = decided at run time.  NRES = 0, OUTS = 1 is the
 // plain bias + LeakyReLU -> fp16 epilogue.
-template <int NOUT, int MODE /*0 = activation buffers, 1 = network output frames*/, bool F32OUT, int NRES, int OUTS, bool RF16 = false>
+template <int NOUT, int MODE /*0 = activation buffers, 1 = network output frames*/, bool F32OUT, int NRES, int OUTS, bool RF16 = false,
+          bool SC = false /*fused 1x1 shortcut*/>
 __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_constant__ TcgParams P) {
-    using C = TcgCfg<NOUT, MODE>;
+    using C = TcgCfg<NOUT, MODE, SC>;
     extern __shared__ uint8_t smem_raw[];
     const int it_begin = P.item_first[blockIdx.x], it_end = P.item_first[blockIdx.x + 1];
     const int G = P.groups, R = P.ring_slots;
     constexpr int NB = C::NB;
-    const uint32_t WB = (uint32_t)(G * 9 * NOUT * TCG_PB);
+    const uint32_t WB = (uint32_t)(G * 9 * NOUT * TCG_PB) + C::SCB;  // stacked 3x3 weights of all groups [+ the shortcut image]
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (sbase - raw);
@@ -113,6 +121,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr bool PLAIN = NRES == 0 && OUTS == 1;
+    static_assert(!SC || PLAIN, "the fused shortcut is implemented for the plain (fp16-only, no residual) epilogue");
     constexpr int NPRE = NRES >= 0 ? (NRES > 0 ? NRES : 1) : (NOUT <= 32 ? 2 : 1);  // residual terms prefetched into registers
     static_assert(NRES < 0 || NOUT * NRES <= (RF16 ? 128 : 64), "prefetched residuals do not fit the register budget");
     const int nres = NRES >= 0 ? NRES : P.nres;
@@ -153,6 +162,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
             mbar_expect_tx(w_bar, WB);
             const uint32_t chunk = 3u * NOUT * TCG_PB;  // one (group, kx) tile
             for (int t = 0; t < 3 * G; ++t) bulk_g2s(w_s + t * chunk, P.wimg + (size_t)t * chunk, chunk, w_bar);
+            if constexpr (SC) bulk_g2s(w_s + 3 * G * chunk, P.wimg + (size_t)3 * G * chunk, C::SCB, w_bar);
             int slot = 0;
             uint32_t phase = 0;
             long long w_empty = 0;
@@ -262,6 +272,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                                 for (int k = 0; k < ks; ++k)
                                     umma_f16(d, a0 + (uint64_t)((kx * TCG_PB + k * 32) >> 4), b0 + (uint64_t)(kx * KXB + ((k * 32) >> 4)), idesc, 1u);
                         }
+                        if constexpr (SC) {
+                            // input row rho is the centre row of output row rho - 1: its first channels through the 1x1 weights
+                            // (column tap kx = 1) into that row's shortcut block
+                            if (g == 0 && rho >= 1 && rho <= rows) {
+                                const uint32_t ds = tmem_base + C::SC_COL0 + ((y0 + (uint32_t)rho - 1u) % NB) * NOUT;
+                                const uint64_t bs = hi64 | (uint64_t)(w_lo + (uint32_t)G * GRPB);
+                                constexpr uint32_t ids = C::IDESC0 | ((uint32_t)(NOUT >> 3) << 17);
+                                for (int k = 0; k < P.sc_ks; ++k)
+                                    umma_f16(ds, a0 + (uint64_t)((TCG_PB + k * 32) >> 4), bs + (uint64_t)((k * 32) >> 4), ids, 1u);
+                            }
+                        }
                         umma_commit(empty_bar(sl));  // this (row, group) slot may be refilled once its MMAs have completed
                         if (++sl == R) sl = 0, ph ^= 1u;
                     }
@@ -293,6 +314,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
             for (int j = 0; j < NOUT; j += 16) {
                 tmem_st16_zero(tmem_base + ((uint32_t)(q * 32) << 16) + b * NOUT + j);
                 if (b < 2) tmem_st16_zero(tmem_base + ((uint32_t)(q * 32) << 16) + (NB + b) * NOUT + j);  // its extension block
+                if constexpr (SC) tmem_st16_zero(tmem_base + ((uint32_t)(q * 32) << 16) + C::SC_COL0 + b * NOUT + j);
             }
             tmem_wait_st();
             tc_fence_before();
@@ -355,6 +377,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                         tmem_st16_zero(xaddr + j0);
                     }
                 }
+                [[maybe_unused]] uint32_t sacc[SC ? NOUT : 1];
+                if constexpr (SC) {
+                    const uint32_t saddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::SC_COL0 + buf * NOUT;
+#pragma unroll
+                    for (int j = 0; j < NOUT; j += 16) tmem_ld16(saddr + j, sacc + j);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < NOUT; j += 16) tmem_st16_zero(saddr + j);
+                }
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
@@ -379,6 +410,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                             float v1 = fmaf(__uint_as_float(acc[j + e + 1]), scale_acc, bb[e + 1]);
                             v0 = v0 < 0.f ? v0 * sl[e] : v0;
                             v1 = v1 < 0.f ? v1 * sl[e + 1] : v1;
+                            if constexpr (SC) {
+                                v0 = v0 * P.sc_cv + __uint_as_float(sacc[j + e]) * P.sc_cr;
+                                v1 = v1 * P.sc_cv + __uint_as_float(sacc[j + e + 1]) * P.sc_cr;
+                            }
                             __half2 h = __floats2half2_rn(v0, v1);
                             pk[e >> 1] = *reinterpret_cast<uint32_t*>(&h);
                         }

@@ -56,7 +56,8 @@ class FusedOp(ctypes.Structure):  # b2sr_fused_op
                 ("res_buf", ctypes.c_int32 * 2), ("res_off", ctypes.c_int32 * 2), ("coef_v", ctypes.c_float * 2),
                 ("coef_r", ctypes.c_float * 2), ("out16_buf", ctypes.c_int32), ("out16_off", ctypes.c_int32),
                 ("out32_buf", ctypes.c_int32), ("out32_off", ctypes.c_int32), ("r", ctypes.c_int32), ("final", ctypes.c_int32),
-                ("reserved", ctypes.c_int32 * 4)]
+                ("sc_cin", ctypes.c_int32), ("sc_coef_v", ctypes.c_float), ("sc_coef_r", ctypes.c_float), ("reserved", ctypes.c_int32),
+                ("sc_w_off", ctypes.c_int64)]
 
 
 class NetDesc(ctypes.Structure):
@@ -174,7 +175,7 @@ class Engine:
         ops = (FusedOp * len(prog.ops))()
         for a, o in zip(ops, prog.ops):
             for k in ("type", "res", "in_buf", "in_off", "cin", "k", "cout", "act", "slope", "nres", "w_off", "b_off",
-                      "out16_buf", "out16_off", "out32_buf", "out32_off", "r", "final"):
+                      "out16_buf", "out16_off", "out32_buf", "out32_off", "r", "final", "sc_cin", "sc_coef_v", "sc_coef_r", "sc_w_off"):
                 setattr(a, k, o[k])
             for q in range(2):
                 a.res_buf[q], a.res_off[q], a.coef_v[q], a.coef_r[q] = o["res_buf"][q], o["res_off"][q], o["coef_v"][q], o["coef_r"][q]

@@ -527,7 +527,8 @@ class FusedProgram:
     output_blob: str = "output"
 
 
-def compile_fused(graph: Graph, input_blob: str = "input", output_blob: str = "output", fp32_chain: int = 3) -> FusedProgram | None:
+def compile_fused(graph: Graph, input_blob: str = "input", output_blob: str = "output", fp32_chain: int = 3,
+                  fuse_shortcuts: bool = True) -> FusedProgram | None:
     """Lower an ncnn graph to the op list of ``b2sr_create_fused`` (include/b2sr.h), or return None when the graph has
     a layer that does not fit the fused form (the caller then uses :func:`compile_graph`).
 
@@ -578,6 +579,29 @@ def compile_fused(graph: Graph, input_blob: str = "input", output_blob: str = "o
             return None  # PReLU / PixelShuffle / free-standing adds: not an RRDB-style graph
     sched.sort(key=lambda e: e[0])
     sched = [e[1] for e in sched]
+    # 1x1 shortcut fusion: "v = act(conv3x3(X)) + conv1x1(X[:c])" with a bias-less, activation-less 1x1 convolution over a
+    # prefix of the same input, consumed by nothing else, becomes one op (the kernel accumulates the 1x1 beside the 3x3)
+    if fuse_shortcuts:
+        by_out = {s_["out"]: s_ for s_ in sched}
+        drop = set()
+        for s_ in sched:
+            if s_["kind"] != FOP_CONV or len(s_["resid"]) != 1:
+                continue
+            other, cv, cr = s_["resid"][0]
+            b_ = by_out.get(other)
+            n_, o_ = s_["node"], s_["node"]["op"]
+            if b_ is None or b_["kind"] != FOP_CONV or b_["resid"] or id(b_) in drop:
+                continue
+            ob = b_["node"]["op"]
+            src_a, src_b = n_["ins"][0], b_["node"]["ins"][0]
+            same_prefix = (src_a in view_fam and src_b in member and member[src_b] == (view_fam[src_a], 0))
+            if (ob["k"] != 1 or ob["act"] != 0 or ob["b_off"] >= 0 or o_["k"] != 3 or o_["cout"] != 32 or ob["cout"] != 32
+                    or ob["cin"] > 64 or ob["cin"] % 16 or not same_prefix or len(consumers.get(other, [])) != 1 or s_["out"] == out_v):
+                continue
+            s_["sc"] = (int(ob["w_off"]), int(ob["cin"]), cv, cr)
+            s_["resid"] = []
+            drop.add(id(b_))
+        sched = [s_ for s_ in sched if id(s_) not in drop]
     if not sched or sched[-1]["out"] != out_v or sched[-1]["kind"] != FOP_CONV or chans[out_v] != 3:
         return None
     made_by = {s["out"]: s for s in sched}
@@ -672,7 +696,11 @@ def compile_fused(graph: Graph, input_blob: str = "input", output_blob: str = "o
         op = {"type": s["kind"], "res": int(res[v]), "in_buf": -1, "in_off": 0, "cin": int(chans[src]), "k": int(o["k"]),
               "cout": int(chans[v]), "act": int(o["act"]), "slope": float(o["slope"]), "w_off": int(o["w_off"]), "b_off": int(o["b_off"]),
               "nres": len(s["resid"]), "res_buf": [-1, -1], "res_off": [0, 0], "coef_v": [1.0, 1.0], "coef_r": [0.0, 0.0],
-              "out16_buf": -1, "out16_off": 0, "out32_buf": -1, "out32_off": 0, "r": int(o["r"]), "final": int(v == out_v)}
+              "out16_buf": -1, "out16_off": 0, "out32_buf": -1, "out32_off": 0, "r": int(o["r"]), "final": int(v == out_v),
+              "sc_cin": 0, "sc_coef_v": 1.0, "sc_coef_r": 0.0, "sc_w_off": -1}
+        if s.get("sc"):
+            op["sc_w_off"], op["sc_cin"] = s["sc"][0], s["sc"][1]
+            op["sc_coef_v"], op["sc_coef_r"] = float(np.float32(s["sc"][2])), float(np.float32(s["sc"][3]))
         if src in view_fam:
             op["in_buf"] = where[("fam", view_fam[src])]
         elif src != input_blob:

@@ -103,8 +103,8 @@ struct Group {  // planes of identical size share one TMA tensor map per activat
     int64_t pix_base;
 };
 
-struct ResItems {  // work items of the planes scaled to resolution factor `res` (fused graph family)
-    int res = 1;
+struct ResItems {  // work items of the planes scaled to resolution factor `res` (fused graph family), cut into <= max_cta ranges
+    int res = 1, max_cta = 0;
     std::vector<TcItem> items;
     std::vector<int> first;
     TcItem* d_items = nullptr;
@@ -187,6 +187,7 @@ struct FusedLaunch {  // one tcgen05 launch of a fused convolution (a 192 -> 64 
     int G = 0;         // channel groups of 64 in the input view
     int cinp = 0;      // input view channels, padded to 16
     int sc_ks = 0;     // fused 1x1 shortcut: K slabs (0 = none)
+    int pair = 0;      // 1: both 32-channel halves of a 64-channel convolution in one launch of 2-CTA clusters (TMA multicast)
     int slots = 0;     // shared-memory ring slots
     uint8_t* wimg = nullptr;
     uint8_t* wimg_flip = nullptr;  // the same image with the ky blocks swapped (rows walked bottom-up)
@@ -209,6 +210,8 @@ struct b2sr_ctx {
     // L2 fetches would pull the neighbouring group in with it (B2SR_L2_PROMO=256 restores that for measurements)
     CUtensorMapL2promotion l2_promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     int flip_rows = 0;             // experiment (B2SR_FLIP=1): alternate the row direction of consecutive fused launches
+    int pair_halves = 1;           // launch split convolutions as 2-CTA clusters sharing their input (B2SR_PAIR=0: two launches)
+    int pair_clusters = 0;         // clusters of two 227 KB CTAs the device can hold at once (measured at the first paired launch)
     int pdl = 1;                   // programmatic dependent launch of the fused convolution kernels (B2SR_PDL=0 disables)
     size_t l2_persist = 0;         // bytes of L2 set aside for persisting accesses (0 = feature off)
     size_t l2_window_max = 0;
@@ -1103,7 +1106,8 @@ static int fused_fit(int NOUT, bool final, int G, bool sc) {
 static int upload_fused_launch(FusedLaunch& L, const b2sr_fused_op& o, const float* wb, bool with_flip) {
     const int K = o.k, PB = TCG_PB;
     const size_t main_bytes = (size_t)L.G * 9 * L.NOUT * PB;
-    std::vector<uint8_t> img(main_bytes + (L.sc_ks ? (size_t)L.NOUT * PB : 0), 0), flp(img.size(), 0);
+    const int parts = L.pair ? 2 : 1;  // a paired launch carries both halves: [image of channels co0..][image of channels co0 + NOUT..]
+    std::vector<uint8_t> img(parts * main_bytes + (L.sc_ks ? (size_t)L.NOUT * PB : 0), 0), flp(img.size(), 0);
     if (L.sc_ks)  // shortcut image behind the 3x3 tiles: [o][64 ch], 128-byte swizzled rows
         for (int oc = 0; oc < L.nco; ++oc)
             for (int ic = 0; ic < o.sc_cin; ++ic) {
@@ -1114,35 +1118,37 @@ static int upload_fused_launch(FusedLaunch& L, const b2sr_fused_op& o, const flo
                 memcpy(&img[main_bytes + a], &hv, 2);
                 memcpy(&flp[main_bytes + a], &hv, 2);
             }
+    for (int part = 0; part < parts; ++part)
     for (int oc = 0; oc < L.nco; ++oc)
         for (int ic = 0; ic < o.cin; ++ic)
             for (int t = 0; t < K * K; ++t) {
-                const float v = wb[o.w_off + ((int64_t)(L.co0 + oc) * o.cin + ic) * K * K + t];
+                const float v = wb[o.w_off + ((int64_t)(L.co0 + part * L.NOUT + oc) * o.cin + ic) * K * K + t];
                 if (!fp16_exact(v))
                     return fail(B2SR_E_UNSUPPORTED, "weight %g (conv out %d in %d tap %d) is not exactly representable in fp16", v, L.co0 + oc, ic, t);
                 const __half hv = __float2half_rn(v);
                 const int ky = K == 3 ? t / 3 : 1, kx = K == 3 ? t % 3 : 1;
                 const int g = ic / 64, c = ic % 64;
                 const uint32_t a = swizzle_addr((uint32_t)(((2 - ky) * L.NOUT + oc) * PB + c * 2), PB);
-                memcpy(&img[((size_t)g * 3 + kx) * 3 * L.NOUT * PB + a], &hv, 2);
+                memcpy(&img[part * main_bytes + ((size_t)g * 3 + kx) * 3 * L.NOUT * PB + a], &hv, 2);
                 const uint32_t af = swizzle_addr((uint32_t)((ky * L.NOUT + oc) * PB + c * 2), PB);  // bottom-up walk: ky <-> 2 - ky
-                memcpy(&flp[((size_t)g * 3 + kx) * 3 * L.NOUT * PB + af], &hv, 2);
+                memcpy(&flp[part * main_bytes + ((size_t)g * 3 + kx) * 3 * L.NOUT * PB + af], &hv, 2);
             }
-    std::vector<float> b(L.NOUT, 0.f), s(L.NOUT, 1.f);
-    for (int oc = 0; oc < L.nco; ++oc) {
-        if (o.b_off >= 0) b[oc] = wb[o.b_off + L.co0 + oc];
-        if (o.act == 2) s[oc] = o.slope;
-    }
+    std::vector<float> b(parts * L.NOUT, 0.f), s(parts * L.NOUT, 1.f);
+    for (int part = 0; part < parts; ++part)
+        for (int oc = 0; oc < L.nco; ++oc) {
+            if (o.b_off >= 0) b[part * L.NOUT + oc] = wb[o.b_off + L.co0 + part * L.NOUT + oc];
+            if (o.act == 2) s[part * L.NOUT + oc] = o.slope;
+        }
     CUDA_TRY(cudaMalloc(&L.wimg, img.size()));
     CUDA_TRY(cudaMemcpy(L.wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
     if (with_flip) {
         CUDA_TRY(cudaMalloc(&L.wimg_flip, flp.size()));
         CUDA_TRY(cudaMemcpy(L.wimg_flip, flp.data(), flp.size(), cudaMemcpyHostToDevice));
     }
-    CUDA_TRY(cudaMalloc(&L.bias, L.NOUT * 4));
-    CUDA_TRY(cudaMemcpy(L.bias, b.data(), L.NOUT * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc(&L.slope, L.NOUT * 4));
-    CUDA_TRY(cudaMemcpy(L.slope, s.data(), L.NOUT * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&L.bias, b.size() * 4));
+    CUDA_TRY(cudaMemcpy(L.bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&L.slope, s.size() * 4));
+    CUDA_TRY(cudaMemcpy(L.slope, s.data(), s.size() * 4, cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -1222,6 +1228,8 @@ extern "C" int b2sr_create_fused(b2sr_ctx** out, int device, const b2sr_fused_op
         // L2-persisting so that the following launches of the dense block (which re-read it) hit L2.  Measured on
         // B200, 540p (199 MB per 192-channel buffer): 34.4 ms/frame without, 38.3 ms with 48 MB set aside, 59 ms with
         // the maximum -- the set-aside starves the normal L2 traffic (halo re-reads, weights, fp32 trunk), so it is off.
+        const char* ce = getenv("B2SR_PAIR");
+        if (ce && atoi(ce) == 0) c->pair_halves = 0;
         const char* pe = getenv("B2SR_PDL");
         if (pe && atoi(pe) == 0) c->pdl = 0;
         const char* le = getenv("B2SR_L2_PROMO");
@@ -1268,8 +1276,11 @@ extern "C" int b2sr_create_fused(b2sr_ctx** out, int device, const b2sr_fused_op
                     break;
                 }
             }
+            const bool pair = parts == 2 && c->pair_halves && o.cout == 2 * NOUT;
+            if (pair) parts = 1;
             for (int part = 0; part < parts && !rc; ++part) {
                 FusedLaunch L;
+                L.pair = pair;
                 L.op = i, L.co0 = part * NOUT, L.nco = std::min(o.cout - L.co0, NOUT), L.NOUT = NOUT, L.G = G, L.cinp = cinp;
                 L.sc_ks = o.sc_cin / 16;
                 L.slots = std::min(12, fused_fit(NOUT, o.final != 0, G, sc));
@@ -1291,17 +1302,17 @@ extern "C" int b2sr_create_fused(b2sr_ctx** out, int device, const b2sr_fused_op
 
 // work items of the plan's planes at resolution factor `res`: the linear sequence (plane, band, row) cut into one
 // contiguous, equally long range per CTA (as build_plan does for res = 1)
-static int fused_items(b2sr_ctx* c, Plan* P, int res, ResItems** out) {
+static int fused_items(b2sr_ctx* c, Plan* P, int res, int max_cta, ResItems** out) {
     for (auto& r : P->res_items)
-        if (r->res == res) {
+        if (r->res == res && r->max_cta == max_cta) {
             *out = r.get();
             return 0;
         }
     std::unique_ptr<ResItems> R(new ResItems());
-    R->res = res;
+    R->res = res, R->max_cta = max_cta;
     int64_t band_rows = 0;
     for (const PlaneDev& pd : P->planes) band_rows += (int64_t)pd.Ht * res * ((pd.Wt * res + TC_BW - 1) / TC_BW);
-    const int ncta = (int)std::min<int64_t>(c->sms, band_rows);
+    const int ncta = (int)std::min<int64_t>(max_cta, band_rows);
     R->first.assign(1, 0);
     int64_t pos = 0;
     int cta = 0;
@@ -1348,11 +1359,20 @@ static int launch_tcg(b2sr_ctx* c, const FusedLaunch& L, const ResItems* R, cons
     // programmatic dependent launch: this launch's prologue (barrier init, TMEM allocation, weight load) overlaps the tail
     // of the previous launch of the stream; the kernel waits (griddepcontrol.wait) before it touches activation buffers
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)R->n_cta), cfg.blockDim = dim3(TC_THREADS), cfg.dynamicSmemBytes = (size_t)smem, cfg.stream = c->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr, cfg.numAttrs = c->pdl ? 1 : 0;
+    cfg.gridDim = dim3((unsigned)(R->n_cta * (L.pair ? 2 : 1))), cfg.blockDim = dim3(TC_THREADS), cfg.dynamicSmemBytes = (size_t)smem, cfg.stream = c->stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (L.pair) {  // clusters of two CTAs: one TMA multicast feeds both halves of the convolution
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (c->pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr, cfg.numAttrs = na;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
     c->n_launch += 1, c->n_tc += 1;
     return 0;
@@ -1428,10 +1448,28 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
             c->n_launch += 1;
             continue;
         }
-        ResItems* R = nullptr;
-        TRY(fused_items(c, P, o.res, &R));
         for (int li = c->fop_first[i]; li < c->fop_first[i + 1]; ++li) {
             const FusedLaunch& L = c->flaunch[li];
+            if (L.pair && !c->pair_clusters) {
+                // how many 2-CTA clusters of this footprint fit the device at once (a GPC with an odd number of SMs loses one)
+                cudaLaunchConfig_t q{};
+                q.gridDim = dim3((unsigned)c->sms / 2 * 2), q.blockDim = dim3(TC_THREADS);
+                q.dynamicSmemBytes = (size_t)TcgCfg<32, 0>::smem_bytes(L.G, L.slots);
+                cudaLaunchAttribute qa[1];
+                qa[0].id = cudaLaunchAttributeClusterDimension;
+                qa[0].val.clusterDim.x = 2, qa[0].val.clusterDim.y = 1, qa[0].val.clusterDim.z = 1;
+                q.attrs = qa, q.numAttrs = 1;
+                auto kq = tcg_conv_kernel<32, 0, false, 1, 3>;
+                CUDA_TRY(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q.dynamicSmemBytes));
+                int ncl = 0;
+                if (cudaOccupancyMaxActiveClusters(&ncl, kq, &q) != cudaSuccess || ncl < 1) {
+                    cudaGetLastError();
+                    ncl = c->sms / 2 - 4;
+                }
+                c->pair_clusters = std::min(ncl, c->sms / 2);
+            }
+            ResItems* R = nullptr;
+            TRY(fused_items(c, P, o.res, L.pair ? c->pair_clusters : c->sms, &R));
             TcgParams p{};
             p.maps = P->d_fmaps, p.map_base = li * G;
             p.items = R->d_items, p.item_first = R->d_first;
@@ -1444,6 +1482,7 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
             p.acc_scale = o.in_buf < 0 ? (1.f / 255.f) : 1.f;
             p.groups = L.G, p.cin = L.cinp, p.k1 = o.k == 1, p.ring_slots = L.slots;
             p.sc_ks = L.sc_ks, p.sc_cv = o.sc_coef_v, p.sc_cr = o.sc_coef_r;
+            p.pair = L.pair, p.pair_wbytes = L.G * 9 * L.NOUT * TCG_PB;
             p.nres = o.nres;
             for (int q = 0; q < o.nres; ++q) {
                 const b2sr_fused_buf& B = c->fbufs[o.res_buf[q]];
@@ -1506,6 +1545,7 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
                     case 1 * 4 + 1: rc = launch_tcg<32, 0, false, 1, 1>(c, L, R, p); break;  // x4 = lrelu(conv) + x2 (fp32 x2)
                     case 1 * 4 + 3: rc = launch_tcg<32, 0, false, 1, 3>(c, L, R, p); break;  // dense-block output: 0.2 v + x
                     case 2 * 4 + 3: rc = launch_tcg<32, 0, false, 2, 3>(c, L, R, p); break;  // RRDB output
+                    case 2 * 4 + 1: rc = launch_tcg<32, 0, false, 2, 1>(c, L, R, p); break;  // last RRDB output (no later residual use)
                     case 100 + 1 * 4 + 1: rc = launch_tcg<32, 0, false, 1, 1, true>(c, L, R, p); break;  // x2, x4 with fp16 residuals
                     case 100 + 2 * 4 + 1: rc = launch_tcg<32, 0, false, 2, 1, true>(c, L, R, p); break;
                     default: rc = launch_tcg<32, 0, false, -1, 0>(c, L, R, p);

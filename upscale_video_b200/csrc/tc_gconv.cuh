@@ -38,6 +38,9 @@ struct TcgParams {
     int32_t k1;                 // 1x1 convolution: only the centre column tap is issued (the others are zero)
     int32_t sc_ks;              // fused 1x1 shortcut over the first sc_ks * 16 channels of the input view (SC kernels)
     float sc_cv, sc_cr;         // v = act(conv + bias) * sc_cv + shortcut * sc_cr
+    int32_t pair;               // launched as clusters of two CTAs that share their input rows (TMA multicast) and compute
+                                // NOUT output channels each: CTA rank r uses weights / bias / slope / output / residual slice r
+    int32_t pair_wbytes;        // bytes between the two weight images
     int32_t flip;               // rows are walked bottom-up (plane row = Ht - 1 - y; wimg has the ky blocks swapped to match)
     int32_t ring_slots;         // shared-memory ring slots (one (row, group) each)
     int32_t nres;               // residual terms
@@ -58,6 +61,28 @@ struct TcgParams {
 // while its predecessor drains; griddep_wait() blocks until the predecessor grid has completed and its memory is visible.
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one TMA load delivered to the same shared-memory offset (and mbarrier) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_4d_multicast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
+                                                      uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+        : "memory");
+}
+// arrive (once all MMAs issued so far have completed) on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
 
 constexpr int TCG_PB = 128;                      // bytes per pixel of one channel group == one SW128 swizzle row
 constexpr int TCG_SUBROWB = TC_PITCH * TCG_PB;   // one ring slot
@@ -96,7 +121,19 @@ template <int NOUT, int MODE /*0 = activation buffers, 1 = network output frames
 __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_constant__ TcgParams P) {
     using C = TcgCfg<NOUT, MODE, SC>;
     extern __shared__ uint8_t smem_raw[];
-    const int it_begin = P.item_first[blockIdx.x], it_end = P.item_first[blockIdx.x + 1];
+    // paired launch: the two CTAs of a cluster walk the same row range; rank r computes output-channel half r
+    const uint32_t rank = P.pair ? cluster_ctarank() : 0u;
+    const int range = P.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int it_begin = P.item_first[range], it_end = P.item_first[range + 1];
+    const uint8_t* wimg = P.wimg + (size_t)rank * P.pair_wbytes;
+    const float* bias_g = P.bias + rank * NOUT;
+    const float* slope_g = P.slope + rank * NOUT;
+    __half* const out16 = P.out16 ? P.out16 + rank * NOUT : nullptr;
+    float* const out32 = P.out32 ? P.out32 + rank * NOUT : nullptr;
+    const void* res_ptr[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+        res_ptr[r] = reinterpret_cast<const uint8_t*>(P.res_ptr[r]) + (size_t)rank * NOUT * (P.res_f32[r] ? 4 : 2);
     const int G = P.groups, R = P.ring_slots;
     constexpr int NB = C::NB;
     const uint32_t WB = (uint32_t)(G * 9 * NOUT * TCG_PB) + C::SCB;  // stacked 3x3 weights of all groups [+ the shortcut image]
@@ -125,12 +162,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
     constexpr int NPRE = NRES >= 0 ? (NRES > 0 ? NRES : 1) : (NOUT <= 32 ? 2 : 1);  // residual terms prefetched into registers
     static_assert(NRES < 0 || NOUT * NRES <= (RF16 ? 128 : 64), "prefetched residuals do not fit the register budget");
     const int nres = NRES >= 0 ? NRES : P.nres;
-    const bool has16 = OUTS ? (OUTS & 1) != 0 : P.out16 != nullptr, has32 = OUTS ? (OUTS & 2) != 0 : P.out32 != nullptr;
+    const bool has16 = OUTS ? (OUTS & 1) != 0 : out16 != nullptr, has32 = OUTS ? (OUTS & 2) != 0 : out32 != nullptr;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < R; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), P.pair ? 2 : 1);  // paired: a slot is free once BOTH CTAs' MMAs have read their copy
         }
         for (int b = 0; b < NB; ++b) {
             mbar_init(tfull_bar(b), 1);
@@ -147,13 +184,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
     }
     if (warp >= 2) {
         for (int i = threadIdx.x - 64; i < NOUT; i += TC_THREADS - 64) {
-            s_bias[i] = P.bias[i];
-            s_slope[i] = P.slope[i];
+            s_bias[i] = bias_g[i];
+            s_slope[i] = slope_g[i];
         }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (P.pair) cluster_sync_all();  // the peer's barriers exist before anything (multicast data, commits) can reach them
     const uint32_t tmem_base = *s_tmem;
 
     if (warp == 0) {
@@ -161,8 +199,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
         if (lane == 0) {
             mbar_expect_tx(w_bar, WB);
             const uint32_t chunk = 3u * NOUT * TCG_PB;  // one (group, kx) tile
-            for (int t = 0; t < 3 * G; ++t) bulk_g2s(w_s + t * chunk, P.wimg + (size_t)t * chunk, chunk, w_bar);
-            if constexpr (SC) bulk_g2s(w_s + 3 * G * chunk, P.wimg + (size_t)3 * G * chunk, C::SCB, w_bar);
+            for (int t = 0; t < 3 * G; ++t) bulk_g2s(w_s + t * chunk, wimg + (size_t)t * chunk, chunk, w_bar);
+            if constexpr (SC) bulk_g2s(w_s + 3 * G * chunk, wimg + (size_t)3 * G * chunk, C::SCB, w_bar);
             int slot = 0;
             uint32_t phase = 0;
             long long w_empty = 0;
@@ -178,7 +216,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                     for (int g = 0; g < G; ++g) {
                         mbar_wait_clocked(empty_bar(slot), phase ^ 1u, 0, w_empty);
                         mbar_expect_tx(full_bar(slot), TCG_SUBROWB);
-                        tma_load_4d(ring_s + slot * TCG_SUBROWB, map, full_bar(slot), g * 64, I.x0 - 1, y, I.plane);
+                        if (!P.pair)
+                            tma_load_4d(ring_s + slot * TCG_SUBROWB, map, full_bar(slot), g * 64, I.x0 - 1, y, I.plane);
+                        else if (rank == 0)  // one load from L2 / HBM fills this slot in both CTAs (each armed its own barrier)
+                            tma_load_4d_multicast(ring_s + slot * TCG_SUBROWB, map, full_bar(slot), g * 64, I.x0 - 1, y, I.plane, (uint16_t)3);
                         if (++slot == R) {
                             slot = 0;
                             phase ^= 1u;
@@ -283,7 +324,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                                     umma_f16(ds, a0 + (uint64_t)((TCG_PB + k * 32) >> 4), bs + (uint64_t)((k * 32) >> 4), ids, 1u);
                             }
                         }
-                        umma_commit(empty_bar(sl));  // this (row, group) slot may be refilled once its MMAs have completed
+                        // this (row, group) slot may be refilled once its MMAs have completed (paired: in both CTAs)
+                        if (P.pair) umma_commit_multicast(empty_bar(sl), (uint16_t)3); else umma_commit(empty_bar(sl));
                         if (++sl == R) sl = 0, ph ^= 1u;
                     }
                     if (rho >= 2) umma_commit(tfull_bar(home0));  // output row rho - 2 is complete (home0 is its home)
@@ -345,11 +387,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                     for (int r = 0; r < NPRE; ++r) {
                         if (r >= nres || pix < 0) continue;
                         if (NRES >= 0 ? !RF16 : P.res_f32[r] != 0) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(P.res_ptr[r]) + pix * P.res_ld[r]);
+                            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(res_ptr[r]) + pix * P.res_ld[r]);
 #pragma unroll
                             for (int j = 0; j < NOUT / 4; ++j) rraw[r][j] = rp[j];
                         } else {
-                            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(P.res_ptr[r]) + pix * P.res_ld[r]);
+                            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(res_ptr[r]) + pix * P.res_ld[r]);
 #pragma unroll
                             for (int j = 0; j < NOUT / 8; ++j) rraw[r][j] = rp[j];
                         }
@@ -421,7 +463,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                         stg[qi ^ ((qi >> 3) & 7)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                     __syncwarp();
-                    uint8_t* outp = reinterpret_cast<uint8_t*>(P.out16);
+                    uint8_t* outp = reinterpret_cast<uint8_t*>(out16);
 #pragma unroll
                     for (int i = 0; i < CH; ++i) {
                         const int qi = i * 32 + lane;
@@ -462,10 +504,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                                         rv[0] = f0.x, rv[1] = f0.y, rv[2] = f1.x, rv[3] = f1.y;
                                     }
                                 } else if (P.res_f32[r]) {  // (a second residual of a 64-channel launch: not prefetched)
-                                    const float4 u = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(P.res_ptr[r]) + pix * P.res_ld[r] + j);
+                                    const float4 u = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(res_ptr[r]) + pix * P.res_ld[r] + j);
                                     rv[0] = u.x, rv[1] = u.y, rv[2] = u.z, rv[3] = u.w;
                                 } else {
-                                    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(P.res_ptr[r]) + pix * P.res_ld[r] + j);
+                                    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(res_ptr[r]) + pix * P.res_ld[r] + j);
                                     const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
                                     rv[0] = f0.x, rv[1] = f0.y, rv[2] = f1.x, rv[3] = f1.y;
                                 }
@@ -482,7 +524,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                     // NOUT / 2 channels (per-thread float4 stores to 32 different lines per instruction were measured to
                     // cost ~1700 cycles per row), then the fp16 copy in one.
                     if (has32) {
-                        uint8_t* outp = reinterpret_cast<uint8_t*>(P.out32);
+                        uint8_t* outp = reinterpret_cast<uint8_t*>(out32);
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
                             __syncwarp();
@@ -502,7 +544,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                         }
                     }
                     if (has16) {
-                        uint8_t* outp = reinterpret_cast<uint8_t*>(P.out16);
+                        uint8_t* outp = reinterpret_cast<uint8_t*>(out16);
                         __syncwarp();
 #pragma unroll
                         for (int i = 0; i < CH; ++i) {
@@ -555,6 +597,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
 
     tc_fence_before();
     __syncthreads();
+    if (P.pair) cluster_sync_all();  // the peer's last commits / multicast writes target this CTA's shared memory: stay until it is done
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();

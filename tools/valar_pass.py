@@ -37,7 +37,7 @@ for _ in range(a.reps):
     eng.run_u8(img)
     ts.append(time.perf_counter() - t0)
 macs = sum(int(np.prod(l.weights["weight"].shape)) for l in ncnn_model.load_model(ncnn_model.packaged_model_dir(), "4x_Valar_v1").convs())
-print("valar %dx%d: best %.1f ms/frame, launches %d (hmma %d)" % (a.h, a.w, min(ts) * 1e3, eng.stat(E.STAT_LAUNCHES), eng.stat(E.STAT_HMMA_LAUNCHES)))
+print("valar %dx%d: best %.1f ms/frame, launches %d (hmma %d)" % (a.h, a.w, min(ts or [float("nan")]) * 1e3, eng.stat(E.STAT_LAUNCHES), eng.stat(E.STAT_HMMA_LAUNCHES)))
 
 if a.batch:
     import torch

@@ -361,6 +361,22 @@ def test_raw_stream_matches_worker_functions(engines, model_dir, tmp_path):
     assert np.array_equal(np.frombuffer(out.getvalue(), np.uint8).reshape(3, 140, 2000, 3), np.stack([comp.run_u8(f) for f in frames]))
 
 
+def test_raw_stream_valar(model_dir, E):
+    """`raw_stream -m r -s 4`: the RRDB upscaler behind the raw-frame pipe (host pipeline, several frames per pass) equals the
+    per-frame worker path bit for bit."""
+    import io
+    from upscale_video_b200 import raw_stream
+    if not os.path.exists(os.path.join(model_dir, "4x_Valar_v1.b2sr")):
+        pytest.skip("4x_Valar_v1 not packaged")
+    frames = np.stack([natural(30, 140, seed=s) for s in (51, 52, 53)])
+    out = io.BytesIO()
+    n = raw_stream.stream(io.BytesIO(frames.tobytes()), out, 140, 30, scale=4, models=["r"], chunk=2, model_path=model_dir)
+    assert n == 3
+    eng = E.Engine.from_files(model_dir, "4x_Valar_v1", 0)
+    assert np.array_equal(np.frombuffer(out.getvalue(), np.uint8).reshape(3, 120, 560, 3), np.stack([eng.run_u8(f) for f in frames]))
+    eng.close()
+
+
 def test_valar_rrdb_fused_tcgen05(E, model_dir, oracle_models):
     """4x_Valar_v1 (RRDB, reference models/4x_Valar_v1.param) on the fused tcgen05 graph kernels (b2sr_create_fused):
     golden crop, a two-tile frame against the oracle (seam at x = 960), band boundaries at 128 columns with a ragged

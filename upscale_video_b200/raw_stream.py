@@ -74,7 +74,8 @@ def stream(fin, fout, width, height, scale=2, models=(), gpu=0, chunk=8, pix_fmt
     ``upscaler`` / ``prepass`` may be passed in as ready engines (tests); otherwise they are built from the model files."""
     model_path = model_path or ncnn_model.packaged_model_dir()
     if upscaler is None and scale > 1:
-        upscaler = _engine.Engine.from_files(model_path, str(scale) + "x_Compact_Pretrain", gpu)
+        # process_file :911-918: `-m r` selects <scale>x_Valar_v1 (RRDB, tcgen05 graph kernels), else <scale>x_Compact_Pretrain
+        upscaler = _engine.Engine.from_files(model_path, str(scale) + ("x_Valar_v1" if "r" in models else "x_Compact_Pretrain"), gpu)
     if prepass is None and "a" in models:
         prepass = _engine.Engine.from_files(model_path, "1" + HURR, gpu)
     if upscaler is None and prepass is None:
@@ -137,7 +138,8 @@ def main(argv=None):
     ap.add_argument("--width", type=int, required=True)
     ap.add_argument("--height", type=int, required=True)
     ap.add_argument("-s", "--scale", type=int, default=2, help="Scale 1, 2 or 4 (1 = pre-pass only). Default is 2.")
-    ap.add_argument("-m", "--models", help="'a' adds the 1x anime touch-up model before upscaling (like upscale_video.py -m a).")
+    ap.add_argument("-m", "--models", help="'a' adds the 1x anime touch-up model before upscaling, 'r' uses the real-life model "
+                                           "4x_Valar_v1 as the upscaler (like upscale_video.py -m a,r).")
     ap.add_argument("-g", "--gpu", type=int, default=0, help="GPU index for this worker (run one worker per GPU, frames interleaved by the caller)")
     ap.add_argument("--chunk", type=int, default=8, help="frames per host<->device chunk")
     ap.add_argument("--pix_fmt", default="bgr24", choices=["bgr24", "rgb24"])
@@ -147,8 +149,10 @@ def main(argv=None):
     a = ap.parse_args(argv)
     models = a.models.split(",") if a.models else []
     for m in models:
-        if m != "a":
-            sys.exit("model option %r is outside this engine's scope (Compact family only)" % m)
+        if m not in ("a", "r"):
+            sys.exit("model option %r is outside this engine's scope ('a' = HurrDeblur pre-pass, 'r' = Valar upscaler)" % m)
+    if "r" in models and a.scale != 4:
+        sys.exit("-m r needs -s 4 (the reference ships 4x_Valar_v1 only)")
     fin = open(a.input, "rb") if a.input else sys.stdin.buffer
     fout = open(a.output, "wb") if a.output else sys.stdout.buffer
     n = stream(fin, fout, a.width, a.height, a.scale, models, a.gpu, a.chunk, a.pix_fmt, a.model_path)

@@ -6,7 +6,7 @@ Upscale chosen extracted frames into an output directory, with the flags and fil
 HurrDeblur through ``process_model``), then ``upscale_frames``; with ``-m`` the result is renamed
 ``N.<models>.png``.
 
-``-m r`` selects the 4x_Valar_v1 RRDB model (generic CUDA-core graph engine).  Not reimplemented (outside the hot path,
+``-m r`` selects the 4x_Valar_v1 RRDB model (fused tcgen05 graph kernels, b2sr_create_fused).  Not reimplemented (outside the hot path,
 SURVEY.md section 2 row 11): ``-m n=K`` (OpenCV NL-means) is rejected with an error instead of being silently ignored.
 """
 import argparse

@@ -165,6 +165,51 @@ def valar_540p(E, ncnn_model, torch, device):
             "frames_per_step": n, "steps": steps, "tcgen05_launches": int(launches)}
 
 
+def side_configs(E, ncnn_model, torch, device):
+    """The other BASELINE configs, each as a short device-resident measurement next to the headline (not part of `value`):
+    configs[2] = 1x_HurrDeblur (whole frame, u8 out) -> 2x_Compact chained on the device at 1080p; configs[3] as literally
+    named (4x_Valar_v1 at 540p, see valar_540p) and its actual 4x pixel-shuffle reading (4x_Compact_Pretrain at 540p)."""
+    out = []
+    mdir = ncnn_model.packaged_model_dir()
+
+    def timed(fn, frames, steps=3):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        return frames * steps / (time.perf_counter() - t0)
+
+    try:
+        hurr = E.Engine.from_files(mdir, "1x_HurrDeblur_SubCompact_nf24-nc8_244k_net_g", device)
+        comp = E.Engine.from_files(mdir, "2x_Compact_Pretrain", device)
+        n = 8
+        d_in = torch.randint(0, 256, (n, H, W, 3), dtype=torch.uint8, device="cuda")
+        d_mid = torch.empty_like(d_in)
+        d_out = torch.empty((n, 2 * H, 2 * W, 3), dtype=torch.uint8, device="cuda")
+
+        def chain():
+            hurr.run_batch_device(d_in, d_mid, n, H, W, 0, 0, sync=True)       # apply_model: untiled, u8 out
+            comp.run_batch_device(d_mid, d_out, n, H, W, TILE, HALO, sync=True)  # upscale_image: 960 + 10 tiling
+        fps = timed(chain, n)
+        out.append({"workload": "synthetic 1080p, 1x_HurrDeblur nf24 -> u8 -> 2x_Compact chained on the device (BASELINE configs[2])",
+                    "frames_per_s": fps, "tflops": fps * 2.0 * (42768 + MAC_PER_PX_NET) * H * W / 1e12, "frames_per_step": n})
+        hurr.close()
+        comp.close()
+        c4 = E.Engine.from_files(mdir, "4x_Compact_Pretrain", device)
+        n, h, w = 16, 540, 960
+        d_in = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda")
+        d_out = torch.empty((n, 4 * h, 4 * w, 3), dtype=torch.uint8, device="cuda")
+        fps = timed(lambda: c4.run_batch_device(d_in, d_out, n, h, w, TILE, HALO, sync=True), n)
+        out.append({"workload": "synthetic 540p, 4x_Compact_Pretrain (the 4x pixel-shuffle model of BASELINE configs[3])",
+                    "frames_per_s": fps, "tflops": fps * 2.0 * 619200 * h * w / 1e12, "frames_per_step": n})
+        c4.close()
+    except Exception as e:
+        out.append({"unavailable": str(e)[:200]})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -174,7 +219,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the short BASELINE configs[3] measurement (4x_Valar_v1, 540p)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short side measurements of BASELINE configs[2] and [3]")
     ap.add_argument("--content", default="noise", choices=["noise", "natural"],
                     help="synthetic frame content: uniform random bytes (default; worst case for switching power) or smooth "
                          "gradients + edges + mild noise")
@@ -262,6 +307,7 @@ def main():
 
     # ---- end to end: pinned host frames in, pinned host frames out, copies inside the timed region ----
     e2e = None
+    h_in = h_out = None
     if not args.no_e2e:
         h_in = torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()
         h_in.copy_(d_in.cpu())
@@ -320,9 +366,13 @@ def main():
     if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only
         fps, threads, desc, dt = cpu_port_fps(reps=1)
         cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": desc, "seconds": dt}
+    io_mb = (d_in.numel() + d_out.numel()) >> 20
     extra = None
     if not args.no_extra and world == 1:
-        extra = valar_540p(E, ncnn_model, torch, local_rank)
+        eng.close()
+        del d_in, d_out, h_in, h_out
+        torch.cuda.empty_cache()
+        extra = [valar_540p(E, ncnn_model, torch, local_rank)] + side_configs(E, ncnn_model, torch, local_rank)
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -330,7 +380,7 @@ def main():
         "config": {"workload": "synthetic 1080p RGB batch, 2x_Compact_Pretrain, 1xB200 per rank (BASELINE configs[1])",
                    "frames_per_gpu_per_step": B, "frame": [H, W, 3], "tile": TILE, "halo": HALO, "content": args.content,
                    "arithmetic": "fp16 weights and activations (tcgen05 kind::f16), fp32 accumulation and epilogue, u8 in/out",
-                   "l2": "inputs+outputs per step are %d MB per GPU, larger than the 126 MB L2" % ((d_in.numel() + d_out.numel()) >> 20),
+                   "l2": "inputs+outputs per step are %d MB per GPU, larger than the 126 MB L2" % io_mb,
                    "parallelism": "frames sharded over %d rank(s), no data-path collective; weights NCCL-broadcast" % world},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": sampler.summary(), "other_configs": extra,

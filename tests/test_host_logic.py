@@ -136,8 +136,16 @@ def _gloo_worker(rank, world, port, model_dir, q):
         return ncnn_model.pack_compact_blob(ncnn_model.load_model(model_dir, "2x_Compact_Pretrain"))
 
     desc, blob = parallel.broadcast_packed_model(load, rank, world, device=None)
-    q.put((rank, len(loads), (desc.cin, desc.nf, desc.n_mid, desc.scale, desc.input_blob), float(blob.sum()), blob.size,
-           parallel.shard_frames(range(10), rank, world)))
+
+    def load_fused():  # an RRDB graph travels as its fused program (op list + buffer table + weights)
+        loads.append(2)
+        return ncnn_model.compile_fused(ncnn_model.load_model(model_dir, "4x_Valar_v1"))
+
+    prog = parallel.broadcast_packed_model(load_fused, rank, world, device=None)
+    fused_sig = (len(prog.ops), len(prog.bufs), prog.scale, prog.ops[2]["sc_cin"], prog.ops[2]["sc_w_off"], prog.ops[-1]["final"],
+                 float(prog.weights.astype("float64").sum()), int(prog.weights.size))
+    q.put((rank, loads, (desc.cin, desc.nf, desc.n_mid, desc.scale, desc.input_blob), float(blob.sum()), blob.size,
+           parallel.shard_frames(range(10), rank, world), fused_sig))
     dist.destroy_process_group()
 
 
@@ -158,9 +166,10 @@ def test_weight_broadcast_gloo_world2(model_dir):
     for p in ps:
         p.join(60)
         assert p.exitcode == 0
-    (r0, l0, d0, s0, n0, f0), (r1, l1, d1, s1, n1, f1) = res
-    assert (l0, l1) == (1, 0) and d0 == d1 == (3, 64, 16, 2, "input") and s0 == s1 and n0 == n1 == 598464 + 1100 + 1088
+    (r0, l0, d0, s0, n0, f0, g0), (r1, l1, d1, s1, n1, f1, g1) = res
+    assert (l0, l1) == ([1, 2], []) and d0 == d1 == (3, 64, 16, 2, "input") and s0 == s1 and n0 == n1 == 598464 + 1100 + 1088
     assert sorted(f0 + f1) == list(range(10)) and not set(f0) & set(f1)
+    assert g0 == g1 and g0[:3] == (353, 12, 4) and g0[3] == 64 and g0[5] == 1  # the fused Valar program arrives intact
 
 
 class _FakeEngine:

@@ -141,17 +141,21 @@ def _ptr(a):
 class Engine:
     """One network bound to one GPU (one per worker process, like the reference's ``net``)."""
 
-    def __init__(self, graph: ncnn_model.Graph = None, device: int = 0, packed=None, generic: bool = False):
+    def __init__(self, graph: ncnn_model.Graph = None, device: int = 0, packed=None, generic: bool = False, program=None):
         """``graph``: a loaded model; or ``packed`` = (CompactDesc, fp32 blob) as produced by
         ``ncnn_model.pack_compact_blob`` (what a rank receives from the start-up weight broadcast).
         SRVGGNetCompact graphs run on the Compact tcgen05 kernels; graphs that lower to fused convolutions (the RRDB
         4x_Valar_v1) on the tcgen05 graph kernels (b2sr_create_fused); anything else, or any graph when
-        ``generic=True`` (cross-checks), on the generic op-by-op graph engine (b2sr_create_graph)."""
+        ``generic=True`` (cross-checks), on the generic op-by-op graph engine (b2sr_create_graph).  ``program`` = a
+        ``ncnn_model.FusedProgram`` (what a rank receives when the broadcast model is an RRDB graph)."""
         self._h = None
         self._lib = load_library()
         self.generic = False
         self.fused = False
         self.program = None
+        if program is not None:  # a FusedProgram received from the start-up broadcast (parallel.broadcast_packed_model)
+            self._init_fused(program, device)
+            return
         if packed is None and not generic and ncnn_model.compact_desc(graph) is None:
             prog = ncnn_model.compile_fused(graph)
             if prog is not None:

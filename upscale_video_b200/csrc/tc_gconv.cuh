@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
         const long long t_begin = clock64();
         mbar_wait(w_bar, 0, 1);
         uint32_t ok_tempty = mbar_test_wait(tempty_bar(0), 0);
+        uint32_t ok_full = 0u;  // the first group of the next input row was already seen in shared memory (probed behind the MMAs)
         // Loop bounds that come from global memory are broadcast with a shuffle: the compiler then knows they are
         // warp-uniform and keeps the whole descriptor arithmetic in uniform registers (UTCHMMA takes uniform operands;
         // with per-thread values every MMA cost five R2UR moves).
@@ -283,12 +284,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                     if (!ok_tempty) mbar_wait_clocked(tempty_bar(hf), (tmask >> hf) & 1u, 3, w_tempty);
                     tmask ^= 1u << hf;
                 }
-                mbar_wait_clocked(full_bar(slot), phase, 2, w_full);  // (the elected lane waits for the later groups itself)
+                if (!ok_full) mbar_wait_clocked(full_bar(slot), phase, 2, w_full);  // (the elected lane waits for the later groups itself)
                 tc_fence_after();
                 if (P.dbg && t_first == 0) t_first = clock64() - t_begin;
                 {  // probe for the next row of this item, latency hidden behind the MMAs
                     const uint32_t hn = (hf + 1u) % NB;
                     ok_tempty = rho + 1 < rows ? mbar_test_wait(tempty_bar(hn), (tmask >> hn) & 1u) : 0u;
+                    int ns = slot + G;
+                    uint32_t np = phase;
+                    if (ns >= R) ns -= R, np ^= 1u;
+                    ok_full = mbar_test_wait(full_bar(ns), np);  // a completed phase stays completed until this warp consumes it
                 }
                 const long long tq0 = P.dbg ? clock64() : 0;
                 if (elect_one_sync()) {

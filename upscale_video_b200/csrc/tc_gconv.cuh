@@ -13,7 +13,17 @@
 // written by one TMA box {64 ch, 136 px} whose channels beyond `cin` are zero-filled by the TMA unit); the issuer walks
 // (row, group) pairs and accumulates all groups of a row into the same TMEM blocks, so a 192-channel input costs three
 // ring slots per row and no concat copy.  The stacked weights of all groups stay resident in shared memory
-// ([g][kx][3 * NOUT rows][64 ch], <= 110.6 KB: a 192 -> 64 convolution is launched as two 192 -> 32 halves).
+// ([g][kx][3 * NOUT rows][64 ch], <= 110.6 KB).  A 192 -> 64 convolution (221 KB of weights) runs as clusters of two CTAs:
+// both walk the same rows, rank r keeps the weights of output channels 32r .. 32r+31, and rank 0 feeds both rings with
+// one multicast TMA load per (row, group).
+//
+// Accumulators: output row y lives in TMEM block y mod NB; the three-block window of an input row never wraps (two
+// extension blocks stand for homes 0 and 1 and are added by the epilogue), and because homes follow plane rows a frame
+// is computed bit-identically whatever the CTA ranges are.  An optional second set of NB blocks accumulates a fused
+// 1x1 shortcut convolution over the first channels of the same input rows (x2 = lrelu(conv3x3([x, x1])) + conv1x1(x)).
+//
+// Launches use programmatic dependent launch: setup (barriers, TMEM, weights) overlaps the previous launch's tail,
+// griddepcontrol.wait precedes the first access to activation buffers.
 //
 // Epilogue (two warp sets on alternate rows): tcgen05.ld -> + bias -> LeakyReLU -> residual terms read from fp32 (or
 // fp16) buffers -> fp32 copy for later residual adds (the RRDB trunk stays unrounded) and / or fp16 copy into a

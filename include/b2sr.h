@@ -233,6 +233,36 @@ void *b2sr_stream(b2sr_ctx *ctx);
 
 const char *b2sr_last_error(void);
 
+/*
+ * Denoise pass (`-m n=<level>`).  Replaces the one library call of the reference's denoise worker,
+ *     cv2.fastNlMeansDenoisingColored(img, None, denoise, denoise, 5, 9)      (upscale/upscale_processing.py:354)
+ * -- BGR -> Lab, non-local means on the L plane (h_luma) and on the (a, b) plane pair (h_color) with a 5x5 template
+ * and a 9x9 search window over a 6-px reflect-101 border, Lab -> BGR -- in OpenCV's own fixed-point arithmetic, so
+ * results are bit-identical to cv2's CPU implementation.  Arguments keep cv2's order and meaning; only the window
+ * sizes the reference passes (5, 9) are built, anything else is B2SR_E_UNSUPPORTED.  A context is bound to one device,
+ * owns its stream and tables and is not thread-safe.  No CPU path: b2sr_nlm_create fails without an sm_100 device.
+ */
+typedef struct b2sr_nlm b2sr_nlm;
+int b2sr_nlm_create(b2sr_nlm **out, int device);
+void b2sr_nlm_destroy(b2sr_nlm *ctx);
+/* One frame, 3 interleaved u8 channels in cv2's BGR order; strides in bytes; in == out is not allowed.  Synchronous. */
+int b2sr_nlm_run_u8(b2sr_nlm *ctx, const uint8_t *in, int h, int w, int in_stride, uint8_t *out, int out_stride,
+                    float h_luma, float h_color, int template_window, int search_window, int memspace);
+/* n packed device-resident frames (n x h x w x 3), one launch; asynchronous on the context's stream unless `sync`. */
+int b2sr_nlm_run_batch_device(b2sr_nlm *ctx, const uint8_t *d_in, uint8_t *d_out, int n, int h, int w, float h_luma,
+                              float h_color, int sync);
+/* n packed host frames (pinned or pageable) through a double-buffered H2D -> kernel -> D2H pipeline; synchronous. */
+int b2sr_nlm_run_batch_host(b2sr_nlm *ctx, const uint8_t *h_in, uint8_t *h_out, int n, int h, int w, float h_luma,
+                            float h_color);
+int b2sr_nlm_synchronize(b2sr_nlm *ctx);
+void *b2sr_nlm_stream(b2sr_nlm *ctx);    /* cudaStream_t of the context */
+double b2sr_nlm_launches(b2sr_nlm *ctx); /* kernels launched by this context */
+/* Host-only views of the tables the kernel uses (no device needed; tests compare them with the oracle's):
+ * the fixed-point weight table of one plane (channels = 1: L, 2: a/b) -- returns its full length and copies
+ * min(length, cap) entries -- and the Lab conversion tables (any pointer may be NULL). */
+int b2sr_nlm_weight_table(float h, int channels, int32_t *out, int cap);
+int b2sr_nlm_lab_tables(int32_t *fwd9, int32_t *inv9, int32_t *l2y256, int32_t *l2fy256, uint16_t *cbrt3072);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,89 @@
+"""Lane-by-lane numpy emulation of ``nlm_kernel`` (upscale_video_b200/csrc/nlm.cuh).
+
+Test infrastructure: it follows the kernel's index arithmetic statement by statement -- tile origin, the staged
+40 x 28 Lab window with the reflect-101 border, lane l on image column x0 + l - 2, shuffles as lane shifts that
+return the lane's own value at the warp edge, the sliding 5-row window and the two-rows-late partner pixel -- so
+that the CPU suite can check the warp algorithm against the oracle without a GPU.  The Lab conversions and the
+weight tables are taken from the product library through its host-only C-ABI entry points.
+"""
+import numpy as np
+
+TW, TH, BORDER = 28, 16, 6
+SW, SH = TW + 2 * BORDER, TH + 2 * BORDER
+
+
+def reflect101(p, n):
+    if n == 1:
+        return 0
+    while p < 0 or p >= n:
+        p = -p if p < 0 else 2 * n - 2 - p
+    return p
+
+
+def shfl_up(v, d):
+    out = v.copy()
+    out[d:] = v[:-d]
+    return out
+
+
+def shfl_down(v, d):
+    out = v.copy()
+    out[:-d] = v[d:]
+    return out
+
+
+def run(lab, w_l, w_ab):
+    """lab: H x W x 3 uint8 (already converted) -> denoised Lab, H x W x 3 uint8."""
+    H, W, _ = lab.shape
+    out = np.zeros_like(lab)
+    lane = np.arange(32)
+    for y0 in range(0, H, TH):
+        for x0 in range(0, W, TW):
+            s = np.zeros((SH, SW, 3), dtype=np.int64)
+            for sy in range(SH):
+                gy = reflect101(y0 + sy - BORDER, H)
+                for sx in range(SW):
+                    s[sy, sx] = lab[gy, reflect101(x0 + sx - BORDER, W)]
+            est = np.zeros((TH, 32, 3), dtype=np.uint64)
+            ws = np.zeros((TH, 32, 2), dtype=np.uint64)
+            cx = lane + BORDER - 2
+            for dy in range(-4, 5):
+                for dx in range(-4, 5):
+                    hl = [np.zeros(32, dtype=np.int64)] * 4
+                    hc = [np.zeros(32, dtype=np.int64)] * 4
+                    q1 = q2 = np.zeros((32, 3), dtype=np.int64)
+                    for r in range(TH + 4):
+                        p = s[BORDER - 2 + r, cx]
+                        q = s[BORDER - 2 + r + dy, cx + dx]
+                        ad = np.abs(p - q)
+                        d_l = ad[:, 0] ** 2
+                        d_c = ad[:, 1] ** 2 + ad[:, 2] ** 2
+                        s_l = d_l + shfl_up(d_l, 1) + shfl_up(d_l, 2) + shfl_down(d_l, 1) + shfl_down(d_l, 2)
+                        s_c = d_c + shfl_up(d_c, 1) + shfl_up(d_c, 2) + shfl_down(d_c, 1) + shfl_down(d_c, 2)
+                        if r >= 4:
+                            o = r - 4
+                            k_l = (hl[0] + hl[1] + hl[2] + hl[3] + s_l) >> 5
+                            k_c = (hc[0] + hc[1] + hc[2] + hc[3] + s_c) >> 5
+                            wl = np.where(k_l < len(w_l), w_l[np.minimum(k_l, len(w_l) - 1)], 0).astype(np.uint64)
+                            wc = np.where(k_c < len(w_ab), w_ab[np.minimum(k_c, len(w_ab) - 1)], 0).astype(np.uint64)
+                            est[o, :, 0] += wl * q2[:, 0].astype(np.uint64)
+                            est[o, :, 1] += wc * q2[:, 1].astype(np.uint64)
+                            est[o, :, 2] += wc * q2[:, 2].astype(np.uint64)
+                            ws[o, :, 0] += wl
+                            ws[o, :, 1] += wc
+                        hl = [hl[1], hl[2], hl[3], s_l]
+                        hc = [hc[1], hc[2], hc[3], s_c]
+                        q2, q1 = q1, q
+            assert est.max() < 2 ** 32 and ws.max() < 2 ** 32  # the kernel's accumulators are 32-bit
+            for l in range(2, 2 + TW):
+                x = x0 + l - 2
+                if x >= W:
+                    continue
+                for o in range(TH):
+                    y = y0 + o
+                    if y >= H:
+                        continue
+                    out[y, x, 0] = (est[o, l, 0] + ws[o, l, 0] // 2) // ws[o, l, 0]
+                    out[y, x, 1] = (est[o, l, 1] + ws[o, l, 1] // 2) // ws[o, l, 1]
+                    out[y, x, 2] = (est[o, l, 2] + ws[o, l, 1] // 2) // ws[o, l, 1]
+    return out

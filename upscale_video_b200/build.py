@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb2sr.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "tc_conv.cuh", "tc_gconv.cuh", "graph_exec.cuh", "simple_kernels.cuh", os.path.join("..", "..", "include", "b2sr.h")]
+HEADERS = ["common.cuh", "tc_conv.cuh", "tc_gconv.cuh", "graph_exec.cuh", "simple_kernels.cuh", "nlm.cuh", "nlm_host.inl", os.path.join("..", "..", "include", "b2sr.h")]
 
 
 def nvcc_path():

@@ -27,6 +27,7 @@
 #include "../../include/b2sr.h"
 #include "common.cuh"
 #include "graph_exec.cuh"
+#include "nlm.cuh"
 #include "simple_kernels.cuh"
 #include "tc_conv.cuh"
 #include "tc_gconv.cuh"
@@ -1916,3 +1917,8 @@ extern "C" int b2sr_synchronize(b2sr_ctx* c) {
 }
 
 extern "C" void* b2sr_stream(b2sr_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------------
+// denoise pass (reference apply_denoise, upscale/upscale_processing.py:350-362)
+// ------------------------------------------------------------------------------------------------
+#include "nlm_host.inl"

@@ -28,6 +28,8 @@ SYMBOLS = [
     "b2sr_create_fused", "b2sr_debug_fused", "b2sr_destroy",
     "b2sr_run_u8", "b2sr_run_f32", "b2sr_run_batch_device", "b2sr_run_batch_host", "b2sr_debug_layer",
     "b2sr_set_option", "b2sr_get_stat", "b2sr_reset_stats", "b2sr_synchronize", "b2sr_stream", "b2sr_last_error",
+    "b2sr_nlm_create", "b2sr_nlm_destroy", "b2sr_nlm_run_u8", "b2sr_nlm_run_batch_device", "b2sr_nlm_run_batch_host",
+    "b2sr_nlm_synchronize", "b2sr_nlm_stream", "b2sr_nlm_launches", "b2sr_nlm_weight_table", "b2sr_nlm_lab_tables",
 ]
 
 
@@ -99,6 +101,20 @@ def load_library(path: str = LIB_PATH):
     lib.b2sr_stream.argtypes = [vp]
     lib.b2sr_stream.restype = vp
     lib.b2sr_last_error.restype = ctypes.c_char_p
+    f32 = ctypes.c_float
+    lib.b2sr_nlm_create.argtypes = [ctypes.POINTER(vp), i32]
+    lib.b2sr_nlm_destroy.argtypes = [vp]
+    lib.b2sr_nlm_destroy.restype = None
+    lib.b2sr_nlm_run_u8.argtypes = [vp, vp, i32, i32, i32, vp, i32, f32, f32, i32, i32, i32]
+    lib.b2sr_nlm_run_batch_device.argtypes = [vp, vp, vp, i32, i32, i32, f32, f32, i32]
+    lib.b2sr_nlm_run_batch_host.argtypes = [vp, vp, vp, i32, i32, i32, f32, f32]
+    lib.b2sr_nlm_synchronize.argtypes = [vp]
+    lib.b2sr_nlm_stream.argtypes = [vp]
+    lib.b2sr_nlm_stream.restype = vp
+    lib.b2sr_nlm_launches.argtypes = [vp]
+    lib.b2sr_nlm_launches.restype = ctypes.c_double
+    lib.b2sr_nlm_weight_table.argtypes = [f32, i32, vp, i32]
+    lib.b2sr_nlm_lab_tables.argtypes = [vp, vp, vp, vp, vp]
     if lib.b2sr_abi_version() != 1:
         raise EngineError("libb2sr.so ABI version %d, expected 1" % lib.b2sr_abi_version())
     _lib = lib
@@ -300,3 +316,85 @@ class Engine:
     @property
     def stream(self) -> int:
         return int(self._lib.b2sr_stream(self._h) or 0)
+
+
+class Denoiser:
+    """``cv2.fastNlMeansDenoisingColored(img, None, h, hColor, 5, 9)`` on one GPU -- the object the denoise worker
+    holds (reference upscale/upscale_processing.py:350-362).  Bit-identical to cv2's CPU result; no CPU path."""
+
+    def __init__(self, device: int = 0):
+        self._h = None
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        _check(self._lib.b2sr_nlm_create(ctypes.byref(h), device), "b2sr_nlm_create")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if self._h is not None:
+            self._lib.b2sr_nlm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_u8(self, img: np.ndarray, h: float, h_color: float = None, template_window: int = 5, search_window: int = 9) -> np.ndarray:
+        """BGR u8 HWC frame -> denoised BGR u8 HWC frame (arguments as cv2's, window sizes 5 / 9 only)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        hh, ww, ch = img.shape
+        assert ch == 3
+        out = np.empty_like(img)
+        _check(self._lib.b2sr_nlm_run_u8(self._h, img.ctypes.data, hh, ww, ww * 3, out.ctypes.data, ww * 3, float(h),
+                                         float(h if h_color is None else h_color), template_window, search_window, MEM_HOST),
+               "b2sr_nlm_run_u8")
+        return out
+
+    def run_batch_device(self, d_in, d_out, n: int, h: int, w: int, level: float, level_color: float = None, sync: bool = False):
+        """n packed device-resident frames (torch cuda uint8 tensors or raw device addresses), one launch."""
+        pi, _ = _ptr(d_in)
+        po, _ = _ptr(d_out)
+        _check(self._lib.b2sr_nlm_run_batch_device(self._h, pi, po, n, h, w, float(level),
+                                                   float(level if level_color is None else level_color), int(sync)),
+               "b2sr_nlm_run_batch_device")
+
+    def run_batch_host(self, h_in, h_out, n: int, h: int, w: int, level: float, level_color: float = None):
+        """n packed host frames (ideally pinned) through the double-buffered H2D -> kernel -> D2H pipeline."""
+        pi, _ = _ptr(h_in)
+        po, _ = _ptr(h_out)
+        _check(self._lib.b2sr_nlm_run_batch_host(self._h, pi, po, n, h, w, float(level),
+                                                 float(level if level_color is None else level_color)),
+               "b2sr_nlm_run_batch_host")
+
+    def synchronize(self):
+        _check(self._lib.b2sr_nlm_synchronize(self._h), "b2sr_nlm_synchronize")
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.b2sr_nlm_stream(self._h) or 0)
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.b2sr_nlm_launches(self._h))
+
+
+def nlm_weight_table(h: float, channels: int) -> np.ndarray:
+    """Host-only: the fixed-point weight table the kernel would use for level ``h`` (no device needed)."""
+    lib = load_library()
+    n = lib.b2sr_nlm_weight_table(float(h), channels, None, 0)
+    if n < 0:
+        _check(n, "b2sr_nlm_weight_table")
+    out = np.empty(n, np.int32)
+    lib.b2sr_nlm_weight_table(float(h), channels, out.ctypes.data, n)
+    return out
+
+
+def nlm_lab_tables() -> dict:
+    """Host-only: the Lab conversion tables the kernel uses."""
+    t = dict(fwd=np.empty(9, np.int32), inv=np.empty(9, np.int32), l2y=np.empty(256, np.int32), l2fy=np.empty(256, np.int32),
+             cbrt=np.empty(3072, np.uint16))
+    _check(load_library().b2sr_nlm_lab_tables(t["fwd"].ctypes.data, t["inv"].ctypes.data, t["l2y"].ctypes.data,
+                                              t["l2fy"].ctypes.data, t["cbrt"].ctypes.data), "b2sr_nlm_lab_tables")
+    return t

@@ -6,8 +6,9 @@ Upscale chosen extracted frames into an output directory, with the flags and fil
 HurrDeblur through ``process_model``), then ``upscale_frames``; with ``-m`` the result is renamed
 ``N.<models>.png``.
 
-``-m r`` selects the 4x_Valar_v1 RRDB model (fused tcgen05 graph kernels, b2sr_create_fused).  Not reimplemented (outside the hot path,
-SURVEY.md section 2 row 11): ``-m n=K`` (OpenCV NL-means) is rejected with an error instead of being silently ignored.
+``-m r`` selects the 4x_Valar_v1 RRDB model (fused tcgen05 graph kernels, b2sr_create_fused); ``-m n=K`` runs the
+NL-means denoise pass first (``process_denoise``, level clamped to 1..30 like reference test_images.py:45-52), on the
+GPU and bit-identical to OpenCV's result.
 """
 import argparse
 import logging
@@ -17,7 +18,7 @@ import sys
 import tempfile
 
 from . import ncnn_model
-from .upscale_processing import get_frames, process_model, upscale_frames
+from .upscale_processing import get_frames, process_denoise, process_model, upscale_frames
 
 
 def process_image(input_frames, temp_dir, output_dir, scale, models, gpus, model_path=None):
@@ -26,10 +27,11 @@ def process_image(input_frames, temp_dir, output_dir, scale, models, gpus, model
     if scale not in [1, 2, 4]:
         sys.exit("Scale must be 1, 2 or 4")
     models = models.split(",") if models else []
-    for m in models:
-        if m.startswith("n="):
-            logging.error("model option %r (OpenCV NL-means) is outside this engine's scope" % m)
-            sys.exit("Error - Exiting")
+    denoise = [m.split("=") for m in models if m.startswith("n=")]
+    if denoise:
+        denoise = min(int(denoise[0][1]), 30)
+        if denoise <= 0:
+            denoise = None
     if "r" in models:
         scale = 4  # real-life imaging model is 4x only (reference test_images.py:40-41)
     if gpus:
@@ -49,6 +51,10 @@ def process_image(input_frames, temp_dir, output_dir, scale, models, gpus, model
     os.chdir(output_dir)
     workers_used = 0
     input_file_tag = "extract"
+    if denoise:
+        logging.info("Starting denoise touchup...")
+        workers_used += process_denoise(input_frames, input_file_tag, denoise, remove=False)
+        input_file_tag = "denoise"
     if "a" in models:
         logging.info("Starting anime touchup...")
         process_model(input_frames, model_path, "x_HurrDeblur_SubCompact_nf24-nc8_244k_net_g", 1, "input", "output",
@@ -77,7 +83,7 @@ if __name__ == "__main__":
     parser.add_argument("-t", "--temp_dir", help="Temp directory where extracted frames are saved. Default is tempfile.gettempdir().")
     parser.add_argument("-o", "--output_dir", required=True, help="Output directory where test images will be saved")
     parser.add_argument("-s", "--scale", type=int, default=2, help="Scale 1, 2 or 4. Default is 2.")
-    parser.add_argument("-m", "--models", help="'a' adds the 1x anime touch-up model before upscaling, 'r' uses the 4x real-life model (Valar).")
+    parser.add_argument("-m", "--models", help="'a' adds the 1x anime touch-up model before upscaling, 'n={denoise level}' NL-means noise reduction, 'r' uses the 4x real-life model (Valar). Example: -m a,n=3,r")
     parser.add_argument("-g", "--gpus", help="Optional gpu #s to use. Example 0,1,3. Default is 0.")
     parser.add_argument("--model_path", help="Directory with the model files (default: packaged models)")
     args = parser.parse_args()

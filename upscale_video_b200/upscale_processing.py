@@ -8,6 +8,8 @@ the hot path:
     init_worker          reference :54-73     (process-global engine instead of ``ncnn.Net``)
     apply_model          reference :258-299   (whole-frame 1x model, e.g. HurrDeblur ``-m a``)
     process_model        reference :302-347
+    apply_denoise        reference :350-362   (``-m n=<level>``: cv2.fastNlMeansDenoisingColored on the GPU, bit-exact)
+    process_denoise      reference :365-392
     process_tile         reference :395-477
     upscale_image        reference :480-542
     upscale_frames       reference :545-601
@@ -18,8 +20,8 @@ sm_100a CUDA).  ``upscale_image`` hands the whole frame to the engine in one cal
 (``b2sr_run_u8``) -- instead of looping over tiles in Python.  ``process_tile`` keeps the reference's per-tile
 contract for callers that use it directly.  Errors are returned as log items, never raised (:289-293, :454-459).
 
-The ffmpeg stages, the NL-means ``-m n=`` filter and the batch bookkeeping of ``process_file`` are outside the
-hot path and are not reimplemented here.
+The ffmpeg stages and the batch bookkeeping of ``process_file`` are outside the hot path and are not
+reimplemented here.
 """
 from __future__ import annotations
 
@@ -141,6 +143,51 @@ def process_model(frames_count, model_path, model_file, scale, model_input, mode
             pool.apply_async(apply_model, args=(input_file_name, output_file_name, remove), callback=logging_callback)
     pool.close()
     pool.join()
+
+
+denoiser = None  # process-global, created by the first apply_denoise task of a worker
+DENOISE_MAX_WORKERS = 8  # the reference sizes this pool by CPU count because NL-means runs on the CPU there; here the
+                         # workers only decode/encode PNGs around a GPU call, and each one holds a CUDA context
+
+
+def apply_denoise(input_file_name, output_file_name, denoise, remove):
+    """One frame through ``fastNlMeansDenoisingColored(img, None, denoise, denoise, 5, 9)`` (reference :350-362).
+    The filter runs on the GPU (``b2sr_nlm_run_u8``) in OpenCV's own fixed-point arithmetic: the PNG written is
+    byte-identical to the reference's.  Unlike the reference, a failure is reported as error items (the convention
+    of the other workers, :289-293) instead of vanishing inside ``apply_async``."""
+    global denoiser
+    try:
+        img = cv2.imread(input_file_name)
+        if denoiser is None:
+            ident = multiprocessing.current_process()._identity
+            ndev = max(1, _engine.device_count())
+            denoiser = _engine.Denoiser(device=((ident[0] - 1) % ndev) if ident else 0)
+        output = denoiser.run_u8(img, denoise, denoise, 5, 9)
+        cv2.imwrite(output_file_name, output)
+    except Exception as e:
+        if denoiser is not None:
+            denoiser.close()
+        denoiser = None
+        return [["error", "Denoise failed"], ["error", e]]
+    if remove:
+        os.remove(input_file_name)
+    return [["info", "Processed Denoise: " + output_file_name]]
+
+
+def process_denoise(frames_count, input_file_tag, denoise, remove=True):
+    """One ``apply_denoise`` task per existing ``N.<input_file_tag>.png`` -> ``N.denoise.png``; returns the number
+    of pool processes, which callers add to ``workers_used`` (reference :365-392)."""
+    frames = range(1, frames_count + 1) if isinstance(frames_count, int) else frames_count
+    pool = multiprocessing.get_context("spawn").Pool(processes=min(os.cpu_count() or 1, DENOISE_MAX_WORKERS))
+    for frame in frames:
+        input_file_name = str(frame) + "." + input_file_tag + ".png"
+        output_file_name = str(frame) + ".denoise.png"
+        if os.path.exists(input_file_name):
+            pool.apply_async(apply_denoise, args=(input_file_name, output_file_name, denoise, remove),
+                             callback=logging_callback)
+    pool.close()
+    pool.join()
+    return pool._processes
 
 
 def tile_rect(y, x, tile_size, height, width, halo=TILE_HALO):

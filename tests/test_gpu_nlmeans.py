@@ -90,7 +90,7 @@ def test_full_1080p_against_cv2_and_properties(E, dn):
     assert np.array_equal(out[2], got[::-1])  # reflect-101 borders commute with a vertical flip
     assert np.array_equal(out[0], dn.run_u8(frames[0], 3))
     # host batch pipeline (more frames than one staging chunk holds)
-    n = 11
+    n = 19  # 8 + 8 + 3: the third chunk reuses staging slot 0
     h_in = torch.from_numpy(np.stack([frames[i % 3] for i in range(n)])).pin_memory()
     h_out = torch.empty_like(h_in).pin_memory()
     dn.run_batch_host(h_in, h_out, n, 1080, 1920, 3)

@@ -1,0 +1,20 @@
+#!/usr/bin/env python
+"""A few launches of the denoise kernel on device-resident 1080p frames -- the command profiled under ncu
+(profiles/r01n_nlm_*): python tools/nlm_pass.py [frames] [level] [launches]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from upscale_video_b200 import engine as E  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+level = float(sys.argv[2]) if len(sys.argv) > 2 else 3
+launches = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+dn = E.Denoiser(0)
+d_in = torch.randint(0, 256, (n, 1080, 1920, 3), dtype=torch.uint8, device="cuda")
+d_out = torch.empty_like(d_in)
+for _ in range(launches):
+    dn.run_batch_device(d_in, d_out, n, 1080, 1920, level, sync=True)
+print("ok", int(d_out[0, ::97, ::89].to(torch.int64).sum()))

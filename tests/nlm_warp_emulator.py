@@ -32,9 +32,15 @@ def shfl_down(v, d):
     return out
 
 
-def run(lab, w_l, w_ab):
+PACK_CLAMP = 13107
+PACK_MAX_TABLE = PACK_CLAMP >> 5
+
+
+def run(lab, w_l, w_ab, packed=None):
     """lab: H x W x 3 uint8 (already converted) -> denoised Lab, H x W x 3 uint8."""
     H, W, _ = lab.shape
+    if packed is None:  # the host's choice (nlm_launch in csrc/nlm_host.inl)
+        packed = len(w_l) <= PACK_MAX_TABLE and len(w_ab) <= PACK_MAX_TABLE
     out = np.zeros_like(lab)
     lane = np.arange(32)
     for y0 in range(0, H, TH):
@@ -58,8 +64,13 @@ def run(lab, w_l, w_ab):
                         ad = np.abs(p - q)
                         d_l = ad[:, 0] ** 2
                         d_c = ad[:, 1] ** 2 + ad[:, 2] ** 2
-                        s_l = d_l + shfl_up(d_l, 1) + shfl_up(d_l, 2) + shfl_down(d_l, 1) + shfl_down(d_l, 2)
-                        s_c = d_c + shfl_up(d_c, 1) + shfl_up(d_c, 2) + shfl_down(d_c, 1) + shfl_down(d_c, 2)
+                        if packed:  # two clamped 16-bit fields in one 32-bit word through the shuffles
+                            v = (np.minimum(d_l, PACK_CLAMP) | (np.minimum(d_c, PACK_CLAMP) << 16)).astype(np.uint32)
+                            sv = v + shfl_up(v, 1) + shfl_up(v, 2) + shfl_down(v, 1) + shfl_down(v, 2)  # uint32: wraps like the GPU
+                            s_l, s_c = (sv & 0xffff).astype(np.int64), (sv >> 16).astype(np.int64)
+                        else:
+                            s_l = d_l + shfl_up(d_l, 1) + shfl_up(d_l, 2) + shfl_down(d_l, 1) + shfl_down(d_l, 2)
+                            s_c = d_c + shfl_up(d_c, 1) + shfl_up(d_c, 2) + shfl_down(d_c, 1) + shfl_down(d_c, 2)
                         if r >= 4:
                             o = r - 4
                             k_l = (hl[0] + hl[1] + hl[2] + hl[3] + s_l) >> 5

@@ -52,6 +52,25 @@ def test_separate_luma_and_colour_levels(dn):
     assert np.array_equal(dn.run_u8(img, 4, 9), N.fast_nl_means_denoising_colored(img, 4, 9))
 
 
+def test_both_kernel_variants_mid_size(dn):
+    """Levels 1..6 run the packed-shuffle variant (weight tables <= 409 entries), higher levels the generic one; a
+    high-contrast image makes the packed variant's clamp bite.  Checked against cv2 itself when importable."""
+    rng = np.random.default_rng(21)
+    img = natural(150, 260, seed=21)
+    img[::7] = 0
+    img[3::7] = 255
+    img[40:90, 100:180] = rng.integers(0, 256, (50, 80, 3), dtype=np.uint8)
+    try:
+        import cv2
+        ref = lambda lv: cv2.fastNlMeansDenoisingColored(cv2.UMat(img), None, lv, lv, 5, 9).get()
+    except ImportError:
+        ref = lambda lv: N.fast_nl_means_denoising_colored(img, lv, lv)
+    for level in (1, 6, 7, 12, 30):
+        got = dn.run_u8(img, level)
+        want = ref(level)
+        assert np.array_equal(got, want), "level %d: %d values differ" % (level, (got != want).sum())
+
+
 def test_constant_image_is_the_lab_round_trip(dn):
     """All template distances are 0, so every weight is equal: the result is Lab2LBGR(LBGR2Lab(x))."""
     img = np.empty((37, 59, 3), np.uint8)

@@ -15,6 +15,17 @@ launches = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 dn = E.Denoiser(0)
 d_in = torch.randint(0, 256, (n, 1080, 1920, 3), dtype=torch.uint8, device="cuda")
 d_out = torch.empty_like(d_in)
-for _ in range(launches):
-    dn.run_batch_device(d_in, d_out, n, 1080, 1920, level, sync=True)
-print("ok", int(d_out[0, ::97, ::89].to(torch.int64).sum()))
+stream = torch.cuda.ExternalStream(dn.stream)
+dn.run_batch_device(d_in, d_out, n, 1080, 1920, level, sync=True)
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(launches + 1)]
+for i in range(launches):
+    with torch.cuda.stream(stream):
+        ev[i].record()
+    dn.run_batch_device(d_in, d_out, n, 1080, 1920, level, sync=False)
+with torch.cuda.stream(stream):
+    ev[launches].record()
+dn.synchronize()
+torch.cuda.synchronize()
+ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(launches)]
+print("ok checksum %d; %d frames per launch, level %g: ms per launch %s -> %.0f frames/s" % (
+    int(d_out[0, ::97, ::89].to(torch.int64).sum()), n, level, ["%.3f" % m for m in ms], n / (min(ms) * 1e-3)))

@@ -1777,9 +1777,21 @@ extern "C" int b2sr_run_batch_host(b2sr_ctx* c, const uint8_t* h_in, uint8_t* h_
         CUDA_TRY(cudaEventCreateWithFlags(&compute_done[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&out_done[i], cudaEventDisableTiming));
     }
+    // Chunk schedule.  The call is synchronous, so the H2D of the first chunk and the D2H of the last one are not hidden
+    // behind compute: both are one frame long (tapered ends), the chunks in between hold B frames.  B2SR_E2E_TAPER=0
+    // restores equal chunks.
+    static const bool taper = !(getenv("B2SR_E2E_TAPER") && atoi(getenv("B2SR_E2E_TAPER")) == 0);
+    std::vector<int> chunks;
+    {
+        int left = n;
+        const int tail = (taper && n >= 3) ? 1 : 0;
+        if (tail) chunks.push_back(1), left -= 2;
+        for (; left > 0; left -= B) chunks.push_back(std::min(B, left));
+        if (tail) chunks.push_back(1);
+    }
     int rc = 0, k = 0;
-    for (int f = 0; f < n && !rc; f += B, ++k) {
-        const int nb = std::min(B, n - f), s = k & 1;
+    for (int f = 0; k < (int)chunks.size() && !rc; f += chunks[k], ++k) {
+        const int nb = chunks[k], s = k & 1;
         // staging slot s is free once the compute that read din[s] and the D2H that read dout[s] (chunk k-2) are done
         if (k >= 2) {
             cudaStreamWaitEvent(c->copy_in, compute_done[s], 0);

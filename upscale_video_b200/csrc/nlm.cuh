@@ -13,8 +13,9 @@
 //   * lane l stands on image column x0 + l - 2 (lanes 2..29 produce output, lanes 0,1,30,31 are template halo);
 //   * for each of the 81 search offsets the warp walks its 20 template rows top to bottom: per row one packed
 //     load of the pixel and one of its shifted partner, squared differences with __vabsdiffu4 + dp4a, the
-//     horizontal 5-sum with four warp shuffles per plane, and the vertical 5-sum as a sliding window in
-//     registers -- the 25-tap template distance costs 2 shared-memory loads and 8 shuffles per pixel and offset;
+//     horizontal 5-sum with four warp shuffles per plane (four for both planes together at the usual small levels,
+//     see PACKED below), and the vertical 5-sum as a sliding window in registers -- the 25-tap template distance
+//     costs 2 shared-memory loads and 4 or 8 shuffles per pixel and offset;
 //   * weights come from the (truncated) fixed-point table in global memory (L1-resident: a few hundred bytes at
 //     the reference's typical level 3); 5 accumulators per output row live in registers (80 per lane).
 // Bound: integer ALU / shuffle issue, not HBM (6 B of algorithmic traffic per pixel against ~4 k instructions).
@@ -97,8 +98,27 @@ __device__ __forceinline__ uint32_t nlm_lab2bgr(const NlmParams& P, int L, int A
     return px;
 }
 
+// PACKED (levels whose weight tables are at most NLM_PACK_MAX_TABLE entries long, i.e. h <= 6 for the colour planes):
+// both squared differences are clamped to NLM_PACK_CLAMP and travel through the warp shuffles as two 16-bit fields of
+// one word -- 4 shuffles per row instead of 8.  Exact: a clamped term alone pushes the template sum to >= NLM_PACK_CLAMP,
+// whose table index (>> 5) is >= NLM_PACK_MAX_TABLE, where the true sum's weight is zero as well; 5 * NLM_PACK_CLAMP
+// still fits 16 bits, so the horizontal sums never carry into the neighbouring field.
+constexpr uint32_t NLM_PACK_CLAMP = 13107;                               // 5 * 13107 = 65535
+constexpr uint32_t NLM_PACK_MAX_TABLE = NLM_PACK_CLAMP >> NLM_BIN_SHIFT;  // 409
+
+template <bool PACKED>
 __global__ void __launch_bounds__(NLM_WARPS * 32) nlm_kernel(const NlmParams P) {
     __shared__ uint32_t s_lab[NLM_WARPS][NLM_SH][NLM_SW];
+    // PACKED: both weight tables (<= 409 entries each, zero-padded to 410) live in shared memory and are indexed with a
+    // clamped index -- min + LDS instead of compare + pointer arithmetic + predicated global load + select
+    __shared__ uint32_t s_w[PACKED ? 2 : 1][PACKED ? NLM_PACK_MAX_TABLE + 1 : 1];
+    if (PACKED) {
+        for (uint32_t i = threadIdx.x; i <= NLM_PACK_MAX_TABLE; i += NLM_WARPS * 32) {
+            s_w[0][i] = i < P.n_l ? (uint32_t)__ldg(P.w_l + i) : 0u;
+            s_w[1][i] = i < P.n_ab ? (uint32_t)__ldg(P.w_ab + i) : 0u;
+        }
+        __syncthreads();
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long t = (long long)blockIdx.x * NLM_WARPS + warp;
     if (t >= P.n_tiles) return;  // warps are independent: no block-wide barrier below
@@ -134,17 +154,32 @@ __global__ void __launch_bounds__(NLM_WARPS * 32) nlm_kernel(const NlmParams P) 
                 const uint32_t ad = __vabsdiffu4(p, q);
                 const uint32_t d_l = __dp4a(ad & 0x000000ffu, ad, 0u);
                 const uint32_t d_c = __dp4a(ad & 0x00ffff00u, ad, 0u);
-                const uint32_t s_l = d_l + __shfl_up_sync(0xffffffffu, d_l, 1) + __shfl_up_sync(0xffffffffu, d_l, 2) +
-                                     __shfl_down_sync(0xffffffffu, d_l, 1) + __shfl_down_sync(0xffffffffu, d_l, 2);
-                const uint32_t s_c = d_c + __shfl_up_sync(0xffffffffu, d_c, 1) + __shfl_up_sync(0xffffffffu, d_c, 2) +
-                                     __shfl_down_sync(0xffffffffu, d_c, 1) + __shfl_down_sync(0xffffffffu, d_c, 2);
+                uint32_t s_l, s_c;
+                if (PACKED) {
+                    const uint32_t v = min(d_l, NLM_PACK_CLAMP) | (min(d_c, NLM_PACK_CLAMP) << 16);
+                    const uint32_t s = v + __shfl_up_sync(0xffffffffu, v, 1) + __shfl_up_sync(0xffffffffu, v, 2) +
+                                       __shfl_down_sync(0xffffffffu, v, 1) + __shfl_down_sync(0xffffffffu, v, 2);
+                    s_l = s & 0xffffu;
+                    s_c = s >> 16;
+                } else {
+                    s_l = d_l + __shfl_up_sync(0xffffffffu, d_l, 1) + __shfl_up_sync(0xffffffffu, d_l, 2) +
+                          __shfl_down_sync(0xffffffffu, d_l, 1) + __shfl_down_sync(0xffffffffu, d_l, 2);
+                    s_c = d_c + __shfl_up_sync(0xffffffffu, d_c, 1) + __shfl_up_sync(0xffffffffu, d_c, 2) +
+                          __shfl_down_sync(0xffffffffu, d_c, 1) + __shfl_down_sync(0xffffffffu, d_c, 2);
+                }
                 if (r >= 4) {
                     // template rows r-4..r are complete: output row o = r - 4, whose partner pixel was loaded at r - 2
                     const int o = r - 4;
                     const uint32_t k_l = (hl0 + hl1 + hl2 + hl3 + s_l) >> NLM_BIN_SHIFT;
                     const uint32_t k_c = (hc0 + hc1 + hc2 + hc3 + s_c) >> NLM_BIN_SHIFT;
-                    const uint32_t w_l = k_l < P.n_l ? (uint32_t)__ldg(P.w_l + k_l) : 0u;
-                    const uint32_t w_c = k_c < P.n_ab ? (uint32_t)__ldg(P.w_ab + k_c) : 0u;
+                    uint32_t w_l, w_c;
+                    if (PACKED) {
+                        w_l = s_w[0][min(k_l, NLM_PACK_MAX_TABLE)];
+                        w_c = s_w[1][min(k_c, NLM_PACK_MAX_TABLE)];
+                    } else {
+                        w_l = k_l < P.n_l ? (uint32_t)__ldg(P.w_l + k_l) : 0u;
+                        w_c = k_c < P.n_ab ? (uint32_t)__ldg(P.w_ab + k_c) : 0u;
+                    }
                     est_l[o] += w_l * (q2 & 0xffu);
                     est_a[o] += w_c * ((q2 >> 8) & 0xffu);
                     est_b[o] += w_c * ((q2 >> 16) & 0xffu);

@@ -200,7 +200,11 @@ static int nlm_launch(b2sr_nlm* c, const uint8_t* d_in, long long in_frame_strid
     P.n_l = c->n_l, P.n_ab = c->n_ab;
     const long long blocks = (P.n_tiles + NLM_WARPS - 1) / NLM_WARPS;
     if (blocks > 0x7fffffffLL) return fail(B2SR_E_INVALID, "too many tiles (%lld)", P.n_tiles);
-    nlm_kernel<<<(unsigned)blocks, NLM_WARPS * 32, 0, c->stream>>>(P);
+    static const bool allow_packed = !(getenv("B2SR_NLM_PACKED") && atoi(getenv("B2SR_NLM_PACKED")) == 0);
+    if (allow_packed && c->n_l <= NLM_PACK_MAX_TABLE && c->n_ab <= NLM_PACK_MAX_TABLE)
+        nlm_kernel<true><<<(unsigned)blocks, NLM_WARPS * 32, 0, c->stream>>>(P);
+    else
+        nlm_kernel<false><<<(unsigned)blocks, NLM_WARPS * 32, 0, c->stream>>>(P);
     CUDA_TRY(cudaGetLastError());
     c->n_launch += 1;
     return 0;

@@ -177,3 +177,25 @@ def test_worker_functions_on_png_files(tmp_path, monkeypatch):
     for n, im in frames.items():
         assert not os.path.exists("%d.extract.png" % n)
         assert np.array_equal(cv2.imread("%d.denoise.png" % n), N.fast_nl_means_denoising_colored(im, 6, 6)), n
+
+
+def test_raw_stream_denoise_chain(dn, tmp_path):
+    """`raw_stream -m a,n=4 -s 2`: denoise -> HurrDeblur -> 2x_Compact behind the raw-frame pipe equals the per-frame worker
+    functions applied in the reference's order (test_images.py:82-144); `-s 1 -m n=4` is the denoise pass alone."""
+    import io
+    from conftest import HURR
+    from upscale_video_b200 import engine as E
+    from upscale_video_b200 import ncnn_model, raw_stream
+    mdir = ncnn_model.packaged_model_dir()
+    frames = np.stack([natural(40, 300, seed=s) for s in (1, 2, 3)])
+    den = np.stack([N.fast_nl_means_denoising_colored(f, 4, 4) for f in frames])
+    out = io.BytesIO()
+    assert raw_stream.stream(io.BytesIO(frames.tobytes()), out, 300, 40, scale=1, models=["n=4"], chunk=2) == 3
+    assert out.getvalue() == den.tobytes()
+    hurr, comp = E.Engine.from_files(mdir, HURR), E.Engine.from_files(mdir, "2x_Compact_Pretrain")
+    expect = np.stack([comp.run_u8(hurr.run_u8(f, tile=0, halo=0)) for f in den])
+    out = io.BytesIO()
+    assert raw_stream.stream(io.BytesIO(frames.tobytes()), out, 300, 40, scale=2, models=["a", "n=4"], chunk=2, model_path=mdir) == 3
+    assert np.array_equal(np.frombuffer(out.getvalue(), np.uint8).reshape(3, 80, 600, 3), expect)
+    hurr.close()
+    comp.close()

@@ -262,6 +262,22 @@ def test_full_size_properties(E, engines):
     assert np.array_equal(h_out.numpy(), batch)
 
 
+def test_host_pipeline_tapered_chunks(E, engines):
+    """b2sr_run_batch_host cuts a synchronous call into chunks of 1, B, ..., B, 1 frames (one-frame ends keep the exposed
+    H2D / D2H short): whatever the schedule, the frames equal the device-resident batch."""
+    import torch
+    eng = engines("2x_Compact_Pretrain")
+    for n in (1, 2, 3, 7, 11):
+        frames = np.stack([natural(270, 480, seed=40 + s) for s in range(n)])
+        d_in = torch.from_numpy(frames).cuda()
+        d_out = torch.empty((n, 540, 960, 3), dtype=torch.uint8, device="cuda")
+        eng.run_batch_device(d_in, d_out, n, 270, 480, sync=True)
+        h_in = torch.from_numpy(frames).pin_memory()
+        h_out = torch.zeros((n, 540, 960, 3), dtype=torch.uint8).pin_memory()
+        eng.run_batch_host(h_in, h_out, n, 270, 480)
+        assert np.array_equal(h_out.numpy(), d_out.cpu().numpy()), n
+
+
 def test_strides_and_device_memory(E, engines):
     import torch
     eng = engines("2x_Compact_Pretrain")

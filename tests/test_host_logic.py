@@ -212,6 +212,27 @@ def test_raw_stream_framing(tmp_path):
     out = io.BytesIO()
     raw_stream.stream(io.BytesIO(frames.tobytes()), out, 8, 6, scale=1, models=["a"], chunk=3, prepass=pre)
     assert [c[3:] for c in pre.calls] == [(0, 0), (0, 0)] and out.getvalue() == frames.tobytes()
+    # -m n=K: the denoiser sees every frame first, with the clamped level; then the upscaler sees its output
+    class FakeDenoiser:
+        def __init__(self):
+            self.calls = []
+
+        def run_batch_host(self, h_in, h_out, n, h, w, level, level_color=None):
+            a = h_in.numpy() if hasattr(h_in, "numpy") else h_in
+            o = h_out.numpy() if hasattr(h_out, "numpy") else h_out
+            self.calls.append((n, h, w, level))
+            o[:n] = 255 - a[:n]
+
+    dn, eng = FakeDenoiser(), _FakeEngine(2)
+    out = io.BytesIO()
+    raw_stream.stream(io.BytesIO(frames.tobytes()), out, 8, 6, scale=2, models=["n=45"], chunk=2, upscaler=eng, denoiser=dn)
+    assert dn.calls == [(2, 6, 8, 30), (2, 6, 8, 30), (1, 6, 8, 30)] and [c[0] for c in eng.calls] == [2, 2, 1]
+    assert np.array_equal(np.frombuffer(out.getvalue(), np.uint8).reshape(5, 12, 16, 3), np.repeat(np.repeat(255 - frames, 2, 1), 2, 2))
+    dn = FakeDenoiser()  # denoise only (scale 1)
+    out = io.BytesIO()
+    raw_stream.stream(io.BytesIO(frames.tobytes()), out, 8, 6, scale=1, models=["n=3"], chunk=4, denoiser=dn)
+    assert out.getvalue() == (255 - frames).tobytes() and dn.calls[0][3] == 3
+    assert raw_stream.denoise_level(["a", "n=0"]) is None and raw_stream.denoise_level(["r"]) is None
     # max_frames and truncation
     out = io.BytesIO()
     assert raw_stream.stream(io.BytesIO(frames.tobytes()), out, 8, 6, scale=2, chunk=2, max_frames=3, upscaler=_FakeEngine(2)) == 3

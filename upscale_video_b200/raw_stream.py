@@ -13,7 +13,9 @@ Frames are read in chunks, pushed through ``Engine.run_batch_host`` (pinned stag
 three streams) and written out in order.  Arithmetic is exactly ``upscale_image``'s: reference tiling (960 + 10),
 ``* 255``, ``cv2.imwrite`` rounding -- only the container around the pixels changes.  ``-m a`` chains the 1x
 HurrDeblur pre-pass in front of the upscaler like ``process_file`` does with ``process_model`` (:888-909), keeping the
-reference's u8 quantisation between the two networks but never leaving the GPU (no ``N.anime.png`` hop).
+reference's u8 quantisation between the two networks but never leaving the GPU (no ``N.anime.png`` hop).  ``-m n=K``
+puts the NL-means denoise pass (``apply_denoise`` :350-362, bit-identical to cv2) in front of both, in the reference's
+order denoise -> anime -> upscale (test_images.py:82-110).
 
 Pixel order: the reference's network sees OpenCV's BGR (``cv2.imread`` -> ``PIXEL_BGR`` unswapped, :263-270), so
 ``--pix_fmt bgr24`` (default) is byte-compatible; with ``rgb24`` the channels are swapped on the way in and out.
@@ -68,20 +70,36 @@ class _Stage:
         self.array = np.empty(shape, np.uint8)
 
 
+def denoise_level(models):
+    """``n=K`` among the model options -> K clamped to 1..30, or None (reference test_images.py:45-52)."""
+    for m in models:
+        if m.startswith("n="):
+            k = min(int(m.split("=")[1]), 30)
+            return k if k > 0 else None
+    return None
+
+
 def stream(fin, fout, width, height, scale=2, models=(), gpu=0, chunk=8, pix_fmt="bgr24", model_path=None, max_frames=None,
-           upscaler=None, prepass=None):
+           upscaler=None, prepass=None, denoiser=None):
     """Upscale raw ``height x width x 3`` u8 frames from ``fin`` to ``fout``.  Returns the number of frames written.
-    ``upscaler`` / ``prepass`` may be passed in as ready engines (tests); otherwise they are built from the model files."""
+    ``upscaler`` / ``prepass`` / ``denoiser`` may be passed in as ready engines (tests); otherwise they are built from the
+    model options."""
     model_path = model_path or ncnn_model.packaged_model_dir()
+    level = denoise_level(models)
+    if denoiser is None and level is not None:
+        denoiser = _engine.Denoiser(gpu)
     if upscaler is None and scale > 1:
         # process_file :911-918: `-m r` selects <scale>x_Valar_v1 (RRDB, tcgen05 graph kernels), else <scale>x_Compact_Pretrain
         upscaler = _engine.Engine.from_files(model_path, str(scale) + ("x_Valar_v1" if "r" in models else "x_Compact_Pretrain"), gpu)
     if prepass is None and "a" in models:
         prepass = _engine.Engine.from_files(model_path, "1" + HURR, gpu)
-    if upscaler is None and prepass is None:
+    if upscaler is None and prepass is None and denoiser is None:
         raise ValueError("nothing to do: scale 1 and no pre-pass model")
+    if denoiser is not None and level is None:
+        raise ValueError("a denoiser needs its level: add 'n=K' to the model options")
     s = upscaler.scale if upscaler is not None else 1
     st_in = _Stage((chunk, height, width, 3))
+    st_dn = _Stage((chunk, height, width, 3)) if (denoiser is not None and (upscaler is not None or prepass is not None)) else None
     st_mid = _Stage((chunk, height, width, 3)) if (prepass is not None and upscaler is not None) else None
     st_out = _Stage((chunk, height * s, width * s, 3))
     dev = None
@@ -105,11 +123,16 @@ def stream(fin, fout, width, height, scale=2, models=(), gpu=0, chunk=8, pix_fmt
         if n == 0:
             break
         src = st_in
+        if denoiser is not None:  # fastNlMeansDenoisingColored(frame, None, K, K, 5, 9) on every frame first
+            dst = st_dn if st_dn is not None else st_out
+            denoiser.run_batch_host(src.tensor if src.tensor is not None else src.array,
+                                    dst.tensor if dst.tensor is not None else dst.array, n, height, width, level)
+            src = dst
         if prepass is not None and upscaler is not None and dev is not None:
             # chained on the device: frames go up once, the 1x model's u8 output (apply_model :263-288 rounding) feeds the
             # upscaler (upscale_image :489-519 tiling) from device memory, results come down once
             torch, d_in, d_mid, d_out = dev
-            d_in[:n].copy_(st_in.tensor[:n])
+            d_in[:n].copy_(src.tensor[:n])
             torch.cuda.synchronize()
             prepass.run_batch_device(d_in, d_mid, n, height, width, tile=0, halo=0, sync=True)
             upscaler.run_batch_device(d_mid, d_out, n, height, width, sync=True)
@@ -138,8 +161,8 @@ def main(argv=None):
     ap.add_argument("--width", type=int, required=True)
     ap.add_argument("--height", type=int, required=True)
     ap.add_argument("-s", "--scale", type=int, default=2, help="Scale 1, 2 or 4 (1 = pre-pass only). Default is 2.")
-    ap.add_argument("-m", "--models", help="'a' adds the 1x anime touch-up model before upscaling, 'r' uses the real-life model "
-                                           "4x_Valar_v1 as the upscaler (like upscale_video.py -m a,r).")
+    ap.add_argument("-m", "--models", help="'a' adds the 1x anime touch-up model before upscaling, 'n={level}' NL-means noise reduction "
+                                           "first, 'r' uses the real-life model 4x_Valar_v1 as the upscaler (like upscale_video.py -m a,n=3,r).")
     ap.add_argument("-g", "--gpu", type=int, default=0, help="GPU index for this worker (run one worker per GPU, frames interleaved by the caller)")
     ap.add_argument("--chunk", type=int, default=8, help="frames per host<->device chunk")
     ap.add_argument("--pix_fmt", default="bgr24", choices=["bgr24", "rgb24"])
@@ -149,8 +172,8 @@ def main(argv=None):
     a = ap.parse_args(argv)
     models = a.models.split(",") if a.models else []
     for m in models:
-        if m not in ("a", "r"):
-            sys.exit("model option %r is outside this engine's scope ('a' = HurrDeblur pre-pass, 'r' = Valar upscaler)" % m)
+        if m not in ("a", "r") and not (m.startswith("n=") and m[2:].lstrip("-").isdigit()):
+            sys.exit("unknown model option %r ('a' = HurrDeblur pre-pass, 'n=K' = denoise, 'r' = Valar upscaler)" % m)
     if "r" in models and a.scale != 4:
         sys.exit("-m r needs -s 4 (the reference ships 4x_Valar_v1 only)")
     fin = open(a.input, "rb") if a.input else sys.stdin.buffer

@@ -2,7 +2,7 @@
 
 Test infrastructure: it follows the kernel's index arithmetic statement by statement -- tile origin, the staged
 40 x 28 Lab window with the reflect-101 border, lane l on image column x0 + l - 2, shuffles as lane shifts that
-return the lane's own value at the warp edge, the sliding 5-row window and the two-rows-late partner pixel -- so
+return the lane's own value at the warp edge, the running 5-row column sums and the two-rows-late partner pixel -- so
 that the CPU suite can check the warp algorithm against the oracle without a GPU.  The Lab conversions and the
 weight tables are taken from the product library through its host-only C-ABI entry points.
 """
@@ -55,8 +55,9 @@ def run(lab, w_l, w_ab, packed=None):
             cx = lane + BORDER - 2
             for dy in range(-4, 5):
                 for dx in range(-4, 5):
-                    hl = [np.zeros(32, dtype=np.int64)] * 4
-                    hc = [np.zeros(32, dtype=np.int64)] * 4
+                    v_l = np.zeros(32, dtype=np.int64)
+                    v_c = np.zeros(32, dtype=np.int64)
+                    dl_hist, dc_hist = [], []
                     q1 = q2 = np.zeros((32, 3), dtype=np.int64)
                     for r in range(TH + 4):
                         p = s[BORDER - 2 + r, cx]
@@ -64,17 +65,22 @@ def run(lab, w_l, w_ab, packed=None):
                         ad = np.abs(p - q)
                         d_l = ad[:, 0] ** 2
                         d_c = ad[:, 1] ** 2 + ad[:, 2] ** 2
-                        if packed:  # two clamped 16-bit fields in one 32-bit word through the shuffles
-                            v = (np.minimum(d_l, PACK_CLAMP) | (np.minimum(d_c, PACK_CLAMP) << 16)).astype(np.uint32)
-                            sv = v + shfl_up(v, 1) + shfl_up(v, 2) + shfl_down(v, 1) + shfl_down(v, 2)  # uint32: wraps like the GPU
-                            s_l, s_c = (sv & 0xffff).astype(np.int64), (sv >> 16).astype(np.int64)
-                        else:
-                            s_l = d_l + shfl_up(d_l, 1) + shfl_up(d_l, 2) + shfl_down(d_l, 1) + shfl_down(d_l, 2)
-                            s_c = d_c + shfl_up(d_c, 1) + shfl_up(d_c, 2) + shfl_down(d_c, 1) + shfl_down(d_c, 2)
-                        if r >= 4:
+                        dl_hist.append(d_l)
+                        dc_hist.append(d_c)
+                        v_l = v_l + d_l  # vertical running sum per column first
+                        v_c = v_c + d_c
+                        if r >= 5:
+                            v_l = v_l - dl_hist[r - 5]
+                            v_c = v_c - dc_hist[r - 5]
+                        if r >= 4:  # then the horizontal 5-sum across lanes
                             o = r - 4
-                            k_l = (hl[0] + hl[1] + hl[2] + hl[3] + s_l) >> 5
-                            k_c = (hc[0] + hc[1] + hc[2] + hc[3] + s_c) >> 5
+                            if packed:  # two clamped 16-bit fields in one 32-bit word through the shuffles
+                                v = (np.minimum(v_l, PACK_CLAMP) | (np.minimum(v_c, PACK_CLAMP) << 16)).astype(np.uint32)
+                                sv = v + shfl_up(v, 1) + shfl_up(v, 2) + shfl_down(v, 1) + shfl_down(v, 2)  # uint32: wraps like the GPU
+                                k_l, k_c = ((sv & 0xffff) >> 5).astype(np.int64), (sv >> 21).astype(np.int64)
+                            else:
+                                k_l = (v_l + shfl_up(v_l, 1) + shfl_up(v_l, 2) + shfl_down(v_l, 1) + shfl_down(v_l, 2)) >> 5
+                                k_c = (v_c + shfl_up(v_c, 1) + shfl_up(v_c, 2) + shfl_down(v_c, 1) + shfl_down(v_c, 2)) >> 5
                             wl = np.where(k_l < len(w_l), w_l[np.minimum(k_l, len(w_l) - 1)], 0).astype(np.uint64)
                             wc = np.where(k_c < len(w_ab), w_ab[np.minimum(k_c, len(w_ab) - 1)], 0).astype(np.uint64)
                             est[o, :, 0] += wl * q2[:, 0].astype(np.uint64)
@@ -82,8 +88,6 @@ def run(lab, w_l, w_ab, packed=None):
                             est[o, :, 2] += wc * q2[:, 2].astype(np.uint64)
                             ws[o, :, 0] += wl
                             ws[o, :, 1] += wc
-                        hl = [hl[1], hl[2], hl[3], s_l]
-                        hc = [hc[1], hc[2], hc[3], s_c]
                         q2, q1 = q1, q
             assert est.max() < 2 ** 32 and ws.max() < 2 ** 32  # the kernel's accumulators are 32-bit
             for l in range(2, 2 + TW):

@@ -13,9 +13,10 @@
 //   * lane l stands on image column x0 + l - 2 (lanes 2..29 produce output, lanes 0,1,30,31 are template halo);
 //   * for each of the 81 search offsets the warp walks its 20 template rows top to bottom: per row one packed
 //     load of the pixel and one of its shifted partner, squared differences with __vabsdiffu4 + dp4a, the
+//     vertical 5-sum as a running sum per column in registers and, for the 16 rows that complete a template, the
 //     horizontal 5-sum with four warp shuffles per plane (four for both planes together at the usual small levels,
-//     see PACKED below), and the vertical 5-sum as a sliding window in registers -- the 25-tap template distance
-//     costs 2 shared-memory loads and 4 or 8 shuffles per pixel and offset;
+//     see PACKED below) -- the 25-tap template distance costs 2 shared-memory loads and 4 or 8 shuffles per pixel
+//     and offset;
 //   * weights come from the (truncated) fixed-point table in global memory (L1-resident: a few hundred bytes at
 //     the reference's typical level 3); 5 accumulators per output row live in registers (80 per lane).
 // Bound: integer ALU / shuffle issue, not HBM (6 B of algorithmic traffic per pixel against ~4 k instructions).
@@ -99,7 +100,7 @@ __device__ __forceinline__ uint32_t nlm_lab2bgr(const NlmParams& P, int L, int A
 }
 
 // PACKED (levels whose weight tables are at most NLM_PACK_MAX_TABLE entries long, i.e. h <= 6 for the colour planes):
-// both squared differences are clamped to NLM_PACK_CLAMP and travel through the warp shuffles as two 16-bit fields of
+// both column sums are clamped to NLM_PACK_CLAMP and travel through the warp shuffles as two 16-bit fields of
 // one word -- 4 shuffles per row instead of 8.  Exact: a clamped term alone pushes the template sum to >= NLM_PACK_CLAMP,
 // whose table index (>> 5) is >= NLM_PACK_MAX_TABLE, where the true sum's weight is zero as well; 5 * NLM_PACK_CLAMP
 // still fits 16 bits, so the horizontal sums never carry into the neighbouring field.
@@ -147,36 +148,37 @@ __global__ void __launch_bounds__(NLM_WARPS * 32) nlm_kernel(const NlmParams P) 
 #pragma unroll 1
         for (int dx = -4; dx <= 4; ++dx) {
             const uint32_t* other = own + dy * NLM_SW + dx;
-            uint32_t hl0 = 0, hl1 = 0, hl2 = 0, hl3 = 0, hc0 = 0, hc1 = 0, hc2 = 0, hc3 = 0, q1 = 0, q2 = 0;
+            uint32_t v_l = 0, v_c = 0, q1 = 0, q2 = 0;
+            uint32_t dl_hist[NLM_TH + 4], dc_hist[NLM_TH + 4];  // compile-time indexed: five of each are live
 #pragma unroll
             for (int r = 0; r < NLM_TH + 4; ++r) {
                 const uint32_t p = own[r * NLM_SW], q = other[r * NLM_SW];
                 const uint32_t ad = __vabsdiffu4(p, q);
-                const uint32_t d_l = __dp4a(ad & 0x000000ffu, ad, 0u);
-                const uint32_t d_c = __dp4a(ad & 0x00ffff00u, ad, 0u);
-                uint32_t s_l, s_c;
-                if (PACKED) {
-                    const uint32_t v = min(d_l, NLM_PACK_CLAMP) | (min(d_c, NLM_PACK_CLAMP) << 16);
-                    const uint32_t s = v + __shfl_up_sync(0xffffffffu, v, 1) + __shfl_up_sync(0xffffffffu, v, 2) +
-                                       __shfl_down_sync(0xffffffffu, v, 1) + __shfl_down_sync(0xffffffffu, v, 2);
-                    s_l = s & 0xffffu;
-                    s_c = s >> 16;
-                } else {
-                    s_l = d_l + __shfl_up_sync(0xffffffffu, d_l, 1) + __shfl_up_sync(0xffffffffu, d_l, 2) +
-                          __shfl_down_sync(0xffffffffu, d_l, 1) + __shfl_down_sync(0xffffffffu, d_l, 2);
-                    s_c = d_c + __shfl_up_sync(0xffffffffu, d_c, 1) + __shfl_up_sync(0xffffffffu, d_c, 2) +
-                          __shfl_down_sync(0xffffffffu, d_c, 1) + __shfl_down_sync(0xffffffffu, d_c, 2);
-                }
+                const uint32_t l = ad & 0xffu;
+                const uint32_t d_l = l * l;                       // dL^2
+                const uint32_t d_c = __dp4a(ad, ad, 0u) - d_l;    // da^2 + db^2 (byte 3 is zero)
+                // vertical 5-sum first, as a running sum per column ...
+                dl_hist[r] = d_l, dc_hist[r] = d_c;
+                v_l += d_l, v_c += d_c;
+                if (r >= 5) v_l -= dl_hist[r - 5], v_c -= dc_hist[r - 5];
                 if (r >= 4) {
-                    // template rows r-4..r are complete: output row o = r - 4, whose partner pixel was loaded at r - 2
+                    // ... then, once rows r-4..r are in, the horizontal 5-sum across lanes: output row o = r - 4, whose
+                    // partner pixel was loaded at r - 2
                     const int o = r - 4;
-                    const uint32_t k_l = (hl0 + hl1 + hl2 + hl3 + s_l) >> NLM_BIN_SHIFT;
-                    const uint32_t k_c = (hc0 + hc1 + hc2 + hc3 + s_c) >> NLM_BIN_SHIFT;
-                    uint32_t w_l, w_c;
+                    uint32_t k_l, k_c, w_l, w_c;
                     if (PACKED) {
+                        const uint32_t v = min(v_l, NLM_PACK_CLAMP) | (min(v_c, NLM_PACK_CLAMP) << 16);
+                        const uint32_t s = v + __shfl_up_sync(0xffffffffu, v, 1) + __shfl_up_sync(0xffffffffu, v, 2) +
+                                           __shfl_down_sync(0xffffffffu, v, 1) + __shfl_down_sync(0xffffffffu, v, 2);
+                        k_l = (s & 0xffffu) >> NLM_BIN_SHIFT;
+                        k_c = s >> (16 + NLM_BIN_SHIFT);
                         w_l = s_w[0][min(k_l, NLM_PACK_MAX_TABLE)];
                         w_c = s_w[1][min(k_c, NLM_PACK_MAX_TABLE)];
                     } else {
+                        k_l = (v_l + __shfl_up_sync(0xffffffffu, v_l, 1) + __shfl_up_sync(0xffffffffu, v_l, 2) +
+                               __shfl_down_sync(0xffffffffu, v_l, 1) + __shfl_down_sync(0xffffffffu, v_l, 2)) >> NLM_BIN_SHIFT;
+                        k_c = (v_c + __shfl_up_sync(0xffffffffu, v_c, 1) + __shfl_up_sync(0xffffffffu, v_c, 2) +
+                               __shfl_down_sync(0xffffffffu, v_c, 1) + __shfl_down_sync(0xffffffffu, v_c, 2)) >> NLM_BIN_SHIFT;
                         w_l = k_l < P.n_l ? (uint32_t)__ldg(P.w_l + k_l) : 0u;
                         w_c = k_c < P.n_ab ? (uint32_t)__ldg(P.w_ab + k_c) : 0u;
                     }
@@ -186,8 +188,6 @@ __global__ void __launch_bounds__(NLM_WARPS * 32) nlm_kernel(const NlmParams P) 
                     ws_l[o] += w_l;
                     ws_ab[o] += w_c;
                 }
-                hl0 = hl1, hl1 = hl2, hl2 = hl3, hl3 = s_l;
-                hc0 = hc1, hc1 = hc2, hc2 = hc3, hc3 = s_c;
                 q2 = q1, q1 = q;
             }
         }

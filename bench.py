@@ -298,6 +298,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's version banner off stdout: one JSON line there
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     # rank 0 reads the model; everyone else receives the packed blob over NCCL (north_star: weight broadcast)

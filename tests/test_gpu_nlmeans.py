@@ -149,6 +149,8 @@ def test_errors_are_codes_not_crashes(E, dn):
     assert lib.b2sr_nlm_run_u8(*args, 0.0, 3.0, 5, 9, E.MEM_HOST) == -1
     assert lib.b2sr_nlm_run_u8(dn._h, img.ctypes.data, 8, 8, 20, out.ctypes.data, 24, 3.0, 3.0, 5, 9, E.MEM_HOST) == -1
     assert lib.b2sr_nlm_run_u8(dn._h, None, 8, 8, 24, out.ctypes.data, 24, 3.0, 3.0, 5, 9, E.MEM_HOST) == -1
+    assert lib.b2sr_nlm_run_u8(dn._h, img.ctypes.data, 8, 8, 24, img.ctypes.data, 24, 3.0, 3.0, 5, 9, E.MEM_HOST) == -1  # in place
+    assert b"overlap" in lib.b2sr_last_error()
     with pytest.raises(E.EngineError):
         E.Denoiser(99)
     assert np.array_equal(dn.run_u8(img, 3), N.fast_nl_means_denoising_colored(img, 3, 3))  # still usable

@@ -215,6 +215,11 @@ extern "C" int b2sr_nlm_run_u8(b2sr_nlm* c, const uint8_t* in, int h, int w, int
     if (!c || !in || !out) return fail(B2SR_E_INVALID, "b2sr_nlm_run_u8: null argument");
     TRY(nlm_check(1, h, w, template_window, search_window));
     if (in_stride < w * 3 || out_stride < w * 3) return fail(B2SR_E_INVALID, "row stride smaller than a row");
+    {   // every output pixel reads a 13 x 13 neighbourhood of the input: the two images must not share memory
+        const uint8_t *a0 = in, *a1 = in + (size_t)(h - 1) * in_stride + (size_t)w * 3;
+        const uint8_t *b0 = out, *b1 = out + (size_t)(h - 1) * out_stride + (size_t)w * 3;
+        if (a0 < b1 && b0 < a1) return fail(B2SR_E_INVALID, "b2sr_nlm_run_u8: input and output overlap (in-place is not supported)");
+    }
     CUDA_TRY(cudaSetDevice(c->device));
     TRY(nlm_set_levels(c, h_luma, h_color));
     if (memspace == B2SR_MEM_DEVICE) {

@@ -29,3 +29,15 @@ torch.cuda.synchronize()
 ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(launches)]
 print("ok checksum %d; %d frames per launch, level %g: ms per launch %s -> %.0f frames/s" % (
     int(d_out[0, ::97, ::89].to(torch.int64).sum()), n, level, ["%.3f" % m for m in ms], n / (min(ms) * 1e-3)))
+
+import time  # noqa: E402
+
+h_in = d_in.cpu().pin_memory()
+h_out = torch.empty_like(h_in).pin_memory()
+dn.run_batch_host(h_in, h_out, n, 1080, 1920, level)
+t0 = time.perf_counter()
+for _ in range(launches):
+    dn.run_batch_host(h_in, h_out, n, 1080, 1920, level)
+dt = (time.perf_counter() - t0) / launches
+print("end to end (pinned host -> device -> pinned host, chunk %s): %.3f ms per %d frames -> %.0f frames/s; equal to device result: %s" % (
+    os.environ.get("B2SR_NLM_CHUNK", "default"), dt * 1e3, n, n / dt, bool(torch.equal(h_out, d_out.cpu()))))

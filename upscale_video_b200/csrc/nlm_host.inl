@@ -258,7 +258,11 @@ extern "C" int b2sr_nlm_run_batch_host(b2sr_nlm* c, const uint8_t* h_in, uint8_t
     CUDA_TRY(cudaSetDevice(c->device));
     TRY(nlm_set_levels(c, h_luma, h_color));
     const size_t frame = (size_t)h * w * 3;
-    const int B = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)64 << 20) / frame));
+    // small chunks: the kernel needs ~0.3 ms per 1080p frame, about what PCIe needs per direction, so the three streams only
+    // overlap well when a chunk is a frame or two (one 1080p frame already fills the GPU twice over: 4692 warp tiles)
+    static const int chunk_env = getenv("B2SR_NLM_CHUNK") ? atoi(getenv("B2SR_NLM_CHUNK")) : 0;
+    const int B = chunk_env > 0 ? std::min(chunk_env, 64)
+                                : (int)std::max<size_t>(1, std::min<size_t>(2, ((size_t)16 << 20) / frame));
     TRY(grow(&c->d_in, &c->cap_in, frame * B));
     TRY(grow(&c->d_out, &c->cap_out, frame * B));
     TRY(grow(&c->d_in2, &c->cap_in2, frame * B));

@@ -39,6 +39,48 @@ def test_logging_callback_exits_on_error(caplog):
         up.logging_callback([["info", "ok"], ["error", "boom"], ["info", "never"]])
 
 
+def test_cli_fails_loudly_without_a_device(tmp_path):
+    """No GPU: the worker initialiser must not throw the Pool into a respawn loop and the error item must end the parent
+    (the reference's sys.exit inside the Pool callback would leave pool.join() hanging on current CPython)."""
+    import subprocess
+    import sys
+    import cv2
+    from upscale_video_b200 import engine
+    if engine.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    (tmp_path / "t" / "upscale_video").mkdir(parents=True)
+    (tmp_path / "o").mkdir()
+    cv2.imwrite(str(tmp_path / "t" / "upscale_video" / "1.extract.png"), np.zeros((20, 30, 3), np.uint8))
+    for models in (None, "n=3"):
+        cmd = [sys.executable, "-m", "upscale_video_b200.test_images", "-i", "1", "-t", str(tmp_path / "t"), "-o", str(tmp_path / "o"),
+               "-s", "2", "-g", "0"] + (["-m", models] if models else [])
+        r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=120)
+        assert r.returncode != 0 and "Error - Exiting" in r.stderr and "no CUDA device" in (r.stdout + r.stderr), r.stdout + r.stderr
+        assert not (tmp_path / "o" / "1.png").exists()
+
+
+def test_logging_callback_on_pool_thread_defers_exit():
+    import threading
+    seen = []
+
+    def handler():  # what the Pool's result-handler thread does
+        try:
+            up.logging_callback([["error", "boom"]])
+            seen.append("returned")
+        except SystemExit:
+            seen.append("exit")
+
+    t = threading.Thread(target=handler)
+    t.start()
+    t.join()
+    assert seen == ["returned"] and up._failed
+    with pytest.raises(SystemExit):
+        up._exit_if_failed()
+    assert not up._failed
+    up._exit_if_failed()  # nothing pending: no exit
+
+
 class _FakeNet:
     """Stands in for the engine in host-logic tests only (no arithmetic is checked with it)."""
     scale = 2

@@ -30,6 +30,7 @@ import math
 import multiprocessing
 import os
 import sys
+import threading
 
 import cv2
 import numpy as np
@@ -37,6 +38,7 @@ import numpy as np
 from . import engine as _engine
 
 net = None
+init_error = None  # why this worker has no engine (set by init_worker), reported by its tasks as error items
 model_input_name = "input"
 model_output_name = "output"
 
@@ -56,8 +58,17 @@ def get_frames(x):
     return frames
 
 
+_failed = False  # an error item arrived on a pool's result-handler thread; the pool functions exit after join()
+
+
 def logging_callback(log_list):
-    """Pool callback: log the worker's items; the first ``error`` item ends the parent (reference :40-51)."""
+    """Pool callback: log the worker's items; the first ``error`` item ends the parent (reference :40-51).
+
+    The reference calls ``sys.exit`` right here.  Pool callbacks run on the pool's result-handler thread, where
+    ``SystemExit`` only kills that thread and leaves ``pool.join()`` waiting forever (CPython 3.8+), so on that thread the
+    failure is recorded instead and ``upscale_frames`` / ``process_model`` / ``process_denoise`` exit the parent as soon
+    as their pool has drained; a direct call from the main thread exits immediately, like the reference."""
+    global _failed
     failed = False
     for level, message in log_list:
         if level == "info":
@@ -68,7 +79,16 @@ def logging_callback(log_list):
             logging.error(message)
             failed = True
         if failed:
-            sys.exit("Error - Exiting")
+            if threading.current_thread() is threading.main_thread():
+                sys.exit("Error - Exiting")
+            _failed = True  # keep logging: the items after the first error carry the reason
+
+
+def _exit_if_failed():
+    global _failed
+    if _failed:
+        _failed = False
+        sys.exit("Error - Exiting")
 
 
 def _worker_slot(workers_used):
@@ -82,17 +102,26 @@ def init_worker(gpus, workers_used, model_path, model_file, scale, model_input, 
     """Pool initializer: bind this worker to ``gpus[slot]`` and load ``<scale><model_file>`` once
     (reference :54-73).  ``model_input``/``model_output`` are kept for signature compatibility; the engine
     recognises the graph's input/output blobs structurally and checks the names match."""
-    global net, model_input_name, model_output_name
+    global net, model_input_name, model_output_name, init_error
+    model_input_name = model_input
+    model_output_name = model_output
+    net, init_error = None, None
     gpu = _worker_slot(workers_used)
     if gpu > len(gpus) - 1:
+        # The reference exits the worker here (:61-63), which makes the Pool respawn it forever.  Same message, but the
+        # worker stays alive and every task it receives returns the error as log items, so the parent stops.
         logging.error("Unable to assign GPU to new worker.")
-        sys.exit("Error - Exiting")
-    net = _engine.Engine.from_files(model_path, str(scale) + model_file, device=int(gpus[gpu]))
+        init_error = "Unable to assign GPU to new worker."
+        return
+    try:
+        net = _engine.Engine.from_files(model_path, str(scale) + model_file, device=int(gpus[gpu]))
+    except Exception as e:  # no device, missing library, bad model file: reported by the first task, never a respawn loop
+        logging.error(e)
+        init_error = e
+        return
     for given, found in ((model_input, net.desc.input_blob), (model_output, net.desc.output_blob)):
         if given and given != found:
             logging.warning("model blob name %r differs from the graph's %r; using the graph's", given, found)
-    model_input_name = model_input
-    model_output_name = model_output
 
 
 def _release_engine():
@@ -110,6 +139,8 @@ def apply_model(input_file, output_file, remove):
     logging_items = []
     img = cv2.imread(input_file)
     try:
+        if net is None:
+            raise _engine.EngineError(init_error or "no engine: init_worker has not run in this process")
         output = net.run_u8(img, tile=0, halo=0)
         if output_file:
             cv2.imwrite(output_file, output)
@@ -143,6 +174,7 @@ def process_model(frames_count, model_path, model_file, scale, model_input, mode
             pool.apply_async(apply_model, args=(input_file_name, output_file_name, remove), callback=logging_callback)
     pool.close()
     pool.join()
+    _exit_if_failed()
 
 
 denoiser = None  # process-global, created by the first apply_denoise task of a worker
@@ -187,6 +219,7 @@ def process_denoise(frames_count, input_file_tag, denoise, remove=True):
                              callback=logging_callback)
     pool.close()
     pool.join()
+    _exit_if_failed()
     return pool._processes
 
 
@@ -208,6 +241,8 @@ def process_tile(img, tile_size, scale, y, x, height, width, output, logging_ite
     (iy0, iy1, ix0, ix1), (cy0, cy1, cx0, cx1) = tile_rect(y, x, tile_size, height, width)
     input_tile = np.ascontiguousarray(img[iy0:iy1, ix0:ix1, :])
     try:
+        if net is None:
+            raise _engine.EngineError(init_error or "no engine: init_worker has not run in this process")
         output_tile = net.run_f32(input_tile, tile=0, halo=0)  # the tile is one zero-padded plane, `* 255` applied
     except Exception as e:
         logging_items.append(["error", "Upscale failed"])
@@ -232,6 +267,8 @@ def upscale_image(input_file_name, output_file_name, scale, frame_batch, frame, 
     for tile_idx in range(1, tiles_x * tiles_y + 1):
         logging_items.append(["debug", f"Processing Tile: {tile_idx}/{tiles_x * tiles_y}"])
     try:
+        if net is None:
+            raise _engine.EngineError(init_error or "no engine: init_worker has not run in this process")
         if scale != net.scale:
             raise ValueError("engine was initialised for scale %d, upscale_image called with %d" % (net.scale, scale))
         output = net.run_u8(img, tile=TILE_SIZE, halo=TILE_HALO)  # all tiles of the frame in one device pass
@@ -271,3 +308,4 @@ def upscale_frames(frame_batch, start_frame, end_frame, input_file_tag, scale, g
                              callback=logging_callback)
     pool.close()
     pool.join()
+    _exit_if_failed()

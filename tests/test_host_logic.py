@@ -280,3 +280,54 @@ def test_raw_stream_framing(tmp_path):
     assert raw_stream.stream(io.BytesIO(frames.tobytes()), out, 8, 6, scale=2, chunk=2, max_frames=3, upscaler=_FakeEngine(2)) == 3
     with pytest.raises(ValueError, match="truncated"):
         raw_stream.stream(io.BytesIO(frames.tobytes()[:-7]), io.BytesIO(), 8, 6, scale=2, chunk=2, upscaler=_FakeEngine(2))
+
+
+def test_raw_stream_overlapped_pump():
+    """raw_stream --overlap: reader / engine / writer on three threads produce the same bytes, in order, as the sequential
+    loop; errors on any stage surface on the caller's thread and nothing hangs."""
+    import io
+    import time
+    from upscale_video_b200 import raw_stream
+    rng = np.random.default_rng(1)
+    frames = rng.integers(0, 256, (23, 6, 8, 3), dtype=np.uint8)
+    want = np.repeat(np.repeat(frames, 2, 1), 2, 2).tobytes()
+
+    class Dribble(io.BytesIO):
+        def read(self, n=-1):
+            return super().read(min(n, 173) if n >= 0 else 173)
+
+    class SlowEngine(_FakeEngine):  # lets the reader run ahead and the writer lag behind
+        def run_batch_host(self, *a, **k):
+            time.sleep(0.002)
+            super().run_batch_host(*a, **k)
+
+    for chunk in (1, 2, 5, 23, 40):
+        eng = SlowEngine(2)
+        out = io.BytesIO()
+        assert raw_stream.stream(Dribble(frames.tobytes()), out, 8, 6, scale=2, chunk=chunk, upscaler=eng, overlap=True) == 23
+        assert out.getvalue() == want and sum(c[0] for c in eng.calls) == 23
+    out = io.BytesIO()  # rgb24 + max_frames
+    assert raw_stream.stream(io.BytesIO(frames.tobytes()), out, 8, 6, scale=2, chunk=4, pix_fmt="rgb24", max_frames=10,
+                             upscaler=_FakeEngine(2), overlap=True) == 10
+    assert out.getvalue() == want[:10 * 12 * 16 * 3]
+    assert raw_stream.stream(io.BytesIO(b""), io.BytesIO(), 8, 6, scale=2, chunk=4, upscaler=_FakeEngine(2), overlap=True) == 0
+    with pytest.raises(ValueError, match="truncated"):  # reader error
+        raw_stream.stream(io.BytesIO(frames.tobytes()[:-7]), io.BytesIO(), 8, 6, scale=2, chunk=2, upscaler=_FakeEngine(2), overlap=True)
+
+    class Broken(_FakeEngine):  # engine error on the third chunk
+        def run_batch_host(self, *a, **k):
+            if len(self.calls) == 2:
+                raise RuntimeError("device lost")
+            super().run_batch_host(*a, **k)
+
+    with pytest.raises(RuntimeError, match="device lost"):
+        raw_stream.stream(io.BytesIO(frames.tobytes()), io.BytesIO(), 8, 6, scale=2, chunk=2, upscaler=Broken(2), overlap=True)
+
+    class ClosedPipe(io.BytesIO):  # writer error
+        def write(self, b):
+            if self.tell() > 3000:
+                raise BrokenPipeError("reader went away")
+            return super().write(b)
+
+    with pytest.raises(BrokenPipeError):
+        raw_stream.stream(io.BytesIO(frames.tobytes()), ClosedPipe(), 8, 6, scale=2, chunk=2, upscaler=SlowEngine(2), overlap=True)

@@ -30,9 +30,10 @@ class Sink:
 
 
 for models, kw in (([], {"upscaler": up}), (["a"], {"upscaler": up, "prepass": pre})):
-    raw_stream.stream(io.BytesIO(frames[:8 * 1080 * 1920 * 3]), Sink(), 1920, 1080, 2, models, chunk=8, **kw)  # warm
-    sink = Sink()
-    t = time.time()
-    k = raw_stream.stream(io.BytesIO(frames), sink, 1920, 1080, 2, models, chunk=8, **kw)
-    dt = time.time() - t
-    print("raw_stream 1080p->4K models=%s: %d frames, %.1f fps, %.2f GB/s out" % (models, k, k / dt, sink.n / dt / 1e9))
+    for overlap in (False, True):  # sequential loop vs reader / engine / writer threads (--overlap)
+        raw_stream.stream(io.BytesIO(frames[:8 * 1080 * 1920 * 3]), Sink(), 1920, 1080, 2, models, chunk=8, overlap=overlap, **kw)  # warm
+        sink = Sink()
+        t = time.time()
+        k = raw_stream.stream(io.BytesIO(frames), sink, 1920, 1080, 2, models, chunk=8, overlap=overlap, **kw)
+        dt = time.time() - t
+        print("raw_stream 1080p->4K models=%s overlap=%s: %d frames, %.1f fps, %.2f GB/s out" % (models, overlap, k, k / dt, sink.n / dt / 1e9))

@@ -80,10 +80,11 @@ def denoise_level(models):
 
 
 def stream(fin, fout, width, height, scale=2, models=(), gpu=0, chunk=8, pix_fmt="bgr24", model_path=None, max_frames=None,
-           upscaler=None, prepass=None, denoiser=None):
+           upscaler=None, prepass=None, denoiser=None, overlap=False):
     """Upscale raw ``height x width x 3`` u8 frames from ``fin`` to ``fout``.  Returns the number of frames written.
     ``upscaler`` / ``prepass`` / ``denoiser`` may be passed in as ready engines (tests); otherwise they are built from the
-    model options."""
+    model options.  ``overlap=True`` reads the next chunk and writes the previous one on helper threads while the engines
+    work on the current one (``--overlap`` on the command line)."""
     model_path = model_path or ncnn_model.packaged_model_dir()
     level = denoise_level(models)
     if denoiser is None and level is not None:
@@ -110,18 +111,20 @@ def stream(fin, fout, width, height, scale=2, models=(), gpu=0, chunk=8, pix_fmt
                torch.empty((chunk, height, width, 3), dtype=torch.uint8, device="cuda"),
                torch.empty((chunk, height * s, width * s, 3), dtype=torch.uint8, device="cuda"))
     swap = pix_fmt == "rgb24"
-    written = 0
-    while max_frames is None or written < max_frames:
+
+    def read_chunk(st_in, want):
+        """Fill up to ``want`` frames of ``st_in`` from the input; returns the number read (short = end of input)."""
         n = 0
-        want = chunk if max_frames is None else min(chunk, max_frames - written)
         while n < want:
             if not _read_frame_into(fin, st_in.array[n]):
                 break
             if swap:
                 st_in.array[n] = st_in.array[n][:, :, ::-1].copy()
             n += 1
-        if n == 0:
-            break
+        return n
+
+    def process(st_in, st_out, n):
+        """Denoise -> 1x pre-pass -> upscaler over the first ``n`` frames of ``st_in`` into ``st_out``."""
         src = st_in
         if denoiser is not None:  # fastNlMeansDenoisingColored(frame, None, K, K, 5, 9) on every frame first
             dst = st_dn if st_dn is not None else st_out
@@ -147,12 +150,108 @@ def stream(fin, fout, width, height, scale=2, models=(), gpu=0, chunk=8, pix_fmt
             if upscaler is not None:  # reference tiling (upscale_image :489-519)
                 upscaler.run_batch_host(src.tensor if src.tensor is not None else src.array,
                                         st_out.tensor if st_out.tensor is not None else st_out.array, n, height, width)
+
+    def write_chunk(st_out, n):
         out = st_out.array[:n]
         fout.write(np.ascontiguousarray(out[:, :, :, ::-1]).data if swap else memoryview(out).cast("B"))
+
+    if overlap:
+        written = _pump(read_chunk, process, write_chunk, chunk, max_frames,
+                        [st_in] + [_Stage((chunk, height, width, 3)) for _ in range(2)],
+                        [st_out] + [_Stage((chunk, height * s, width * s, 3)) for _ in range(2)])
+        fout.flush()
+        return written
+    written = 0
+    while max_frames is None or written < max_frames:
+        want = chunk if max_frames is None else min(chunk, max_frames - written)
+        n = read_chunk(st_in, want)
+        if n == 0:
+            break
+        process(st_in, st_out, n)
+        write_chunk(st_out, n)
         written += n
         if n < want:
             break
     fout.flush()
+    return written
+
+
+def _pump(read_chunk, process, write_chunk, chunk, max_frames, in_slots, out_slots):
+    """Three-stage pipeline over rings of staging buffers: a reader thread fills input slots while the caller's thread runs
+    the engines and a writer thread drains output slots (file I/O and the ctypes engine calls all release the GIL).  Frames
+    leave in input order; an exception on any stage (e.g. a truncated frame) stops the others and is re-raised here."""
+    import queue
+    import threading
+    free_in, filled, free_out, to_write = queue.Queue(), queue.Queue(), queue.Queue(), queue.Queue()
+    for st in in_slots:
+        free_in.put(st)
+    for st in out_slots:
+        free_out.put(st)
+    errors = []
+    stop = threading.Event()
+
+    def reader():
+        try:
+            left = max_frames
+            while not stop.is_set() and (left is None or left > 0):
+                st = free_in.get()
+                if st is None:
+                    break
+                want = chunk if left is None else min(chunk, left)
+                n = read_chunk(st, want)
+                if n:
+                    filled.put((st, n))
+                    if left is not None:
+                        left -= n
+                if n < want:
+                    break
+        except BaseException as e:  # noqa: BLE001 -- re-raised on the caller's thread
+            errors.append(e)
+        finally:
+            filled.put(None)
+
+    def writer():
+        while True:
+            item = to_write.get()
+            if item is None:
+                break
+            st, n = item
+            try:
+                if not errors:
+                    write_chunk(st, n)
+            except BaseException as e:  # noqa: BLE001 -- e.g. a closed pipe; re-raised on the caller's thread
+                errors.append(e)
+                stop.set()
+            free_out.put(st)  # always hand the slot back: the caller's thread must never starve on free_out
+
+    tr, tw = threading.Thread(target=reader, daemon=True), threading.Thread(target=writer, daemon=True)
+    tr.start()
+    tw.start()
+    written = 0
+    try:
+        while True:
+            item = filled.get()
+            if item is None:
+                break
+            st_in, n = item
+            if errors:
+                free_in.put(st_in)
+                continue
+            st_out = free_out.get()
+            process(st_in, st_out, n)
+            free_in.put(st_in)
+            to_write.put((st_out, n))
+            written += n
+    except BaseException as e:  # noqa: BLE001
+        errors.append(e)
+    finally:
+        stop.set()
+        free_in.put(None)   # wake a reader waiting for a slot
+        to_write.put(None)
+        tw.join()
+        tr.join(timeout=5)  # a reader blocked inside a pipe read is abandoned (daemon thread)
+    if errors:
+        raise errors[0]
     return written
 
 
@@ -166,6 +265,7 @@ def main(argv=None):
     ap.add_argument("-g", "--gpu", type=int, default=0, help="GPU index for this worker (run one worker per GPU, frames interleaved by the caller)")
     ap.add_argument("--chunk", type=int, default=8, help="frames per host<->device chunk")
     ap.add_argument("--pix_fmt", default="bgr24", choices=["bgr24", "rgb24"])
+    ap.add_argument("--overlap", action="store_true", help="read, compute and write on three threads (rings of three staging chunks)")
     ap.add_argument("--model_path")
     ap.add_argument("-i", "--input", help="raw input file (default stdin)")
     ap.add_argument("-o", "--output", help="raw output file (default stdout)")
@@ -178,7 +278,7 @@ def main(argv=None):
         sys.exit("-m r needs -s 4 (the reference ships 4x_Valar_v1 only)")
     fin = open(a.input, "rb") if a.input else sys.stdin.buffer
     fout = open(a.output, "wb") if a.output else sys.stdout.buffer
-    n = stream(fin, fout, a.width, a.height, a.scale, models, a.gpu, a.chunk, a.pix_fmt, a.model_path)
+    n = stream(fin, fout, a.width, a.height, a.scale, models, a.gpu, a.chunk, a.pix_fmt, a.model_path, overlap=a.overlap)
     print("raw_stream: %d frames" % n, file=sys.stderr)
 
 

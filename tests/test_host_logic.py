@@ -331,3 +331,13 @@ def test_raw_stream_overlapped_pump():
 
     with pytest.raises(BrokenPipeError):
         raw_stream.stream(io.BytesIO(frames.tobytes()), ClosedPipe(), 8, 6, scale=2, chunk=2, upscaler=SlowEngine(2), overlap=True)
+
+
+def test_denoise_worker_device_choice(monkeypatch):
+    monkeypatch.setenv("B2SR_DENOISE_GPUS", "2, 5")
+    assert up._denoise_device() == 2  # not a pool worker: slot 0
+    monkeypatch.setattr(up.multiprocessing.current_process(), "_identity", (4,), raising=False)
+    assert up._denoise_device() == 5  # fourth child of the parent -> slot 3 -> listed[1]
+    monkeypatch.delenv("B2SR_DENOISE_GPUS")
+    monkeypatch.setattr(up._engine, "device_count", lambda: 3)
+    assert up._denoise_device() == 0  # slot 3 over 3 devices

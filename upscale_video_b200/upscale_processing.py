@@ -182,6 +182,18 @@ DENOISE_MAX_WORKERS = 8  # the reference sizes this pool by CPU count because NL
                          # workers only decode/encode PNGs around a GPU call, and each one holds a CUDA context
 
 
+def _denoise_device():
+    """GPU of this denoise worker.  ``process_denoise`` has no ``gpus`` argument in the reference (NL-means runs on the CPU
+    there), so workers are spread round-robin over the devices listed in the environment variable ``B2SR_DENOISE_GPUS``
+    (``"0,2"``; inherited by the spawned workers) or, without it, over all visible devices."""
+    ident = multiprocessing.current_process()._identity
+    slot = (ident[0] - 1) if ident else 0
+    listed = [int(g) for g in os.environ.get("B2SR_DENOISE_GPUS", "").split(",") if g.strip()]
+    if listed:
+        return listed[slot % len(listed)]
+    return slot % max(1, _engine.device_count())
+
+
 def apply_denoise(input_file_name, output_file_name, denoise, remove):
     """One frame through ``fastNlMeansDenoisingColored(img, None, denoise, denoise, 5, 9)`` (reference :350-362).
     The filter runs on the GPU (``b2sr_nlm_run_u8``) in OpenCV's own fixed-point arithmetic: the PNG written is
@@ -191,9 +203,7 @@ def apply_denoise(input_file_name, output_file_name, denoise, remove):
     try:
         img = cv2.imread(input_file_name)
         if denoiser is None:
-            ident = multiprocessing.current_process()._identity
-            ndev = max(1, _engine.device_count())
-            denoiser = _engine.Denoiser(device=((ident[0] - 1) % ndev) if ident else 0)
+            denoiser = _engine.Denoiser(device=_denoise_device())
         output = denoiser.run_u8(img, denoise, denoise, 5, 9)
         cv2.imwrite(output_file_name, output)
     except Exception as e:

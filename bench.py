@@ -448,7 +448,8 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only
         fps, threads, desc, dt = cpu_port_fps(reps=3)
-        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": desc, "seconds": dt}
+        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": desc + ", 3 repetitions",
+               "seconds": 3 * dt, "seconds_per_repetition": dt}
     io_mb = (d_in.numel() + d_out.numel()) >> 20
     extra = None
     if not args.no_extra and world == 1:

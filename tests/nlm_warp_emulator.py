@@ -36,9 +36,10 @@ PACK_CLAMP = 13107
 PACK_MAX_TABLE = PACK_CLAMP >> 5
 
 
-def run(lab, w_l, w_ab, packed=None):
+def run(lab, w_l, w_ab, packed=None, th=TH):
     """lab: H x W x 3 uint8 (already converted) -> denoised Lab, H x W x 3 uint8."""
     H, W, _ = lab.shape
+    TH, SH = th, th + 2 * BORDER  # noqa: N806 -- rows per warp tile is a template parameter of the kernel (B2SR_NLM_TH)
     if packed is None:  # the host's choice (nlm_launch in csrc/nlm_host.inl)
         packed = len(w_l) <= PACK_MAX_TABLE and len(w_ab) <= PACK_MAX_TABLE
     out = np.zeros_like(lab)

@@ -93,6 +93,17 @@ def test_kernel_warp_algorithm_emulated(name):
     assert np.array_equal(N.lab_to_bgr(lab), g["y"])
 
 
+@pytest.mark.parametrize("th", [8, 12])
+def test_kernel_other_tile_heights_emulated(th):
+    """The experiment switch B2SR_NLM_TH (8 or 12 rows per warp tile instead of 16) changes only the tiling."""
+    import nlm_warp_emulator as EM
+    from upscale_video_b200 import engine as E
+    g = golden("nlm_noise_l30")
+    tabs = [E.nlm_weight_table(30, cn).astype(np.int64) for cn in (1, 2)]
+    lab = EM.run(N.bgr_to_lab(g["x"]), tabs[0], tabs[1], packed=False, th=th)
+    assert np.array_equal(N.lab_to_bgr(lab), g["y"])
+
+
 def test_apply_denoise_reports_errors_as_items(tmp_path, monkeypatch):
     """Without a device the worker returns error items and leaves the input in place (never a silent CPU result)."""
     cv2 = pytest.importorskip("cv2")

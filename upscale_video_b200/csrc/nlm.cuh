@@ -26,10 +26,9 @@
 namespace b2sr {
 
 constexpr int NLM_TW = 28;           // output columns per warp: 32 lanes minus the 2 + 2 template halo lanes
-constexpr int NLM_TH = 16;           // output rows per warp
+constexpr int NLM_TH = 16;           // output rows per warp (default; the kernel takes it as a template parameter)
 constexpr int NLM_BORDER = 6;        // search 9/2 + template 5/2
 constexpr int NLM_SW = NLM_TW + 2 * NLM_BORDER;  // staged columns (40)
-constexpr int NLM_SH = NLM_TH + 2 * NLM_BORDER;  // staged rows (28)
 constexpr int NLM_WARPS = 4;
 constexpr int NLM_BIN_SHIFT = 5;     // template distance -> table index: sum >> 5 (32 = next power of two of 25)
 
@@ -107,8 +106,9 @@ __device__ __forceinline__ uint32_t nlm_lab2bgr(const NlmParams& P, int L, int A
 constexpr uint32_t NLM_PACK_CLAMP = 13107;                               // 5 * 13107 = 65535
 constexpr uint32_t NLM_PACK_MAX_TABLE = NLM_PACK_CLAMP >> NLM_BIN_SHIFT;  // 409
 
-template <bool PACKED>
+template <bool PACKED, int TH>
 __global__ void __launch_bounds__(NLM_WARPS * 32) nlm_kernel(const NlmParams P) {
+    constexpr int NLM_SH = TH + 2 * NLM_BORDER;  // staged rows (28 for TH = 16)
     __shared__ uint32_t s_lab[NLM_WARPS][NLM_SH][NLM_SW];
     // PACKED: both weight tables (<= 409 entries each, zero-padded to 410) live in shared memory and are indexed with a
     // clamped index -- min + LDS instead of compare + pointer arithmetic + predicated global load + select
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(NLM_WARPS * 32) nlm_kernel(const NlmParams P) 
     if (t >= P.n_tiles) return;  // warps are independent: no block-wide barrier below
     const int frame = (int)(t / P.tiles_per_frame);
     const int rem = (int)(t % P.tiles_per_frame);
-    const int x0 = (rem % P.tiles_x) * NLM_TW, y0 = (rem / P.tiles_x) * NLM_TH;
+    const int x0 = (rem % P.tiles_x) * NLM_TW, y0 = (rem / P.tiles_x) * TH;
     const uint8_t* src = P.in + frame * P.in_frame_stride;
 
     // stage: BGR -> Lab, reflect-101 at the image border
@@ -137,9 +137,9 @@ __global__ void __launch_bounds__(NLM_WARPS * 32) nlm_kernel(const NlmParams P) 
     }
     __syncwarp();
 
-    uint32_t est_l[NLM_TH], est_a[NLM_TH], est_b[NLM_TH], ws_l[NLM_TH], ws_ab[NLM_TH];
+    uint32_t est_l[TH], est_a[TH], est_b[TH], ws_l[TH], ws_ab[TH];
 #pragma unroll
-    for (int o = 0; o < NLM_TH; ++o) est_l[o] = est_a[o] = est_b[o] = ws_l[o] = ws_ab[o] = 0;
+    for (int o = 0; o < TH; ++o) est_l[o] = est_a[o] = est_b[o] = ws_l[o] = ws_ab[o] = 0;
 
     const int cx = lane + NLM_BORDER - 2;  // staged column of this lane's pixel (image column x0 + lane - 2)
     const uint32_t* own = &s_lab[warp][NLM_BORDER - 2][cx];  // first template row of output row 0
@@ -149,9 +149,9 @@ __global__ void __launch_bounds__(NLM_WARPS * 32) nlm_kernel(const NlmParams P) 
         for (int dx = -4; dx <= 4; ++dx) {
             const uint32_t* other = own + dy * NLM_SW + dx;
             uint32_t v_l = 0, v_c = 0, q1 = 0, q2 = 0;
-            uint32_t dl_hist[NLM_TH + 4], dc_hist[NLM_TH + 4];  // compile-time indexed: five of each are live
+            uint32_t dl_hist[TH + 4], dc_hist[TH + 4];  // compile-time indexed: five of each are live
 #pragma unroll
-            for (int r = 0; r < NLM_TH + 4; ++r) {
+            for (int r = 0; r < TH + 4; ++r) {
                 const uint32_t p = own[r * NLM_SW], q = other[r * NLM_SW];
                 const uint32_t ad = __vabsdiffu4(p, q);
                 const uint32_t l = ad & 0xffu;
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(NLM_WARPS * 32) nlm_kernel(const NlmParams P) 
     if (lane >= 2 && lane < 2 + NLM_TW && x < P.W) {
         uint8_t* dst = P.out + frame * P.out_frame_stride + x * 3;
 #pragma unroll
-        for (int o = 0; o < NLM_TH; ++o) {
+        for (int o = 0; o < TH; ++o) {
             const int y = y0 + o;
             if (y < P.H) {
                 const uint32_t L = (est_l[o] + ws_l[o] / 2) / ws_l[o];

@@ -189,7 +189,11 @@ static int nlm_launch(b2sr_nlm* c, const uint8_t* d_in, long long in_frame_strid
     P.in_stride = in_stride, P.out_stride = out_stride;
     P.H = h, P.W = w;
     P.tiles_x = (w + NLM_TW - 1) / NLM_TW;
-    P.tiles_per_frame = P.tiles_x * ((h + NLM_TH - 1) / NLM_TH);
+    // rows per warp tile: 16 by default; B2SR_NLM_TH=12 or 8 trades template-halo rework (20/16 -> 16/12 -> 12/8 rows walked per
+    // output row) for registers and occupancy (80 -> 60 -> 40 accumulators per lane) -- an experiment switch
+    static const int th_env = getenv("B2SR_NLM_TH") ? atoi(getenv("B2SR_NLM_TH")) : 0;
+    const int TH = (th_env == 8 || th_env == 12) ? th_env : NLM_TH;
+    P.tiles_per_frame = P.tiles_x * ((h + TH - 1) / TH);
     P.n_tiles = (long long)P.tiles_per_frame * n;
     memcpy(P.fwd, c->host_tabs.fwd, sizeof P.fwd);
     memcpy(P.inv, c->host_tabs.inv, sizeof P.inv);
@@ -201,10 +205,13 @@ static int nlm_launch(b2sr_nlm* c, const uint8_t* d_in, long long in_frame_strid
     const long long blocks = (P.n_tiles + NLM_WARPS - 1) / NLM_WARPS;
     if (blocks > 0x7fffffffLL) return fail(B2SR_E_INVALID, "too many tiles (%lld)", P.n_tiles);
     static const bool allow_packed = !(getenv("B2SR_NLM_PACKED") && atoi(getenv("B2SR_NLM_PACKED")) == 0);
-    if (allow_packed && c->n_l <= NLM_PACK_MAX_TABLE && c->n_ab <= NLM_PACK_MAX_TABLE)
-        nlm_kernel<true><<<(unsigned)blocks, NLM_WARPS * 32, 0, c->stream>>>(P);
-    else
-        nlm_kernel<false><<<(unsigned)blocks, NLM_WARPS * 32, 0, c->stream>>>(P);
+    const bool packed = allow_packed && c->n_l <= NLM_PACK_MAX_TABLE && c->n_ab <= NLM_PACK_MAX_TABLE;
+    const dim3 grid((unsigned)blocks), block(NLM_WARPS * 32);
+#define NLM_LAUNCH(PK, T) nlm_kernel<PK, T><<<grid, block, 0, c->stream>>>(P)
+    if (TH == 8) packed ? NLM_LAUNCH(true, 8) : NLM_LAUNCH(false, 8);
+    else if (TH == 12) packed ? NLM_LAUNCH(true, 12) : NLM_LAUNCH(false, 12);
+    else packed ? NLM_LAUNCH(true, 16) : NLM_LAUNCH(false, 16);
+#undef NLM_LAUNCH
     CUDA_TRY(cudaGetLastError());
     c->n_launch += 1;
     return 0;

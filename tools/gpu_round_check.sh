@@ -10,6 +10,7 @@ if [ "$1" = "nlm" ]; then
   timeout 120 python tools/nlm_pass.py 16 3 5 > gpurun_out/r01n_nlm_pass.log 2>&1
   B2SR_NLM_PACKED=0 timeout 120 python tools/nlm_pass.py 16 3 5 > gpurun_out/r01n_nlm_pass_generic.log 2>&1
   timeout 120 python tools/nlm_pass.py 16 10 5 > gpurun_out/r01n_nlm_pass_l10.log 2>&1
+  for th in 12 8; do B2SR_NLM_TH=$th timeout 120 python tools/nlm_pass.py 16 3 5 > gpurun_out/r01n_nlm_pass_th$th.log 2>&1; done
   timeout 200 ncu --set full --clock-control none --import-source on -k regex:nlm_kernel -c 1 -o gpurun_out/r01n_nlm_kernel python tools/nlm_pass.py 4 3 2 > gpurun_out/r01n_ncu_full.log 2>&1
   timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 50 --csv --log-file gpurun_out/r01n_nlm_launches.csv python tools/nlm_pass.py 16 3 3 > /dev/null 2>&1
   tail -n 3 gpurun_out/r01n_nlm_pass*.log gpurun_out/r01n_ncu_full.log

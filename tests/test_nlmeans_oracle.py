@@ -56,6 +56,29 @@ def test_oracle_planes_equal_cv2():
     assert np.array_equal(N.fast_nl_means_denoising_colored(img, 4, 9), cv2.fastNlMeansDenoisingColored(img, None, 4, 9, 5, 9))
 
 
+def test_oracle_equals_cv2_random_shapes_and_levels():
+    """Property test: any small image (including ones narrower than the 6-px border), any level pair."""
+    cv2 = pytest.importorskip("cv2")
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=60, deadline=None, derandomize=True)
+    @hyp.given(st.integers(1, 20), st.integers(1, 20), st.integers(1, 30), st.integers(1, 30), st.integers(0, 2 ** 31 - 1),
+               st.sampled_from(["noise", "smooth", "two-level"]))
+    def check(h, w, level, level_color, seed, kind):
+        rng = np.random.default_rng(seed)
+        if kind == "noise":
+            img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        elif kind == "smooth":
+            img = np.clip(rng.integers(0, 256, 3)[None, None, :] + rng.normal(0, 4, (h, w, 3)), 0, 255).astype(np.uint8)
+        else:
+            img = (rng.integers(0, 2, (h, w, 1)) * 255).astype(np.uint8).repeat(3, axis=2)
+        ref = cv2.fastNlMeansDenoisingColored(img, None, level, level_color, 5, 9)
+        assert np.array_equal(N.fast_nl_means_denoising_colored(img, level, level_color), ref)
+
+    check()
+
+
 @pytest.mark.parametrize("name", NLM_GOLDENS)
 def test_oracle_goldens(name):
     g = golden(name)

@@ -38,12 +38,23 @@ TILE, HALO = 960, 10
 MAC_PER_PX_MID = 64 * 64 * 9                 # one nf->nf convolution
 MAC_PER_PX_NET = 598464                      # whole 2x_Compact graph
 METRIC = "1080p frames/sec (2x_Compact_Pretrain)"
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture
-# (profiles/), per launch of the same shape as the bench's; None until a capture of the current kernel exists
-TRAFFIC_BYTES_PER_LAUNCH = 1202084608 + 390978560
-TRAFFIC_NOTE = ("tc_pipe_kernel, 16 frames per launch (profiles/r01g_pipe_kernel_16frames_dram_metrics.csv): 1.20 GB read = "
-                "16-channel fp16 input planes written by prep_kernel + u8 frames for the residual, 0.39 GB written = the u8 output "
-                "frames; all inter-layer activations stay in L2")
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_traffic.json")
+
+
+def load_traffic(key, frames_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu capture of THIS
+    round's kernel (profiles/r02_traffic.json, written by tools/ncu_traffic.py from the ncu CSV kept beside it).  Returns
+    (bytes or None, note).  The capture's launch shape must be the bench's; otherwise the figure is scaled per frame and says so."""
+    try:
+        d = json.load(open(TRAFFIC_FILE))[key]
+    except Exception:
+        return None, "no ncu capture of the current kernel committed (profiles/r02_traffic.json)"
+    per_frame = (d["dram_read_bytes"] + d["dram_write_bytes"]) / float(d["frames_per_launch"])
+    note = "%s: %.3f GB read + %.3f GB written per launch of %d frames (%s)" % (
+        d["kernel"], d["dram_read_bytes"] / 1e9, d["dram_write_bytes"] / 1e9, d["frames_per_launch"], d["source"])
+    if abs(frames_per_launch - d["frames_per_launch"]) > 1e-6:
+        note += "; scaled per frame to this run's %g frames per launch" % frames_per_launch
+    return per_frame * frames_per_launch, note
 
 
 def load_peaks():
@@ -94,9 +105,10 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def cpu_port_fps(sample_hw=(540, 960), reps=1, threads=None):
-    """Times the CPU oracle (f32, what ncnn's CPU path computes in) on a crop of one synthetic frame and scales
-    by area to frames/s.  Returns (fps, threads, description, seconds)."""
+def cpu_port_fps(sample_hw=(H, W), reps=1, threads=None):
+    """Times the CPU oracle (f32, what ncnn's CPU path computes in) on one whole synthetic 1080p frame -- all four
+    reference tiles (970x970, 970x970, 130x970, 130x970), i.e. the bench's own config -- or, with a smaller `sample_hw`,
+    on a crop scaled by area.  Returns (fps, threads, description, seconds per repetition)."""
     from oracle import oracle
     from upscale_video_b200 import ncnn_model
     threads = threads or os.cpu_count() or 1
@@ -111,37 +123,116 @@ def cpu_port_fps(sample_hw=(540, 960), reps=1, threads=None):
         oracle.upscale_image_array(layers, img, SCALE, "f32", TILE, HALO)
     dt = (time.time() - t0) / reps
     fps = (h * w) / float(H * W) / dt
-    return fps, threads, "%dx%d crop (1/%.1f of a 1080p frame), f32 C oracle with OpenMP, scaled by area" % (
-        h, w, H * W / float(h * w)), dt
+    if (h, w) == (H, W):
+        desc = "one whole 1080p frame per repetition (4 reference tiles, 960 + 10), f32 C oracle with OpenMP"
+    else:
+        desc = "%dx%d crop (1/%.1f of a 1080p frame), f32 C oracle with OpenMP, scaled by area" % (h, w, H * W / float(h * w))
+    return fps, threads, desc, dt
+
+
+def cpu_torch_fps(threads=None, reps=1):
+    """the same graph, tiling and pre/post-processing on torch-CPU (oneDNN conv2d, fp32, channels
+    first), `torch.set_num_threads(all host threads)` -- a second CPU restatement timed next to the C oracle.  One whole
+    1080p frame (4 reference tiles) per repetition.  Returns (fps, threads, seconds per repetition)."""
+    import torch
+    import torch.nn.functional as F
+    from upscale_video_b200 import ncnn_model
+    from upscale_video_b200.upscale_processing import tile_rect
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    desc, blob = ncnn_model.pack_compact_blob(ncnn_model.load_model(ncnn_model.packaged_model_dir(), MODEL))
+    blob = torch.from_numpy(np.ascontiguousarray(blob, np.float32))
+    layers, off = [], 0
+    shapes = [(desc.nf, desc.cin)] + [(desc.nf, desc.nf)] * desc.n_mid + [(desc.cin * desc.scale ** 2, desc.nf)]
+    for i, (co, ci) in enumerate(shapes):
+        w = blob[off:off + co * ci * 9].reshape(co, ci, 3, 3); off += co * ci * 9
+        b = blob[off:off + co]; off += co
+        sl = None
+        if i < len(shapes) - 1:
+            sl = blob[off:off + co]; off += co
+        layers.append((w, b, sl))
+    assert off == blob.numel()
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+
+    def frame():
+        out = np.zeros((H * SCALE, W * SCALE, 3), np.float64)
+        for ty in range((H + TILE - 1) // TILE):
+            for tx in range((W + TILE - 1) // TILE):
+                (iy0, iy1, ix0, ix1), (cy0, cy1, cx0, cx1) = tile_rect(ty, tx, TILE, H, W, HALO)
+                x0 = torch.from_numpy(img[iy0:iy1, ix0:ix1].astype(np.float32)).permute(2, 0, 1)[None] * np.float32(1 / 255.0)
+                v = x0
+                for w, b, sl in layers:
+                    v = F.conv2d(v, w, b, padding=1)
+                    if sl is not None:
+                        v = F.prelu(v, sl)
+                y = F.pixel_shuffle(v, SCALE) + F.interpolate(x0, scale_factor=SCALE, mode="nearest")
+                y = (y[0].permute(1, 2, 0) * 255.0).numpy()
+                oy, ox = (cy0 - iy0) * SCALE, (cx0 - ix0) * SCALE
+                out[cy0 * SCALE:cy1 * SCALE, cx0 * SCALE:cx1 * SCALE] = y[oy:oy + (cy1 - cy0) * SCALE, ox:ox + (cx1 - cx0) * SCALE]
+        return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+    with torch.no_grad():
+        t0 = time.time()
+        for _ in range(reps):
+            frame()
+        dt = (time.time() - t0) / reps
+    return 1.0 / dt, threads, dt
+
+
+REF_MAX_TIMED, REF_MAX_WARM = 3, 1  # one step = one whole frame = ~13 s on 16 threads: the arm times at most this many
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's arithmetic on the host CPU (port: ncnn_vulkan cannot be installed)."""
+    """--impl reference: the reference's arithmetic on the host CPU (port: ncnn_vulkan cannot be installed), on the bench's
+    own config: every step is one whole synthetic 1080p frame through all four reference tiles."""
     if rank != 0:
         return
+    warm, steps = min(args.warmup, REF_MAX_WARM), max(1, min(args.steps, REF_MAX_TIMED))
     fps_list = []
     info = None
-    for i in range(args.warmup + args.steps):
+    for i in range(warm + steps):
         fps, threads, desc, dt = cpu_port_fps(reps=1)
-        if i >= args.warmup:
+        if i >= warm:
             fps_list.append(fps)
         info = (threads, desc, dt)
     fps = float(np.mean(fps_list))
+    sample = info[1] + "; %d step(s) timed after %d warm-up (requested %d / %d: capped so the arm ends within minutes)" % (
+        steps, warm, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * info[2], "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "synthetic 1080p RGB batch, 2x_Compact_Pretrain, reference tiling 960+10", "step": info[1]},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": info[0], "kind": "port", "sample": info[1]},
+        "config": {"workload": "synthetic 1080p RGB batch, 2x_Compact_Pretrain, reference tiling 960+10 (BASELINE configs[1])",
+                   "frame": [H, W, 3], "tile": TILE, "halo": HALO, "frames_per_step": 1, "steps_requested": args.steps,
+                   "warmup_requested": args.warmup, "step": info[1]},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": info[0], "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def valar_540p(E, ncnn_model, torch, device):
-    """BASELINE configs[3]: synthetic 540p, 4x_Valar_v1 (RRDB) on the fused tcgen05 graph kernels -- a short side
-    measurement reported next to the headline (not part of `value`): 4 device-resident frames per step, 2 timed steps."""
+def _event_timed(torch, stream_int, device, fn, steps, warm=2):
+    """ms per call of `fn` (asynchronous launches on the engine's stream), CUDA events on that stream."""
+    stream = torch.cuda.ExternalStream(stream_int, device=torch.device("cuda", device))
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record()
+    for _ in range(steps):
+        fn()
+    with torch.cuda.stream(stream):
+        e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def valar_540p(E, ncnn_model, torch, device, peaks, steps=10):
+    """BASELINE configs[3]: synthetic 540p, 4x_Valar_v1 (RRDB) -- a side measurement reported next to the headline (not
+    part of `value`): 4 device-resident frames per step, `steps` steps timed with CUDA events on the engine's stream,
+    with its own roofline block (bound: tensor; algorithmic FLOPs = 2 x 18 068 160 MAC per input pixel)."""
     try:
         eng = E.Engine.from_files(ncnn_model.packaged_model_dir(), "4x_Valar_v1", device)
     except Exception as e:  # model not packaged
@@ -151,36 +242,33 @@ def valar_540p(E, ncnn_model, torch, device):
     d_out = torch.empty((n, h * 4, w * 4, 3), dtype=torch.uint8, device="cuda")
     eng.run_batch_device(d_in, d_out, n, h, w, TILE, HALO, sync=True)
     eng.reset_stats()
-    t0 = time.perf_counter()
-    steps = 2
-    for _ in range(steps):
-        eng.run_batch_device(d_in, d_out, n, h, w, TILE, HALO, sync=True)
-    dt = time.perf_counter() - t0
-    launches = eng.stat(E.STAT_TC_LAUNCHES)
+    ms = _event_timed(torch, eng.stream, device, lambda: eng.run_batch_device(d_in, d_out, n, h, w, TILE, HALO, sync=False), steps)
+    eng.synchronize()
+    launches = eng.stat(E.STAT_TC_LAUNCHES) / (steps + 2)
+    pipes = eng.stat(E.STAT_PIPE_LAUNCHES) / (steps + 2)
     eng.close()
-    fps = n * steps / dt
+    fps = n / (ms * 1e-3)
     mac_px = 18068160
-    return {"workload": "synthetic 540p, 4x_Valar_v1 RRDB (BASELINE configs[3]), fused tcgen05 graph kernels, 1xB200",
-            "frames_per_s": fps, "ms_per_frame": 1e3 / fps, "tflops": fps * 2.0 * mac_px * h * w / 1e12,
-            "frames_per_step": n, "steps": steps, "tcgen05_launches": int(launches)}
+    tf = fps * 2.0 * mac_px * h * w / 1e12
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    traffic, tnote = load_traffic("valar_540p", n)
+    return {"workload": "synthetic 540p, 4x_Valar_v1 RRDB (BASELINE configs[3]), tcgen05 graph kernels, 1xB200",
+            "frames_per_s": fps, "ms_per_frame": 1e3 / fps, "tflops": tf,
+            "frames_per_step": n, "steps": steps, "timer": "CUDA events on the engine's stream", "tcgen05_launches_per_step": launches,
+            "persistent_rrdb_launches_per_step": pipes,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                         "frac_of_burst_peak": tf / peaks["bf16_tflops"], "flop_per_step": 2.0 * mac_px * h * w * n,
+                         "traffic": traffic, "traffic_note": tnote,
+                         "algorithmic_bytes_per_step": n * (h * w * 3 + 16 * h * w * 3)}}
 
 
-def side_configs(E, ncnn_model, torch, device):
-    """The other BASELINE configs, each as a short device-resident measurement next to the headline (not part of `value`):
-    configs[2] = 1x_HurrDeblur (whole frame, u8 out) -> 2x_Compact chained on the device at 1080p; configs[3] as literally
-    named (4x_Valar_v1 at 540p, see valar_540p) and its actual 4x pixel-shuffle reading (4x_Compact_Pretrain at 540p)."""
+def side_configs(E, ncnn_model, torch, device, steps=10):
+    """The other BASELINE configs, each as a short device-resident measurement next to the headline (not part of `value`),
+    timed with CUDA events over `steps` steps: configs[2] = 1x_HurrDeblur (whole frame, u8 out) -> 2x_Compact chained on the
+    device at 1080p; configs[3]'s actual 4x pixel-shuffle reading (4x_Compact_Pretrain at 540p); the denoise pass."""
     out = []
     mdir = ncnn_model.packaged_model_dir()
-
-    def timed(fn, frames, steps=3):
-        fn()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            fn()
-        torch.cuda.synchronize()
-        return frames * steps / (time.perf_counter() - t0)
-
+    dev = torch.device("cuda", device)
     try:
         hurr = E.Engine.from_files(mdir, "1x_HurrDeblur_SubCompact_nf24-nc8_244k_net_g", device)
         comp = E.Engine.from_files(mdir, "2x_Compact_Pretrain", device)
@@ -188,22 +276,45 @@ def side_configs(E, ncnn_model, torch, device):
         d_in = torch.randint(0, 256, (n, H, W, 3), dtype=torch.uint8, device="cuda")
         d_mid = torch.empty_like(d_in)
         d_out = torch.empty((n, 2 * H, 2 * W, 3), dtype=torch.uint8, device="cuda")
+        sh, sc = torch.cuda.ExternalStream(hurr.stream, device=dev), torch.cuda.ExternalStream(comp.stream, device=dev)
+        mid_ready, mid_free = torch.cuda.Event(), torch.cuda.Event()
 
-        def chain():
-            hurr.run_batch_device(d_in, d_mid, n, H, W, 0, 0, sync=True)       # apply_model: untiled, u8 out
-            comp.run_batch_device(d_mid, d_out, n, H, W, TILE, HALO, sync=True)  # upscale_image: 960 + 10 tiling
-        fps = timed(chain, n)
+        def chain():  # the two engines own one stream each: events order d_mid's producer and consumer, nothing blocks the host
+            sh.wait_event(mid_free)
+            hurr.run_batch_device(d_in, d_mid, n, H, W, 0, 0, sync=False)       # apply_model: untiled, u8 out
+            mid_ready.record(sh)
+            sc.wait_event(mid_ready)
+            comp.run_batch_device(d_mid, d_out, n, H, W, TILE, HALO, sync=False)  # upscale_image: 960 + 10 tiling
+            mid_free.record(sc)
+        mid_free.record(sc)
+        for _ in range(2):
+            chain()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(sh)
+        for _ in range(steps):
+            chain()
+        e1.record(sc)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        hurr.reset_stats()
+        ms_h = _event_timed(torch, hurr.stream, device, lambda: hurr.run_batch_device(d_in, d_mid, n, H, W, 0, 0, sync=False), steps)
+        fps = n / (ms * 1e-3)
         out.append({"workload": "synthetic 1080p, 1x_HurrDeblur nf24 -> u8 -> 2x_Compact chained on the device (BASELINE configs[2])",
-                    "frames_per_s": fps, "tflops": fps * 2.0 * (42768 + MAC_PER_PX_NET) * H * W / 1e12, "frames_per_step": n})
+                    "frames_per_s": fps, "tflops": fps * 2.0 * (42768 + MAC_PER_PX_NET) * H * W / 1e12, "frames_per_step": n,
+                    "steps": steps, "timer": "CUDA events (first engine's stream -> second engine's stream)",
+                    "hurrdeblur_alone_frames_per_s": n / (ms_h * 1e-3), "hurrdeblur_alone_tflops": n / (ms_h * 1e-3) * 2.0 * 42768 * H * W / 1e12,
+                    "hurrdeblur_schedule": "pipelined" if hurr.stat(E.STAT_PIPE_LAUNCHES) > 0 else "layer by layer"})
         hurr.close()
         comp.close()
         c4 = E.Engine.from_files(mdir, "4x_Compact_Pretrain", device)
         n, h, w = 16, 540, 960
         d_in = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda")
         d_out = torch.empty((n, 4 * h, 4 * w, 3), dtype=torch.uint8, device="cuda")
-        fps = timed(lambda: c4.run_batch_device(d_in, d_out, n, h, w, TILE, HALO, sync=True), n)
+        ms = _event_timed(torch, c4.stream, device, lambda: c4.run_batch_device(d_in, d_out, n, h, w, TILE, HALO, sync=False), steps)
+        fps = n / (ms * 1e-3)
         out.append({"workload": "synthetic 540p, 4x_Compact_Pretrain (the 4x pixel-shuffle model of BASELINE configs[3])",
-                    "frames_per_s": fps, "tflops": fps * 2.0 * 619200 * h * w / 1e12, "frames_per_step": n})
+                    "frames_per_s": fps, "tflops": fps * 2.0 * 619200 * h * w / 1e12, "frames_per_step": n, "steps": steps,
+                    "timer": "CUDA events on the engine's stream"})
         c4.close()
     except Exception as e:
         out.append({"unavailable": str(e)[:200]})
@@ -225,7 +336,7 @@ def denoise_1080p(E, torch, device, level=3):
         for _ in range(2):
             dn.run_batch_device(d_in, d_out, n, H, W, level, sync=True)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        steps = 5
+        steps = 10
         with torch.cuda.stream(stream):
             ev0.record()
         for _ in range(steps):
@@ -442,21 +553,28 @@ def main():
         "mean_launch_ms": k_ms / max(k_n, 1),
         "share_of_step": (k_ms / all_ms if all_ms else None),
         "whole_net_tflops": value / world * 2.0 * MAC_PER_PX_NET * H * W / 1e12,
-        "traffic": TRAFFIC_BYTES_PER_LAUNCH,
-        "traffic_note": TRAFFIC_NOTE,
     }
-    cpu = None
+    roofline["traffic"], roofline["traffic_note"] = load_traffic("compact2x_1080p", frames_per_launch)
+    roofline["algorithmic_bytes_per_launch"] = frames_per_launch * (H * W * 3 + SCALE * SCALE * H * W * 3)
+    cpu = cpu_torch = None
     if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only
-        fps, threads, desc, dt = cpu_port_fps(reps=3)
-        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": desc + ", 3 repetitions",
-               "seconds": 3 * dt, "seconds_per_repetition": dt}
+        fps, threads, desc, dt = cpu_port_fps(reps=1)
+        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": desc + ", 1 repetition",
+               "seconds": dt}
+        try:  # the second CPU restatement, torch-CPU / oneDNN, same frame and tiling
+            tfps, tthreads, tdt = cpu_torch_fps(threads)
+            cpu_torch = {"value": tfps, "unit": "frames/s", "cores": tthreads, "kind": "port (torch %s CPU conv2d, oneDNN, fp32)" % torch.__version__,
+                         "sample": "one whole 1080p frame (4 reference tiles), 1 repetition", "seconds": tdt,
+                         "faster_than_c_oracle": bool(tfps > fps)}
+        except Exception as e:
+            cpu_torch = {"unavailable": str(e)[:200]}
     io_mb = (d_in.numel() + d_out.numel()) >> 20
     extra = None
     if not args.no_extra and world == 1:
         eng.close()
         del d_in, d_out, h_in, h_out
         torch.cuda.empty_cache()
-        extra = [alt, valar_540p(E, ncnn_model, torch, local_rank)] + side_configs(E, ncnn_model, torch, local_rank)
+        extra = [alt, valar_540p(E, ncnn_model, torch, local_rank, peaks)] + side_configs(E, ncnn_model, torch, local_rank)
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -466,7 +584,7 @@ def main():
                    "arithmetic": "fp16 weights and activations (tcgen05 kind::f16), fp32 accumulation and epilogue, u8 in/out",
                    "l2": "inputs+outputs per step are %d MB per GPU, larger than the 126 MB L2" % io_mb,
                    "parallelism": "frames sharded over %d rank(s), no data-path collective; weights NCCL-broadcast" % world},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_torch": cpu_torch, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": sampler.summary(), "other_configs": extra,
     }
     print(json.dumps(line), flush=True)

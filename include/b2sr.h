@@ -70,6 +70,10 @@ extern "C" {
 #define B2SR_OPT_MAX_BATCH 3   /* frames per internal pass of b2sr_run_batch_device (0 = choose from free memory) */
 #define B2SR_OPT_RING_ROWS 4   /* pipelined schedule: rows per inter-layer activation ring (0 = auto: all rings together ~36 MB, L2-resident) */
 #define B2SR_OPT_PIPE_DEBUG 5  /* pipelined schedule: print per-layer stall accounting to stderr after every launch (synchronises) */
+#define B2SR_OPT_SM_LIMIT 6    /* SMs the persistent (pipelined) grids may count on, 0 = all of the device.  The persistent kernels are
+                                  launched cooperatively, so a grid the driver cannot make fully co-resident (MPS clients, a second
+                                  context's persistent kernel) is refused and the pass runs layer by layer instead; this option
+                                  states the limit up front (e.g. CUDA_MPS_ACTIVE_THREAD_PERCENTAGE) */
 
 /* b2sr_get_stat keys */
 #define B2SR_STAT_LAUNCHES 1       /* kernels launched by this context since creation / last reset */
@@ -81,6 +85,7 @@ extern "C" {
 #define B2SR_STAT_PIPE_LAUNCHES 7  /* pipelined whole-network kernels launched */
 #define B2SR_STAT_PIPE_MS 8        /* profile mode: summed device time of the pipelined launches, ms */
 #define B2SR_STAT_HMMA_LAUNCHES 9  /* generic graph engine: convolutions launched on the warp-level MMA (wmma) kernel */
+#define B2SR_STAT_PIPE_FALLBACKS 10 /* passes that ran layer by layer because the persistent grid did not fit / was refused */
 
 typedef struct b2sr_ctx b2sr_ctx;
 

@@ -169,6 +169,10 @@ def run_graph(layers, x, precision="f64", input_name="input", output_name="outpu
     real = np.float64 if precision == "f64" else np.float32
     blobs = {}
     i, n = 0, len(layers)
+    last_use = {}  # blob -> index of the last layer that reads it: freed right after (a 540p RRDB frame has 2127 blobs)
+    for j, L in enumerate(layers):
+        for b in L["bottoms"]:
+            last_use[b] = j
     while i < n:
         L = layers[i]
         t, P = L["type"], L["params"]
@@ -219,6 +223,9 @@ def run_graph(layers, x, precision="f64", input_name="input", output_name="outpu
             blobs[L["tops"][0]] = np.concatenate([blobs[b] for b in L["bottoms"]], axis=2)
         else:
             raise NotImplementedError(t)
+        for b in L["bottoms"]:
+            if last_use.get(b) == i and b != output_name:
+                blobs.pop(b, None)
         i += 1
     return blobs[output_name]
 

@@ -84,8 +84,14 @@ def test_hurr_goldens_and_chain(engines):
     c = golden("chain_hurr_compact2x")
     # the golden chains from the oracle's own stage-1 output; feed that to isolate stage 2, then the full chain
     assert_parity(engines("2x_Compact_Pretrain").run_u8(g["y"]), c["y"], "chain stage 2")
+    # End to end, the bar is NOT +-1: stage 1 is within 1 LSB of the oracle, and a 1-LSB difference in the u8 image handed to
+    # stage 2 is a different INPUT to a network whose gain around edges exceeds 1 -- the oracle itself moves by up to 3 LSB
+    # when its stage-2 input is perturbed by +-1 (tests/test_oracle_golden.py::test_chain_sensitivity_of_the_oracle_itself).  So the honest statement
+    # for configs[2] is: every stage <= 1 LSB against the oracle applied to the bytes that stage actually received
+    # (asserted above and in tests/test_zz_gpu_cli.py), end-to-end <= 3 LSB with the > 1 LSB fraction reported.
     d = np.abs(engines("2x_Compact_Pretrain").run_u8(y1).astype(int) - c["y"].astype(int))
-    assert d.max() <= 3  # a 1-LSB difference after stage 1 is amplified by the second network; stated, not hidden
+    _record_chain = dict(max_lsb=int(d.max()), frac_gt1=float((d > 1).mean()), frac_gt0=float((d > 0).mean()))
+    assert d.max() <= 3 and (d > 1).mean() < 0.01, _record_chain
 
 
 def test_float_canvas(engines):
@@ -494,3 +500,77 @@ def test_compact_models_through_generic_engine(E, engines, model_dir, oracle_mod
                else oracle.apply_model_array(oracle_models(name), img, "f64"))
         assert np.abs(a.astype(int) - ref.astype(int)).max() <= 1 and (a != ref).mean() < 0.002, name  # fp32 path: almost exact
         gen.close()
+
+
+def _record(name, **kv):
+    """Measured parity figures go to gpurun_out/ (when that scratch dir exists) so tolerances can be set from data."""
+    import json
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_measured.jsonl"), "a") as f:
+            f.write(json.dumps(dict(name=name, **kv)) + "\n")
+
+
+def test_valar_540p_full_frame_vs_oracle(E, model_dir, oracle_models):
+    """BASELINE configs[3] at its stated size: one 960x540 frame of natural-looking content through 4x_Valar_v1
+    (reference models/4x_Valar_v1.param:1-1208, 420 convolutions, no input residual) against the f32 CPU oracle run on
+    this box's host threads (~2 min on 16 threads); bar <= 1 LSB on all 24.9 M output values."""
+    if not os.path.exists(os.path.join(model_dir, "4x_Valar_v1.b2sr")):
+        pytest.skip("4x_Valar_v1 not packaged")
+    staged = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "sample.png")
+    if os.path.exists(staged):  # the reference's own fixture, when it was staged: a real photograph-like frame
+        import cv2
+        img = np.ascontiguousarray(cv2.imread(staged)[300:840, 400:1360])
+        what = "sample.png[300:840, 400:1360]"
+    else:
+        img = natural(540, 960, seed=31)
+        what = "natural(540, 960)"
+    assert img.shape == (540, 960, 3)
+    eng = E.Engine.from_files(model_dir, "4x_Valar_v1", 0)
+    out = eng.run_u8(img)
+    eng.close()
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    ref = oracle.upscale_image_array(oracle_models("4x_Valar_v1"), img, 4, "f32")
+    d = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+    _record("valar_540p_full_frame", content=what, max_lsb=int(d.max()), mismatch_fraction=float((d > 0).mean()))
+    assert out.shape == (2160, 3840, 3) and d.max() <= 1, "valar 540p %s: max |diff| = %d LSB" % (what, d.max())
+    assert (d > 0).mean() <= 0.05, "valar 540p %s: %.2f%% of values differ" % (what, 100 * (d > 0).mean())
+
+
+def test_persistent_grid_guard_falls_back(E, model_dir, oracle_models):
+    """The persistent kernel's CTAs wait on one another, so it is launched cooperatively and only when layers x bands fits
+    the SMs the context may use.  With the SM budget cut below 18 x 8 (B2SR_OPT_SM_LIMIT, what an MPS share or a second
+    persistent kernel on the device amounts to) the pass must run layer by layer -- same bytes out -- not spin into a trap."""
+    eng = E.Engine.from_files(model_dir, "2x_Compact_Pretrain", 0)
+    img = natural(70, 1000, seed=41)
+    a = eng.run_u8(img)
+    assert eng.stat(E.STAT_PIPE_LAUNCHES) == 1 and eng.stat(E.STAT_PIPE_FALLBACKS) == 0
+    eng.set_option(E.OPT_SM_LIMIT, 100)
+    eng.reset_stats()
+    b = eng.run_u8(img)
+    assert eng.stat(E.STAT_PIPE_LAUNCHES) == 0 and eng.stat(E.STAT_PIPE_FALLBACKS) == 1 and eng.stat(E.STAT_TC_LAUNCHES) == 18
+    assert np.array_equal(a, b)
+    eng.set_option(E.OPT_IMPL, E.IMPL_PIPELINED)  # explicitly requested but not allowed to fit: an error item, not a hang
+    with pytest.raises(E.EngineError, match="co-resident"):
+        eng.run_u8(img)
+    eng.set_option(E.OPT_IMPL, E.IMPL_AUTO)
+    eng.set_option(E.OPT_SM_LIMIT, 0)
+    eng.reset_stats()
+    assert np.array_equal(eng.run_u8(img), a) and eng.stat(E.STAT_PIPE_LAUNCHES) == 1
+    # two contexts on one device, both persistent, launched back to back from two host threads: cooperative launches
+    # serialise instead of interleaving half-resident grids
+    import threading
+    other = E.Engine.from_files(model_dir, "2x_Compact_Pretrain", 0)
+    res = [None, None]
+
+    def work(i, e):
+        for _ in range(4):
+            res[i] = e.run_u8(img)
+    ts = [threading.Thread(target=work, args=(0, eng)), threading.Thread(target=work, args=(1, other))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert np.array_equal(res[0], a) and np.array_equal(res[1], a)
+    other.close()
+    eng.close()

@@ -86,3 +86,20 @@ def test_tile_rects_1080p():
     shapes = [(r[3] - r[2], r[5] - r[4]) for r in rects]
     assert shapes == [(970, 970), (970, 970), (130, 970), (130, 970)]
     assert [(r[3] - r[2], r[5] - r[4]) for r in oracle.tile_rects(540, 960)] == [(540, 960)]
+
+
+def test_chain_sensitivity_of_the_oracle_itself(oracle_models):
+    """BASELINE configs[2] (HurrDeblur -> u8 -> 2x_Compact): why "<= 1 LSB end to end" cannot be the bar for ANY
+    implementation of the chain.  The reference quantises stage 1 to u8 on disk (apply_model :288) and stage 2 re-reads it
+    (:487); a stage-1 result within 1 LSB of the oracle's is a different stage-2 INPUT, and the upscaler's gain exceeds 1
+    around edges: perturbing 2 % of the oracle's own stage-2 input values by +-1 moves the oracle's own stage-2 output by
+    more than 1 LSB in places.  The GPU tests therefore assert <= 1 LSB per stage against the oracle applied to the bytes
+    that stage actually received, and <= 3 LSB with < 1 % of values beyond 1 LSB end to end."""
+    y = golden("hurr1x_crop")["y"]
+    rng = np.random.default_rng(0)
+    mask = rng.random(y.shape) < 0.02
+    p = np.clip(y.astype(int) + np.where(mask, rng.choice([-1, 1], y.shape), 0), 0, 255).astype(np.uint8)
+    m = oracle_models("2x_Compact_Pretrain")
+    a, b = oracle.upscale_image_array(m, y, 2, "f64"), oracle.upscale_image_array(m, p, 2, "f64")
+    d = np.abs(a.astype(int) - b.astype(int))
+    assert d.max() >= 2 and (d > 1).mean() < 0.01

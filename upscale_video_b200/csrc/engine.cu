@@ -234,6 +234,9 @@ struct b2sr_ctx {
     size_t cap_rings = 0;
     int ring_rows = 0;  // 0 = sized so that all rings together stay L2-resident
     int pipe_debug = 0;
+    int sm_limit = 0;          // B2SR_OPT_SM_LIMIT: treat the device as having this many SMs free for persistent grids (0 = all)
+    int pipe_unavailable = 0;  // a cooperative launch was refused (SMs taken by MPS / another context): stay on the layer schedule
+    double n_pipe_fallback = 0;
     long long* d_dbg = nullptr;
     uint8_t *d_in = nullptr, *d_out = nullptr;  // staging for host-memory calls
     size_t cap_in = 0, cap_out = 0;
@@ -269,6 +272,28 @@ static inline int pad_channels(int c) { return c <= 32 ? 32 : 64; }
 static inline uint32_t swizzle_addr(uint32_t a, int row_bytes) {
     const uint32_t mask = row_bytes == 128 ? 7u : (row_bytes == 64 ? 3u : 1u);
     return a ^ (((a >> 7) & mask) << 4);
+}
+
+// This library holds sm_100a code only (arch-specific, not forward compatible): any other part -- including sm_101 / sm_103,
+// which report major 10 too -- would fail at the first launch with "no kernel image"; refuse it up front instead.
+static int check_device(int device, cudaDeviceProp* prop) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(B2SR_E_NODEVICE, "no CUDA device is visible (this library has no CPU path)");
+    }
+    if (device < 0 || device >= ndev) return fail(B2SR_E_NODEVICE, "device %d out of range (%d visible)", device, ndev);
+    CUDA_TRY(cudaGetDeviceProperties(prop, device));
+    if (prop->major != 10 || prop->minor != 0)
+        return fail(B2SR_E_NODEVICE, "device %d (%s) is sm_%d%d; this library contains sm_100a code only", device, prop->name,
+                    prop->major, prop->minor);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaFuncAttributes fa;  // the image must actually load on this part
+    if (cudaFuncGetAttributes(&fa, prep_kernel) != cudaSuccess) {
+        const char* why = cudaGetErrorString(cudaGetLastError());
+        return fail(B2SR_E_NODEVICE, "device %d (%s): the sm_100a kernels of this library do not load (%s)", device, prop->name, why);
+    }
+    return 0;
 }
 
 static bool fp16_exact(float v) { return __half2float(__float2half_rn(v)) == v; }
@@ -371,18 +396,8 @@ extern "C" int b2sr_create(b2sr_ctx** out, int device, const void* weights, size
     const size_t need = ((size_t)nf * cin * 9 + 2 * nf + (size_t)d->n_mid * ((size_t)nf * nf * 9 + 2 * nf) + (size_t)cl * nf * 9 + cl) * 4;
     if (nbytes != need) return fail(B2SR_E_INVALID, "weight blob is %zu bytes, network description needs %zu", nbytes, need);
 
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        return fail(B2SR_E_NODEVICE, "no CUDA device is visible (this library has no CPU path)");
-    }
-    if (device < 0 || device >= ndev) return fail(B2SR_E_NODEVICE, "device %d out of range (%d visible)", device, ndev);
     cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
-        return fail(B2SR_E_NODEVICE, "device %d (%s) is sm_%d%d; this library contains sm_100a code only", device, prop.name,
-                    prop.major, prop.minor);
-    CUDA_TRY(cudaSetDevice(device));
+    TRY(check_device(device, &prop));
     TRY(get_encode());
 
     b2sr_ctx* c = new b2sr_ctx();
@@ -425,12 +440,18 @@ extern "C" int b2sr_create(b2sr_ctx** out, int device, const void* weights, size
 // planning: planes (reference tiles), launch classes, work items, tensor maps
 // ------------------------------------------------------------------------------------------------
 static int build_plan(b2sr_ctx* c, int n, int h, int w, int tile, int halo, Plan** out) {
-    for (auto& p : c->plans)
+    for (size_t i = 0; i < c->plans.size(); ++i) {
+        Plan* p = c->plans[i].get();
         if (p->n == n && p->h == h && p->w == w && p->tile == tile && p->halo == halo) {
-            *out = p.get();
+            if (i + 1 != c->plans.size()) std::rotate(c->plans.begin() + i, c->plans.begin() + i + 1, c->plans.end());  // LRU: most recent last
+            *out = p;
             return 0;
         }
-    if (c->plans.size() > 8) c->plans.erase(c->plans.begin());
+    }
+    if (c->plans.size() > 8) {
+        cudaStreamSynchronize(c->stream);  // the evicted plan's device tables may still be in use by launches in flight
+        c->plans.erase(c->plans.begin());
+    }
     std::unique_ptr<Plan> P(new Plan());
     P->n = n, P->h = h, P->w = w, P->tile = tile, P->halo = halo;
     // reference process_tile :398-427 (tile = 0: the whole frame is one plane, apply_model :263-281)
@@ -717,18 +738,37 @@ static int simple_layer(b2sr_ctx* c, Plan* P, int li, const __half* in, void* ou
 // ------------------------------------------------------------------------------------------------
 // pipelined schedule: one persistent launch, CTA = (layer, band), activations in L2-resident row rings
 // ------------------------------------------------------------------------------------------------
+// The CTAs of the persistent kernel spin on each other's counters, so the whole grid must be co-resident.  Three guards:
+// (1) layers x bands must not exceed the SMs this context may count on (B2SR_OPT_SM_LIMIT lowers that, e.g. under MPS with
+// an active-thread percentage); (2) the launch is cooperative, so the driver itself refuses a grid it cannot make fully
+// resident (cudaErrorCooperativeLaunchTooLarge) instead of starting part of it; (3) a refusal is not an error: the pass
+// falls back to the layer-by-layer schedule (same kernels, same results) and the context stops trying.
+static int usable_sms(const b2sr_ctx* c) { return c->sm_limit > 0 ? std::min(c->sm_limit, c->sms) : c->sms; }
+
 static bool pipe_fits(const b2sr_ctx* c, const Plan* P) {
     const int L = (int)c->layers.size();
-    return L <= B2SR_PIPE_MAX_LAYERS && P->nb >= 1 && (int64_t)L * P->nb <= c->sms;
+    return !c->pipe_unavailable && L <= B2SR_PIPE_MAX_LAYERS && P->nb >= 1 && (int64_t)L * P->nb <= usable_sms(c);
 }
+
+#define B2SR_PIPE_REFUSED 1  // (positive: not an error code of the ABI)
 
 template <int CF, int NL, int S, bool F32OUT>
 static int launch_pipe(b2sr_ctx* c, const PipeParams& Q) {
     const int smem = TcPipeCfg<CF, NL, S>::smem_bytes();
     auto kern = tc_pipe_kernel<CF, NL, S, F32OUT>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<Q.n_layers * Q.nb, TC_THREADS, smem, c->stream>>>(Q);
-    CUDA_TRY(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(Q.n_layers * Q.nb)), cfg.blockDim = dim3(TC_THREADS), cfg.dynamicSmemBytes = (size_t)smem, cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, Q);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
+        cudaGetLastError();
+        return B2SR_PIPE_REFUSED;
+    }
+    if (e != cudaSuccess) return fail(B2SR_E_CUDA, "persistent kernel launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
 
@@ -820,6 +860,13 @@ static int run_pipe(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, 
     PIPE_CASE(64, 16, 1)
 #undef PIPE_CASE
     if (rc == B2SR_E_UNSUPPORTED) return fail(rc, "no pipelined kernel for nf-pad %d, last-pad %d, scale %d", CF, c->NL, S);
+    if (rc == B2SR_PIPE_REFUSED) {
+        if (c->profile) {  // the record opened by prof_begin has no end event: drop it
+            c->ev_pool.push_back(c->prof.back().a), c->ev_pool.push_back(c->prof.back().b);
+            c->prof.pop_back();
+        }
+        return rc;
+    }
     TRY(rc);
     TRY(prof_end(c));
     c->n_launch += 1, c->n_tc += 1, c->n_pipe += 1;
@@ -852,18 +899,8 @@ extern "C" int b2sr_create_graph(b2sr_ctx** out, int device, const b2sr_graph_op
     if (n_ops < 1 || n_slots < 2 || n_slots > 4096 || in_slot < 0 || in_slot >= n_slots || out_slot < 0 || out_slot >= n_slots)
         return fail(B2SR_E_INVALID, "b2sr_create_graph: bad graph description");
     if (scale != 1 && scale != 2 && scale != 4) return fail(B2SR_E_UNSUPPORTED, "scale = %d (need 1, 2 or 4)", scale);
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        return fail(B2SR_E_NODEVICE, "no CUDA device is visible (this library has no CPU path)");
-    }
-    if (device < 0 || device >= ndev) return fail(B2SR_E_NODEVICE, "device %d out of range (%d visible)", device, ndev);
     cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
-        return fail(B2SR_E_NODEVICE, "device %d (%s) is sm_%d%d; this library contains sm_100a code only", device, prop.name,
-                    prop.major, prop.minor);
-    CUDA_TRY(cudaSetDevice(device));
+    TRY(check_device(device, &prop));
     TRY(get_encode());
     const float* wb = (const float*)weights;
     const int64_t nfl = (int64_t)(nbytes / 4);
@@ -1207,18 +1244,8 @@ extern "C" int b2sr_create_fused(b2sr_ctx** out, int device, const b2sr_fused_op
         if (o.w_off < 0 || o.w_off + nw > nfl || (o.b_off >= 0 && o.b_off + o.cout > nfl)) return fail(B2SR_E_INVALID, "op %d: weights outside the blob", i);
     }
     if (!ops[n_ops - 1].final) return fail(B2SR_E_INVALID, "the last op must produce the network output");
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        return fail(B2SR_E_NODEVICE, "no CUDA device is visible (this library has no CPU path)");
-    }
-    if (device < 0 || device >= ndev) return fail(B2SR_E_NODEVICE, "device %d out of range (%d visible)", device, ndev);
     cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
-        return fail(B2SR_E_NODEVICE, "device %d (%s) is sm_%d%d; this library contains sm_100a code only", device, prop.name,
-                    prop.major, prop.minor);
-    CUDA_TRY(cudaSetDevice(device));
+    TRY(check_device(device, &prop));
     TRY(get_encode());
     b2sr_ctx* c = new b2sr_ctx();
     c->device = device, c->sms = prop.multiProcessorCount, c->family = B2SR_FAMILY_FUSED;
@@ -1611,9 +1638,18 @@ static int run_plan(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, 
     const int nl = (int)c->layers.size();
     if (upto < 0 || upto >= nl) upto = nl - 1;
     if (upto == nl - 1 && (c->impl == 0 || c->impl == 3)) {  // whole network: pipelined schedule when it fits the GPU
-        if (pipe_fits(c, P)) return run_pipe(c, P, d_frames, d_out, f32out);
+        if (pipe_fits(c, P)) {
+            const int rc = run_pipe(c, P, d_frames, d_out, f32out);
+            if (rc != B2SR_PIPE_REFUSED) return rc;
+            // the driver could not make the grid co-resident (SMs held by MPS clients, another context's persistent kernel,
+            // a MIG / green-context partition smaller than reported): same network layer by layer from here on
+            c->pipe_unavailable = 1;
+            fprintf(stderr, "b2sr: device %d cannot hold the %d x %d persistent grid right now; using the layer-by-layer schedule\n", c->device, nl, P->nb);
+        }
         if (c->impl == 3)
-            return fail(B2SR_E_UNSUPPORTED, "pipelined schedule needs layers x bands = %d x %d CTAs, device has %d SMs", nl, P->nb, c->sms);
+            return fail(B2SR_E_UNSUPPORTED, "pipelined schedule needs layers x bands = %d x %d co-resident CTAs, device offers %d SMs%s", nl, P->nb,
+                        usable_sms(c), c->pipe_unavailable ? " (a cooperative launch was refused)" : "");
+        if ((int)c->layers.size() <= B2SR_PIPE_MAX_LAYERS) c->n_pipe_fallback += 1;
     }
     TRY(ensure_scratch(c, P->total_px, true));
     TRY(encode_maps(c, P));
@@ -1680,7 +1716,7 @@ static int frames_per_pass(const b2sr_ctx* c, int h, int w, int tile) {
     const double px = (double)h * w * 1.06;
     // the pipelined schedule keeps only the 16-channel input planes per frame: long passes amortise its fill/drain
     const int tw = tile > 0 ? std::min(w, tile + 20) : w;
-    const bool pipe = (c->impl == 0 || c->impl == 3) && (int64_t)c->layers.size() * ((tw + TC_BW - 1) / TC_BW) <= c->sms;
+    const bool pipe = (c->impl == 0 || c->impl == 3) && !c->pipe_unavailable && (int64_t)c->layers.size() * ((tw + TC_BW - 1) / TC_BW) <= usable_sms(c);
     if (pipe) return (int)std::max(1.0, std::min(32.0, floor(7.0e7 / px)));
     return (int)std::max(1.0, std::min(16.0, floor(9.0e6 / px)));
 }
@@ -1862,6 +1898,11 @@ extern "C" int b2sr_set_option(b2sr_ctx* c, int key, int64_t value) {
         case B2SR_OPT_PIPE_DEBUG:
             c->pipe_debug = (int)value;
             return 0;
+        case B2SR_OPT_SM_LIMIT:
+            if (value < 0 || value > 100000) return fail(B2SR_E_INVALID, "sm limit %lld", (long long)value);
+            c->sm_limit = (int)value;
+            c->pipe_unavailable = 0;  // a new limit is a new chance for the persistent schedule
+            return 0;
         case B2SR_OPT_RING_ROWS:
             if (value != 0 && (value < 4 || value > 4096)) return fail(B2SR_E_INVALID, "ring rows %lld (need 0 = auto, or 4..4096)", (long long)value);
             c->ring_rows = (int)value;
@@ -1874,7 +1915,7 @@ extern "C" int b2sr_reset_stats(b2sr_ctx* c) {
     if (!c) return fail(B2SR_E_INVALID, "null context");
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->n_launch = c->n_tc = c->n_pipe = c->n_hmma = 0;
+    c->n_launch = c->n_tc = c->n_pipe = c->n_hmma = c->n_pipe_fallback = 0;
     for (auto& r : c->prof) {
         c->ev_pool.push_back(r.a);
         c->ev_pool.push_back(r.b);
@@ -1897,6 +1938,9 @@ extern "C" int b2sr_get_stat(b2sr_ctx* c, int key, double* value) {
             return 0;
         case B2SR_STAT_HMMA_LAUNCHES:
             *value = c->n_hmma;
+            return 0;
+        case B2SR_STAT_PIPE_FALLBACKS:
+            *value = c->n_pipe_fallback;
             return 0;
         case B2SR_STAT_TC_MID_MS:
         case B2SR_STAT_TC_MID_COUNT:

@@ -115,18 +115,8 @@ extern "C" void b2sr_nlm_destroy(b2sr_nlm* c) {
 extern "C" int b2sr_nlm_create(b2sr_nlm** out, int device) {
     if (!out) return fail(B2SR_E_INVALID, "b2sr_nlm_create: null argument");
     *out = nullptr;
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        return fail(B2SR_E_NODEVICE, "no CUDA device is visible (this library has no CPU path)");
-    }
-    if (device < 0 || device >= ndev) return fail(B2SR_E_NODEVICE, "device %d out of range (%d visible)", device, ndev);
     cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
-        return fail(B2SR_E_NODEVICE, "device %d (%s) is sm_%d%d; this library contains sm_100a code only", device, prop.name,
-                    prop.major, prop.minor);
-    CUDA_TRY(cudaSetDevice(device));
+    TRY(check_device(device, &prop));
     b2sr_nlm* c = new b2sr_nlm();
     c->device = device;
     nlm_build_lab_tables(&c->host_tabs);

@@ -148,11 +148,16 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// Counter polls are relaxed GPU-scope loads (served by L2) and are NOT followed by an acquire fence: what they gate is
-// a TMA load (async proxy, reads L2 directly, no L1 in between) or a global store, issued after the poll through a
-// control dependency, while the writer published the counter with a GPU-scope release after its data reached L2.
-// A per-row fence.acq_rel.gpu in the TMA-issuing thread was measured to serialise the row pipeline (each fence waits
-// for the loads in flight): 85 fps instead of ~400.
+// Inter-CTA hand-off of a ring row (pipelined mode), as a chain the PTX memory model covers end to end:
+//   writer CTA:  epilogue warps st.global (generic proxy) -> fence.acq_rel.cta + progress word -> publisher: st.release.gpu done[]
+//   reader CTA:  poller warp ld.acquire.gpu done[] -> fence.acq_rel.cta + st.shared s_avail -> producer lane ld.shared s_avail
+//                -> fence.acq_rel.cta -> fence.proxy.async (generic -> async proxy, once per advance of `seen`, not per row)
+//                -> cp.async.bulk.tensor (TMA, async proxy) of the row.
+// The acquire sits in the poller warp, off every critical path.  (A fence.acq_rel.gpu per row in the TMA-issuing thread
+// was measured to serialise the row pipeline -- each fence waits for the loads in flight: 85 fps instead of ~400.)
+// The reverse edge (ring slot reuse): the issuer stores cons[] only after the row's mbarrier phase completed, i.e. after
+// the TMA read of the slot has finished; the writer's poller acquires cons[] before its epilogue overwrites the slot.
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -330,6 +335,8 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
                                     __nanosleep(20);
                                     if (clock64() - t0 > 20000000000LL) flag_timeout(P.done_in + band * B2SR_FLAG_STRIDE, g + 1u, 10);
                                 }
+                                __threadfence_block();       // pairs with the poller's fence before it stored s_avail
+                                fence_proxy_async_global();  // rows up to `seen` were written through the generic proxy; TMA reads them
                                 waited += clock64() - t0;
                             }
                         } else {
@@ -512,13 +519,15 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
             const long long t_start = clock64();
             while (*reinterpret_cast<volatile uint32_t*>(s_finished) < need_fin) {
                 if (ring_in) {
-                    const uint32_t a = ld_relaxed_gpu(d0), b = ld_relaxed_gpu(d1), c = ld_relaxed_gpu(d2);  // independent loads
+                    const uint32_t a = ld_acquire_gpu(d0), b = ld_acquire_gpu(d1), c = ld_acquire_gpu(d2);
                     const uint32_t m = a < b ? (a < c ? a : c) : (b < c ? b : c);
+                    __threadfence_block();
                     *s_avail = m;
                 }
                 if (ring_out) {
-                    const uint32_t a = ld_relaxed_gpu(c0), b = ld_relaxed_gpu(c1), c = ld_relaxed_gpu(c2);
+                    const uint32_t a = ld_acquire_gpu(c0), b = ld_acquire_gpu(c1), c = ld_acquire_gpu(c2);
                     const uint32_t m = a < b ? (a < c ? a : c) : (b < c ? b : c);
+                    __threadfence_block();
                     *s_consmin = m;
                 }
                 __nanosleep(200);
@@ -579,6 +588,7 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
                                     __nanosleep(20);
                                     if (clock64() - t0 > 20000000000LL) flag_timeout(P.cons_next + band * B2SR_FLAG_STRIDE, g - RR + 1u, 20);
                                 }
+                                __threadfence_block();  // pairs with the poller's fence before it stored s_consmin
                                 waited += clock64() - t0;
                             }
                             __syncwarp();

@@ -7,6 +7,9 @@ spawn pool with one worker per ``-g`` entry (repeats = several workers on one GP
 
 The reference times its bundled ``sample.png``; that file belongs to the reference repo, so here ``-i`` names the
 frame to use and, without it, a synthetic 1920x1278 frame (sample.png's size) is written to a temp file.
+
+Adapted from ``test_gpus.py`` of davlee1972/upscale_video -- Copyright (c) 2022, David Lee (MIT licence) -- the command line,
+flags, file naming and log lines are that tool's contract and are kept; the engine underneath is this repository's.
 """
 import argparse
 import logging

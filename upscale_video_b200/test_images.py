@@ -9,6 +9,9 @@ HurrDeblur through ``process_model``), then ``upscale_frames``; with ``-m`` the 
 ``-m r`` selects the 4x_Valar_v1 RRDB model (fused tcgen05 graph kernels, b2sr_create_fused); ``-m n=K`` runs the
 NL-means denoise pass first (``process_denoise``, level clamped to 1..30 like reference test_images.py:45-52), on the
 GPU and bit-identical to OpenCV's result.
+
+Adapted from ``test_images.py`` of davlee1972/upscale_video -- Copyright (c) 2022, David Lee (MIT licence) -- the command line,
+flags, file naming and log lines are that tool's contract and are kept; the engine underneath is this repository's.
 """
 import argparse
 import logging
@@ -53,6 +56,9 @@ def process_image(input_frames, temp_dir, output_dir, scale, models, gpus, model
     input_file_tag = "extract"
     if denoise:
         logging.info("Starting denoise touchup...")
+        # process_denoise has no gpus argument in the reference (NL-means runs on the CPU there): hand the -g selection to
+        # the spawned denoise workers through the environment so that `-g 1` touches GPU 1 only
+        os.environ["B2SR_DENOISE_GPUS"] = ",".join(str(g) for g in sorted(set(gpus)))
         workers_used += process_denoise(input_frames, input_file_tag, denoise, remove=False)
         input_file_tag = "denoise"
     if "a" in models:

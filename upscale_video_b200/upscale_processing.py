@@ -185,19 +185,21 @@ DENOISE_MAX_WORKERS = 8  # the reference sizes this pool by CPU count because NL
 def _denoise_device():
     """GPU of this denoise worker.  ``process_denoise`` has no ``gpus`` argument in the reference (NL-means runs on the CPU
     there), so workers are spread round-robin over the devices listed in the environment variable ``B2SR_DENOISE_GPUS``
-    (``"0,2"``; inherited by the spawned workers) or, without it, over all visible devices."""
+    (``"0,2"``; inherited by the spawned workers; ``test_images`` sets it from ``-g``) or, without it, all use device 0 --
+    a worker never touches a GPU the user did not select."""
     ident = multiprocessing.current_process()._identity
     slot = (ident[0] - 1) if ident else 0
     listed = [int(g) for g in os.environ.get("B2SR_DENOISE_GPUS", "").split(",") if g.strip()]
     if listed:
         return listed[slot % len(listed)]
-    return slot % max(1, _engine.device_count())
+    return 0
 
 
 def apply_denoise(input_file_name, output_file_name, denoise, remove):
     """One frame through ``fastNlMeansDenoisingColored(img, None, denoise, denoise, 5, 9)`` (reference :350-362).
     The filter runs on the GPU (``b2sr_nlm_run_u8``) in OpenCV's own fixed-point arithmetic: the PNG written is
-    byte-identical to the reference's.  Unlike the reference, a failure is reported as error items (the convention
+    byte-identical to what OpenCV's CPU implementation produces (the reference passes a ``cv2.UMat``; on a machine with an
+    OpenCL runtime OpenCV may take its OpenCL kernel instead, whose floating-point result is not bit-defined).  Unlike the reference, a failure is reported as error items (the convention
     of the other workers, :289-293) instead of vanishing inside ``apply_async``."""
     global denoiser
     try:

@@ -75,6 +75,10 @@ extern "C" {
                                   context's persistent kernel) is refused and the pass runs layer by layer instead; this option
                                   states the limit up front (e.g. CUDA_MPS_ACTIVE_THREAD_PERCENTAGE) */
 
+#define B2SR_OPT_SEG_PIPE 7    /* fused family: 1 = runs of convolutions as persistent segment launches (an RRDB of 4x_Valar_v1 = one
+                                  cooperative launch, dense-block buffers in L2-resident rings: 8.8x less DRAM traffic, bit-identical
+                                  results, but measured slower on B200 -- DESIGN.md section 3), 0 (default) = one launch per convolution */
+
 /* b2sr_get_stat keys */
 #define B2SR_STAT_LAUNCHES 1       /* kernels launched by this context since creation / last reset */
 #define B2SR_STAT_TC_LAUNCHES 2    /* ... of which tcgen05 convolution kernels */
@@ -198,6 +202,14 @@ typedef struct b2sr_fused_op {
 } b2sr_fused_op;
 int b2sr_create_fused(b2sr_ctx **out, int device, const b2sr_fused_op *ops, int n_ops, const b2sr_fused_buf *bufs, int n_bufs,
                       int scale, const void *weights, size_t nbytes);
+/* Host-only planning aid (no device needed): how b2sr_create_fused would cut the program into persistent segments -- runs of
+ * consecutive convolutions executed as ONE cooperative launch each, CTA = (stage, band), with every buffer slice that is
+ * written and read inside the run kept in an L2-resident row ring -- on a device with `sms` SMs.  out[0] = number of
+ * segments; per segment {op_begin, op_end, n_stages, n_ring_instances}, n_stages records of 13 ints {op, half, variant,
+ * in_inst, grp_ring[3], out16_inst, out32_inst, res_inst[2], gate_op, bp_op}, n_ring_instances records {buffer,
+ * last_reader}.  Returns the number of ints of the description (at most `cap` are written). */
+int b2sr_fused_describe_segments(const b2sr_fused_op *ops, int n_ops, const b2sr_fused_buf *bufs, int n_bufs, int sms,
+                                 int32_t *out, int cap);
 /* Bring-up aid (fused family): run ops [0, upto] on one untiled u8 image and return buffer `buf` (all its channels,
  * converted to float) as (h * res) x (w * res) x channels floats on the host. */
 int b2sr_debug_fused(b2sr_ctx *ctx, const uint8_t *in, int h, int w, int upto, int buf, float *out);

@@ -415,7 +415,15 @@ def test_valar_rrdb_fused_tcgen05(E, model_dir, oracle_models):
     # 420 convolutions (1 head, 23 x 3 x (5 + the 1x1 shortcut), 1 trunk, 4 tail): every 1x1 shortcut rides on the launch
     # of the 3x3 convolution it is added to (-69); every 192 -> 64 convolution is ONE launch of 2-CTA clusters (its two
     # 32-channel halves share the input rows through TMA multicast)
-    assert eng.stat(E.STAT_TC_LAUNCHES) == 420 - 69 and eng.stat(E.STAT_HMMA_LAUNCHES) == 0
+    assert eng.stat(E.STAT_TC_LAUNCHES) == 420 - 69 and eng.stat(E.STAT_PIPE_LAUNCHES) == 0 and eng.stat(E.STAT_HMMA_LAUNCHES) == 0
+    # the opt-in schedule: the 23 RRDBs as 23 persistent segment launches (15 convolutions = 18 stages x bands CTAs each,
+    # dense-block buffers in L2-resident rings): head + 23 + trunk convolution + 4 tail convolutions, same bytes out
+    eng.set_option(E.OPT_SEG_PIPE, 1)
+    eng.reset_stats()
+    piped = eng.run_u8(g["x"])
+    assert eng.stat(E.STAT_PIPE_LAUNCHES) == 23 and eng.stat(E.STAT_TC_LAUNCHES) == 1 + 23 + 1 + 4
+    assert np.array_equal(out, piped), "persistent segments and per-convolution launches must agree bit for bit"
+    eng.set_option(E.OPT_SEG_PIPE, 0)
     assert_parity(out, g["y"], "valar golden (tcgen05)", max_mismatch=0.05)
     assert np.array_equal(out, eng.run_u8(g["x"]))
     img = natural(20, 980, seed=13)  # seam at x = 960
@@ -442,6 +450,20 @@ def test_valar_rrdb_fused_tcgen05(E, model_dir, oracle_models):
     eng.run_batch_device(d_in, d_out, 3, 64, 200, sync=True)
     for i in range(3):
         assert np.array_equal(d_out[i].cpu().numpy(), eng.run_u8(frames[i])), "valar frame %d: batch != single" % i
+    # the two schedules on a batch with seams, ragged bands and several planes per pass, and with short rings (8 rows:
+    # every stage is back-pressured all the time)
+    frames = np.stack([natural(150, 1000, seed=s) for s in (31, 32)])
+    d_in = torch.from_numpy(frames).cuda()
+    d_a = torch.empty((2, 600, 4000, 3), dtype=torch.uint8, device="cuda")
+    d_b, d_c = torch.empty_like(d_a), torch.empty_like(d_a)
+    eng.set_option(E.OPT_SEG_PIPE, 1)
+    eng.run_batch_device(d_in, d_a, 2, 150, 1000, sync=True)
+    eng.set_option(E.OPT_RING_ROWS, 8)
+    eng.run_batch_device(d_in, d_c, 2, 150, 1000, sync=True)
+    eng.set_option(E.OPT_RING_ROWS, 0)
+    eng.set_option(E.OPT_SEG_PIPE, 0)
+    eng.run_batch_device(d_in, d_b, 2, 150, 1000, sync=True)
+    assert torch.equal(d_a, d_b) and torch.equal(d_c, d_b), "valar: persistent segments != per-convolution launches"
     gen = E.Engine(ncnn_model.load_model(model_dir, "4x_Valar_v1"), 0, generic=True)
     gen.set_option(E.OPT_IMPL, E.IMPL_SIMPLE)
     d = np.abs(eng.run_u8(img).astype(int) - gen.run_u8(img).astype(int))

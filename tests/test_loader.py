@@ -227,3 +227,30 @@ def test_fused_program_equals_graph_interpreter(model_dir):
 def test_compact_graphs_do_not_lower_to_fused(model_dir):
     """PReLU / PixelShuffle graphs are served by the Compact kernels; compile_fused must decline them."""
     assert M.compile_fused(M.load_model(model_dir, "2x_Compact_Pretrain")) is None
+
+
+def test_valar_persistent_segments_plan(model_dir):
+    """Host-only: how the fused 4x_Valar_v1 program is cut into persistent segments (b2sr_fused_describe_segments): one
+    segment per RRDB (15 convolutions = 18 stages on a 148-SM part, 8 bands wide), dense-block slices and the fp32 trunk
+    copies between the blocks in rings, the segment's input and output in frame buffers, every stage gated by the op that
+    wrote the newest slice it reads and back-pressured by the last reader of the ring it writes."""
+    import os
+    from upscale_video_b200 import engine as E
+    if not os.path.exists(os.path.join(model_dir, "4x_Valar_v1.b2sr")):
+        pytest.skip("4x_Valar_v1 not packaged")
+    prog = M.compile_fused(M.load_model(model_dir, "4x_Valar_v1"))
+    segs = E.fused_segments(prog, sms=148)
+    assert len(segs) == 23
+    for k, s in enumerate(segs):
+        assert (s["op_begin"], s["op_end"]) == (1 + 15 * k, 15 + 15 * k) and len(s["stages"]) == 18
+        st = s["stages"]
+        assert [x["op"] - s["op_begin"] for x in st] == [0, 1, 2, 3, 4, 4, 5, 6, 7, 8, 9, 9, 10, 11, 12, 13, 14, 14]
+        assert st[0]["in_inst"] == -1 and st[0]["gate_op"] == -1          # x1 of the first block reads the frame buffer
+        assert st[1]["grp_ring"] == [0, 1, 0] and st[6]["grp_ring"] == [1, 0, 0]
+        for x in st[1:]:
+            assert x["gate_op"] == x["op"] - 1                            # a chain: each op waits for the one before it
+        assert all(x["out16_inst"] == -1 and x["out32_inst"] == -1 and x["bp_op"] == -1 for x in st[16:])  # RRDB output: frames
+        for x in st[:16]:
+            assert x["out16_inst"] >= 0 and s["inst"][x["out16_inst"]]["last_reader"] == x["bp_op"]
+    small = E.fused_segments(prog, sms=48)  # room for 6 stages of 8 bands: one dense block (x1..x4 + the two halves of x5) per segment
+    assert len(small) == 69 and all(len(s["stages"]) == 6 and s["op_end"] - s["op_begin"] == 4 for s in small)

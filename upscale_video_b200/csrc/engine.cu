@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <map>
 #include <memory>
+#include <set>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -119,8 +120,12 @@ struct Plan {
     std::vector<PlaneDev> planes;
     std::vector<int> plane_group;  // planes[i] belongs to groups[plane_group[i]]
     std::vector<std::unique_ptr<ResItems>> res_items;
-    CUtensorMap* d_fmaps = nullptr;  // fused family: [launch][group] input tensor maps
+    CUtensorMap* d_fmaps = nullptr;  // fused family: [launch][group] input tensor maps, then [segment stage][group] ring maps
     uint64_t fmaps_gen = 0;          // buffer generation the maps were encoded for
+    TcgParams* d_fstages = nullptr;  // fused family, pipelined segments: parameters of every stage
+    uint64_t fstages_key = 0;        // (buffer generation, ring generation, ring rows) the stage table was built for
+    uint32_t* d_fflags = nullptr;    // `done` counters of one segment launch: [stage][band], B2SR_FLAG_STRIDE words apart
+    int f_rr = 0;                    // ring rows the ring maps were encoded for
     std::vector<Group> groups;
     std::vector<TcItem> items;
     std::vector<int> item_first;  // CTA k of a launch processes items [item_first[k], item_first[k+1])
@@ -153,6 +158,8 @@ struct Plan {
             if (r->d_first) cudaFree(r->d_first);
         }
         if (d_fmaps) cudaFree(d_fmaps);
+        if (d_fstages) cudaFree(d_fstages);
+        if (d_fflags) cudaFree(d_fflags);
         if (d_pitems) cudaFree(d_pitems);
         if (d_pband_first) cudaFree(d_pband_first);
         if (d_pmaps) cudaFree(d_pmaps);
@@ -196,6 +203,28 @@ struct FusedLaunch {  // one tcgen05 launch of a fused convolution (a 192 -> 64 
     float* slope = nullptr;
 };
 
+// Pipelined execution of a run of fused convolutions (tcg_pipe_kernel): one persistent launch per segment.
+struct RingInst {  // a buffer (or the part of it) that is written AND read inside a segment: lives in an L2-resident row ring
+    int buf = -1;
+    std::vector<std::pair<int, int>> written, touched;  // channel ranges [lo, hi)
+    std::vector<int> writer_op;                          // op that wrote written[i]
+    int last_reader = -1;                                // last op of the segment that reads it
+    size_t offset = 0;                                   // byte offset inside the ring arena (set per plan)
+};
+struct FusedStage {  // one CTA row of the persistent grid: one (half of a) fused convolution
+    int launch = 0, op = 0, half = 0, variant = 0;
+    int in_inst = -1, grp_ring[3] = {0, 0, 0};
+    int out16_inst = -1, out32_inst = -1, res_inst[2] = {-1, -1};
+    int gate_op = -1, bp_op = -1;  // op whose stages' `done` gates the ring input rows / frees the output ring slots
+};
+struct FusedSegment {
+    int op_begin = 0, op_end = 0;
+    std::vector<FusedStage> stages;
+    std::vector<RingInst> inst;
+    std::vector<int> op_first_stage;  // stage index of op (op_begin + k)'s first stage; size = n ops + 1
+    int stage_base = 0;               // index of this segment's first stage among all segments' stages
+};
+
 struct b2sr_ctx {
     int device = 0, sms = 0;
     int family = B2SR_FAMILY_COMPACT;
@@ -214,6 +243,12 @@ struct b2sr_ctx {
     int pair_halves = 1;           // launch split convolutions as 2-CTA clusters sharing their input (B2SR_PAIR=0: two launches)
     int pair_clusters = 0;         // clusters of two 227 KB CTAs the device can hold at once (measured at the first paired launch)
     int pdl = 1;                   // programmatic dependent launch of the fused convolution kernels (B2SR_PDL=0 disables)
+    std::vector<FusedSegment> fsegs;  // runs of convolutions executed as one persistent launch each (an RRDB of 4x_Valar_v1)
+    int fseg_stages = 0;              // stages of all segments
+    int seg_pipe = 0;                 // opt-in (B2SR_SEG_PIPE=1 / B2SR_OPT_SEG_PIPE): measured slower than one launch per convolution, see DESIGN.md
+    uint8_t* frings = nullptr;        // ring arena of the pipelined segments
+    size_t cap_frings = 0;
+    uint64_t fring_gen = 1;
     size_t l2_persist = 0;         // bytes of L2 set aside for persisting accesses (0 = feature off)
     size_t l2_window_max = 0;
     std::vector<GraphOp> gops;  // B2SR_FAMILY_GRAPH
@@ -327,7 +362,7 @@ extern "C" void b2sr_destroy(b2sr_ctx* c) {
     for (void* p : c->fbuf_ptr)
         if (p) cudaFree(p);
     for (void* p : {(void*)c->in16, (void*)c->ping, (void*)c->pong, (void*)c->lastf, (void*)c->d_in, (void*)c->d_out,
-                    (void*)c->d_in2, (void*)c->d_out2, (void*)c->rings, (void*)c->d_dbg})
+                    (void*)c->d_in2, (void*)c->d_out2, (void*)c->rings, (void*)c->d_dbg, (void*)c->frings})
         if (p) cudaFree(p);
     for (auto& r : c->prof) {
         cudaEventDestroy(r.a);
@@ -1190,6 +1225,284 @@ static int upload_fused_launch(FusedLaunch& L, const b2sr_fused_op& o, const flo
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// pipelined segments of the fused program (tcg_pipe_kernel): analysis at create time
+// ------------------------------------------------------------------------------------------------
+typedef std::vector<std::pair<int, int>> Ranges;  // channel ranges [lo, hi)
+static bool rng_overlaps(const Ranges& R, int lo, int hi) {
+    for (auto& r : R)
+        if (lo < r.second && r.first < hi) return true;
+    return false;
+}
+static bool rng_covers(const Ranges& R, int lo, int hi) {
+    int pos = lo;
+    for (bool moved = true; pos < hi && moved;) {
+        moved = false;
+        for (auto& r : R)
+            if (r.first <= pos && r.second > pos) pos = r.second, moved = true;
+    }
+    return pos >= hi;
+}
+
+static bool seg_candidate(const b2sr_ctx* c, int j) {
+    const b2sr_fused_op& o = c->fops[j];
+    if (o.type != B2SR_FOP_CONV || o.res != 1 || o.k != 3 || o.final || o.in_buf < 0 || o.cin > 192) return false;
+    if (c->fop_first[j] == c->fop_first[j + 1]) return false;
+    for (int li = c->fop_first[j]; li < c->fop_first[j + 1]; ++li)
+        if (c->flaunch[li].NOUT != 32) return false;
+    return true;
+}
+static int seg_op_stages(const b2sr_ctx* c, int j) {
+    int n = 0;
+    for (int li = c->fop_first[j]; li < c->fop_first[j + 1]; ++li) n += c->flaunch[li].pair ? 2 : 1;
+    return n;
+}
+
+// Who reads the value op j writes into channels [lo, hi) of buffer `buf` before it is overwritten: ops inside the segment
+// (<= seg_end) and / or after it.
+static void value_readers(const b2sr_ctx* c, int j, int buf, int lo, int hi, int seg_end, bool* inside, bool* outside) {
+    *inside = *outside = false;
+    for (int k = j + 1; k < (int)c->fops.size(); ++k) {
+        const b2sr_fused_op& o = c->fops[k];
+        bool reads = o.in_buf == buf && o.in_off < hi && lo < o.in_off + o.cin;
+        if (o.type == B2SR_FOP_CONV)
+            for (int q = 0; q < o.nres; ++q) reads = reads || (o.res_buf[q] == buf && o.res_off[q] < hi && lo < o.res_off[q] + o.cout);
+        if (reads) (k <= seg_end ? *inside : *outside) = true;
+        const bool kills = (o.out16_buf == buf && o.out16_off <= lo && hi <= o.out16_off + o.cout) ||
+                           (o.out32_buf == buf && o.out32_off <= lo && hi <= o.out32_off + o.cout);
+        if (kills) break;
+    }
+}
+
+// Decides, for the run of convolutions [ob, oe], which buffer slices become rings and how the stages gate one another.
+// Returns false when the run does not have the shape the persistent kernel supports (it then runs launch by launch).
+// The flow control uses ONE counter per (stage, band) and waits on one op only, which is sound when the ops form a chain:
+//  * input gating waits for the op p* that wrote the newest ring slice of the input view; every other ring slice the stage
+//    reads (input view or residual) must come from p* or from an op p* itself (transitively) reads through its ring inputs --
+//    then "p* published row y + 1 on bands b-1..b+1" implies those rows exist too;
+//  * a ring slot is reused once the LAST op that reads the ring has finished with the row; every other reader must be an op
+//    that last reader (transitively) depends on.
+static bool analyse_segment(const b2sr_ctx* c, int ob, int oe, FusedSegment* S) {
+    const int nbuf = (int)c->fbufs.size();
+    std::vector<int> cur(nbuf, -1);
+    std::vector<Ranges> frame_read(nbuf), frame_written(nbuf), pre_touch(nbuf);
+    std::map<int, std::vector<int>> dep;                 // op -> ops it (transitively) reads through ring conv inputs
+    std::vector<std::vector<int>> inst_readers;          // per ring instance: reading ops
+    auto in_dep = [&](int op, int q) { return std::find(dep[op].begin(), dep[op].end(), q) != dep[op].end(); };
+    *S = FusedSegment();
+    S->op_begin = ob, S->op_end = oe;
+    for (int j = ob; j <= oe; ++j) {
+        const b2sr_fused_op& o = c->fops[j];
+        S->op_first_stage.push_back((int)S->stages.size());
+        std::vector<int> prod_in, prod_res;
+        auto classify = [&](int buf, int lo, int hi, int* inst, std::vector<int>* producers) -> int {  // 1 ring, 0 frame, -1 unsupported mix
+            const int ci = cur[buf];
+            if (ci >= 0 && rng_covers(S->inst[ci].written, lo, hi)) {
+                *inst = ci;
+                for (size_t w = 0; w < S->inst[ci].written.size(); ++w)
+                    if (lo < S->inst[ci].written[w].second && S->inst[ci].written[w].first < hi) producers->push_back(S->inst[ci].writer_op[w]);
+                S->inst[ci].touched.push_back({lo, hi});
+                S->inst[ci].last_reader = j;
+                inst_readers[ci].push_back(j);
+                return 1;
+            }
+            if (ci >= 0 && rng_overlaps(S->inst[ci].written, lo, hi)) return -1;
+            frame_read[buf].push_back({lo, hi});
+            (ci >= 0 ? S->inst[ci].touched : pre_touch[buf]).push_back({lo, hi});
+            return 0;
+        };
+        FusedStage proto;
+        proto.op = j;
+        const int G = (o.cin + 63) / 64;
+        if (G > 3) return false;
+        for (int g = 0; g < G; ++g) {
+            int inst = -1;
+            const int cls = classify(o.in_buf, o.in_off + 64 * g, o.in_off + std::min(64 * g + 64, o.cin), &inst, &prod_in);
+            if (cls < 0) return false;
+            proto.grp_ring[g] = cls;
+            if (cls == 1) {
+                if (proto.in_inst >= 0 && proto.in_inst != inst) return false;
+                proto.in_inst = inst;
+            }
+        }
+        for (int q = 0; q < o.nres; ++q) {
+            int inst = -1;
+            const int cls = classify(o.res_buf[q], o.res_off[q], o.res_off[q] + o.cout, &inst, &prod_res);
+            if (cls < 0) return false;
+            proto.res_inst[q] = cls == 1 ? inst : -1;
+        }
+        if (!prod_in.empty()) {
+            const int pstar = *std::max_element(prod_in.begin(), prod_in.end());
+            for (const std::vector<int>* P : {&prod_in, &prod_res})
+                for (int q : *P)
+                    if (q != pstar && !in_dep(pstar, q)) return false;
+            proto.gate_op = pstar;
+            std::vector<int>& d = dep[j];
+            for (int q : prod_in) {
+                d.push_back(q);
+                d.insert(d.end(), dep[q].begin(), dep[q].end());
+            }
+            std::sort(d.begin(), d.end());
+            d.erase(std::unique(d.begin(), d.end()), d.end());
+        } else if (!prod_res.empty()) {
+            return false;  // a ring residual without a ring input to gate on
+        }
+        // writes
+        auto place = [&](int buf, int lo, int hi, int* inst_out) -> bool {
+            bool inside = false, outside = false;
+            value_readers(c, j, buf, lo, hi, oe, &inside, &outside);
+            if (outside) {
+                if (inside) return false;  // would need both a ring and a frame copy
+                frame_written[buf].push_back({lo, hi});
+                *inst_out = -1;
+                return true;
+            }
+            int ci = cur[buf];
+            if (ci < 0 || rng_overlaps(S->inst[ci].touched, lo, hi)) {
+                RingInst R;
+                R.buf = buf;
+                if (ci < 0) R.touched = pre_touch[buf];
+                if (rng_overlaps(R.touched, lo, hi)) R.touched.clear();  // (a fresh instance: the frame copy keeps serving the earlier readers)
+                S->inst.push_back(R);
+                inst_readers.push_back({});
+                ci = cur[buf] = (int)S->inst.size() - 1;
+            }
+            S->inst[ci].written.push_back({lo, hi});
+            S->inst[ci].touched.push_back({lo, hi});
+            S->inst[ci].writer_op.push_back(j);
+            *inst_out = ci;
+            return true;
+        };
+        if (o.out16_buf >= 0 && !place(o.out16_buf, o.out16_off, o.out16_off + o.cout, &proto.out16_inst)) return false;
+        if (o.out32_buf >= 0 && !place(o.out32_buf, o.out32_off, o.out32_off + o.cout, &proto.out32_inst)) return false;
+        // epilogue variant (the same template instances the per-launch path picks)
+        const int outs = (o.out16_buf >= 0 ? 1 : 0) | (o.out32_buf >= 0 ? 2 : 0);
+        bool resf32 = true, resf16 = true;
+        for (int q = 0; q < o.nres; ++q) {
+            resf32 = resf32 && c->fbufs[o.res_buf[q]].dtype == 4;
+            resf16 = resf16 && c->fbufs[o.res_buf[q]].dtype == 2;
+        }
+        if (o.sc_cin) proto.variant = B2SR_TCG_VARIANT_SC;
+        else if (o.nres == 0 && outs == 1) proto.variant = B2SR_TCG_VARIANT_PLAIN;
+        else if (o.nres == 1 && outs == 1 && resf16) proto.variant = B2SR_TCG_VARIANT_R16;
+        else if (o.nres == 1 && outs == 3 && resf32) proto.variant = B2SR_TCG_VARIANT_R1_O3;
+        else if (o.nres == 2 && outs == 3 && resf32) proto.variant = B2SR_TCG_VARIANT_R2_O3;
+        else proto.variant = B2SR_TCG_VARIANT_GENERIC;
+        for (int li = c->fop_first[j]; li < c->fop_first[j + 1]; ++li)
+            for (int half = 0; half < (c->flaunch[li].pair ? 2 : 1); ++half) {
+                FusedStage st = proto;
+                st.launch = li, st.half = half;
+                S->stages.push_back(st);
+            }
+    }
+    S->op_first_stage.push_back((int)S->stages.size());
+    for (int b = 0; b < nbuf; ++b)
+        for (auto& w : frame_written[b])
+            if (rng_overlaps(frame_read[b], w.first, w.second)) return false;  // a stage would read a frame slice another stage is writing
+    if (S->inst.empty()) return false;  // nothing stays on chip: no point
+    for (size_t i = 0; i < S->inst.size(); ++i) {
+        const int rk = S->inst[i].last_reader;
+        for (int q : inst_readers[i])
+            if (q != rk && !in_dep(rk, q)) return false;
+    }
+    for (FusedStage& st : S->stages) {
+        const int a = st.out16_inst >= 0 ? S->inst[st.out16_inst].last_reader : -1, b = st.out32_inst >= 0 ? S->inst[st.out32_inst].last_reader : -1;
+        if (a >= 0 && b >= 0 && a != b) return false;
+        st.bp_op = a >= 0 ? a : b;
+    }
+    return true;
+}
+
+static void build_segments(b2sr_ctx* c) {
+    c->fsegs.clear();
+    c->fseg_stages = 0;
+    const char* e = getenv("B2SR_SEG_PIPE");
+    if (e) c->seg_pipe = atoi(e) != 0;  // (B2SR_OPT_SEG_PIPE switches it at run time)
+    const int n_ops = (int)c->fops.size(), max_stages = c->sms / 8;  // planes of the reference's tiling are <= 980 px = 8 bands wide
+    for (int i = 0; i < n_ops;) {
+        if (!seg_candidate(c, i)) {
+            ++i;
+            continue;
+        }
+        int j = i, stages = 0;
+        while (j < n_ops && seg_candidate(c, j) && stages + seg_op_stages(c, j) <= max_stages) stages += seg_op_stages(c, j), ++j;
+        FusedSegment S;
+        if (j - i >= 2 && analyse_segment(c, i, j - 1, &S)) {
+            S.stage_base = c->fseg_stages;
+            c->fseg_stages += (int)S.stages.size();
+            c->fsegs.push_back(S);
+        }
+        i = std::max(j, i + 1);
+    }
+}
+
+// How every convolution of the fused program is launched (output-channel padding, halves, ring slots); with `wb` the
+// weight images are uploaded as well (without: host-only planning, used by b2sr_fused_describe_segments).
+static int plan_fused_launches(b2sr_ctx* c, const float* wb) {
+    const int n_ops = (int)c->fops.size();
+    int rc = 0;
+    for (int i = 0; i < n_ops && !rc; ++i) {
+        const b2sr_fused_op& o = c->fops[i];
+        c->fop_first.push_back((int)c->flaunch.size());
+        if (o.type != B2SR_FOP_CONV) continue;
+        const int cinp = o.in_buf < 0 ? 16 : o.cin, G = (cinp + 63) / 64;
+        int NOUT = o.final ? 16 : o.cout, parts = 1;
+        // the stacked weights of all groups stay resident in shared memory beside >= 4 ring slots; a wide
+        // convolution that does not fit (192 -> 64: 221 KB) is launched as two halves of 32 output channels
+        const bool sc = o.sc_cin != 0;
+        if (fused_fit(NOUT, o.final != 0, G, sc) < 4) {
+            if (NOUT == 64 && fused_fit(32, false, G, false) >= 4) {
+                NOUT = 32, parts = 2;
+            } else {
+                rc = fail(B2SR_E_UNSUPPORTED, "op %d: %d -> %d convolution does not fit shared memory", i, o.cin, o.cout);
+                break;
+            }
+        }
+        const bool pair = parts == 2 && c->pair_halves && o.cout == 2 * NOUT;
+        if (pair) parts = 1;
+        for (int part = 0; part < parts && !rc; ++part) {
+            FusedLaunch L;
+            L.pair = pair;
+            L.op = i, L.co0 = part * NOUT, L.nco = std::min(o.cout - L.co0, NOUT), L.NOUT = NOUT, L.G = G, L.cinp = cinp;
+            L.sc_ks = o.sc_cin / 16;
+            L.slots = std::min(12, fused_fit(NOUT, o.final != 0, G, sc));
+            if (wb) rc = upload_fused_launch(L, o, wb, c->flip_rows != 0);
+            c->flaunch.push_back(L);  // (pushed even on failure so that b2sr_destroy frees what was allocated)
+        }
+    }
+    c->fop_first.push_back((int)c->flaunch.size());
+    return rc;
+}
+
+// Host-only (no device needed): how the fused program would be cut into persistent segments on a device with `sms` SMs.
+// out[0] = number of segments, then per segment: op_begin, op_end, n_stages, n_ring_instances, followed by n_stages
+// records of 12 ints {op, half, variant, in_inst, grp_ring[0..2], out16_inst, out32_inst, res_inst[0..1], gate_op} and one
+// more int per stage {bp_op}; then per ring instance {buffer, last_reader}.  Returns the number of ints needed (<= cap
+// were written), or a negative error.
+extern "C" int b2sr_fused_describe_segments(const b2sr_fused_op* ops, int n_ops, const b2sr_fused_buf* bufs, int n_bufs, int sms,
+                                            int32_t* out, int cap) {
+    if (!ops || !bufs || n_ops < 1 || n_bufs < 1 || sms < 1) return fail(B2SR_E_INVALID, "b2sr_fused_describe_segments: bad argument");
+    b2sr_ctx c;
+    c.sms = sms, c.family = B2SR_FAMILY_FUSED;
+    c.fops.assign(ops, ops + n_ops);
+    c.fbufs.assign(bufs, bufs + n_bufs);
+    TRY(plan_fused_launches(&c, nullptr));
+    build_segments(&c);
+    std::vector<int32_t> v;
+    v.push_back((int32_t)c.fsegs.size());
+    for (const FusedSegment& S : c.fsegs) {
+        v.insert(v.end(), {S.op_begin, S.op_end, (int32_t)S.stages.size(), (int32_t)S.inst.size()});
+        for (const FusedStage& st : S.stages)
+            v.insert(v.end(), {st.op, st.half, st.variant, st.in_inst, st.grp_ring[0], st.grp_ring[1], st.grp_ring[2], st.out16_inst,
+                               st.out32_inst, st.res_inst[0], st.res_inst[1], st.gate_op, st.bp_op});
+        for (const RingInst& R : S.inst) v.insert(v.end(), {R.buf, R.last_reader});
+    }
+    if (out)
+        for (int i = 0; i < cap && i < (int)v.size(); ++i) out[i] = v[i];
+    return (int)v.size();
+}
+
 extern "C" int b2sr_create_fused(b2sr_ctx** out, int device, const b2sr_fused_op* ops, int n_ops, const b2sr_fused_buf* bufs,
                                  int n_bufs, int scale, const void* weights, size_t nbytes) {
     if (!out || !ops || !bufs || !weights) return fail(B2SR_E_INVALID, "b2sr_create_fused: null argument");
@@ -1287,36 +1600,8 @@ extern "C" int b2sr_create_fused(b2sr_ctx** out, int device, const b2sr_fused_op
             rc = fail(B2SR_E_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
             break;
         }
-        for (int i = 0; i < n_ops && !rc; ++i) {
-            const b2sr_fused_op& o = c->fops[i];
-            c->fop_first.push_back((int)c->flaunch.size());
-            if (o.type != B2SR_FOP_CONV) continue;
-            const int cinp = o.in_buf < 0 ? 16 : o.cin, G = (cinp + 63) / 64;
-            int NOUT = o.final ? 16 : o.cout, parts = 1;
-            // the stacked weights of all groups stay resident in shared memory beside >= 4 ring slots; a wide
-            // convolution that does not fit (192 -> 64: 221 KB) is launched as two halves of 32 output channels
-            const bool sc = o.sc_cin != 0;
-            if (fused_fit(NOUT, o.final != 0, G, sc) < 4) {
-                if (NOUT == 64 && fused_fit(32, false, G, false) >= 4) {
-                    NOUT = 32, parts = 2;
-                } else {
-                    rc = fail(B2SR_E_UNSUPPORTED, "op %d: %d -> %d convolution does not fit shared memory", i, o.cin, o.cout);
-                    break;
-                }
-            }
-            const bool pair = parts == 2 && c->pair_halves && o.cout == 2 * NOUT;
-            if (pair) parts = 1;
-            for (int part = 0; part < parts && !rc; ++part) {
-                FusedLaunch L;
-                L.pair = pair;
-                L.op = i, L.co0 = part * NOUT, L.nco = std::min(o.cout - L.co0, NOUT), L.NOUT = NOUT, L.G = G, L.cinp = cinp;
-                L.sc_ks = o.sc_cin / 16;
-                L.slots = std::min(12, fused_fit(NOUT, o.final != 0, G, sc));
-                rc = upload_fused_launch(L, o, wb, c->flip_rows != 0);
-                c->flaunch.push_back(L);  // (pushed even on failure so that b2sr_destroy frees what was allocated)
-            }
-        }
-        c->fop_first.push_back((int)c->flaunch.size());
+        rc = plan_fused_launches(c, wb);
+        if (!rc) build_segments(c);
     } while (0);
     if (rc) {
         std::string keep = g_err;
@@ -1406,6 +1691,180 @@ static int launch_tcg(b2sr_ctx* c, const FusedLaunch& L, const ResItems* R, cons
     return 0;
 }
 
+// Parameters of launch `li` of the fused program that do not depend on how the work is cut into CTAs.
+static void fused_fill_params(b2sr_ctx* c, Plan* P, int li, void* d_out, TcgParams& p) {
+    const FusedLaunch& L = c->flaunch[li];
+    const b2sr_fused_op& o = c->fops[L.op];
+    const int G = (int)P->groups.size();
+    p.maps = P->d_fmaps, p.map_base = li * G;
+    p.wimg = L.wimg, p.bias = L.bias, p.slope = L.slope;
+    p.acc_scale = o.in_buf < 0 ? (1.f / 255.f) : 1.f;
+    p.groups = L.G, p.cin = L.cinp, p.k1 = o.k == 1, p.ring_slots = L.slots;
+    p.sc_ks = L.sc_ks, p.sc_cv = o.sc_coef_v, p.sc_cr = o.sc_coef_r;
+    p.pair = L.pair, p.pair_wbytes = L.G * 9 * L.NOUT * TCG_PB;
+    p.nres = o.nres;
+    for (int q = 0; q < o.nres; ++q) {
+        const b2sr_fused_buf& B = c->fbufs[o.res_buf[q]];
+        p.res_ptr[q] = (const uint8_t*)c->fbuf_ptr[o.res_buf[q]] + (size_t)(o.res_off[q] + L.co0) * B.dtype;
+        p.res_ld[q] = B.channels, p.res_f32[q] = B.dtype == 4;
+        p.coef_v[q] = o.coef_v[q], p.coef_r[q] = o.coef_r[q];
+    }
+    if (o.out16_buf >= 0) {
+        p.out16 = (__half*)c->fbuf_ptr[o.out16_buf] + o.out16_off + L.co0;
+        p.out16_ld = c->fbufs[o.out16_buf].channels;
+    }
+    if (o.out32_buf >= 0) {
+        p.out32 = (float*)c->fbuf_ptr[o.out32_buf] + o.out32_off + L.co0;
+        p.out32_ld = c->fbufs[o.out32_buf].channels;
+    }
+    p.frames_out = d_out, p.frame_h = P->h * o.res, p.frame_w = P->w * o.res;
+}
+
+
+// Ring arena layout, ring tensor maps and the stage table of every pipelined segment, for the planes of P.
+static int prepare_segments(b2sr_ctx* c, Plan* P) {
+    const int G = (int)P->groups.size(), nb = P->nb;
+    const int RR = c->ring_rows > 0 ? std::max(8, c->ring_rows) : 24;
+    // Every ring: RR rows x Wmax pixels x the buffer's channels.  24 rows: an RRDB segment then holds 3 x 8.9 MB of dense
+    // block + 2 x 6 MB of fp32 trunk (960-px planes) -- inside what the L2 keeps without spilling.
+    size_t need = 0;
+    for (FusedSegment& S : c->fsegs) {
+        size_t off = 0;
+        for (RingInst& R : S.inst) {
+            const b2sr_fused_buf& B = c->fbufs[R.buf];
+            R.offset = off;
+            off += ((size_t)RR * P->Wmax * B.channels * B.dtype + 1023) / 1024 * 1024;
+        }
+        need = std::max(need, off);
+    }
+    if (need > c->cap_frings) {
+        cudaStreamSynchronize(c->stream);
+        if (c->frings) cudaFree(c->frings);
+        c->frings = nullptr, c->cap_frings = 0;
+        CUDA_TRY(cudaMalloc(&c->frings, need));
+        c->cap_frings = need;
+        c->fring_gen += 1;
+    }
+    if (c->pipe_debug && !c->d_dbg) CUDA_TRY(cudaMalloc(&c->d_dbg, 148 * 16 * sizeof(long long)));
+    const uint64_t key = (c->fbuf_gen << 24) ^ (c->fring_gen << 8) ^ (uint64_t)RR ^ ((uint64_t)P->Wmax << 44) ^ ((uint64_t)(c->pipe_debug != 0) << 60);
+    if (P->fstages_key == key && P->d_fstages) return 0;
+    int seg_max = 0;
+    for (const FusedSegment& S : c->fsegs) seg_max = std::max(seg_max, (int)S.stages.size());
+    if (!P->d_fstages) CUDA_TRY(cudaMalloc(&P->d_fstages, (size_t)c->fseg_stages * sizeof(TcgParams)));
+    if (!P->d_fflags) CUDA_TRY(cudaMalloc(&P->d_fflags, (size_t)seg_max * nb * B2SR_FLAG_STRIDE * sizeof(uint32_t)));
+    std::vector<CUtensorMap> rmaps((size_t)c->fseg_stages * G);
+    memset(rmaps.data(), 0, rmaps.size() * sizeof(CUtensorMap));
+    std::vector<TcgParams> table(c->fseg_stages);
+    const size_t fl = (size_t)nb * B2SR_FLAG_STRIDE;  // counter words per stage
+    for (const FusedSegment& S : c->fsegs)
+        for (size_t t = 0; t < S.stages.size(); ++t) {
+            const FusedStage& st = S.stages[t];
+            const FusedLaunch& L = c->flaunch[st.launch];
+            const b2sr_fused_op& o = c->fops[st.op];
+            const int sg = S.stage_base + (int)t;
+            TcgParams& p = table[sg];
+            memset(&p, 0, sizeof p);
+            fused_fill_params(c, P, st.launch, nullptr, p);
+            p.items = P->d_pitems, p.item_first = P->d_pband_first;
+            p.pair = 0, p.flip = 0, p.dbg = c->pipe_debug ? c->d_dbg : nullptr;
+            p.half = st.half, p.variant = st.variant;
+            p.nb = nb, p.RR = RR, p.Wmax = P->Wmax;
+            p.ring_map_base = (int)c->flaunch.size() * G + sg * G;
+            if (st.in_inst >= 0) {
+                const int Cb = c->fbufs[o.in_buf].channels;
+                for (int g = 0; g < G; ++g) {
+                    const Group& gr = P->groups[g];
+                    cuuint64_t dims[4] = {(cuuint64_t)L.cinp, (cuuint64_t)gr.Wt, (cuuint64_t)RR, 1};
+                    cuuint64_t strides[3] = {(cuuint64_t)Cb * 2, (cuuint64_t)P->Wmax * Cb * 2, (cuuint64_t)RR * P->Wmax * Cb * 2};
+                    cuuint32_t box[4] = {64, (cuuint32_t)TC_PITCH, 1, 1};
+                    cuuint32_t es[4] = {1, 1, 1, 1};
+                    void* basep = (void*)((__half*)(c->frings + S.inst[st.in_inst].offset) + o.in_off);
+                    CUresult e = g_encode(&rmaps[(size_t)sg * G + g], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, basep, dims, strides, box, es,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, c->l2_promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    if (e != CUDA_SUCCESS) return fail(B2SR_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for the ring of op %d group %d", (int)e, st.op, g);
+                }
+            }
+            for (int g = 0; g < 3; ++g) p.grp_ring[g] = st.grp_ring[g];
+            if (st.out16_inst >= 0) {
+                p.out16 = (__half*)(c->frings + S.inst[st.out16_inst].offset) + o.out16_off + L.co0;
+                p.out16_ring = 1;
+            }
+            if (st.out32_inst >= 0) {
+                p.out32 = (float*)(c->frings + S.inst[st.out32_inst].offset) + o.out32_off + L.co0;
+                p.out32_ring = 1;
+            }
+            for (int q = 0; q < o.nres; ++q)
+                if (st.res_inst[q] >= 0) {
+                    p.res_ptr[q] = c->frings + S.inst[st.res_inst[q]].offset + (size_t)(o.res_off[q] + L.co0) * c->fbufs[o.res_buf[q]].dtype;
+                    p.res_ring[q] = 1;
+                }
+            auto op_stages = [&](int op, const uint32_t** dst) -> int {
+                const int a = S.op_first_stage[op - S.op_begin], b = S.op_first_stage[op - S.op_begin + 1];
+                if (b - a > 2) return -1;
+                for (int k = a; k < b; ++k) dst[k - a] = P->d_fflags + (size_t)k * fl;
+                return b - a;
+            };
+            if (st.gate_op >= 0 && (p.n_in = op_stages(st.gate_op, p.done_in)) < 0) return fail(B2SR_E_UNSUPPORTED, "segment stage waits on more than two stages");
+            if (st.bp_op >= 0 && (p.n_bp = op_stages(st.bp_op, p.bp)) < 0) return fail(B2SR_E_UNSUPPORTED, "segment stage waits on more than two stages");
+            p.done_out = P->d_fflags + t * fl;
+        }
+    CUDA_TRY(cudaMemcpyAsync(P->d_fmaps + c->flaunch.size() * (size_t)G, rmaps.data(), rmaps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(P->d_fstages, table.data(), table.size() * sizeof(TcgParams), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    P->fstages_key = key;
+    return 0;
+}
+
+// One persistent cooperative launch for the convolutions of segment S (B2SR_PIPE_REFUSED: the grid cannot be co-resident).
+static int launch_segment(b2sr_ctx* c, Plan* P, const FusedSegment& S) {
+    const int nb = P->nb, ns = (int)S.stages.size();
+    int smem = 0;
+    for (const FusedStage& st : S.stages) {
+        const FusedLaunch& L = c->flaunch[st.launch];
+        smem = std::max(smem, L.sc_ks ? TcgCfg<32, 0, true>::smem_bytes(L.G, L.slots) : TcgCfg<32, 0>::smem_bytes(L.G, L.slots));
+    }
+    CUDA_TRY(cudaFuncSetAttribute(tcg_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaMemsetAsync(P->d_fflags, 0, (size_t)ns * nb * B2SR_FLAG_STRIDE * sizeof(uint32_t), c->stream));
+    TcgPipeParams Q{};
+    Q.stages = P->d_fstages + S.stage_base, Q.n_stages = ns, Q.nb = nb;
+    double px = 0;
+    for (const TcItem& it : P->pitems) px += (double)it.rows * std::max(0, it.w);
+    TRY(prof_begin(c, 3, px));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(ns * nb)), cfg.blockDim = dim3(TC_THREADS), cfg.dynamicSmemBytes = (size_t)smem, cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, tcg_pipe_kernel, Q);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
+        cudaGetLastError();
+        if (c->profile) {
+            c->ev_pool.push_back(c->prof.back().a), c->ev_pool.push_back(c->prof.back().b);
+            c->prof.pop_back();
+        }
+        return B2SR_PIPE_REFUSED;
+    }
+    if (e != cudaSuccess) return fail(B2SR_E_CUDA, "persistent segment launch failed: %s", cudaGetErrorString(e));
+    TRY(prof_end(c));
+    c->n_launch += 1, c->n_tc += 1, c->n_pipe += 1;
+    if (c->pipe_debug && S.stage_base == 0) {  // stall accounting of the first segment (synchronises)
+        std::vector<long long> h(148 * 16);
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        CUDA_TRY(cudaMemcpy(h.data(), c->d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "b2sr segment ops %d..%d, %d stages x %d bands; per stage, mean over bands, kcycles: issuer total | issuer waits: data (full) tmem (tempty) | "
+                "producer: gate wait, slot (empty) wait | epilogue warp 2: total, wait tfull, back-pressure wait, tmem ld/zero\n", S.op_begin, S.op_end, ns, nb);
+        for (int t = 0; t < ns; ++t) {
+            double v[16] = {0};
+            for (int b = 0; b < nb; ++b)
+                for (int j = 0; j < 16; ++j) v[j] += (double)h[(size_t)(t * nb + b) * 16 + j] / nb / 1e3;
+            fprintf(stderr, "  stage %2d (op %3d half %d variant %d): %8.0f | %7.0f %7.0f | %7.0f %7.0f | %8.0f %7.0f %7.0f %7.0f\n", t, S.stages[t].op, S.stages[t].half,
+                    S.stages[t].variant, v[0], v[1], v[2], v[11], v[4], v[6], v[5], v[12], v[10]);
+        }
+    }
+    return 0;
+}
+
 // Runs ops [0, upto] (upto < 0: the whole program) for the planes of P.
 static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, bool f32out, int upto) {
     const int n_ops = (int)c->fops.size(), G = (int)P->groups.size();
@@ -1448,11 +1907,18 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
                                 L.cinp, Cb, (unsigned long long)Ht, (unsigned long long)Wt);
             }
         }
-        if (!P->d_fmaps) CUDA_TRY(cudaMalloc(&P->d_fmaps, maps.size() * sizeof(CUtensorMap)));
+        if (!P->d_fmaps) CUDA_TRY(cudaMalloc(&P->d_fmaps, (maps.size() + (size_t)c->fseg_stages * G) * sizeof(CUtensorMap)));
         CUDA_TRY(cudaMemcpyAsync(P->d_fmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         P->fmaps_gen = c->fbuf_gen;
     }
+    // whole program on the planes of the reference's tiling: runs of convolutions go as one persistent launch each
+    int seg_max = 0;
+    for (const FusedSegment& S : c->fsegs) seg_max = std::max(seg_max, (int)S.stages.size());
+    bool use_segs = c->seg_pipe && !c->pipe_unavailable && !c->fsegs.empty() && !c->flip_rows &&
+                    P->nb >= 1 && (int64_t)seg_max * P->nb <= usable_sms(c);
+    if (use_segs) TRY(prepare_segments(c, P));
+    size_t next_seg = 0;
     {
         dim3 grid((unsigned)std::min(2048, (P->max_plane_px + 255) / 256), (unsigned)P->planes.size());
         TRY(prof_begin(c, 0, 0));
@@ -1463,6 +1929,19 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
     }
     for (int i = 0; i <= upto; ++i) {
         const b2sr_fused_op& o = c->fops[i];
+        while (next_seg < c->fsegs.size() && c->fsegs[next_seg].op_begin < i) ++next_seg;
+        if (use_segs && next_seg < c->fsegs.size() && c->fsegs[next_seg].op_begin == i && c->fsegs[next_seg].op_end <= upto) {
+            const int rc = launch_segment(c, P, c->fsegs[next_seg]);
+            if (rc == 0) {
+                i = c->fsegs[next_seg].op_end;
+                continue;
+            }
+            if (rc != B2SR_PIPE_REFUSED) return rc;
+            c->pipe_unavailable = 1, use_segs = false;  // the driver cannot make the grid co-resident: launch by launch from here on
+            c->n_pipe_fallback += 1;
+            fprintf(stderr, "b2sr: device %d cannot hold a %zu x %d persistent grid right now; running the convolutions launch by launch\n",
+                    c->device, c->fsegs[next_seg].stages.size(), P->nb);
+        }
         if (o.type == B2SR_FOP_NEAREST) {
             const int ri = o.res / o.r;
             const size_t work = (size_t)P->max_plane_px * o.res * o.res * (o.cin / 8);
@@ -1499,34 +1978,14 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
             ResItems* R = nullptr;
             TRY(fused_items(c, P, o.res, L.pair ? c->pair_clusters : c->sms, &R));
             TcgParams p{};
-            p.maps = P->d_fmaps, p.map_base = li * G;
+            fused_fill_params(c, P, li, d_out, p);
             p.items = R->d_items, p.item_first = R->d_first;
             // Experiment, off by default (B2SR_FLIP=1): alternate launches walk their rows in opposite directions, so that what
             // the previous launch touched LAST is what this one touches FIRST and may still be in L2 (a 540p dense-block
             // buffer is 199 MB).  Measured on B200: no gain (540p 31.0 vs 30.8 ms, batches of 4: 30.7 vs 29.6 ms) -- all 148
             // CTAs sweep their own ranges at once, so no part of the buffer is markedly "more recent" than the rest.
             p.flip = c->flip_rows && (li & 1) && L.wimg_flip;
-            p.wimg = p.flip ? L.wimg_flip : L.wimg, p.bias = L.bias, p.slope = L.slope;
-            p.acc_scale = o.in_buf < 0 ? (1.f / 255.f) : 1.f;
-            p.groups = L.G, p.cin = L.cinp, p.k1 = o.k == 1, p.ring_slots = L.slots;
-            p.sc_ks = L.sc_ks, p.sc_cv = o.sc_coef_v, p.sc_cr = o.sc_coef_r;
-            p.pair = L.pair, p.pair_wbytes = L.G * 9 * L.NOUT * TCG_PB;
-            p.nres = o.nres;
-            for (int q = 0; q < o.nres; ++q) {
-                const b2sr_fused_buf& B = c->fbufs[o.res_buf[q]];
-                p.res_ptr[q] = (const uint8_t*)c->fbuf_ptr[o.res_buf[q]] + (size_t)(o.res_off[q] + L.co0) * B.dtype;
-                p.res_ld[q] = B.channels, p.res_f32[q] = B.dtype == 4;
-                p.coef_v[q] = o.coef_v[q], p.coef_r[q] = o.coef_r[q];
-            }
-            if (o.out16_buf >= 0) {
-                p.out16 = (__half*)c->fbuf_ptr[o.out16_buf] + o.out16_off + L.co0;
-                p.out16_ld = c->fbufs[o.out16_buf].channels;
-            }
-            if (o.out32_buf >= 0) {
-                p.out32 = (float*)c->fbuf_ptr[o.out32_buf] + o.out32_off + L.co0;
-                p.out32_ld = c->fbufs[o.out32_buf].channels;
-            }
-            p.frames_out = d_out, p.frame_h = P->h * o.res, p.frame_w = P->w * o.res;
+            if (p.flip) p.wimg = L.wimg_flip;
             if (c->l2_persist && o.in_buf >= 0) {
                 const b2sr_fused_buf& B = c->fbufs[o.in_buf];
                 const size_t bytes = (size_t)P->total_px * B.res * B.res * B.channels * B.dtype;
@@ -1903,6 +2362,9 @@ extern "C" int b2sr_set_option(b2sr_ctx* c, int key, int64_t value) {
             c->sm_limit = (int)value;
             c->pipe_unavailable = 0;  // a new limit is a new chance for the persistent schedule
             return 0;
+        case B2SR_OPT_SEG_PIPE:
+            c->seg_pipe = value != 0;
+            return 0;
         case B2SR_OPT_RING_ROWS:
             if (value != 0 && (value < 4 || value > 4096)) return fail(B2SR_E_INVALID, "ring rows %lld (need 0 = auto, or 4..4096)", (long long)value);
             c->ring_rows = (int)value;
@@ -1955,7 +2417,7 @@ extern "C" int b2sr_get_stat(b2sr_ctx* c, int key, double* value) {
                 CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
                 all_ms += ms;
                 if (r.kind == 1) mid_ms += ms, cnt += 1, px += r.px;
-                if (r.kind == 2) pipe_ms += ms;
+                if (r.kind == 2 || r.kind == 3) pipe_ms += ms;
             }
             *value = key == B2SR_STAT_TC_MID_MS ? mid_ms : key == B2SR_STAT_TC_MID_COUNT ? cnt : key == B2SR_STAT_ALL_MS ? all_ms
                      : key == B2SR_STAT_PIPE_MS ? pipe_ms : px;

@@ -150,7 +150,8 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
 }
 // Inter-CTA hand-off of a ring row (pipelined mode), as a chain the PTX memory model covers end to end:
 //   writer CTA:  epilogue warps st.global (generic proxy) -> fence.acq_rel.cta + progress word -> publisher: st.release.gpu done[]
-//   reader CTA:  poller warp ld.acquire.gpu done[] -> fence.acq_rel.cta + st.shared s_avail -> producer lane ld.shared s_avail
+//   reader CTA:  poller warp ld.relaxed.gpu done[] x3 (independent) + ONE fence.acq_rel.gpu -> fence.acq_rel.cta + st.shared s_avail
+//                -> producer lane ld.shared s_avail
 //                -> fence.acq_rel.cta -> fence.proxy.async (generic -> async proxy, once per advance of `seen`, not per row)
 //                -> cp.async.bulk.tensor (TMA, async proxy) of the row.
 // The acquire sits in the poller warp, off every critical path.  (A fence.acq_rel.gpu per row in the TMA-issuing thread
@@ -158,6 +159,7 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
 // The reverse edge (ring slot reuse): the issuer stores cons[] only after the row's mbarrier phase completed, i.e. after
 // the TMA read of the slot has finished; the writer's poller acquires cons[] before its epilogue overwrites the slot.
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -518,18 +520,20 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
             const uint32_t* c2 = ring_out ? P.cons_next + nb_hi * B2SR_FLAG_STRIDE : nullptr;
             const long long t_start = clock64();
             while (*reinterpret_cast<volatile uint32_t*>(s_finished) < need_fin) {
+                // independent relaxed loads (one L2 round trip for all six), then ONE acquire fence before the shared words
+                uint32_t ma = 0u, mc = 0u;
                 if (ring_in) {
-                    const uint32_t a = ld_acquire_gpu(d0), b = ld_acquire_gpu(d1), c = ld_acquire_gpu(d2);
-                    const uint32_t m = a < b ? (a < c ? a : c) : (b < c ? b : c);
-                    __threadfence_block();
-                    *s_avail = m;
+                    const uint32_t a = ld_relaxed_gpu(d0), b = ld_relaxed_gpu(d1), c = ld_relaxed_gpu(d2);
+                    ma = a < b ? (a < c ? a : c) : (b < c ? b : c);
                 }
                 if (ring_out) {
-                    const uint32_t a = ld_acquire_gpu(c0), b = ld_acquire_gpu(c1), c = ld_acquire_gpu(c2);
-                    const uint32_t m = a < b ? (a < c ? a : c) : (b < c ? b : c);
-                    __threadfence_block();
-                    *s_consmin = m;
+                    const uint32_t a = ld_relaxed_gpu(c0), b = ld_relaxed_gpu(c1), c = ld_relaxed_gpu(c2);
+                    mc = a < b ? (a < c ? a : c) : (b < c ? b : c);
                 }
+                fence_acq_rel_gpu();
+                __threadfence_block();
+                if (ring_in) *s_avail = ma;
+                if (ring_out) *s_consmin = mc;
                 __nanosleep(200);
                 if (clock64() - t_start > 40000000000LL) flag_timeout(ring_in ? d1 : c1, 0xffffffffu, 40);
             }

@@ -65,6 +65,22 @@ struct TcgParams {
     void* frames_out;           // final convolution: packed frames (u8 or float), frame_h x frame_w x 3
     int32_t frame_h, frame_w;
     long long* dbg;             // optional [CTA][8] stall accounting (B2SR_OPT_PIPE_DEBUG)
+    // ---- pipelined mode (tcg_pipe_kernel): CTA = (stage, band) of a segment of consecutive convolutions; every buffer
+    // slice that is written AND read inside the segment lives in an L2-resident ring of RR rows (pitch Wmax pixels, the
+    // buffer's own channel layout) instead of a frame-sized HBM buffer; flow control is per band and row through one
+    // monotonic `done` counter per (stage, band), B2SR_FLAG_STRIDE words apart.
+    int32_t nb, RR, Wmax;
+    int32_t ring_map_base;      // maps[ring_map_base + TcItem::map]: ring instance read by this stage's input view
+    int32_t grp_ring[3];        // channel group g of the input view comes from the ring (else from the frame buffer)
+    int32_t out16_ring, out32_ring, res_ring[2];  // which outputs / residual sources are rings
+    int32_t n_in;               // stages whose `done` gates this stage's ring input rows (the op that wrote last): 0..2
+    const uint32_t* done_in[2];
+    uint32_t* done_out;         // rows this stage's band CTAs have written and released
+    int32_t n_bp;               // stages whose `done` frees this stage's output ring slots (the last op that reads them): 0..2
+    const uint32_t* bp[2];
+    int32_t variant;            // which template instance runs this stage (tcg_pipe_kernel)
+    int32_t half;               // which 32-channel half of a 64-channel convolution this stage computes (weights / bias /
+                                // output / residual slices are offset like a cluster rank's in the paired launch)
 };
 
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may become resident
@@ -96,7 +112,8 @@ __device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mas
 
 constexpr int TCG_PB = 128;                      // bytes per pixel of one channel group == one SW128 swizzle row
 constexpr int TCG_SUBROWB = TC_PITCH * TCG_PB;   // one ring slot
-constexpr int TCG_BAR_WORDS = 2 * TC_MAX_SLOTS + 2 * TC_NBLK + 2;
+constexpr int TCG_PIPE_WORDS = 8;  // 8-byte slots for the pipelined mode's shared words (progress, polled minima)
+constexpr int TCG_BAR_WORDS = 2 * TC_MAX_SLOTS + 2 * TC_NBLK + 2 + TCG_PIPE_WORDS;
 
 template <int NOUT, int MODE, bool SC = false>
 struct TcgCfg {
@@ -126,15 +143,12 @@ struct TcgCfg {
 // NRES = number of residual terms, all read from fp32 buffers (RF16: all from fp16 buffers), or -1 = everything taken
 // from the parameters at run time; OUTS = bit 0: fp16 copy, bit 1: fp32 copy, or 0 = decided at run time.  NRES = 0, OUTS = 1 is the
 // plain bias + LeakyReLU -> fp16 epilogue.
-template <int NOUT, int MODE /*0 = activation buffers, 1 = network output frames*/, bool F32OUT, int NRES, int OUTS, bool RF16 = false,
-          bool SC = false /*fused 1x1 shortcut*/>
-__global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_constant__ TcgParams P) {
+template <int NOUT, int MODE /*0 = activation buffers, 1 = network output frames*/, bool F32OUT, int NRES, int OUTS, bool RF16,
+          bool SC /*fused 1x1 shortcut*/, bool PIPE /*CTA = (stage, band) of a persistent segment launch*/>
+__device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin, const int it_end, const int band, const uint32_t rank,
+                                         uint8_t* smem_raw) {
     using C = TcgCfg<NOUT, MODE, SC>;
-    extern __shared__ uint8_t smem_raw[];
-    // paired launch: the two CTAs of a cluster walk the same row range; rank r computes output-channel half r
-    const uint32_t rank = P.pair ? cluster_ctarank() : 0u;
-    const int range = P.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int it_begin = P.item_first[range], it_end = P.item_first[range + 1];
+    static_assert(!PIPE || MODE == 0, "pipelined stages write activation buffers");
     const uint8_t* wimg = P.wimg + (size_t)rank * P.pair_wbytes;
     const float* bias_g = P.bias + rank * NOUT;
     const float* slope_g = P.slope + rank * NOUT;
@@ -165,6 +179,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
     auto tempty_bar = [&](int b) { return bar_s + 8u * (2 * TC_MAX_SLOTS + TC_NBLK + b); };
     const uint32_t w_bar = bar_s + 8u * (2 * TC_MAX_SLOTS + 2 * TC_NBLK);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(gbase + bar_off + 8 * (2 * TC_MAX_SLOTS + 2 * TC_NBLK + 1));
+    // pipelined mode: progress words of the 8 epilogue warps (2 + CTA-local index of the last row stored), and the minima the
+    // poller warp keeps fresh: rows available in the input ring (bands b-1..b+1 of the gating stages) and rows the readers of
+    // this stage's output ring slots have finished
+    volatile uint32_t* s_prog = reinterpret_cast<volatile uint32_t*>(gbase + bar_off + 8 * (2 * TC_MAX_SLOTS + 2 * TC_NBLK + 2));
+    volatile uint32_t* s_avail = s_prog + 4 * TC_NSETS;
+    volatile uint32_t* s_bpmin = s_prog + 4 * TC_NSETS + 1;
+    uint32_t* s_finished = const_cast<uint32_t*>(s_prog) + 4 * TC_NSETS + 2;
+    static_assert((4 * TC_NSETS + 3) * 4 <= TCG_PIPE_WORDS * 8, "pipelined-mode words do not fit their slots");
+    const bool ring_in = PIPE && P.n_in > 0, ring_out = PIPE && (P.out16_ring || P.out32_ring);
+    const uint32_t RR = PIPE ? (uint32_t)P.RR : 1u;
+    const int nb_lo = band > 0 ? band - 1 : 0, nb_hi = PIPE && band + 1 < P.nb ? band + 1 : (PIPE ? P.nb - 1 : 0);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr bool PLAIN = NRES == 0 && OUTS == 1;
@@ -184,6 +209,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
             mbar_init(tempty_bar(b), 4);
         }
         mbar_init(w_bar, 1);
+        if constexpr (PIPE) {
+            for (int w = 0; w < 4 * TC_NSETS; ++w) s_prog[w] = (uint32_t)(w >> 2);
+            *s_avail = 0u;
+            *s_bpmin = 0u;
+            *s_finished = 0u;
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -201,7 +232,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (P.pair) cluster_sync_all();  // the peer's barriers exist before anything (multicast data, commits) can reach them
+    if (!PIPE && P.pair) cluster_sync_all();  // the peer's barriers exist before anything (multicast data, commits) can reach them
     const uint32_t tmem_base = *s_tmem;
 
     if (warp == 0) {
@@ -213,20 +244,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
             if constexpr (SC) bulk_g2s(w_s + 3 * G * chunk, wimg + (size_t)3 * G * chunk, C::SCB, w_bar);
             int slot = 0;
             uint32_t phase = 0;
-            long long w_empty = 0;
+            long long w_empty = 0, w_gate = 0;
             const long long t_begin = clock64();
-            griddep_wait();  // everything above (barriers, TMEM, weights: constants) overlapped the previous launch's tail
+            if constexpr (!PIPE) griddep_wait();  // everything above (barriers, TMEM, weights: constants) overlapped the previous launch's tail
+            uint32_t seen = 0u;  // last value read from s_avail
             for (int it = it_begin; it < it_end; ++it) {
                 const TcItem I = P.items[it];
+                if (PIPE && I.w <= 0) continue;
                 const CUtensorMap* map = P.maps + (P.map_base + I.map);
+                [[maybe_unused]] const CUtensorMap* rmap = PIPE ? P.maps + (P.ring_map_base + I.map) : nullptr;
                 const int rows_in = I.rows + 2;
                 for (int rho = 0; rho < rows_in; ++rho) {
                     int y = I.y0 - 1 + rho;  // rows outside the plane are zero-filled by TMA = the conv's zero padding
-                    if (P.flip) y = I.Ht - 1 - y;
+                    if (!PIPE && P.flip) y = I.Ht - 1 - y;
+                    [[maybe_unused]] int ry = -1;  // ring row of this input row (any out-of-bounds coordinate reads as zeros)
+                    if constexpr (PIPE) {
+                        if (ring_in && y >= 0 && y < I.Ht) {
+                            const uint32_t gy = (uint32_t)(I.grow0 + y);
+                            ry = (int)(gy % RR);
+                            if (seen < gy + 1u) {  // rows 0..gy of bands b-1, b, b+1 of the gating stages written and released?
+                                const long long t0 = clock64();
+                                while ((seen = *s_avail) < gy + 1u) {
+                                    __nanosleep(20);
+                                    if (clock64() - t0 > 20000000000LL) flag_timeout(P.done_in[0] + band * B2SR_FLAG_STRIDE, gy + 1u, 10);
+                                }
+                                __threadfence_block();       // pairs with the poller's fence before it stored s_avail
+                                fence_proxy_async_global();  // the rows were written through the generic proxy; TMA reads them
+                                w_gate += clock64() - t0;
+                            }
+                        }
+                    }
                     for (int g = 0; g < G; ++g) {
                         mbar_wait_clocked(empty_bar(slot), phase ^ 1u, 0, w_empty);
                         mbar_expect_tx(full_bar(slot), TCG_SUBROWB);
-                        if (!P.pair)
+                        if (PIPE && P.grp_ring[g])
+                            tma_load_4d(ring_s + slot * TCG_SUBROWB, rmap, full_bar(slot), g * 64, I.x0 - 1, ry, 0);
+                        else if (PIPE || !P.pair)
                             tma_load_4d(ring_s + slot * TCG_SUBROWB, map, full_bar(slot), g * 64, I.x0 - 1, y, I.plane);
                         else if (rank == 0)  // one load from L2 / HBM fills this slot in both CTAs (each armed its own barrier)
                             tma_load_4d_multicast(ring_s + slot * TCG_SUBROWB, map, full_bar(slot), g * 64, I.x0 - 1, y, I.plane, (uint16_t)3);
@@ -239,10 +292,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
             }
             // all input rows of this CTA are requested: the next launch of the stream may start taking the SMs that CTAs
             // of this grid free (it does its own prologue, then waits for this grid to complete before touching buffers)
-            griddep_launch_dependents();
+            if constexpr (!PIPE) griddep_launch_dependents();
+            if (ring_in) atomicAdd(s_finished, 1u);
             if (P.dbg) {
                 P.dbg[blockIdx.x * 16 + 4] = w_empty;
                 P.dbg[blockIdx.x * 16 + 7] = clock64() - t_begin;
+                P.dbg[blockIdx.x * 16 + 11] = w_gate;
             }
         }
     } else if (warp == 1) {
@@ -270,6 +325,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
         const int itb = __shfl_sync(0xffffffffu, it_begin, 0), ite = __shfl_sync(0xffffffffu, it_end, 0);
         uint32_t tmask = 0;  // bit h: parity of the next use of accumulator block h (tempty barrier phase)
         for (int it = itb; it < ite; ++it) {
+            if (PIPE && __shfl_sync(0xffffffffu, P.items[it].w, 0) <= 0) continue;  // band absent from this plane
             const int rows = __shfl_sync(0xffffffffu, P.items[it].rows, 0);
             // Homes follow the plane row (y % NB), not the CTA's row count: which rows are summed from two blocks
             // then does not depend on how the launch was cut into CTA ranges, so a frame computes bit-identically
@@ -340,7 +396,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                             }
                         }
                         // this (row, group) slot may be refilled once its MMAs have completed (paired: in both CTAs)
-                        if (P.pair) umma_commit_multicast(empty_bar(sl), (uint16_t)3); else umma_commit(empty_bar(sl));
+                        if (!PIPE && P.pair) umma_commit_multicast(empty_bar(sl), (uint16_t)3); else umma_commit(empty_bar(sl));
                         if (++sl == R) sl = 0, ph ^= 1u;
                     }
                     if (rho >= 2) umma_commit(tfull_bar(home0));  // output row rho - 2 is complete (home0 is its home)
@@ -380,11 +436,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
         }
         const float scale_acc = P.acc_scale;
         const int c = q * 32 + lane;
-        griddep_wait();  // residual buffers are read and output buffers written only after the previous launch has completed
-        long long w_tfull = 0, t_tmem = 0;
+        if constexpr (!PIPE) griddep_wait();  // residual buffers are read and output buffers written only after the previous launch has completed
+        long long w_tfull = 0, t_tmem = 0, w_bp = 0;
         const long long t_begin = clock64();
+        [[maybe_unused]] uint32_t bp_seen = 0u;  // last value read from s_bpmin
+        [[maybe_unused]] uint32_t av_seen = 0u;  // last value read from s_avail (gate of ring residual prefetches)
         for (int it = it_begin; it < it_end; ++it) {
             const TcItem I = P.items[it];
+            if (PIPE && I.w <= 0) continue;
             const bool valid = c < I.w;
             for (int t = 0; t < I.rows; ++t, ++tile_cnt) {
                 const uint32_t buf = (uint32_t)(I.y0 + t) % NB;  // home block of this output row
@@ -395,20 +454,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                 // latency (measured: ~700 cycles per dependent chunk, 4-8 chunks per row) hides behind the MMAs
                 [[maybe_unused]] long long pix = -1;
                 [[maybe_unused]] uint4 rraw[PLAIN ? 1 : NPRE][PLAIN ? 1 : NOUT / 4];
-                const int yy = P.flip ? I.Ht - 1 - (I.y0 + t) : I.y0 + t;  // plane row of this output row
+                const int yy = (!PIPE && P.flip) ? I.Ht - 1 - (I.y0 + t) : I.y0 + t;  // plane row of this output row
                 if constexpr (MODE == 0) pix = valid ? (long long)I.pix_off + (long long)yy * I.Wt + I.x0 + c : -1;
+                // pipelined mode: a buffer that lives in a ring is addressed by (global row mod RR, column); which of the
+                // residual sources / outputs are rings is a property of the stage
+                [[maybe_unused]] const uint32_t grow = PIPE ? (uint32_t)(I.grow0 + yy) : 0u;
+                [[maybe_unused]] const long long rpix = (PIPE && valid) ? (long long)(grow % RR) * P.Wmax + I.x0 + c : -1;
+                const long long pix16 = (PIPE && P.out16_ring) ? rpix : pix, pix32 = (PIPE && P.out32_ring) ? rpix : pix;
+                const long long pixr[2] = {(PIPE && P.res_ring[0]) ? rpix : pix, (PIPE && P.res_ring[1]) ? rpix : pix};
+                if constexpr (PIPE && MODE == 0 && !PLAIN) {
+                    // A residual that lives in a ring is prefetched long before this row's accumulator is complete, so the
+                    // prefetch needs its own gate: the row was written by the gating op p* itself (published once done >= grow + 1)
+                    // or by an op p* reads through its ring inputs (published before p* could finish row grow - 1).
+                    if ((P.res_ring[0] || P.res_ring[1]) && av_seen < grow + 1u) {
+                        const long long t0 = clock64();
+                        while ((av_seen = *s_avail) < grow + 1u) {
+                            __nanosleep(20);
+                            if (clock64() - t0 > 20000000000LL) flag_timeout(P.done_in[0] + band * B2SR_FLAG_STRIDE, grow + 1u, 25);
+                        }
+                        __threadfence_block();
+                    }
+                }
                 if constexpr (MODE == 0 && !PLAIN) {
 #pragma unroll
                     for (int r = 0; r < NPRE; ++r) {
                         if (r >= nres || pix < 0) continue;
+                        // (pipelined mode reads residuals with ld.global.cg: a ring slot is rewritten by another SM during
+                        // the launch, so a stale L1 line must never be hit)
                         if (NRES >= 0 ? !RF16 : P.res_f32[r] != 0) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(res_ptr[r]) + pix * P.res_ld[r]);
+                            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(res_ptr[r]) + pixr[r] * P.res_ld[r]);
 #pragma unroll
-                            for (int j = 0; j < NOUT / 4; ++j) rraw[r][j] = rp[j];
+                            for (int j = 0; j < NOUT / 4; ++j) rraw[r][j] = PIPE ? __ldcg(rp + j) : rp[j];
                         } else {
-                            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(res_ptr[r]) + pix * P.res_ld[r]);
+                            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(res_ptr[r]) + pixr[r] * P.res_ld[r]);
 #pragma unroll
-                            for (int j = 0; j < NOUT / 8; ++j) rraw[r][j] = rp[j];
+                            for (int j = 0; j < NOUT / 8; ++j) rraw[r][j] = PIPE ? __ldcg(rp + j) : rp[j];
                         }
                     }
                 }
@@ -448,6 +528,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(buf));
                 if (P.dbg) t_tmem += clock64() - tq0;
+                if constexpr (PIPE) {
+                    // The ring slot of this row still holds row grow - RR.  Input row i is read by output rows i-1, i, i+1 of
+                    // the stages that read this ring (and by their epilogues as a residual of row i): all of that is over
+                    // once those stages have FINISHED rows 0..i+1, i.e. done >= i + 2, on bands b-1..b+1.
+                    if (ring_out && grow + 2u > RR && bp_seen < grow + 2u - RR) {
+                        const long long t0 = clock64();
+                        while ((bp_seen = *s_bpmin) < grow + 2u - RR) {
+                            __nanosleep(20);
+                            if (clock64() - t0 > 20000000000LL) flag_timeout(P.bp[0] + band * B2SR_FLAG_STRIDE, grow + 2u - RR, 20);
+                        }
+                        __threadfence_block();  // pairs with the poller's fence before it stored s_bpmin
+                        w_bp += clock64() - t0;
+                    }
+                    __syncwarp();
+                }
 
                 if constexpr (MODE == 0 && PLAIN) {
                     // bias + LeakyReLU -> fp16, via swizzled per-warp staging, then 128-bit coalesced global stores
@@ -483,7 +578,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                     for (int i = 0; i < CH; ++i) {
                         const int qi = i * 32 + lane;
                         const uint4 v4 = stg[qi ^ ((qi >> 3) & 7)];
-                        const long long o = __shfl_sync(0xffffffffu, pix, qi / CH);
+                        const long long o = __shfl_sync(0xffffffffu, pix16, qi / CH);
                         if (o >= 0) *reinterpret_cast<uint4*>(outp + (size_t)o * P.out16_ld * 2 + (qi % CH) * 16) = v4;
                     }
                     __syncwarp();
@@ -519,10 +614,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                                         rv[0] = f0.x, rv[1] = f0.y, rv[2] = f1.x, rv[3] = f1.y;
                                     }
                                 } else if (P.res_f32[r]) {  // (a second residual of a 64-channel launch: not prefetched)
-                                    const float4 u = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(res_ptr[r]) + pix * P.res_ld[r] + j);
+                                    const float4 u = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(res_ptr[r]) + pixr[r] * P.res_ld[r] + j));
                                     rv[0] = u.x, rv[1] = u.y, rv[2] = u.z, rv[3] = u.w;
                                 } else {
-                                    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(res_ptr[r]) + pix * P.res_ld[r] + j);
+                                    const uint2 u = __ldcg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(res_ptr[r]) + pixr[r] * P.res_ld[r] + j));
                                     const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
                                     rv[0] = f0.x, rv[1] = f0.y, rv[2] = f1.x, rv[3] = f1.y;
                                 }
@@ -553,7 +648,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                             for (int i = 0; i < CH; ++i) {
                                 const int qi = i * 32 + lane;
                                 const uint4 v4 = stg[qi ^ ((qi >> 3) & 7)];
-                                const long long o = __shfl_sync(0xffffffffu, pix, qi / CH);
+                                const long long o = __shfl_sync(0xffffffffu, pix32, qi / CH);
                                 if (o >= 0) *reinterpret_cast<uint4*>(outp + ((size_t)o * P.out32_ld + half * (NOUT / 2)) * 4 + (qi % CH) * 16) = v4;
                             }
                         }
@@ -577,7 +672,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                         for (int i = 0; i < CH; ++i) {
                             const int qi = i * 32 + lane;
                             const uint4 v4 = stg[qi ^ ((qi >> 3) & 7)];
-                            const long long o = __shfl_sync(0xffffffffu, pix, qi / CH);
+                            const long long o = __shfl_sync(0xffffffffu, pix16, qi / CH);
                             if (o >= 0) *reinterpret_cast<uint4*>(outp + (size_t)o * P.out16_ld * 2 + (qi % CH) * 16) = v4;
                         }
                     }
@@ -601,23 +696,167 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
                         }
                     }
                 }
+                if constexpr (PIPE) {
+                    // report the row to the publisher with CTA-scope ordering only; its single GPU-scope release covers every
+                    // warp's stores by cumulativity
+                    __syncwarp();
+                    if (lane == 0) {
+                        __threadfence_block();
+                        s_prog[warp - 2] = tile_cnt + 2u;
+                    }
+                    __syncwarp();
+                }
             }
         }
+        if constexpr (PIPE) if (lane == 0) atomicAdd(s_finished, 1u);
         if (P.dbg && warp == 2 && lane == 0) {
             P.dbg[blockIdx.x * 16 + 5] = w_tfull;
             P.dbg[blockIdx.x * 16 + 6] = clock64() - t_begin;
             P.dbg[blockIdx.x * 16 + 10] = t_tmem;
+            P.dbg[blockIdx.x * 16 + 12] = w_bp;
         }
+    } else if constexpr (PIPE) {
+      if (warp == 2 + 4 * TC_NSETS) {
+        // ======================= publisher (pipelined mode) =======================
+        // Turns the epilogue warps' progress words into one monotonic "rows of this (stage, band) written and released"
+        // counter in global memory; it polls, so a slow release only batches several rows into one update.
+        if (lane == 0) {
+            static_assert(TC_NSETS == 2, "the progress-word arithmetic below assumes two epilogue sets");
+            uint32_t n_local = 0;
+            for (int it = it_begin; it < it_end; ++it)
+                if (P.items[it].w > 0) n_local += (uint32_t)P.items[it].rows;
+            const uint32_t g_end = it_end > it_begin ? (uint32_t)(P.items[it_end - 1].grow0 + P.items[it_end - 1].Ht) : 0u;
+            uint32_t cnt = 0, t = 0, published = 0;
+            int it = it_begin;
+            const long long t_start = clock64();
+            for (;;) {
+                uint32_t m = n_local;  // rows [0, m) are complete: every warp is past them
+#pragma unroll
+                for (int w = 0; w < 4 * TC_NSETS; ++w) {
+                    const uint32_t v = s_prog[w];
+                    m = v < m ? v : m;
+                }
+                uint32_t adv = m - cnt;
+                while (it < it_end) {  // move (it, t) forward by `adv` rows, stepping over absent bands and finished items
+                    const TcItem* Ip = P.items + it;
+                    const uint32_t rows = Ip->w > 0 ? (uint32_t)Ip->rows : 0u;
+                    if (t + adv < rows) {
+                        t += adv;
+                        adv = 0;
+                        break;
+                    }
+                    adv -= rows - t;
+                    ++it;
+                    t = 0;
+                }
+                cnt = m;
+                const uint32_t g = it < it_end ? (uint32_t)(P.items[it].grow0 + P.items[it].y0) + t : g_end;
+                if (g > published) {
+                    __threadfence_block();  // acquire side of the progress words ...
+                    st_release_gpu(P.done_out + band * B2SR_FLAG_STRIDE, g);  // ... then one GPU-scope release for all eight warps' stores
+                    published = g;
+                }
+                if (it >= it_end) break;
+                __nanosleep(40);
+                if (clock64() - t_start > 20000000000LL) flag_timeout(P.done_out + band * B2SR_FLAG_STRIDE, g_end, 30);
+            }
+        }
+      } else if (warp == 3 + 4 * TC_NSETS) {
+        // ======================= counter poller (pipelined mode) =======================
+        // Keeps shared-memory minima of the neighbours' global counters fresh (acquire loads, off every critical path).
+        if ((ring_in || ring_out) && lane == 0) {
+            const uint32_t need_fin = (ring_in ? 1u : 0u) + (ring_out ? 4u * TC_NSETS : 0u);
+            const long long t_start = clock64();
+            while (*reinterpret_cast<volatile uint32_t*>(s_finished) < need_fin) {
+                // all counters are read with independent relaxed loads (one L2 round trip for the lot), then ONE acquire
+                // fence orders them before the shared-memory words the other warps act on
+                uint32_t ma = 0xffffffffu, mb = 0xffffffffu;
+                if (ring_in) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        if (k < P.n_in) {
+                            const uint32_t v0 = ld_relaxed_gpu(P.done_in[k] + nb_lo * B2SR_FLAG_STRIDE), v1 = ld_relaxed_gpu(P.done_in[k] + band * B2SR_FLAG_STRIDE),
+                                           v2 = ld_relaxed_gpu(P.done_in[k] + nb_hi * B2SR_FLAG_STRIDE);
+                            const uint32_t m = v0 < v1 ? (v0 < v2 ? v0 : v2) : (v1 < v2 ? v1 : v2);
+                            ma = m < ma ? m : ma;
+                        }
+                }
+                if (ring_out) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        if (k < P.n_bp) {
+                            const uint32_t v0 = ld_relaxed_gpu(P.bp[k] + nb_lo * B2SR_FLAG_STRIDE), v1 = ld_relaxed_gpu(P.bp[k] + band * B2SR_FLAG_STRIDE),
+                                           v2 = ld_relaxed_gpu(P.bp[k] + nb_hi * B2SR_FLAG_STRIDE);
+                            const uint32_t m = v0 < v1 ? (v0 < v2 ? v0 : v2) : (v1 < v2 ? v1 : v2);
+                            mb = m < mb ? m : mb;
+                        }
+                }
+                fence_acq_rel_gpu();
+                __threadfence_block();
+                if (ring_in) *s_avail = ma;
+                if (ring_out) *s_bpmin = mb;
+                __nanosleep(64);
+                if (clock64() - t_start > 40000000000LL) flag_timeout(ring_in ? P.done_in[0] : P.bp[0], 0xffffffffu, 40);
+            }
+        }
+      }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (P.pair) cluster_sync_all();  // the peer's last commits / multicast writes target this CTA's shared memory: stay until it is done
+    if (!PIPE && P.pair) cluster_sync_all();  // the peer's last commits / multicast writes target this CTA's shared memory: stay until it is done
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TCOLS)
                      : "memory");
+    }
+}
+
+// one launch per convolution (or per 2-CTA-cluster pair of its two halves)
+template <int NOUT, int MODE, bool F32OUT, int NRES, int OUTS, bool RF16 = false, bool SC = false>
+__global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_constant__ TcgParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    // paired launch: the two CTAs of a cluster walk the same row range; rank r computes output-channel half r
+    const uint32_t rank = P.pair ? cluster_ctarank() : 0u;
+    const int range = P.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    tcg_body<NOUT, MODE, F32OUT, NRES, OUTS, RF16, SC, false>(P, P.item_first[range], P.item_first[range + 1], 0, rank, smem_raw);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pipelined mode: ONE persistent (cooperative) launch for a segment of consecutive convolutions -- an RRDB of
+// 4x_Valar_v1 is 15 convolutions = 18 stages (each 192 -> 64 convolution is two 32-channel stages) x 8 bands = 144 CTAs.
+// CTA (s, b) keeps stage s's weights resident and streams band b of every plane of the pass top to bottom.  The
+// dense-block buffers [x | x1 | x2 | x3 | x4] and the fp32 trunk copies between the blocks never leave L2: each is a
+// ring of RR rows; a stage pulls input rows with TMA as soon as the stage that wrote the newest slice of its input view
+// has published them (`done` counters of bands b-1..b+1), and overwrites a ring slot once the last readers of that
+// ring have finished with the row it held.  Only the segment's input (x, fp32 x) and output go through HBM.
+// Accumulator homes follow plane rows exactly as in the per-launch kernel, so results are bit-identical to it.
+// ------------------------------------------------------------------------------------------------
+#define B2SR_TCG_VARIANT_PLAIN 0   // x1, x3: lrelu(conv + b) -> fp16
+#define B2SR_TCG_VARIANT_SC 1      // x2: lrelu(conv3x3 + b) + conv1x1(x) -> fp16
+#define B2SR_TCG_VARIANT_R16 2     // x4: lrelu(conv + b) + x2 (fp16 residual) -> fp16
+#define B2SR_TCG_VARIANT_R1_O3 3   // dense-block output half: 0.2 v + x (fp32 residual) -> fp16 + fp32
+#define B2SR_TCG_VARIANT_R2_O3 4   // RRDB output half: two fp32 residual terms -> fp16 + fp32
+#define B2SR_TCG_VARIANT_GENERIC 5 // anything else with 32 output channels (run-time residual / output forms)
+
+struct TcgPipeParams {
+    const TcgParams* stages;  // device array [n_stages]
+    int32_t n_stages, nb;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tcg_pipe_kernel(const __grid_constant__ TcgPipeParams Q) {
+    extern __shared__ uint8_t smem_raw[];
+    const int stage = (int)blockIdx.x / Q.nb, band = (int)blockIdx.x % Q.nb;
+    const TcgParams P = Q.stages[stage];
+    const int it_begin = P.item_first[band], it_end = P.item_first[band + 1];
+    switch (P.variant) {
+        case B2SR_TCG_VARIANT_PLAIN: tcg_body<32, 0, false, 0, 1, false, false, true>(P, it_begin, it_end, band, (uint32_t)P.half, smem_raw); break;
+        case B2SR_TCG_VARIANT_SC: tcg_body<32, 0, false, 0, 1, false, true, true>(P, it_begin, it_end, band, (uint32_t)P.half, smem_raw); break;
+        case B2SR_TCG_VARIANT_R16: tcg_body<32, 0, false, 1, 1, true, false, true>(P, it_begin, it_end, band, (uint32_t)P.half, smem_raw); break;
+        case B2SR_TCG_VARIANT_R1_O3: tcg_body<32, 0, false, 1, 3, false, false, true>(P, it_begin, it_end, band, (uint32_t)P.half, smem_raw); break;
+        case B2SR_TCG_VARIANT_R2_O3: tcg_body<32, 0, false, 2, 3, false, false, true>(P, it_begin, it_end, band, (uint32_t)P.half, smem_raw); break;
+        default: tcg_body<32, 0, false, -1, 0, false, false, true>(P, it_begin, it_end, band, (uint32_t)P.half, smem_raw); break;
     }
 }
 

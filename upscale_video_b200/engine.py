@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2sr.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
-OPT_IMPL, OPT_PROFILE, OPT_MAX_BATCH, OPT_RING_ROWS, OPT_PIPE_DEBUG, OPT_SM_LIMIT = 1, 2, 3, 4, 5, 6
+OPT_IMPL, OPT_PROFILE, OPT_MAX_BATCH, OPT_RING_ROWS, OPT_PIPE_DEBUG, OPT_SM_LIMIT, OPT_SEG_PIPE = 1, 2, 3, 4, 5, 6, 7
 STAT_LAUNCHES, STAT_TC_LAUNCHES, STAT_TC_MID_MS, STAT_TC_MID_COUNT, STAT_ALL_MS, STAT_TC_MID_PIXELS = 1, 2, 3, 4, 5, 6
 STAT_PIPE_LAUNCHES, STAT_PIPE_MS, STAT_HMMA_LAUNCHES, STAT_PIPE_FALLBACKS = 7, 8, 9, 10
 IMPL_AUTO, IMPL_SIMPLE, IMPL_TCGEN05, IMPL_PIPELINED = 0, 1, 2, 3  # IMPL_TCGEN05 = tcgen05 kernels launched layer by layer
@@ -25,7 +25,7 @@ IMPL_AUTO, IMPL_SIMPLE, IMPL_TCGEN05, IMPL_PIPELINED = 0, 1, 2, 3  # IMPL_TCGEN0
 # every symbol include/b2sr.h declares (tests check the library exports exactly these)
 SYMBOLS = [
     "b2sr_abi_version", "b2sr_device_count", "b2sr_default_device", "b2sr_device_name", "b2sr_create", "b2sr_create_graph",
-    "b2sr_create_fused", "b2sr_debug_fused", "b2sr_destroy",
+    "b2sr_create_fused", "b2sr_fused_describe_segments", "b2sr_debug_fused", "b2sr_destroy",
     "b2sr_run_u8", "b2sr_run_f32", "b2sr_run_batch_device", "b2sr_run_batch_host", "b2sr_debug_layer",
     "b2sr_set_option", "b2sr_get_stat", "b2sr_reset_stats", "b2sr_synchronize", "b2sr_stream", "b2sr_last_error",
     "b2sr_nlm_create", "b2sr_nlm_destroy", "b2sr_nlm_run_u8", "b2sr_nlm_run_batch_device", "b2sr_nlm_run_batch_host",
@@ -86,6 +86,7 @@ def load_library(path: str = LIB_PATH):
     lib.b2sr_create.argtypes = [ctypes.POINTER(vp), i32, vp, ctypes.c_size_t, ctypes.POINTER(NetDesc)]
     lib.b2sr_create_graph.argtypes = [ctypes.POINTER(vp), i32, ctypes.POINTER(GraphOp), i32, i32, i32, i32, i32, vp, ctypes.c_size_t]
     lib.b2sr_create_fused.argtypes = [ctypes.POINTER(vp), i32, ctypes.POINTER(FusedOp), i32, ctypes.POINTER(FusedBuf), i32, i32, vp, ctypes.c_size_t]
+    lib.b2sr_fused_describe_segments.argtypes = [ctypes.POINTER(FusedOp), i32, ctypes.POINTER(FusedBuf), i32, i32, vp, i32]
     lib.b2sr_debug_fused.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.b2sr_destroy.argtypes = [vp]
     lib.b2sr_destroy.restype = None
@@ -154,6 +155,49 @@ def _ptr(a):
     raise TypeError("unsupported buffer type %r" % type(a))
 
 
+def _fused_arrays(prog):
+    """ctypes arrays of b2sr_fused_op / b2sr_fused_buf for a ``ncnn_model.FusedProgram``."""
+    ops = (FusedOp * len(prog.ops))()
+    for a, o in zip(ops, prog.ops):
+        for k in ("type", "res", "in_buf", "in_off", "cin", "k", "cout", "act", "slope", "nres", "w_off", "b_off",
+                  "out16_buf", "out16_off", "out32_buf", "out32_off", "r", "final", "sc_cin", "sc_coef_v", "sc_coef_r", "sc_w_off"):
+            setattr(a, k, o[k])
+        for q in range(2):
+            a.res_buf[q], a.res_off[q], a.coef_v[q], a.coef_r[q] = o["res_buf"][q], o["res_off"][q], o["coef_v"][q], o["coef_r"][q]
+    bufs = (FusedBuf * len(prog.bufs))()
+    for a, b in zip(bufs, prog.bufs):
+        a.channels, a.dtype, a.res = b["channels"], b["dtype"], b["res"]
+    return ops, bufs
+
+
+def fused_segments(prog, sms: int = 148):
+    """Host-only: the persistent segments ``b2sr_create_fused`` would form for ``prog`` on a device with ``sms`` SMs
+    (list of dicts; see b2sr_fused_describe_segments in include/b2sr.h).  Needs no GPU."""
+    lib = load_library()
+    ops, bufs = _fused_arrays(prog)
+    n = lib.b2sr_fused_describe_segments(ops, len(prog.ops), bufs, len(prog.bufs), sms, None, 0)
+    if n < 0:
+        _check(n, "b2sr_fused_describe_segments")
+    out = np.zeros(n, np.int32)
+    lib.b2sr_fused_describe_segments(ops, len(prog.ops), bufs, len(prog.bufs), sms, out.ctypes.data, n)
+    v, pos, segs = out.tolist(), 1, []
+    for _ in range(v[0]):
+        ob, oe, ns, ni = v[pos:pos + 4]
+        pos += 4
+        stages = []
+        for _ in range(ns):
+            r = v[pos:pos + 13]
+            pos += 13
+            stages.append(dict(op=r[0], half=r[1], variant=r[2], in_inst=r[3], grp_ring=r[4:7], out16_inst=r[7], out32_inst=r[8],
+                               res_inst=r[9:11], gate_op=r[11], bp_op=r[12]))
+        inst = []
+        for _ in range(ni):
+            inst.append(dict(buf=v[pos], last_reader=v[pos + 1]))
+            pos += 2
+        segs.append(dict(op_begin=ob, op_end=oe, stages=stages, inst=inst))
+    return segs
+
+
 class Engine:
     """One network bound to one GPU (one per worker process, like the reference's ``net``)."""
 
@@ -192,16 +236,7 @@ class Engine:
 
     def _init_fused(self, prog, device):
         """RRDB-style graphs: every convolution (+ bias, LeakyReLU, residual adds) on the tcgen05 graph kernel."""
-        ops = (FusedOp * len(prog.ops))()
-        for a, o in zip(ops, prog.ops):
-            for k in ("type", "res", "in_buf", "in_off", "cin", "k", "cout", "act", "slope", "nres", "w_off", "b_off",
-                      "out16_buf", "out16_off", "out32_buf", "out32_off", "r", "final", "sc_cin", "sc_coef_v", "sc_coef_r", "sc_w_off"):
-                setattr(a, k, o[k])
-            for q in range(2):
-                a.res_buf[q], a.res_off[q], a.coef_v[q], a.coef_r[q] = o["res_buf"][q], o["res_off"][q], o["coef_v"][q], o["coef_r"][q]
-        bufs = (FusedBuf * len(prog.bufs))()
-        for a, b in zip(bufs, prog.bufs):
-            a.channels, a.dtype, a.res = b["channels"], b["dtype"], b["res"]
+        ops, bufs = _fused_arrays(prog)
         w = np.ascontiguousarray(prog.weights, np.float32)
         h = ctypes.c_void_p()
         _check(self._lib.b2sr_create_fused(ctypes.byref(h), device, ops, len(prog.ops), bufs, len(prog.bufs), prog.scale,

@@ -380,3 +380,89 @@ def test_compat_shim_serves_the_reference_cli_imports():
         sys.path.remove(compat)
         for m in ("upscale", "upscale.upscale_processing", "ncnn_vulkan"):
             sys.modules.pop(m, None)
+
+
+def test_raw_stream_multi_gpu_dynamic_queue(tmp_path):
+    """raw_stream.stream_multi: one worker thread per -g entry over one dynamic queue of chunks (reference upscale_frames
+    :565-598 with raw chunks instead of PNG names), in-order writer; bytes equal the single-GPU stream for a pipe input and
+    for a seekable file (which the workers read themselves with preadv); errors surface, nothing hangs."""
+    import io
+    import random
+    import threading
+    import time
+    from upscale_video_b200 import raw_stream
+    rng = np.random.default_rng(2)
+    frames = rng.integers(0, 256, (37, 6, 8, 3), dtype=np.uint8)
+    want = np.repeat(np.repeat(frames, 2, 1), 2, 2).tobytes()
+    seen = {}
+    lock = threading.Lock()
+
+    class Jitter(_FakeEngine):  # workers finish out of order
+        def __init__(self, gpu):
+            super().__init__(2)
+            self.gpu = gpu
+
+        def run_batch_host(self, h_in, h_out, n, h, w, *a, **k):
+            time.sleep(random.random() * 0.004)
+            with lock:
+                seen[self.gpu] = seen.get(self.gpu, 0) + n
+            super().run_batch_host(h_in, h_out, n, h, w, *a, **k)
+
+    class Pipe(io.BytesIO):  # not seekable: one reader thread
+        def seekable(self):
+            return False
+
+        def fileno(self):
+            raise OSError("no fd")
+
+    for chunk in (1, 3, 4, 40):
+        seen.clear()
+        out = io.BytesIO()
+        n = raw_stream.stream_multi(Pipe(frames.tobytes()), out, 8, 6, scale=2, gpus=[0, 1, 1, 2], chunk=chunk,
+                                    make_engines=lambda g: (None, None, Jitter(g)))
+        assert n == 37 and out.getvalue() == want and sum(seen.values()) == 37
+    assert len(seen) == 1  # one chunk of 40: one worker did everything
+    path = tmp_path / "frames.raw"
+    path.write_bytes(frames.tobytes())
+    for chunk, mf in ((2, None), (5, 11), (4, 37)):
+        seen.clear()
+        out = io.BytesIO()
+        with open(path, "rb") as f:
+            n = raw_stream.stream_multi(f, out, 8, 6, scale=2, gpus=[0, 1, 2], chunk=chunk, max_frames=mf, make_engines=lambda g: (None, None, Jitter(g)))
+        k = 37 if mf is None else mf
+        assert n == k and out.getvalue() == want[:k * 12 * 16 * 3]
+    assert len(seen) == 3  # every worker took chunks
+    # rgb24 in and out, denoise -> pre-pass -> upscale chain per worker
+    class Neg:
+        def run_batch_host(self, h_in, h_out, n, h, w, level, level_color=None):
+            a = h_in.numpy() if hasattr(h_in, "numpy") else h_in
+            o = h_out.numpy() if hasattr(h_out, "numpy") else h_out
+            o[:n] = 255 - a[:n]
+
+    out = io.BytesIO()
+    raw_stream.stream_multi(Pipe(frames.tobytes()), out, 8, 6, scale=2, models=["n=3", "a"], gpus=[0, 0], chunk=3, pix_fmt="rgb24",
+                            make_engines=lambda g: (Neg(), _FakeEngine(1), _FakeEngine(2)))
+    assert out.getvalue() == np.repeat(np.repeat(255 - frames, 2, 1), 2, 2).tobytes()
+    # truncated inputs, a failing engine, a closed output pipe
+    with pytest.raises(ValueError, match="truncated"):
+        raw_stream.stream_multi(Pipe(frames.tobytes()[:-5]), io.BytesIO(), 8, 6, scale=2, gpus=[0, 1], chunk=2, make_engines=lambda g: (None, None, _FakeEngine(2)))
+    path.write_bytes(frames.tobytes()[:-5])
+    with open(path, "rb") as f, pytest.raises(ValueError, match="truncated"):
+        raw_stream.stream_multi(f, io.BytesIO(), 8, 6, scale=2, gpus=[0, 1], chunk=2, make_engines=lambda g: (None, None, _FakeEngine(2)))
+
+    class Broken(_FakeEngine):
+        def run_batch_host(self, *a, **k):
+            raise RuntimeError("device lost")
+
+    with pytest.raises(RuntimeError, match="device lost"):
+        raw_stream.stream_multi(Pipe(frames.tobytes()), io.BytesIO(), 8, 6, scale=2, gpus=[0, 1], chunk=2,
+                                make_engines=lambda g: (None, None, Broken(2) if g == 1 else Jitter(g)))
+
+    class ClosedPipe(io.BytesIO):
+        def write(self, b):
+            if self.tell() > 3000:
+                raise BrokenPipeError("reader went away")
+            return super().write(b)
+
+    with pytest.raises(BrokenPipeError):
+        raw_stream.stream_multi(Pipe(frames.tobytes()), ClosedPipe(), 8, 6, scale=2, gpus=[0, 1, 2], chunk=2, make_engines=lambda g: (None, None, Jitter(g)))

@@ -61,6 +61,8 @@ struct TcParams {
     uint32_t* cons_self;        // input rows this layer's band CTAs have pulled into shared memory
     uint32_t* cons_next;        // the same counters of the next layer (back-pressure on this layer's ring)
     long long* dbg;             // pipelined mode, optional: this CTA's 8 stall-accounting words
+    int32_t direct_in;          // pipelined mode, first layer: read the packed u8 frames directly (no fp16 input planes in HBM)
+    const uint8_t* frames_end;  // one past the last byte of frames_in (bounds of the aligned word copies)
 };
 
 #define B2SR_PIPE_MAX_LAYERS 20

@@ -797,7 +797,10 @@ static int launch_pipe(b2sr_ctx* c, const PipeParams& Q) {
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
+    // (B2SR_COOP=0: plain launch -- a profiling aid only: `ncu --set full` replays a kernel many times and does not collect
+    // cooperative launches in multi-pass mode; without the attribute co-residency is the caller's responsibility again)
+    static const bool coop = !(getenv("B2SR_COOP") && atoi(getenv("B2SR_COOP")) == 0);
+    cfg.attrs = attr, cfg.numAttrs = coop ? 1 : 0;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, Q);
     if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
         cudaGetLastError();
@@ -848,7 +851,10 @@ static int run_pipe(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, 
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         P->bound_rings = c->rings, P->bound_rr = RR;
     }
-    {
+    // The first layer's CTAs read the packed u8 frames themselves (tc_conv.cuh, frame-row producer); B2SR_DIRECT_IN=0 restores
+    // the separate prep_kernel pass that expands the frames to 16-channel fp16 planes in HBM first.
+    static const bool direct_in = !(getenv("B2SR_DIRECT_IN") && atoi(getenv("B2SR_DIRECT_IN")) == 0);
+    if (!direct_in) {
         dim3 grid((unsigned)std::min(2048, (P->max_plane_px + 255) / 256), (unsigned)P->planes.size());
         TRY(prof_begin(c, 0, 0));
         prep_kernel<<<grid, 256, 0, c->stream>>>(d_frames, P->h, P->w, P->d_planes, c->in16);
@@ -878,6 +884,8 @@ static int run_pipe(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, 
         p.out = l == L - 1 ? d_out : (void*)(c->rings + (size_t)l * ring_px * CF);
         p.frames_in = d_frames, p.frame_h = P->h, p.frame_w = P->w, p.scale = c->desc.scale;
         p.ring_in = l > 0, p.ring_out = l < L - 1;
+        p.direct_in = l == 0 && direct_in;
+        p.frames_end = d_frames + (size_t)P->n * P->h * P->w * 3;
         p.RR = RR, p.Wmax = P->Wmax, p.nb = nb;
         p.done_in = l > 0 ? done + (size_t)(l - 1) * fl : nullptr;
         p.done_out = done + (size_t)l * fl;

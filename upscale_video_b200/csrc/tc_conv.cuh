@@ -307,9 +307,144 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
+    if constexpr (PIPE && CPIX == 16) {
+      if (warp == 0 && P.direct_in) {
+        // ======================= frame-row producer (first layer of the pipelined schedule) =======================
+        // The network input is read straight from the packed u8 frames: the reference's Mat.from_pixels(PIXEL_BGR) + tile
+        // slicing (upscale_processing.py:430-442) happen on the way into shared memory, with no fp16 copy of the frames in
+        // HBM and no separate pass over them.  The band's 136-pixel window of one frame row (408 bytes) is copied as aligned
+        // 4-byte words with cp.async into a small staging ring, FR_DEPTH rows ahead (hides the HBM latency without holding
+        // registers); the warp then expands the row to the 16-channel fp16 swizzle-32B ring row the MMA descriptors expect:
+        // channels 0-2 = the pixel's bytes (0..255 is exact in fp16; * 1/255 is folded into this layer's epilogue), 3-15 zero,
+        // pixels outside the plane (= the reference tile) zero = the convolution's zero padding.
+        constexpr int FR_DEPTH = 6, FR_SLOTS = 8, FR_BYTES = 512;  // staging: 8 rows of 128 words
+        static_assert(PB == 32, "one 16-channel fp16 pixel is 32 bytes");
+        static_assert(TC_PITCH * 3 + 8 <= FR_BYTES, "staging row too small");
+        const uint32_t fr_off = (uint32_t)((C::WB + R * ROWB + C::STG + C::MISC + 15) & ~15);
+        const uint32_t fr_s = sbase + fr_off;
+        if (lane == 0) {
+            mbar_expect_tx(w_bar, C::WB);
+            for (int t = 0; t < 9; ++t) bulk_g2s(w_s + t * (NOUT * PB), P.wimg + (size_t)t * (NOUT * PB), NOUT * PB, w_bar);
+        }
+        for (int i = lane; i < R * TC_PITCH; i += 32) {  // the all-zero half (channels 8..15) of every pixel of every slot, once
+            const uint32_t a = ring_s + (uint32_t)(i / TC_PITCH) * ROWB + (uint32_t)(i % TC_PITCH) * 32u + 16u;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a ^ (((a >> 7) & 1u) << 4)), "r"(0u) : "memory");
+        }
+        // (item, input row) iterator of the rows being REQUESTED, FR_DEPTH ahead of the rows being expanded.  Everything that
+        // depends on the item only is kept in registers (the item table is in global memory, and this warp's L1 is busy).
+        int it_f = it_begin - 1, rho_f = 0, n_req = 0, f_rows_in = 0, f_y_first = 0, f_Ht = 0;
+        uintptr_t f_w0 = 0, f_b0 = 0, f_b1 = 0;  // row 0 of the plane: window start, first / one-past-last needed byte
+        const uintptr_t f_lo = reinterpret_cast<uintptr_t>(P.frames_in), f_hi = reinterpret_cast<uintptr_t>(P.frames_end);
+        const size_t f_pitch = (size_t)P.frame_w * 3;
+        auto next_item = [&]() {
+            for (++it_f; it_f < it_end; ++it_f) {
+                const TcItem I = P.items[it_f];
+                if (I.w <= 0) continue;
+                const uint8_t* rowp = P.frames_in + ((size_t)((size_t)I.frame * P.frame_h + I.fy0) * P.frame_w + I.fx0) * 3;
+                f_w0 = reinterpret_cast<uintptr_t>(rowp) + (uintptr_t)((ptrdiff_t)(I.x0 - 1) * 3);
+                f_b0 = reinterpret_cast<uintptr_t>(rowp + (size_t)max(I.x0 - 1, 0) * 3);
+                f_b1 = reinterpret_cast<uintptr_t>(rowp + (size_t)min(I.x0 - 1 + TC_PITCH, I.Wt) * 3);
+                f_rows_in = I.rows + 2, f_y_first = I.y0 - 1, f_Ht = I.Ht;
+                break;
+            }
+            rho_f = 0;
+        };
+        next_item();
+        auto request = [&]() {  // cp.async the next row's words into staging slot n_req % FR_SLOTS; always commits one group
+            if (it_f < it_end) {
+                const int y = f_y_first + rho_f;
+                if (y >= 0 && y < f_Ht) {
+                    const uintptr_t off = (uintptr_t)y * f_pitch;
+                    const uintptr_t base = (f_w0 + off) & ~(uintptr_t)3;  // aligned word holding the window's first byte
+                    const uintptr_t b0 = f_b0 + off, b1 = f_b1 + off;
+                    const uint32_t dst = fr_s + (uint32_t)(n_req % FR_SLOTS) * FR_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int j = lane + 32 * k;  // word j of the staging row
+                        const uintptr_t wa = base + (uintptr_t)j * 4;
+                        if (wa + 4 > b0 && wa < b1) {  // the word holds at least one needed byte
+                            if (wa >= f_lo && wa + 4 <= f_hi) {
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)j * 4), "l"(wa) : "memory");
+                            } else {  // the word straddles an end of the frame buffer: its in-range bytes one by one
+                                for (int e = 0; e < 4; ++e)
+                                    if (wa + e >= b0 && wa + e < b1)
+                                        asm volatile("st.shared.u8 [%0], %1;" ::"r"(dst + (uint32_t)j * 4 + e), "r"((uint32_t)*reinterpret_cast<const uint8_t*>(wa + e)) : "memory");
+                            }
+                        }
+                    }
+                }
+                if (++rho_f == f_rows_in) next_item();
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            ++n_req;
+        };
+        for (int i = 0; i < FR_DEPTH; ++i) request();
+        int slot = 0, n_done = 0;
+        uint32_t phase = 0;
+        long long w_empty = 0, w_data = 0, t_expand = 0, t_fence = 0, t_req = 0;
+        const long long t_begin = clock64();
+        for (int it = it_begin; it < it_end; ++it) {
+            const TcItem* Ip = P.items + it;
+            if (Ip->w <= 0) continue;
+            const int rows_in = Ip->rows + 2, x_first = Ip->x0 - 1, Wt = Ip->Wt, Ht = Ip->Ht, y_first = Ip->y0 - 1;
+            const uint8_t* row0 = P.frames_in + ((size_t)((size_t)Ip->frame * P.frame_h + Ip->fy0) * P.frame_w + Ip->fx0) * 3 + (ptrdiff_t)x_first * 3;
+            for (int rho = 0; rho < rows_in; ++rho, ++n_done) {
+                const int y = y_first + rho;
+                const long long tw0 = P.dbg ? clock64() : 0;
+                asm volatile("cp.async.wait_group %0;" ::"n"(FR_DEPTH - 1) : "memory");  // this row's words have landed (own copies)
+                const long long tw1 = P.dbg ? clock64() : 0;
+                if (lane == 0) mbar_wait(empty_bar(slot), phase ^ 1u, 0);
+                __syncwarp();  // ... and everybody else's
+                const long long tw2 = P.dbg ? clock64() : 0;
+                if (P.dbg) w_data += tw1 - tw0, w_empty += tw2 - tw1;
+                // byte offset of the window inside its staging row = misalignment of the window's first byte
+                const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(row0 + (size_t)y * P.frame_w * 3) & 3u);
+                const uint32_t src = fr_s + (uint32_t)(n_done % FR_SLOTS) * FR_BYTES + mis;
+                const bool row_in = y >= 0 && y < Ht;
+#pragma unroll
+                for (int k = 0; k < (TC_PITCH + 31) / 32; ++k) {
+                    const int pp = lane + 32 * k;
+                    if (pp < TC_PITCH) {
+                        const int x = x_first + pp;
+                        uint32_t c0 = 0u, c1 = 0u, c2 = 0u;
+                        if (row_in && x >= 0 && x < Wt) {
+                            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c0) : "r"(src + (uint32_t)pp * 3));
+                            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c1) : "r"(src + (uint32_t)pp * 3 + 1));
+                            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c2) : "r"(src + (uint32_t)pp * 3 + 2));
+                        }
+                        const __half2 h01 = __floats2half2_rn((float)c0, (float)c1);
+                        const __half2 h2 = __floats2half2_rn((float)c2, 0.f);
+                        const uint32_t a = ring_s + (uint32_t)slot * ROWB + (uint32_t)pp * 32u;
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %3};" ::"r"(a ^ (((a >> 7) & 1u) << 4)),
+                                     "r"(*reinterpret_cast<const uint32_t*>(&h01)), "r"(*reinterpret_cast<const uint32_t*>(&h2)), "r"(0u)
+                                     : "memory");
+                    }
+                }
+                const long long tw3 = P.dbg ? clock64() : 0;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> the tensor core's (async proxy) reads
+                __syncwarp();  // every lane's stores are fenced, and everybody is done reading this staging slot
+                if (lane == 0) mbar_arrive(full_bar(slot));
+                const long long tw4 = P.dbg ? clock64() : 0;
+                request();
+                if (P.dbg) t_expand += tw3 - tw2, t_fence += tw4 - tw3, t_req += clock64() - tw4;
+                if (++slot == R) {
+                    slot = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (P.dbg && lane == 0) {
+            P.dbg[0] = clock64() - t_begin;
+            P.dbg[1] = w_data;  // (printed in the "starved" column: waiting for the frame bytes)
+            P.dbg[6] = w_empty;
+            (void)t_expand, (void)t_fence, (void)t_req;  // measured on B200: expand 550, fence + arrive 68, request 680 cycles per row
+        }
+      }
+    }
     if (warp == 0) {
         // ======================= TMA producer =======================
-        if (lane == 0) {
+        if (lane == 0 && !(PIPE && CPIX == 16 && P.direct_in)) {
             mbar_expect_tx(w_bar, C::WB);
             for (int t = 0; t < 9; ++t)  // 9 chunks of the [kx][3*NOUT rows][CPIX] image
                 bulk_g2s(w_s + t * (NOUT * PB), P.wimg + (size_t)t * (NOUT * PB), NOUT * PB, w_bar);
@@ -743,7 +878,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pipe_kernel(const __grid_con
 template <int CF, int NL, int S>
 struct TcPipeCfg {
     static constexpr int a_ = TcCfg<16, CF, 0>::smem_bytes(), b_ = TcCfg<CF, CF, 0>::smem_bytes(), c_ = TcCfg<CF, NL, S>::smem_bytes();
-    static constexpr int smem_bytes() { return a_ > b_ ? (a_ > c_ ? a_ : c_) : (b_ > c_ ? b_ : c_); }
+    static constexpr int a2_ = a_ + 8 * 512 + 16;  // + the first layer's frame-row staging ring (direct u8 input)
+    static constexpr int smem_bytes() { return a2_ > b_ ? (a2_ > c_ ? a2_ : c_) : (b_ > c_ ? b_ : c_); }
 };
 
 }  // namespace b2sr

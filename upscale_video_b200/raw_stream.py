@@ -176,6 +176,211 @@ def stream(fin, fout, width, height, scale=2, models=(), gpu=0, chunk=8, pix_fmt
     return written
 
 
+class _Worker:
+    """The engines of one ``-g`` entry plus its private intermediate buffers (one per worker thread of ``stream_multi``)."""
+
+    def __init__(self, gpu, width, height, scale, models, chunk, model_path, level, make_engines=None):
+        self.gpu, self.width, self.height, self.level = gpu, width, height, level
+        if make_engines is not None:  # tests: (denoiser, prepass, upscaler) for this worker
+            self.denoiser, self.prepass, self.upscaler = make_engines(gpu)
+        else:
+            self.denoiser = _engine.Denoiser(gpu) if level is not None else None
+            self.upscaler = (_engine.Engine.from_files(model_path, str(scale) + ("x_Valar_v1" if "r" in models else "x_Compact_Pretrain"), gpu)
+                             if scale > 1 else None)
+            self.prepass = _engine.Engine.from_files(model_path, "1" + HURR, gpu) if "a" in models else None
+        if self.upscaler is None and self.prepass is None and self.denoiser is None:
+            raise ValueError("nothing to do: scale 1 and no pre-pass model")
+        self.scale = self.upscaler.scale if self.upscaler is not None else 1
+        stages = sum(e is not None for e in (self.denoiser, self.prepass, self.upscaler))
+        self.tmp = [_Stage((chunk, height, width, 3)) for _ in range(min(2, stages - 1))]  # ping / pong between the stages
+
+    def process(self, st_in, st_out, n):
+        """denoise -> 1x pre-pass -> upscaler (the reference's order, test_images.py:82-110) over ``n`` frames."""
+        buf = lambda st: st.tensor if st.tensor is not None else st.array  # noqa: E731
+        steps = []
+        if self.denoiser is not None:
+            steps.append(lambda a, b: self.denoiser.run_batch_host(a, b, n, self.height, self.width, self.level))
+        if self.prepass is not None:
+            steps.append(lambda a, b: self.prepass.run_batch_host(a, b, n, self.height, self.width, tile=0, halo=0))
+        if self.upscaler is not None:
+            steps.append(lambda a, b: self.upscaler.run_batch_host(a, b, n, self.height, self.width))
+        src = st_in
+        for i, step in enumerate(steps):
+            dst = st_out if i == len(steps) - 1 else self.tmp[i % 2]
+            step(buf(src), buf(dst))
+            src = dst
+
+
+def stream_multi(fin, fout, width, height, scale=2, models=(), gpus=(0,), chunk=4, pix_fmt="bgr24", model_path=None, max_frames=None,
+                 make_engines=None):
+    """``stream`` over several GPUs: one worker thread per ``gpus`` entry (repeats allowed, like ``-g 0,0,1``), each with its
+    own engines, taking chunks of frames from ONE dynamic queue -- the reference's frame sharding (``Pool.apply_async`` per
+    frame over one worker per ``-g`` entry, upscale_processing.py:565-598) with chunks of raw frames instead of PNG file names
+    -- and one writer that emits the chunks in input order.  The engine calls, pipe reads and writes all release the GIL.
+
+    Input: a pipe is read by one reader thread; a seekable file (``fin.fileno()`` + ``seekable()``) is read by the workers
+    themselves with ``os.preadv`` at the chunk's offset, so that the input side scales with the number of workers too.
+    Every chunk gets its input AND output staging slots in sequence order before it is queued, and output slots are freed
+    in sequence order by the writer, so the oldest chunk in flight can always finish (no slot deadlock).
+    Returns the number of frames written; bytes out are identical to ``stream`` on one GPU."""
+    import os
+    import queue
+    import threading
+    model_path = model_path or ncnn_model.packaged_model_dir()
+    models = list(models)
+    level = denoise_level(models)
+    gpus = list(gpus)
+    nw = len(gpus)
+    if nw < 1:
+        raise ValueError("no GPU given")
+    swap = pix_fmt == "rgb24"
+    frame_bytes = height * width * 3
+    direct = False
+    try:
+        direct = bool(fin.seekable()) and fin.fileno() >= 0 and hasattr(os, "preadv")
+    except Exception:
+        direct = False
+    start_off = fin.tell() if direct else 0
+    truncated = 0
+    if direct:  # a seekable input's length is known: no speculative chunks past its end
+        avail = max(0, os.fstat(fin.fileno()).st_size - start_off)
+        truncated = avail % frame_bytes
+        max_frames = avail // frame_bytes if max_frames is None else min(max_frames, avail // frame_bytes)
+    workers, errors = [None] * nw, []
+    stop = threading.Event()
+
+    def build(i):
+        try:
+            workers[i] = _Worker(gpus[i], width, height, scale, models, chunk, model_path, level, make_engines)
+        except BaseException as e:  # noqa: BLE001 -- re-raised on the caller's thread
+            errors.append(e)
+
+    ts = [threading.Thread(target=build, args=(i,)) for i in range(nw)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errors:
+        raise errors[0]
+    s = workers[0].scale
+    n_slots = 2 * nw + 1
+    free_in, free_out, work = queue.Queue(), queue.Queue(), queue.Queue()
+    for _ in range(n_slots):
+        free_in.put(_Stage((chunk, height, width, 3)))
+        free_out.put(_Stage((chunk, height * s, width * s, 3)))
+    done, done_cv = {}, threading.Condition()  # seq -> (out slot, n) | None (= end of stream marker)
+
+    def get(q):
+        while not stop.is_set():
+            try:
+                return q.get(timeout=0.1)
+            except queue.Empty:
+                continue
+        return None
+
+    def fail(e):
+        errors.append(e)
+        stop.set()
+        with done_cv:
+            done_cv.notify_all()
+
+    def dispatcher():
+        """Numbers the chunks, reserves their slots in order, and (pipe input) reads them."""
+        seq, left = 0, max_frames
+        try:
+            while not stop.is_set() and (left is None or left > 0):
+                st_in, st_out = get(free_in), get(free_out)
+                if st_in is None or st_out is None:
+                    break
+                want = chunk if left is None else min(chunk, left)
+                if direct:
+                    n = -want  # the worker reads these `want` frames at the chunk's offset itself
+                else:
+                    n = 0
+                    while n < want and _read_frame_into(fin, st_in.array[n]):
+                        n += 1
+                    if n == 0:
+                        break
+                work.put((seq, st_in, st_out, n))
+                seq += 1
+                if left is not None:
+                    left -= abs(n)
+                if not direct and n < want:
+                    break
+        except BaseException as e:  # noqa: BLE001
+            fail(e)
+        finally:
+            for _ in range(nw):
+                work.put(None)
+            with done_cv:
+                done.setdefault(("end", seq), None)
+                done_cv.notify_all()
+
+    def worker(i):
+        w = workers[i]
+        try:
+            while True:
+                item = get(work)
+                if item is None:
+                    break
+                seq, st_in, st_out, n = item
+                if n < 0:  # seekable input: read this chunk here, in parallel with the other workers
+                    want, got = -n, 0
+                    mv = memoryview(st_in.array).cast("B")[:want * frame_bytes]
+                    off = start_off + seq * chunk * frame_bytes
+                    while got < len(mv):
+                        k = os.preadv(fin.fileno(), [mv[got:]], off + got)
+                        if k <= 0:
+                            break
+                        got += k
+                    if got != len(mv):
+                        raise ValueError("short read: %d of %d bytes at offset %d" % (got, len(mv), off))
+                    n = want
+                if n > 0:
+                    if swap:
+                        st_in.array[:n] = st_in.array[:n, :, :, ::-1].copy()
+                    w.process(st_in, st_out, n)
+                free_in.put(st_in)
+                with done_cv:
+                    done[seq] = (st_out, n)
+                    done_cv.notify_all()
+        except BaseException as e:  # noqa: BLE001
+            fail(e)
+
+    threads = [threading.Thread(target=dispatcher, daemon=True)] + [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(nw)]
+    for t in threads:
+        t.start()
+    written, nxt = 0, 0
+    try:
+        while True:
+            with done_cv:
+                while nxt not in done and ("end", nxt) not in done and not stop.is_set():
+                    done_cv.wait(timeout=0.1)
+                if stop.is_set() and errors:
+                    break
+                if nxt not in done:
+                    break  # ("end", nxt): every chunk before the end marker has been written
+                st_out, n = done.pop(nxt)
+            if n > 0:
+                out = st_out.array[:n]
+                fout.write(np.ascontiguousarray(out[:, :, :, ::-1]).data if swap else memoryview(out).cast("B"))
+                written += n
+            free_out.put(st_out)
+            nxt += 1
+    except BaseException as e:  # noqa: BLE001 -- e.g. a closed output pipe
+        errors.append(e)
+    finally:
+        stop.set()
+        for t in threads:
+            t.join(timeout=5)
+    if errors:
+        raise errors[0]
+    fout.flush()
+    if truncated and (max_frames is None or written >= max_frames):
+        raise ValueError("truncated input: %d bytes of a %d-byte frame" % (truncated, frame_bytes))
+    return written
+
+
 def _pump(read_chunk, process, write_chunk, chunk, max_frames, in_slots, out_slots):
     """Three-stage pipeline over rings of staging buffers: a reader thread fills input slots while the caller's thread runs
     the engines and a writer thread drains output slots (file I/O and the ctypes engine calls all release the GIL).  Frames
@@ -256,16 +461,18 @@ def _pump(read_chunk, process, write_chunk, chunk, max_frames, in_slots, out_slo
 
 
 def main(argv=None):
-    ap = argparse.ArgumentParser(description="Upscale a raw bgr24/rgb24 frame stream (stdin -> stdout) on one GPU")
+    ap = argparse.ArgumentParser(description="Upscale a raw bgr24/rgb24 frame stream (stdin -> stdout) on one or several GPUs")
     ap.add_argument("--width", type=int, required=True)
     ap.add_argument("--height", type=int, required=True)
     ap.add_argument("-s", "--scale", type=int, default=2, help="Scale 1, 2 or 4 (1 = pre-pass only). Default is 2.")
     ap.add_argument("-m", "--models", help="'a' adds the 1x anime touch-up model before upscaling, 'n={level}' NL-means noise reduction "
                                            "first, 'r' uses the real-life model 4x_Valar_v1 as the upscaler (like upscale_video.py -m a,n=3,r).")
-    ap.add_argument("-g", "--gpu", type=int, default=0, help="GPU index for this worker (run one worker per GPU, frames interleaved by the caller)")
+    ap.add_argument("-g", "--gpus", default="0", help="GPU numbers, one worker per entry, repeats allowed (like upscale_video.py -g 0,0,1). "
+                                                         "Several entries: one dynamic queue of frame chunks over all workers, output in order.")
     ap.add_argument("--chunk", type=int, default=8, help="frames per host<->device chunk")
     ap.add_argument("--pix_fmt", default="bgr24", choices=["bgr24", "rgb24"])
-    ap.add_argument("--overlap", action="store_true", help="read, compute and write on three threads (rings of three staging chunks)")
+    ap.add_argument("--overlap", action="store_true", default=True, help="read, compute and write on three threads (default)")
+    ap.add_argument("--no-overlap", dest="overlap", action="store_false", help="one thread: read, compute, write in turn")
     ap.add_argument("--model_path")
     ap.add_argument("-i", "--input", help="raw input file (default stdin)")
     ap.add_argument("-o", "--output", help="raw output file (default stdout)")
@@ -278,7 +485,14 @@ def main(argv=None):
         sys.exit("-m r needs -s 4 (the reference ships 4x_Valar_v1 only)")
     fin = open(a.input, "rb") if a.input else sys.stdin.buffer
     fout = open(a.output, "wb") if a.output else sys.stdout.buffer
-    n = stream(fin, fout, a.width, a.height, a.scale, models, a.gpu, a.chunk, a.pix_fmt, a.model_path, overlap=a.overlap)
+    try:
+        gpus = [int(g) for g in a.gpus.split(",")]
+    except ValueError:
+        sys.exit("Invalid gpus")
+    if len(gpus) > 1:
+        n = stream_multi(fin, fout, a.width, a.height, a.scale, models, gpus, min(a.chunk, 4), a.pix_fmt, a.model_path)
+    else:
+        n = stream(fin, fout, a.width, a.height, a.scale, models, gpus[0], a.chunk, a.pix_fmt, a.model_path, overlap=a.overlap)
     print("raw_stream: %d frames" % n, file=sys.stderr)
 
 

@@ -155,26 +155,77 @@ def apply_model(input_file, output_file, remove):
     return logging_items
 
 
+# ---- persistent per-GPU workers ---------------------------------------------------------------
+# The reference builds a new pool -- new processes, new ncnn.Net, model files re-read, shaders rebuilt -- for every call of
+# upscale_frames / process_model, i.e. once per 10-minute batch (:565-577 called from :923-947).  Here the pool of a given
+# (gpus, model) is created once per parent process and reused by later calls: the workers keep their CUDA context, engine,
+# TMA descriptors and scratch.  B2SR_PERSISTENT_WORKERS=0 restores a pool per call.
+_pools = {}  # (gpus, model_path, model_file, scale) -> Pool
+
+
+def _persistent():
+    return os.environ.get("B2SR_PERSISTENT_WORKERS", "1") != "0"
+
+
+def _init_pool_worker(gpus, ident_base, model_path, model_file, scale, model_input, model_output):
+    """Initializer of the pools this module creates itself: like ``init_worker``, with the worker slot taken relative to
+    the parent's child counter AT POOL CREATION (``ident_base``) instead of the caller's ``workers_used`` bookkeeping --
+    which assumes every earlier call spawned fresh processes, no longer true once pools are reused."""
+    init_worker(gpus, ident_base, model_path, model_file, scale, model_input, model_output)
+
+
 def _pool(gpus, workers_used, model_path, model_file, scale, model_input, model_output):
-    # `spawn`, like the reference (:321, :565): no CUDA context may be inherited from the parent
-    return multiprocessing.get_context("spawn").Pool(
-        processes=len(gpus), initializer=init_worker,
-        initargs=(gpus, workers_used, model_path, model_file, scale, model_input, model_output))
+    """(pool, reused).  `spawn`, like the reference (:321, :565): no CUDA context may be inherited from the parent."""
+    key = (tuple(int(g) for g in gpus), os.path.abspath(model_path), model_file, int(scale))
+    if _persistent() and key in _pools:
+        return _pools[key], True
+    # the parent's child counter: the next process it starts gets identity (base + 1,)
+    base = next(multiprocessing.process._process_counter)
+    pool = multiprocessing.get_context("spawn").Pool(
+        processes=len(gpus), initializer=_init_pool_worker,
+        initargs=(list(gpus), base, model_path, model_file, scale, model_input, model_output))
+    if _persistent():
+        _pools[key] = pool
+    return pool, False
+
+
+def _finish(pool, results):
+    """What ``pool.close(); pool.join()`` does for the reference (:600-601): return when every task has run.  A reused
+    pool stays open for the next call."""
+    if _persistent():
+        for r in results:
+            r.wait()
+    else:
+        pool.close()
+        pool.join()
+    _exit_if_failed()
+
+
+def release_workers():
+    """Stop the persistent workers (also registered with ``atexit``)."""
+    while _pools:
+        _, pool = _pools.popitem()
+        pool.close()
+        pool.join()
+
+
+import atexit  # noqa: E402
+
+atexit.register(release_workers)
 
 
 def process_model(frames_count, model_path, model_file, scale, model_input, model_output, input_file_tag,
                   output_file_tag, gpus, workers_used, remove=True):
     """One ``apply_model`` task per existing ``N.<input_file_tag>.png`` (reference :302-347)."""
     frames = range(1, frames_count + 1) if isinstance(frames_count, int) else frames_count
-    pool = _pool(gpus, workers_used, model_path, model_file, scale, model_input, model_output)
+    pool, _ = _pool(gpus, workers_used, model_path, model_file, scale, model_input, model_output)
+    results = []
     for frame in frames:
         input_file_name = "%s.%s.png" % (frame, input_file_tag)
         output_file_name = "%s.%s.png" % (frame, output_file_tag)
         if os.path.exists(input_file_name):
-            pool.apply_async(apply_model, args=(input_file_name, output_file_name, remove), callback=logging_callback)
-    pool.close()
-    pool.join()
-    _exit_if_failed()
+            results.append(pool.apply_async(apply_model, args=(input_file_name, output_file_name, remove), callback=logging_callback))
+    _finish(pool, results)
 
 
 denoiser = None  # process-global, created by the first apply_denoise task of a worker
@@ -310,14 +361,13 @@ def upscale_frames(frame_batch, start_frame, end_frame, input_file_tag, scale, g
     ``N.<input_file_tag>.png`` (reference :545-601).  Frames whose input is missing were finished by an earlier
     run and are skipped -- the reference's resume contract."""
     frames = frame_batch if (frame_batch and isinstance(frame_batch, list)) else range(start_frame, end_frame + 1)
-    pool = _pool(gpus, workers_used, model_path, model_file, scale, model_input, model_output)
+    pool, _ = _pool(gpus, workers_used, model_path, model_file, scale, model_input, model_output)
+    results = []
     for frame in frames:
         input_file_name = "%s.%s.png" % (frame, input_file_tag)
         output_file_name = "%s.png" % frame
         if os.path.exists(input_file_name):
-            pool.apply_async(upscale_image,
-                             args=(input_file_name, output_file_name, scale, frame_batch, frame, end_frame, remove),
-                             callback=logging_callback)
-    pool.close()
-    pool.join()
-    _exit_if_failed()
+            results.append(pool.apply_async(upscale_image,
+                                            args=(input_file_name, output_file_name, scale, frame_batch, frame, end_frame, remove),
+                                            callback=logging_callback))
+    _finish(pool, results)

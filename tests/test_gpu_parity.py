@@ -611,3 +611,26 @@ def test_persistent_grid_guard_falls_back(E, model_dir, oracle_models):
     assert np.array_equal(res[0], a) and np.array_equal(res[1], a)
     other.close()
     eng.close()
+
+
+def test_raw_stream_multi_worker_identical(engines, model_dir, tmp_path):
+    """raw_stream.stream_multi (`-g 0,0`: two worker threads with their own engines on GPU 0, one dynamic chunk queue, in-order
+    writer) writes exactly the bytes of the single-GPU stream -- from a pipe and from a seekable file -- including the
+    chained `-m a` mode."""
+    import io
+    from upscale_video_b200 import raw_stream
+    frames = np.stack([natural(70, 1000, seed=s) for s in range(60, 67)])
+    comp, hurr = engines("2x_Compact_Pretrain"), engines(HURR)
+    expect = np.stack([comp.run_u8(f) for f in frames]).tobytes()
+    out = io.BytesIO()
+    assert raw_stream.stream_multi(io.BytesIO(frames.tobytes()), out, 1000, 70, scale=2, gpus=[0, 0], chunk=2, model_path=model_dir) == 7
+    assert out.getvalue() == expect
+    p = tmp_path / "in.raw"
+    p.write_bytes(frames.tobytes())
+    out = io.BytesIO()
+    with open(p, "rb") as f:
+        assert raw_stream.stream_multi(f, out, 1000, 70, scale=2, gpus=[0, 0, 0], chunk=2, model_path=model_dir) == 7
+    assert out.getvalue() == expect
+    out = io.BytesIO()
+    raw_stream.stream_multi(io.BytesIO(frames.tobytes()), out, 1000, 70, scale=2, models=["a"], gpus=[0, 0], chunk=3, model_path=model_dir)
+    assert out.getvalue() == np.stack([comp.run_u8(hurr.run_u8(f, tile=0, halo=0)) for f in frames]).tobytes()

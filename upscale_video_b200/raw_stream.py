@@ -218,8 +218,9 @@ def stream_multi(fin, fout, width, height, scale=2, models=(), gpus=(0,), chunk=
     frame over one worker per ``-g`` entry, upscale_processing.py:565-598) with chunks of raw frames instead of PNG file names
     -- and one writer that emits the chunks in input order.  The engine calls, pipe reads and writes all release the GIL.
 
-    Input: a pipe is read by one reader thread; a seekable file (``fin.fileno()`` + ``seekable()``) is read by the workers
-    themselves with ``os.preadv`` at the chunk's offset, so that the input side scales with the number of workers too.
+    Input: a pipe is read by one reader thread; a seekable file (``fin.fileno()`` + ``seekable()``) is read by one reader
+    thread PER WORKER with ``os.preadv`` at the chunks' offsets, so that the input side scales with the number of GPUs too
+    (and stays overlapped with the engines).
     Every chunk gets its input AND output staging slots in sequence order before it is queued, and output slots are freed
     in sequence order by the writer, so the oldest chunk in flight can always finish (no slot deadlock).
     Returns the number of frames written; bytes out are identical to ``stream`` on one GPU."""
@@ -264,7 +265,7 @@ def stream_multi(fin, fout, width, height, scale=2, models=(), gpus=(0,), chunk=
         raise errors[0]
     s = workers[0].scale
     n_slots = 2 * nw + 1
-    free_in, free_out, work = queue.Queue(), queue.Queue(), queue.Queue()
+    free_in, free_out, work, toread = queue.Queue(), queue.Queue(), queue.Queue(), queue.Queue()
     for _ in range(n_slots):
         free_in.put(_Stage((chunk, height, width, 3)))
         free_out.put(_Stage((chunk, height * s, width * s, 3)))
@@ -294,27 +295,51 @@ def stream_multi(fin, fout, width, height, scale=2, models=(), gpus=(0,), chunk=
                     break
                 want = chunk if left is None else min(chunk, left)
                 if direct:
-                    n = -want  # the worker reads these `want` frames at the chunk's offset itself
+                    n = want
+                    toread.put((seq, st_in, st_out, want))  # a file reader thread fills the slot, then queues the chunk
                 else:
                     n = 0
                     while n < want and _read_frame_into(fin, st_in.array[n]):
                         n += 1
                     if n == 0:
                         break
-                work.put((seq, st_in, st_out, n))
+                    work.put((seq, st_in, st_out, n))
                 seq += 1
                 if left is not None:
-                    left -= abs(n)
+                    left -= n
                 if not direct and n < want:
                     break
         except BaseException as e:  # noqa: BLE001
             fail(e)
         finally:
             for _ in range(nw):
-                work.put(None)
+                (toread if direct else work).put(None)
             with done_cv:
                 done.setdefault(("end", seq), None)
                 done_cv.notify_all()
+
+    def file_reader():
+        """Seekable input: preadv the chunk at its offset into its slot (several of these run in parallel)."""
+        try:
+            while True:
+                item = get(toread)
+                if item is None:
+                    break
+                seq, st_in, st_out, want = item
+                mv = memoryview(st_in.array).cast("B")[:want * frame_bytes]
+                off, got = start_off + seq * chunk * frame_bytes, 0
+                while got < len(mv):
+                    k = os.preadv(fin.fileno(), [mv[got:]], off + got)
+                    if k <= 0:
+                        break
+                    got += k
+                if got != len(mv):
+                    raise ValueError("short read: %d of %d bytes at offset %d" % (got, len(mv), off))
+                work.put((seq, st_in, st_out, want))
+        except BaseException as e:  # noqa: BLE001
+            fail(e)
+        finally:
+            work.put(None)
 
     def worker(i):
         w = workers[i]
@@ -324,18 +349,6 @@ def stream_multi(fin, fout, width, height, scale=2, models=(), gpus=(0,), chunk=
                 if item is None:
                     break
                 seq, st_in, st_out, n = item
-                if n < 0:  # seekable input: read this chunk here, in parallel with the other workers
-                    want, got = -n, 0
-                    mv = memoryview(st_in.array).cast("B")[:want * frame_bytes]
-                    off = start_off + seq * chunk * frame_bytes
-                    while got < len(mv):
-                        k = os.preadv(fin.fileno(), [mv[got:]], off + got)
-                        if k <= 0:
-                            break
-                        got += k
-                    if got != len(mv):
-                        raise ValueError("short read: %d of %d bytes at offset %d" % (got, len(mv), off))
-                    n = want
                 if n > 0:
                     if swap:
                         st_in.array[:n] = st_in.array[:n, :, :, ::-1].copy()
@@ -348,6 +361,8 @@ def stream_multi(fin, fout, width, height, scale=2, models=(), gpus=(0,), chunk=
             fail(e)
 
     threads = [threading.Thread(target=dispatcher, daemon=True)] + [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(nw)]
+    if direct:
+        threads += [threading.Thread(target=file_reader, daemon=True) for _ in range(nw)]
     for t in threads:
         t.start()
     written, nxt = 0, 0

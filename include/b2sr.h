@@ -251,6 +251,21 @@ void *b2sr_stream(b2sr_ctx *ctx);
 const char *b2sr_last_error(void);
 
 /*
+ * Start-up weight broadcast (the reference has every worker read the model files itself,
+ * upscale/upscale_processing.py:70-71).  Every rank creates its context from the same network description -- rank `root`
+ * with the real parameters, the others with any blob of the right size (zeros pass the fp16-exactness check) -- then
+ * b2sr_bcast_weights makes the device-side parameter buffers of all ranks identical with one grouped ncclBroadcast on the
+ * context's stream.  `nccl_comm` is an ncclComm_t: the application's own, or one made with the helpers below (rank 0
+ * calls b2sr_nccl_unique_id and ships the 128 bytes to the other ranks by any means; everybody calls b2sr_nccl_comm_init).
+ * NCCL is resolved at run time (dlopen of the copy already in the process, else libnccl.so.2); B2SR_E_UNSUPPORTED if absent.
+ * No collective is used after start-up: frames shard with no data-path communication.
+ */
+int b2sr_bcast_weights(b2sr_ctx *ctx, void *nccl_comm, int root);
+int b2sr_nccl_unique_id(void *id128);
+int b2sr_nccl_comm_init(void **comm, int n_ranks, int rank, const void *id128, int device);
+int b2sr_nccl_comm_destroy(void *comm);
+
+/*
  * Denoise pass (`-m n=<level>`).  Replaces the one library call of the reference's denoise worker,
  *     cv2.fastNlMeansDenoisingColored(img, None, denoise, denoise, 5, 9)      (upscale/upscale_processing.py:354)
  * -- BGR -> Lab, non-local means on the L plane (h_luma) and on the (a, b) plane pair (h_color) with a 5x5 template

@@ -2444,6 +2444,122 @@ extern "C" int b2sr_synchronize(b2sr_ctx* c) {
 
 extern "C" void* b2sr_stream(b2sr_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
+
+// ------------------------------------------------------------------------------------------------
+// start-up weight broadcast over NCCL: every rank creates its context from the same network
+// description -- rank `root` with the real parameters, the others with anything of the right size (zeros) -- and one
+// grouped ncclBroadcast per device-side parameter buffer makes them identical.  Nothing is communicated afterwards.
+// NCCL is resolved at run time (the copy already loaded into the process -- e.g. torch's -- else libnccl.so.2), so the
+// library itself has no link-time dependency on it.
+// ------------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, const void*, int) = nullptr;  // ncclUniqueId is passed BY VALUE (128 bytes) in the real ABI: see nccl_comm_init below
+    int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+struct NcclId {
+    char bytes[128];
+};
+NcclApi g_nccl;
+int load_nccl() {
+    if (g_nccl.lib) return 0;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(B2SR_E_UNSUPPORTED, "NCCL is not available in this process (%s)", dlerror());
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, const void*, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+    g_nccl.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclBroadcast");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.GroupStart || !g_nccl.GroupEnd || !g_nccl.Broadcast)
+        return fail(B2SR_E_UNSUPPORTED, "libnccl.so.2 lacks an expected symbol");
+    g_nccl.lib = h;
+    return 0;
+}
+int nccl_fail(const char* what, int rc) {
+    return fail(B2SR_E_CUDA, "%s failed: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "NCCL error");
+}
+}  // namespace
+
+extern "C" int b2sr_nccl_unique_id(void* id128) {
+    if (!id128) return fail(B2SR_E_INVALID, "b2sr_nccl_unique_id: null argument");
+    TRY(load_nccl());
+    const int rc = g_nccl.GetUniqueId(id128);
+    return rc ? nccl_fail("ncclGetUniqueId", rc) : 0;
+}
+
+extern "C" int b2sr_nccl_comm_init(void** comm, int n_ranks, int rank, const void* id128, int device) {
+    if (!comm || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(B2SR_E_INVALID, "b2sr_nccl_comm_init: bad argument");
+    TRY(load_nccl());
+    CUDA_TRY(cudaSetDevice(device));
+    NcclId id;
+    memcpy(id.bytes, id128, sizeof id.bytes);
+    // ncclResult_t ncclCommInitRank(ncclComm_t* comm, int nranks, ncclUniqueId commId, int rank): the id travels by value
+    auto init = (int (*)(void**, int, NcclId, int))(void*)g_nccl.CommInitRank;
+    const int rc = init(comm, n_ranks, id, rank);
+    return rc ? nccl_fail("ncclCommInitRank", rc) : 0;
+}
+
+extern "C" int b2sr_nccl_comm_destroy(void* comm) {
+    if (!comm) return 0;
+    TRY(load_nccl());
+    const int rc = g_nccl.CommDestroy(comm);
+    return rc ? nccl_fail("ncclCommDestroy", rc) : 0;
+}
+
+extern "C" int b2sr_bcast_weights(b2sr_ctx* c, void* nccl_comm, int root) {
+    if (!c || !nccl_comm || root < 0) return fail(B2SR_E_INVALID, "b2sr_bcast_weights: bad argument");
+    TRY(load_nccl());
+    CUDA_TRY(cudaSetDevice(c->device));
+    std::vector<std::pair<void*, size_t>> bufs;  // every device-side parameter buffer of the context, in creation order
+    for (const LayerDev& L : c->layers) {
+        const size_t PB = (size_t)L.cinp * 2;
+        bufs.push_back({L.wimg, (size_t)9 * L.noutp * PB});
+        bufs.push_back({L.wplain, (size_t)9 * L.cinp * L.noutp * 2});
+        bufs.push_back({L.bias, (size_t)L.noutp * 4});
+        if (L.slope) bufs.push_back({L.slope, (size_t)L.noutp * 4});
+    }
+    for (const FusedLaunch& L : c->flaunch) {
+        const b2sr_fused_op& o = c->fops[L.op];
+        const int parts = L.pair ? 2 : 1;
+        const size_t img = (size_t)parts * L.G * 9 * L.NOUT * TCG_PB + (L.sc_ks ? (size_t)L.NOUT * TCG_PB : 0);
+        (void)o;
+        bufs.push_back({L.wimg, img});
+        if (L.wimg_flip) bufs.push_back({L.wimg_flip, img});
+        bufs.push_back({L.bias, (size_t)parts * L.NOUT * 4});
+        bufs.push_back({L.slope, (size_t)parts * L.NOUT * 4});
+    }
+    for (const GraphOp& g : c->gops) {
+        const b2sr_graph_op& o = g.op;
+        if (o.type == B2SR_OP_CONV) {
+            bufs.push_back({g.w, (size_t)o.k * o.k * o.cin * g.coutp * 4});
+            if (g.wh) bufs.push_back({g.wh, (size_t)o.k * o.k * o.cin * o.cout * 2});
+            if (g.b) bufs.push_back({g.b, (size_t)o.cout * 4});
+        } else if (o.type == B2SR_OP_PRELU) {
+            bufs.push_back({g.w, (size_t)o.in_c[0] * 4});
+        }
+    }
+    int rc = g_nccl.GroupStart();
+    if (rc) return nccl_fail("ncclGroupStart", rc);
+    for (auto& b : bufs)
+        if (b.first && b.second && !rc) rc = g_nccl.Broadcast(b.first, b.first, b.second, /*ncclUint8*/ 1, root, nccl_comm, c->stream);
+    const int rc2 = g_nccl.GroupEnd();
+    if (rc) return nccl_fail("ncclBroadcast", rc);
+    if (rc2) return nccl_fail("ncclGroupEnd", rc2);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // denoise pass (reference apply_denoise, upscale/upscale_processing.py:350-362)
 // ------------------------------------------------------------------------------------------------

@@ -28,6 +28,7 @@ SYMBOLS = [
     "b2sr_create_fused", "b2sr_fused_describe_segments", "b2sr_debug_fused", "b2sr_destroy",
     "b2sr_run_u8", "b2sr_run_f32", "b2sr_run_batch_device", "b2sr_run_batch_host", "b2sr_debug_layer",
     "b2sr_set_option", "b2sr_get_stat", "b2sr_reset_stats", "b2sr_synchronize", "b2sr_stream", "b2sr_last_error",
+    "b2sr_bcast_weights", "b2sr_nccl_unique_id", "b2sr_nccl_comm_init", "b2sr_nccl_comm_destroy",
     "b2sr_nlm_create", "b2sr_nlm_destroy", "b2sr_nlm_run_u8", "b2sr_nlm_run_batch_device", "b2sr_nlm_run_batch_host",
     "b2sr_nlm_synchronize", "b2sr_nlm_stream", "b2sr_nlm_launches", "b2sr_nlm_weight_table", "b2sr_nlm_lab_tables",
 ]
@@ -102,6 +103,10 @@ def load_library(path: str = LIB_PATH):
     lib.b2sr_stream.argtypes = [vp]
     lib.b2sr_stream.restype = vp
     lib.b2sr_last_error.restype = ctypes.c_char_p
+    lib.b2sr_bcast_weights.argtypes = [vp, vp, i32]
+    lib.b2sr_nccl_unique_id.argtypes = [vp]
+    lib.b2sr_nccl_comm_init.argtypes = [ctypes.POINTER(vp), i32, i32, vp, i32]
+    lib.b2sr_nccl_comm_destroy.argtypes = [vp]
     f32 = ctypes.c_float
     lib.b2sr_nlm_create.argtypes = [ctypes.POINTER(vp), i32]
     lib.b2sr_nlm_destroy.argtypes = [vp]
@@ -351,6 +356,32 @@ class Engine:
     @property
     def stream(self) -> int:
         return int(self._lib.b2sr_stream(self._h) or 0)
+
+    def bcast_weights(self, comm: "NcclComm", root: int = 0):
+        """Make this engine's device-side parameters equal rank ``root``'s (``b2sr_bcast_weights``): the start-up weight
+        broadcast for ranks that did not read the model files."""
+        _check(self._lib.b2sr_bcast_weights(self._h, comm.handle, root), "b2sr_bcast_weights")
+
+
+class NcclComm:
+    """An ncclComm_t made through the C ABI's helpers (``b2sr_nccl_unique_id`` / ``b2sr_nccl_comm_init``) -- for callers that do
+    not own a communicator.  ``exchange(id_bytes_or_None) -> id_bytes`` ships rank 0's 128-byte id to every rank (e.g.
+    a torch.distributed broadcast over gloo, a file, an environment variable)."""
+
+    def __init__(self, rank: int, world: int, device: int, exchange):
+        lib = load_library()
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            _check(lib.b2sr_nccl_unique_id(buf), "b2sr_nccl_unique_id")
+        ident = exchange(bytes(buf.raw) if rank == 0 else None)
+        h = ctypes.c_void_p()
+        _check(lib.b2sr_nccl_comm_init(ctypes.byref(h), world, rank, bytes(ident), device), "b2sr_nccl_comm_init")
+        self.handle, self._lib = h, lib
+
+    def close(self):
+        if self.handle:
+            self._lib.b2sr_nccl_comm_destroy(self.handle)
+            self.handle = None
 
 
 class Denoiser:

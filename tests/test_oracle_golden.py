@@ -103,3 +103,48 @@ def test_chain_sensitivity_of_the_oracle_itself(oracle_models):
     a, b = oracle.upscale_image_array(m, y, 2, "f64"), oracle.upscale_image_array(m, p, 2, "f64")
     d = np.abs(a.astype(int) - b.astype(int))
     assert d.max() >= 2 and (d > 1).mean() < 0.01
+
+
+def test_rrdb_op_semantics_hand_vectors():
+    """Per-op known answers, computed by hand, for the ncnn layers only 4x_Valar_v1 uses (reference
+    models/4x_Valar_v1.param:6-22, :1203): Convolution with fused LeakyReLU (9=2, -23310=1,0.2), bias-less 1x1 Convolution,
+    Concat along channels, Eltwise SUM with coefficients (-23301=2,c0,c1: out = c0 * in0 + c1 * in1, operand order = bottom
+    order) and Interp nearest x2 (0=1: source index = floor(dst / 2)).  ncnn's documented parameter ids, from the public
+    operator table: Convolution 0 = num_output, 1 = kernel, 4 = pad, 5 = bias_term, 9 = activation_type (2 = LeakyReLU),
+    10 = activation_params; Eltwise 0 = op_type (1 = SUM), 1 = coeffs; Interp 0 = resize_type (1 = nearest), 1/2 = scales;
+    Concat 0 = axis (0 = channels of a CHW blob)."""
+    def layer(t, bottoms, tops, params=None, arrays=None):
+        return {"type": t, "name": tops[0], "bottoms": bottoms, "tops": tops, "params": params or {}, "arrays": arrays or {}}
+
+    x = np.array([[[1.0, -2.0], [3.0, -4.0]],
+                  [[-5.0, 6.0], [7.0, -8.0]]])  # H = 2, W = 2, C = 2 (HWC)
+    w1 = np.array([[1.0, 1.0], [1.0, -1.0], [0.5, 0.0]], np.float32).reshape(3, 2, 1, 1)  # 1x1 conv 2 -> 3, OIHW
+    b1 = np.array([0.0, 1.0, -10.0], np.float32)
+    layers = [
+        layer("Input", [], ["input"]),
+        layer("Split", ["input"], ["a", "b", "c"]),
+        # y = lrelu_0.2(conv1x1(x) + b): per pixel (s, d, h) = (x0 + x1, x0 - x1 + 1, 0.5 x0 - 10)
+        layer("Convolution", ["a"], ["y"], {0: 3, 1: 1, 4: 0, 5: 1, 6: 6, 9: 2, 10: [0.2]}, {"weight": w1, "bias": b1}),
+        # z = bias-less 1x1 conv 2 -> 2 that swaps the channels
+        layer("Convolution", ["b"], ["z"], {0: 2, 1: 1, 4: 0, 5: 0, 6: 4},
+              {"weight": np.array([[0.0, 1.0], [1.0, 0.0]], np.float32).reshape(2, 2, 1, 1)}),
+        layer("Eltwise", ["z", "c"], ["e"], {0: 1, 1: [0.2, 1.0]}),  # e = 0.2 z + 1.0 x
+        layer("Concat", ["y", "e"], ["cat"], {0: 0}),                # channels: y0 y1 y2 e0 e1
+        layer("Interp", ["cat"], ["output"], {0: 1, 1: 2.0, 2: 2.0}),
+    ]
+    out = oracle.run_graph(layers, x, "f64")
+    assert out.shape == (4, 4, 5)
+    lrelu = lambda v: v if v >= 0 else 0.2 * v  # noqa: E731
+    for yy in range(2):
+        for xx in range(2):
+            x0, x1 = x[yy, xx]
+            want = [lrelu(x0 + x1), lrelu(x0 - x1 + 1.0), lrelu(0.5 * x0 - 10.0), 0.2 * x1 + x0, 0.2 * x0 + x1]
+            for dy in range(2):
+                for dx in range(2):  # nearest x2: every source pixel fills a 2 x 2 block
+                    # (0.2 is stored as a float32 coefficient / slope in the .param file)
+                    assert np.allclose(out[2 * yy + dy, 2 * xx + dx], want, rtol=0, atol=1e-7), (yy, xx, dy, dx)
+    # spot values: pixel (0, 0) = (1, -2): y = (lrelu(-1), 4, lrelu(-9.5)) = (-0.2, 4, -1.9); e = (0.2 * -2 + 1, 0.2 * 1 - 2) = (0.6, -1.8)
+    assert np.allclose(out[1, 1], [-0.2, 4.0, -1.9, 0.6, -1.8], atol=1e-7)
+    # Eltwise operand order matters: swapping the bottoms must change the result
+    layers[4] = layer("Eltwise", ["c", "z"], ["e"], {0: 1, 1: [0.2, 1.0]})
+    assert np.allclose(oracle.run_graph(layers, x, "f64")[0, 0, 3:], [0.2 * 1.0 - 2.0, 0.2 * -2.0 + 1.0], atol=1e-7)

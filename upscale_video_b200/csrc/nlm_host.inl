@@ -179,10 +179,14 @@ static int nlm_launch(b2sr_nlm* c, const uint8_t* d_in, long long in_frame_strid
     P.in_stride = in_stride, P.out_stride = out_stride;
     P.H = h, P.W = w;
     P.tiles_x = (w + NLM_TW - 1) / NLM_TW;
-    // rows per warp tile: 16 by default; B2SR_NLM_TH=12 or 8 trades template-halo rework (20/16 -> 16/12 -> 12/8 rows walked per
-    // output row) for registers and occupancy (80 -> 60 -> 40 accumulators per lane) -- an experiment switch
+    // Rows per warp tile (B2SR_NLM_TH overrides): fewer rows = more template-halo rework (20/16 -> 16/12 -> 12/8 rows walked per
+    // output row) but fewer accumulators per lane (80 -> 60 -> 40) and more resident warps.  Measured on B200, 16 frames of
+    // 1080p per launch (profiles/r02i_checks.log): packed variant (levels <= 6) 16 rows 3 319 / 12 rows 3 388 / 8 rows 3 235
+    // frames/s; generic variant (level 10) 2 608 / 2 500 / 2 902 -- so 12 rows for the packed kernel, 8 for the generic one.
     static const int th_env = getenv("B2SR_NLM_TH") ? atoi(getenv("B2SR_NLM_TH")) : 0;
-    const int TH = (th_env == 8 || th_env == 12) ? th_env : NLM_TH;
+    static const bool allow_packed = !(getenv("B2SR_NLM_PACKED") && atoi(getenv("B2SR_NLM_PACKED")) == 0);
+    const bool packed = allow_packed && c->n_l <= NLM_PACK_MAX_TABLE && c->n_ab <= NLM_PACK_MAX_TABLE;
+    const int TH = (th_env == 8 || th_env == 12 || th_env == 16) ? th_env : (packed ? 12 : 8);
     P.tiles_per_frame = P.tiles_x * ((h + TH - 1) / TH);
     P.n_tiles = (long long)P.tiles_per_frame * n;
     memcpy(P.fwd, c->host_tabs.fwd, sizeof P.fwd);
@@ -194,8 +198,6 @@ static int nlm_launch(b2sr_nlm* c, const uint8_t* d_in, long long in_frame_strid
     P.n_l = c->n_l, P.n_ab = c->n_ab;
     const long long blocks = (P.n_tiles + NLM_WARPS - 1) / NLM_WARPS;
     if (blocks > 0x7fffffffLL) return fail(B2SR_E_INVALID, "too many tiles (%lld)", P.n_tiles);
-    static const bool allow_packed = !(getenv("B2SR_NLM_PACKED") && atoi(getenv("B2SR_NLM_PACKED")) == 0);
-    const bool packed = allow_packed && c->n_l <= NLM_PACK_MAX_TABLE && c->n_ab <= NLM_PACK_MAX_TABLE;
     const dim3 grid((unsigned)blocks), block(NLM_WARPS * 32);
 #define NLM_LAUNCH(PK, T) nlm_kernel<PK, T><<<grid, block, 0, c->stream>>>(P)
     if (TH == 8) packed ? NLM_LAUNCH(true, 8) : NLM_LAUNCH(false, 8);

@@ -70,6 +70,18 @@ class _Stage:
         self.array = np.empty(shape, np.uint8)
 
 
+_stage_cache = {}  # shape -> idle _Stage objects: pinned allocations are slow (~0.1 s per 100 MB), repeated calls reuse them
+
+
+def _take_stage(shape):
+    idle = _stage_cache.get(tuple(shape))
+    return idle.pop() if idle else _Stage(shape)
+
+
+def _give_stage(st):
+    _stage_cache.setdefault(tuple(st.array.shape), []).append(st)
+
+
 def denoise_level(models):
     """``n=K`` among the model options -> K clamped to 1..30, or None (reference test_images.py:45-52)."""
     for m in models:
@@ -266,9 +278,11 @@ def stream_multi(fin, fout, width, height, scale=2, models=(), gpus=(0,), chunk=
     s = workers[0].scale
     n_slots = 2 * nw + 1
     free_in, free_out, work, toread = queue.Queue(), queue.Queue(), queue.Queue(), queue.Queue()
-    for _ in range(n_slots):
-        free_in.put(_Stage((chunk, height, width, 3)))
-        free_out.put(_Stage((chunk, height * s, width * s, 3)))
+    all_slots = [_take_stage((chunk, height, width, 3)) for _ in range(n_slots)] + [_take_stage((chunk, height * s, width * s, 3)) for _ in range(n_slots)]
+    for st in all_slots[:n_slots]:
+        free_in.put(st)
+    for st in all_slots[n_slots:]:
+        free_out.put(st)
     done, done_cv = {}, threading.Condition()  # seq -> (out slot, n) | None (= end of stream marker)
 
     def get(q):
@@ -388,6 +402,9 @@ def stream_multi(fin, fout, width, height, scale=2, models=(), gpus=(0,), chunk=
         stop.set()
         for t in threads:
             t.join(timeout=5)
+        if not any(t.is_alive() for t in threads):  # (a thread stuck in a pipe read keeps its slot: do not recycle then)
+            for st in all_slots:
+                _give_stage(st)
     if errors:
         raise errors[0]
     fout.flush()

@@ -51,7 +51,12 @@ for i in range(iters):
     pipe.set_option(E.OPT_MAX_BATCH, mb)
     layer.set_option(E.OPT_MAX_BATCH, mb)
     pipe.reset_stats()
-    pipe.run_batch_device(x, ya, n, h, w, tile, 10, sync=True)
+    try:  # the persistent schedule explicitly (the narrow HurrDeblur network defaults to one launch per layer) ...
+        pipe.set_option(E.OPT_IMPL, E.IMPL_PIPELINED)
+        pipe.run_batch_device(x, ya, n, h, w, tile, 10, sync=True)
+    except E.EngineError:  # ... unless layers x bands does not fit the device: whatever `auto` picks
+        pipe.set_option(E.OPT_IMPL, E.IMPL_AUTO)
+        pipe.run_batch_device(x, ya, n, h, w, tile, 10, sync=True)
     used_pipe = pipe.stat(E.STAT_PIPE_LAUNCHES) > 0
     layer.run_batch_device(x, yb, n, h, w, tile, 10, sync=True)
     same = bool(torch.equal(ya, yb))

@@ -172,6 +172,15 @@ def test_three_device_schedules_agree(E, engines, model_dir):
     c = pipe.run_u8(img)
     pipe.set_option(E.OPT_RING_ROWS, 0)
     assert np.array_equal(layer.run_u8(img), c)
+    # the narrow nf = 24 network: `auto` = one launch per layer (measured 2.7x faster than its persistent grid); the
+    # persistent schedule stays available on request and must agree bit for bit
+    hurr = E.Engine.from_files(model_dir, HURR, 0)
+    img = natural(90, 500, seed=3)
+    a = hurr.run_u8(img, tile=0, halo=0)
+    assert hurr.stat(E.STAT_PIPE_LAUNCHES) == 0 and hurr.stat(E.STAT_TC_LAUNCHES) == 10 and hurr.stat(E.STAT_PIPE_FALLBACKS) == 0
+    hurr.set_option(E.OPT_IMPL, E.IMPL_PIPELINED)
+    assert np.array_equal(hurr.run_u8(img, tile=0, halo=0), a) and hurr.stat(E.STAT_PIPE_LAUNCHES) == 1
+    hurr.close()
     simple.close()
     layer.close()
 

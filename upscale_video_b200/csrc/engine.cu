@@ -171,6 +171,8 @@ struct Plan {
     }
 };
 
+#define B2SR_DBG_WORDS (320 * 16)  // stall-accounting words: up to 320 CTAs (two per SM) x 16
+
 struct ProfRec {
     cudaEvent_t a, b;
     int kind;  // 0 other, 1 tcgen05 mid conv
@@ -785,6 +787,13 @@ static bool pipe_fits(const b2sr_ctx* c, const Plan* P) {
     return !c->pipe_unavailable && L <= B2SR_PIPE_MAX_LAYERS && P->nb >= 1 && (int64_t)L * P->nb <= usable_sms(c);
 }
 
+// Which schedule `impl = 0` (auto) picks.  Measured on B200 (tools/hurr_check.py, 8 frames per pass): for the nf = 24 network
+// (1x_HurrDeblur) one launch per layer is 2.7x FASTER than the persistent grid -- 0.164 vs 0.445 ms per 540p frame: its layers
+// are issue-bound (~1 000 cycles per band row for 288 cycles of MMAs), the persistent grid only occupies layers x bands = 80 SMs,
+// and the 64-byte-per-pixel activations cost little HBM time -- so the persistent schedule is the default for 64-channel
+// networks only (there it removes 9 GB of activation traffic per frame).
+static bool auto_pipe(const b2sr_ctx* c) { return c->impl == 3 || (c->impl == 0 && c->CF > 32); }
+
 #define B2SR_PIPE_REFUSED 1  // (positive: not an error code of the ABI)
 
 template <int CF, int NL, int S, bool F32OUT>
@@ -867,8 +876,8 @@ static int run_pipe(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, 
     PipeParams Q{};
     Q.n_layers = L, Q.nb = nb;
     if (c->pipe_debug) {
-        if (!c->d_dbg) CUDA_TRY(cudaMalloc(&c->d_dbg, 148 * 16 * sizeof(long long)));
-        CUDA_TRY(cudaMemsetAsync(c->d_dbg, 0, 148 * 8 * sizeof(long long), c->stream));
+        if (!c->d_dbg) CUDA_TRY(cudaMalloc(&c->d_dbg, B2SR_DBG_WORDS * sizeof(long long)));
+        CUDA_TRY(cudaMemsetAsync(c->d_dbg, 0, B2SR_DBG_WORDS * sizeof(long long), c->stream));
         Q.dbg = c->d_dbg;
     }
     uint32_t* done = P->d_flags;
@@ -914,7 +923,7 @@ static int run_pipe(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, 
     TRY(prof_end(c));
     c->n_launch += 1, c->n_tc += 1, c->n_pipe += 1;
     if (c->pipe_debug) {
-        std::vector<long long> h(148 * 8);
+        std::vector<long long> h(B2SR_DBG_WORDS);
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         CUDA_TRY(cudaMemcpy(h.data(), c->d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         fprintf(stderr, "b2sr pipe timing, %% of CTA time, mean over %d bands: layer kcycles | producer: starved(done) wait-empty | mma: wait-full wait-tempty | epilogue w2: back-pressure wait-tfull\n", nb);
@@ -1753,7 +1762,7 @@ static int prepare_segments(b2sr_ctx* c, Plan* P) {
         c->cap_frings = need;
         c->fring_gen += 1;
     }
-    if (c->pipe_debug && !c->d_dbg) CUDA_TRY(cudaMalloc(&c->d_dbg, 148 * 16 * sizeof(long long)));
+    if (c->pipe_debug && !c->d_dbg) CUDA_TRY(cudaMalloc(&c->d_dbg, B2SR_DBG_WORDS * sizeof(long long)));
     const uint64_t key = (c->fbuf_gen << 24) ^ (c->fring_gen << 8) ^ (uint64_t)RR ^ ((uint64_t)P->Wmax << 44) ^ ((uint64_t)(c->pipe_debug != 0) << 60);
     if (P->fstages_key == key && P->d_fstages) return 0;
     int seg_max = 0;
@@ -1776,6 +1785,7 @@ static int prepare_segments(b2sr_ctx* c, Plan* P) {
             p.items = P->d_pitems, p.item_first = P->d_pband_first;
             p.pair = 0, p.flip = 0, p.dbg = c->pipe_debug ? c->d_dbg : nullptr;
             p.half = st.half, p.variant = st.variant;
+            p.nogate = getenv("B2SR_SEG_NOGATE") && atoi(getenv("B2SR_SEG_NOGATE")) != 0;
             p.nb = nb, p.RR = RR, p.Wmax = P->Wmax;
             p.ring_map_base = (int)c->flaunch.size() * G + sg * G;
             if (st.in_inst >= 0) {
@@ -1857,7 +1867,7 @@ static int launch_segment(b2sr_ctx* c, Plan* P, const FusedSegment& S) {
     TRY(prof_end(c));
     c->n_launch += 1, c->n_tc += 1, c->n_pipe += 1;
     if (c->pipe_debug && S.stage_base == 0) {  // stall accounting of the first segment (synchronises)
-        std::vector<long long> h(148 * 16);
+        std::vector<long long> h(B2SR_DBG_WORDS);
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         CUDA_TRY(cudaMemcpy(h.data(), c->d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         fprintf(stderr, "b2sr segment ops %d..%d, %d stages x %d bands; per stage, mean over bands, kcycles: issuer total | issuer waits: data (full) tmem (tempty) | "
@@ -2007,8 +2017,8 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
             }
             const bool dbg = c->pipe_debug && (li < c->pipe_debug || li >= (int)c->flaunch.size() - 5);
             if (dbg) {
-                if (!c->d_dbg) CUDA_TRY(cudaMalloc(&c->d_dbg, 148 * 16 * sizeof(long long)));
-                CUDA_TRY(cudaMemsetAsync(c->d_dbg, 0, 148 * 16 * sizeof(long long), c->stream));
+                if (!c->d_dbg) CUDA_TRY(cudaMalloc(&c->d_dbg, B2SR_DBG_WORDS * sizeof(long long)));
+                CUDA_TRY(cudaMemsetAsync(c->d_dbg, 0, B2SR_DBG_WORDS * sizeof(long long), c->stream));
                 p.dbg = c->d_dbg;
             }
             TRY(prof_begin(c, 1, R->out_px));
@@ -2049,7 +2059,7 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
             TRY(rc);
             TRY(prof_end(c));
             if (dbg) {
-                std::vector<long long> h(148 * 16);
+                std::vector<long long> h(B2SR_DBG_WORDS);
                 CUDA_TRY(cudaStreamSynchronize(c->stream));
                 CUDA_TRY(cudaMemcpy(h.data(), c->d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
                 double v[16] = {0};
@@ -2104,7 +2114,7 @@ static int run_plan(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out, 
     if (c->family == B2SR_FAMILY_FUSED) return run_fused(c, P, d_frames, d_out, f32out, -1);
     const int nl = (int)c->layers.size();
     if (upto < 0 || upto >= nl) upto = nl - 1;
-    if (upto == nl - 1 && (c->impl == 0 || c->impl == 3)) {  // whole network: pipelined schedule when it fits the GPU
+    if (upto == nl - 1 && auto_pipe(c)) {  // whole network: persistent schedule when it fits the GPU (and pays: auto_pipe)
         if (pipe_fits(c, P)) {
             const int rc = run_pipe(c, P, d_frames, d_out, f32out);
             if (rc != B2SR_PIPE_REFUSED) return rc;
@@ -2183,7 +2193,7 @@ static int frames_per_pass(const b2sr_ctx* c, int h, int w, int tile) {
     const double px = (double)h * w * 1.06;
     // the pipelined schedule keeps only the 16-channel input planes per frame: long passes amortise its fill/drain
     const int tw = tile > 0 ? std::min(w, tile + 20) : w;
-    const bool pipe = (c->impl == 0 || c->impl == 3) && !c->pipe_unavailable && (int64_t)c->layers.size() * ((tw + TC_BW - 1) / TC_BW) <= usable_sms(c);
+    const bool pipe = auto_pipe(c) && !c->pipe_unavailable && (int64_t)c->layers.size() * ((tw + TC_BW - 1) / TC_BW) <= usable_sms(c);
     if (pipe) return (int)std::max(1.0, std::min(32.0, floor(7.0e7 / px)));
     return (int)std::max(1.0, std::min(16.0, floor(9.0e6 / px)));
 }

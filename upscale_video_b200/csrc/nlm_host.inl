@@ -182,11 +182,12 @@ static int nlm_launch(b2sr_nlm* c, const uint8_t* d_in, long long in_frame_strid
     // Rows per warp tile (B2SR_NLM_TH overrides): fewer rows = more template-halo rework (20/16 -> 16/12 -> 12/8 rows walked per
     // output row) but fewer accumulators per lane (80 -> 60 -> 40) and more resident warps.  Measured on B200, 16 frames of
     // 1080p per launch (profiles/r02i_checks.log): packed variant (levels <= 6) 16 rows 3 319 / 12 rows 3 388 / 8 rows 3 235
-    // frames/s; generic variant (level 10) 2 608 / 2 500 / 2 902 -- so 12 rows for the packed kernel, 8 for the generic one.
+    // frames/s (within run-to-run noise: the bench measured 2 824 with 12 rows against 3 015 - 3 078 with 16 on other boxes);
+    // generic variant (level 10) 2 608 / 2 500 / 2 902 -- so 16 rows stay for the packed kernel, 8 for the generic one.
     static const int th_env = getenv("B2SR_NLM_TH") ? atoi(getenv("B2SR_NLM_TH")) : 0;
     static const bool allow_packed = !(getenv("B2SR_NLM_PACKED") && atoi(getenv("B2SR_NLM_PACKED")) == 0);
     const bool packed = allow_packed && c->n_l <= NLM_PACK_MAX_TABLE && c->n_ab <= NLM_PACK_MAX_TABLE;
-    const int TH = (th_env == 8 || th_env == 12 || th_env == 16) ? th_env : (packed ? 12 : 8);
+    const int TH = (th_env == 8 || th_env == 12 || th_env == 16) ? th_env : (packed ? 16 : 8);
     P.tiles_per_frame = P.tiles_x * ((h + TH - 1) / TH);
     P.n_tiles = (long long)P.tiles_per_frame * n;
     memcpy(P.fwd, c->host_tabs.fwd, sizeof P.fwd);

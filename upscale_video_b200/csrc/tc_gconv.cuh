@@ -79,6 +79,7 @@ struct TcgParams {
     int32_t n_bp;               // stages whose `done` frees this stage's output ring slots (the last op that reads them): 0..2
     const uint32_t* bp[2];
     int32_t variant;            // which template instance runs this stage (tcg_pipe_kernel)
+    int32_t nogate;             // measurement only (B2SR_SEG_NOGATE=1): ignore every counter -- stages free-run on stale data, results are garbage
     int32_t half;               // which 32-channel half of a 64-channel convolution this stage computes (weights / bias /
                                 // output / residual slices are offset like a cluster rank's in the paired launch)
 };
@@ -262,7 +263,7 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
                         if (ring_in && y >= 0 && y < I.Ht) {
                             const uint32_t gy = (uint32_t)(I.grow0 + y);
                             ry = (int)(gy % RR);
-                            if (seen < gy + 1u) {  // rows 0..gy of bands b-1, b, b+1 of the gating stages written and released?
+                            if (seen < gy + 1u && !P.nogate) {  // rows 0..gy of bands b-1, b, b+1 of the gating stages written and released?
                                 const long long t0 = clock64();
                                 while ((seen = *s_avail) < gy + 1u) {
                                     __nanosleep(20);
@@ -466,7 +467,7 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
                     // A residual that lives in a ring is prefetched long before this row's accumulator is complete, so the
                     // prefetch needs its own gate: the row was written by the gating op p* itself (published once done >= grow + 1)
                     // or by an op p* reads through its ring inputs (published before p* could finish row grow - 1).
-                    if ((P.res_ring[0] || P.res_ring[1]) && av_seen < grow + 1u) {
+                    if ((P.res_ring[0] || P.res_ring[1]) && av_seen < grow + 1u && !P.nogate) {
                         const long long t0 = clock64();
                         while ((av_seen = *s_avail) < grow + 1u) {
                             __nanosleep(20);
@@ -532,7 +533,7 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
                     // The ring slot of this row still holds row grow - RR.  Input row i is read by output rows i-1, i, i+1 of
                     // the stages that read this ring (and by their epilogues as a residual of row i): all of that is over
                     // once those stages have FINISHED rows 0..i+1, i.e. done >= i + 2, on bands b-1..b+1.
-                    if (ring_out && grow + 2u > RR && bp_seen < grow + 2u - RR) {
+                    if (ring_out && grow + 2u > RR && bp_seen < grow + 2u - RR && !P.nogate) {
                         const long long t0 = clock64();
                         while ((bp_seen = *s_bpmin) < grow + 2u - RR) {
                             __nanosleep(20);
@@ -847,8 +848,19 @@ struct TcgPipeParams {
 
 __global__ void __launch_bounds__(TC_THREADS, 1) tcg_pipe_kernel(const __grid_constant__ TcgPipeParams Q) {
     extern __shared__ uint8_t smem_raw[];
+    // The stage's parameters live in SHARED memory: the per-launch kernel reads them from the constant bank (kernel
+    // parameter), a local-memory copy here turned every P.field of the epilogue into a local load that misses the small L1
+    // the streaming loads and stores keep flushing -- measured 10 000 - 14 000 cycles per row and warp in the residual
+    // epilogues, 6 x what they take with the parameters in shared memory.
+    __shared__ TcgParams sP;
     const int stage = (int)blockIdx.x / Q.nb, band = (int)blockIdx.x % Q.nb;
-    const TcgParams P = Q.stages[stage];
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(Q.stages + stage);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sP);
+        for (int i = threadIdx.x; i < (int)(sizeof(TcgParams) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const TcgParams& P = sP;
     const int it_begin = P.item_first[band], it_end = P.item_first[band + 1];
     switch (P.variant) {
         case B2SR_TCG_VARIANT_PLAIN: tcg_body<32, 0, false, 0, 1, false, false, true>(P, it_begin, it_end, band, (uint32_t)P.half, smem_raw); break;

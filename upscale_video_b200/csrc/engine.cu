@@ -1853,7 +1853,8 @@ static int launch_segment(b2sr_ctx* c, Plan* P, const FusedSegment& S) {
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
+    static const bool coop = !(getenv("B2SR_COOP") && atoi(getenv("B2SR_COOP")) == 0);  // (profiling aid, see launch_pipe)
+    cfg.attrs = attr, cfg.numAttrs = coop ? 1 : 0;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, tcg_pipe_kernel, Q);
     if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
         cudaGetLastError();

@@ -728,6 +728,11 @@ static int tc_layer(b2sr_ctx* c, Plan* P, int li, int in_buf, void* out, const u
         p.acc_scale = first ? (1.f / 255.f) : 1.f;
         p.out = out;
         p.frames_in = frames, p.frame_h = fh, p.frame_w = fw, p.scale = c->desc.scale;
+        if (c->pipe_debug) {
+            if (!c->d_dbg) CUDA_TRY(cudaMalloc(&c->d_dbg, B2SR_DBG_WORDS * sizeof(long long)));
+            CUDA_TRY(cudaMemsetAsync(c->d_dbg, 0, B2SR_DBG_WORDS * sizeof(long long), c->stream));
+            p.dbg = c->d_dbg;
+        }
         TRY(prof_begin(c, (!first && !last) ? 1 : 0, P->out_px));
         int rc = B2SR_E_UNSUPPORTED;
         const int CF = c->CF, S = c->desc.scale;
@@ -750,6 +755,16 @@ static int tc_layer(b2sr_ctx* c, Plan* P, int li, int in_buf, void* out, const u
         }
         TRY(rc);
         TRY(prof_end(c));
+        if (c->pipe_debug) {  // stall accounting of this layer's launch (synchronises)
+            std::vector<long long> h(B2SR_DBG_WORDS);
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            CUDA_TRY(cudaMemcpy(h.data(), c->d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int k = 0; k < P->n_cta; ++k)
+                for (int j = 0; j < 8; ++j) v[j] += (double)h[(size_t)k * 8 + j] / P->n_cta;
+            fprintf(stderr, "b2sr layer %2d (%d CTAs), kcycles mean: producer total %7.0f (wait slot %6.0f) | issuer: wait data %6.0f, wait tmem %6.0f | epilogue w2: wait tfull %6.0f\n",
+                    li, P->n_cta, v[0] / 1e3, v[6] / 1e3, v[3] / 1e3, v[4] / 1e3, v[5] / 1e3);
+        }
     }
     return 0;
 }

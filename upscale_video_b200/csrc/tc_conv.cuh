@@ -103,7 +103,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who
     }
 }
 __device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, int who, long long& waited) {
-    if (mbar_try_wait(bar, parity)) return;
+    if (mbar_test_wait(bar, parity)) return;  // (test_wait never suspends: a true result costs nothing and counts nothing)
     const long long t0 = clock64();
     mbar_wait(bar, parity, who);
     waited += clock64() - t0;
@@ -490,7 +490,7 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
                 }
             }
             if (ring_in) atomicAdd(s_finished, 1u);
-            if (PIPE && P.dbg) {
+            if (P.dbg) {
                 P.dbg[0] = clock64() - t_begin;
                 P.dbg[1] = waited;
                 P.dbg[6] = w_empty;
@@ -585,7 +585,7 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
             }
             g0 += (uint32_t)rows;
         }
-        if (PIPE && P.dbg && lane == 0) {
+        if (P.dbg && lane == 0) {
             P.dbg[3] = w_full;
             P.dbg[4] = w_tempty;
         }
@@ -832,7 +832,7 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
             }
         }
         if (ring_out && lane == 0) atomicAdd(s_finished, 1u);
-        if (PIPE && P.dbg && warp == 2 && lane == 0) {
+        if (P.dbg && warp == 2 && lane == 0) {
             P.dbg[2] = waited;
             P.dbg[5] = w_tfull;
         }
@@ -854,6 +854,12 @@ __device__ __forceinline__ void tc_conv_body(const TcParams& P, const int it_beg
 template <int CPIX, int NOUT, int SHUF, bool F32OUT>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const __grid_constant__ TcParams P) {
     extern __shared__ uint8_t smem_raw[];
+    if (P.dbg) {  // optional stall accounting (B2SR_OPT_PIPE_DEBUG): this CTA's 8 words
+        TcParams Q = P;
+        Q.dbg = P.dbg + (size_t)blockIdx.x * 8;
+        tc_conv_body<CPIX, NOUT, SHUF, F32OUT, false>(Q, Q.item_first[blockIdx.x], Q.item_first[blockIdx.x + 1], 0, smem_raw);
+        return;
+    }
     tc_conv_body<CPIX, NOUT, SHUF, F32OUT, false>(P, P.item_first[blockIdx.x], P.item_first[blockIdx.x + 1], 0, smem_raw);
 }
 

@@ -122,6 +122,16 @@ def test_other_models_vs_oracle(model, scale, engines, oracle_models):
     assert_parity(got, ref, model)
 
 
+@pytest.mark.parametrize("h,w", [(20, 960), (20, 961), (20, 969), (20, 970), (20, 971), (20, 1920), (20, 1921), (961, 40), (970, 24)])
+def test_tile_boundary_sizes(h, w, engines, oracle_models):
+    """Frame sizes on and around the reference's tile arithmetic (960-px tiles, a 10-px halo only where >= 10 px of image
+    remain on that side, reference :409-427): one tile exactly, one tile + 1..11 columns (the second tile is narrower than
+    its halo), two tiles exactly, and the same in y."""
+    img = natural(h, w, seed=h + w)
+    ref = oracle.upscale_image_array(oracle_models("2x_Compact_Pretrain"), img, 2, "f32")
+    assert_parity(engines("2x_Compact_Pretrain").run_u8(img), ref, "%dx%d" % (h, w))
+
+
 def test_tile_seams_four_tiles(engines, oracle_models):
     """A frame with seams in both directions (2 x 2 reference tiles): 980 x 1000."""
     img = natural(980, 1000, seed=11)
@@ -310,6 +320,17 @@ def test_strides_and_device_memory(E, engines):
     d_out = torch.zeros((74, 262, 3), dtype=torch.uint8, device="cuda")
     rc = lib.b2sr_run_u8(eng._h, d_in.data_ptr(), 37, 131, 0, d_out.data_ptr(), 0, 960, 10, E.MEM_DEVICE)
     assert rc == 0 and np.array_equal(d_out.cpu().numpy(), ref)
+    # device frames at every byte alignment, and ending exactly at the end of their allocation: the first layer copies the
+    # frame rows as ALIGNED 4-byte words (cp.async) and fetches the words that straddle either end of the buffer byte by byte
+    for shift in (1, 2, 3):
+        for (h, w) in ((37, 131), (5, 1), (3, 130), (9, 257)):
+            im = natural(h, w, seed=100 + shift)
+            want = eng.run_u8(im)
+            buf = torch.zeros(h * w * 3 + shift, dtype=torch.uint8, device="cuda")  # frame occupies the LAST h*w*3 bytes
+            buf[shift:] = torch.from_numpy(im.reshape(-1)).cuda()
+            out = torch.zeros((h * 2, w * 2, 3), dtype=torch.uint8, device="cuda")
+            rc = lib.b2sr_run_batch_device(eng._h, buf.data_ptr() + shift, out.data_ptr(), 1, h, w, 960, 10, 1)
+            assert rc == 0 and np.array_equal(out.cpu().numpy(), want), (shift, h, w)
 
 
 def test_errors_are_codes_not_crashes(E, engines):

@@ -78,6 +78,11 @@ extern "C" {
 #define B2SR_OPT_SEG_PIPE 7    /* fused family: 1 = runs of convolutions as persistent segment launches (an RRDB of 4x_Valar_v1 = one
                                   cooperative launch, dense-block buffers in L2-resident rings: 8.8x less DRAM traffic, bit-identical
                                   results, but measured slower on B200 -- DESIGN.md section 3), 0 (default) = one launch per convolution */
+#define B2SR_OPT_PAIR2 8       /* fused family: 1 = dense-block convolutions in the CTA-pair form (2-CTA clusters over band pairs,
+                                  tcgen05.mma.cta_group::2, M = 256: one instruction stream per two bands, half of the stacked weights per
+                                  CTA; same results for the 32-channel convolutions, <= 1 LSB apart for the 64-channel ones whose
+                                  accumulator ring is shorter; measured 33.4 vs 28.3 ms per 540p frame on B200 -- DESIGN.md section 3),
+                                  0 (default) = one CTA per band */
 
 /* b2sr_get_stat keys */
 #define B2SR_STAT_LAUNCHES 1       /* kernels launched by this context since creation / last reset */

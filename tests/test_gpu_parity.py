@@ -517,6 +517,40 @@ def test_valar_rrdb_fused_tcgen05(E, model_dir, oracle_models):
     eng.close()
 
 
+def test_valar_cta_pair_schedule(E, model_dir, oracle_models):
+    """The opt-in CTA-pair form of the dense-block convolutions (B2SR_OPT_PAIR2: 2-CTA clusters over band pairs,
+    tcgen05.mma.cta_group::2 with M = 256, phantom rows above and below every CTA range): an odd band count (the last
+    pair's second CTA has no columns), seams, several planes per pass, ranges cut inside bands.  The 32-channel convolutions
+    accumulate in the same order as the default schedule; the 64-channel ones use a 6-block instead of an 8-block accumulator
+    ring, so rows whose sum is split over an extension block differ in the last fp32 bit: the schedules agree within 1 LSB
+    and both meet the oracle."""
+    import torch
+    if not os.path.exists(os.path.join(model_dir, "4x_Valar_v1.b2sr")):
+        pytest.skip("4x_Valar_v1 not packaged")
+    eng = E.Engine.from_files(model_dir, "4x_Valar_v1", 0)
+    models = oracle_models("4x_Valar_v1")
+    img = natural(37, 300, seed=14)  # three bands: one full pair + a pair whose second band is empty
+    base = eng.run_u8(img)
+    eng.set_option(E.OPT_PAIR2, 1)
+    eng.reset_stats()
+    pair = eng.run_u8(img)
+    assert eng.stat(E.STAT_TC_LAUNCHES) == 420 - 69
+    d = np.abs(pair.astype(int) - base.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.06, "pair form vs default: max %d, %.3f%%" % (d.max(), 100 * (d > 0).mean())
+    assert_parity(pair, oracle.upscale_image_array(models, img, 4, "f32"), "valar 37x300 (cta pairs)", max_mismatch=0.05)
+    assert np.array_equal(pair, eng.run_u8(img)), "pair form is not deterministic"
+    frames = np.stack([natural(150, 1000, seed=s) for s in (31, 32)])  # two tiles per frame (seam at 960), 8 + 1 bands
+    d_in = torch.from_numpy(frames).cuda()
+    d_a = torch.empty((2, 600, 4000, 3), dtype=torch.uint8, device="cuda")
+    d_b = torch.empty_like(d_a)
+    eng.run_batch_device(d_in, d_a, 2, 150, 1000, sync=True)
+    eng.set_option(E.OPT_PAIR2, 0)
+    eng.run_batch_device(d_in, d_b, 2, 150, 1000, sync=True)
+    dd = (d_a.to(torch.int16) - d_b.to(torch.int16)).abs()
+    assert int(dd.max()) <= 1 and float((dd > 0).float().mean()) < 0.06
+    eng.close()
+
+
 @pytest.mark.parametrize("shape", [(1, 1), (2, 3), (3, 129), (9, 128), (17, 257)])
 def test_valar_edge_shapes(E, model_dir, oracle_models, shape):
     """Degenerate and band-boundary shapes through the fused tcgen05 graph kernels: 1-pixel planes (every tap but the

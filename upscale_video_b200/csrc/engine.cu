@@ -106,7 +106,7 @@ struct Group {  // planes of identical size share one TMA tensor map per activat
 };
 
 struct ResItems {  // work items of the planes scaled to resolution factor `res` (fused graph family), cut into <= max_cta ranges
-    int res = 1, max_cta = 0;
+    int res = 1, max_cta = 0, pairs = 0;  // pairs: items are band PAIRS (256 columns), one range per 2-CTA cluster
     std::vector<TcItem> items;
     std::vector<int> first;
     TcItem* d_items = nullptr;
@@ -234,6 +234,9 @@ struct b2sr_ctx {
     std::vector<b2sr_fused_op> fops;
     std::vector<b2sr_fused_buf> fbufs;
     std::vector<FusedLaunch> flaunch;
+    std::vector<FusedLaunch> flaunch2;  // CTA-pair (cta_group::2) form of the ops that have one: whole convolution, full weight image
+    std::vector<int> fop_pair2;         // op -> index into flaunch2, or -1
+    int pair2 = 0;                      // use the CTA-pair form where it exists (B2SR_PAIR2=1 / B2SR_OPT_PAIR2); measured slower: opt-in
     std::vector<int> fop_first;   // launches of op i: flaunch[fop_first[i] .. fop_first[i+1])
     std::vector<void*> fbuf_ptr;
     std::vector<size_t> fbuf_cap;  // bytes
@@ -358,9 +361,10 @@ extern "C" void b2sr_destroy(b2sr_ctx* c) {
     }
     for (float* p : c->slot_buf)
         if (p) cudaFree(p);
-    for (auto& L : c->flaunch)
-        for (void* p : {(void*)L.wimg, (void*)L.wimg_flip, (void*)L.bias, (void*)L.slope})
-            if (p) cudaFree(p);
+    for (auto* vec : {&c->flaunch, &c->flaunch2})
+        for (auto& L : *vec)
+            for (void* p : {(void*)L.wimg, (void*)L.wimg_flip, (void*)L.bias, (void*)L.slope})
+                if (p) cudaFree(p);
     for (void* p : c->fbuf_ptr)
         if (p) cudaFree(p);
     for (void* p : {(void*)c->in16, (void*)c->ping, (void*)c->pong, (void*)c->lastf, (void*)c->d_in, (void*)c->d_out,
@@ -1138,7 +1142,7 @@ static int run_graph(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
                         const unsigned nbw = (unsigned)(((H + GW_TY - 1) / GW_TY) * ((W + GW_TX - 1) / GW_TX));
 #define WMMA_CASE(kk, nf)                                                                                                   \
     if (o.k == kk && o.cout == nf * 16) {                                                                                   \
-        CUDA_TRY(cudaFuncSetAttribute(g_conv_wmma_kernel<kk, nf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        CUDA_TRY(cudaFuncSetAttribute(g_conv_wmma_kernel<kk, nf>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2SR_SMEM_LIMIT)); \
         g_conv_wmma_kernel<kk, nf><<<nbw, GW_THREADS, smem, c->stream>>>(in0, ld0, H, W, o.cin, g.wh, g.b, o.act, o.slope, outp, ldo); \
     }
                         WMMA_CASE(3, 2)
@@ -1504,6 +1508,24 @@ static int plan_fused_launches(b2sr_ctx* c, const float* wb) {
         }
     }
     c->fop_first.push_back((int)c->flaunch.size());
+    // CTA-pair form: the whole convolution (all output channels) as one launch of 2-CTA clusters over band pairs; every CTA
+    // keeps half of the stacked weights, so even the 192 -> 64 convolution (221 KB) fits
+    c->fop_pair2.assign(n_ops, -1);
+    for (int i = 0; i < n_ops && !rc; ++i) {
+        const b2sr_fused_op& o = c->fops[i];
+        if (o.type != B2SR_FOP_CONV || o.k != 3 || o.final || o.in_buf < 0 || (o.cout != 32 && o.cout != 64)) continue;
+        const int G = (o.cin + 63) / 64;
+        const bool sc = o.sc_cin != 0;
+        const int fit = sc ? TcgCfg<32, 0, true>::ring_fit2(G) : (o.cout == 64 ? TcgCfg<64, 0>::ring_fit2(G) : TcgCfg<32, 0>::ring_fit2(G));
+        if (fit < 4 || (sc && o.cout != 32)) continue;
+        FusedLaunch L;
+        L.op = i, L.co0 = 0, L.nco = o.cout, L.NOUT = o.cout, L.G = G, L.cinp = o.cin, L.pair = 0;
+        L.sc_ks = o.sc_cin / 16;
+        L.slots = std::min(12, fit);
+        if (wb) rc = upload_fused_launch(L, o, wb, false);
+        c->fop_pair2[i] = (int)c->flaunch2.size();
+        c->flaunch2.push_back(L);
+    }
     return rc;
 }
 
@@ -1603,6 +1625,8 @@ extern "C" int b2sr_create_fused(b2sr_ctx** out, int device, const b2sr_fused_op
         // the maximum -- the set-aside starves the normal L2 traffic (halo re-reads, weights, fp32 trunk), so it is off.
         const char* ce = getenv("B2SR_PAIR");
         if (ce && atoi(ce) == 0) c->pair_halves = 0;
+        const char* c2 = getenv("B2SR_PAIR2");
+        if (c2) c->pair2 = atoi(c2) != 0;
         const char* pe = getenv("B2SR_PDL");
         if (pe && atoi(pe) == 0) c->pdl = 0;
         const char* le = getenv("B2SR_L2_PROMO");
@@ -1647,16 +1671,17 @@ extern "C" int b2sr_create_fused(b2sr_ctx** out, int device, const b2sr_fused_op
 
 // work items of the plan's planes at resolution factor `res`: the linear sequence (plane, band, row) cut into one
 // contiguous, equally long range per CTA (as build_plan does for res = 1)
-static int fused_items(b2sr_ctx* c, Plan* P, int res, int max_cta, ResItems** out) {
+static int fused_items(b2sr_ctx* c, Plan* P, int res, int max_cta, ResItems** out, int pairs = 0) {
     for (auto& r : P->res_items)
-        if (r->res == res && r->max_cta == max_cta) {
+        if (r->res == res && r->max_cta == max_cta && r->pairs == pairs) {
             *out = r.get();
             return 0;
         }
     std::unique_ptr<ResItems> R(new ResItems());
-    R->res = res, R->max_cta = max_cta;
+    R->res = res, R->max_cta = max_cta, R->pairs = pairs;
+    const int BW = pairs ? 2 * TC_BW : TC_BW;  // columns per item
     int64_t band_rows = 0;
-    for (const PlaneDev& pd : P->planes) band_rows += (int64_t)pd.Ht * res * ((pd.Wt * res + TC_BW - 1) / TC_BW);
+    for (const PlaneDev& pd : P->planes) band_rows += (int64_t)pd.Ht * res * ((pd.Wt * res + BW - 1) / BW);
     const int ncta = (int)std::min<int64_t>(max_cta, band_rows);
     R->first.assign(1, 0);
     int64_t pos = 0;
@@ -1665,14 +1690,14 @@ static int fused_items(b2sr_ctx* c, Plan* P, int res, int max_cta, ResItems** ou
     for (size_t pi = 0; pi < P->planes.size(); ++pi) {
         const PlaneDev& pd = P->planes[pi];
         const int Ht = pd.Ht * res, Wt = pd.Wt * res;
-        for (int x0 = 0; x0 < Wt; x0 += TC_BW) {
+        for (int x0 = 0; x0 < Wt; x0 += BW) {
             int y0 = 0;
             while (y0 < Ht) {
                 const int64_t room = cut_at(cta + 1) - pos;
                 const int rows = (int)std::min<int64_t>(Ht - y0, room);
                 TcItem it{};
                 it.map = P->plane_group[pi], it.plane = pd.gplane, it.x0 = x0, it.y0 = y0;
-                it.rows = rows, it.w = std::min(TC_BW, Wt - x0);
+                it.rows = rows, it.w = std::min(BW, Wt - x0);
                 it.Ht = Ht, it.Wt = Wt, it.pix_off = pd.pix_off * res * res;
                 it.frame = pd.frame, it.fy0 = pd.fy0 * res, it.fx0 = pd.fx0 * res;
                 it.cy0 = pd.cy0 * res, it.cy1 = pd.cy1 * res, it.cx0 = pd.cx0 * res, it.cx1 = pd.cx1 * res;
@@ -1700,7 +1725,9 @@ template <int NOUT, int MODE, bool F32OUT, int NRES, int OUTS, bool RF16 = false
 static int launch_tcg(b2sr_ctx* c, const FusedLaunch& L, const ResItems* R, const TcgParams& p) {
     auto kern = tcg_conv_kernel<NOUT, MODE, F32OUT, NRES, OUTS, RF16, SC>;
     const int smem = TcgCfg<NOUT, MODE, SC>::smem_bytes(L.G, L.slots);
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // (the attribute is per function and process-wide: always the limit, so that engines of other threads that launch the same
+    // instance with another ring depth can never lower it under a launch in flight)
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B2SR_SMEM_LIMIT));
     // programmatic dependent launch: this launch's prologue (barrier init, TMEM allocation, weight load) overlaps the tail
     // of the previous launch of the stream; the kernel waits (griddepcontrol.wait) before it touches activation buffers
     cudaLaunchConfig_t cfg{};
@@ -1752,6 +1779,14 @@ static void fused_fill_params(b2sr_ctx* c, Plan* P, int li, void* d_out, TcgPara
     p.frames_out = d_out, p.frame_h = P->h * o.res, p.frame_w = P->w * o.res;
 }
 
+
+// Parameters of the CTA-pair form of op i: the op's first ordinary launch supplies the input maps (same input view).
+static void fused_fill_params2(b2sr_ctx* c, Plan* P, int i, const FusedLaunch& L, TcgParams& p) {
+    fused_fill_params(c, P, c->fop_first[i], nullptr, p);  // maps, residuals, outputs (channel offset 0 of the op)
+    p.wimg = L.wimg, p.bias = L.bias, p.slope = L.slope;
+    p.groups = L.G, p.cin = L.cinp, p.ring_slots = L.slots, p.sc_ks = L.sc_ks;
+    p.pair = 0, p.pair_wbytes = 0, p.flip = 0;
+}
 
 // Ring arena layout, ring tensor maps and the stage table of every pipelined segment, for the planes of P.
 static int prepare_segments(b2sr_ctx* c, Plan* P) {
@@ -1856,7 +1891,7 @@ static int launch_segment(b2sr_ctx* c, Plan* P, const FusedSegment& S) {
         const FusedLaunch& L = c->flaunch[st.launch];
         smem = std::max(smem, L.sc_ks ? TcgCfg<32, 0, true>::smem_bytes(L.G, L.slots) : TcgCfg<32, 0>::smem_bytes(L.G, L.slots));
     }
-    CUDA_TRY(cudaFuncSetAttribute(tcg_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(tcg_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2SR_SMEM_LIMIT));
     CUDA_TRY(cudaMemsetAsync(P->d_fflags, 0, (size_t)ns * nb * B2SR_FLAG_STRIDE * sizeof(uint32_t), c->stream));
     TcgPipeParams Q{};
     Q.stages = P->d_fstages + S.stage_base, Q.n_stages = ns, Q.nb = nb;
@@ -1897,6 +1932,50 @@ static int launch_segment(b2sr_ctx* c, Plan* P, const FusedSegment& S) {
         }
     }
     return 0;
+}
+
+template <int NOUT, int NRES, int OUTS, bool RF16 = false, bool SC = false>
+static int launch_tcg2(b2sr_ctx* c, const FusedLaunch& L, const ResItems* R, const TcgParams& p) {
+    auto kern = tcg_pair2_kernel<NOUT, NRES, OUTS, RF16, SC>;
+    const int smem = TcgCfg<NOUT, 0, SC>::smem_bytes2(L.G, L.slots);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B2SR_SMEM_LIMIT));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(R->n_cta * 2)), cfg.blockDim = dim3(TC_THREADS), cfg.dynamicSmemBytes = (size_t)smem, cfg.stream = c->stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
+    ++na;
+    if (c->pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr, cfg.numAttrs = na;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
+    c->n_launch += 1, c->n_tc += 1;
+    return 0;
+}
+
+// Clusters of two 227 KB CTAs the device can hold at once (a GPC with an odd number of SMs loses one).
+static int pair_cluster_count(b2sr_ctx* c) {
+    if (c->pair_clusters) return c->pair_clusters;
+    cudaLaunchConfig_t q{};
+    q.gridDim = dim3((unsigned)c->sms / 2 * 2), q.blockDim = dim3(TC_THREADS);
+    q.dynamicSmemBytes = (size_t)TcgCfg<32, 0>::smem_bytes(3, 5);
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 2, qa[0].val.clusterDim.y = 1, qa[0].val.clusterDim.z = 1;
+    q.attrs = qa, q.numAttrs = 1;
+    auto kq = tcg_conv_kernel<32, 0, false, 1, 3>;
+    if (cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, B2SR_SMEM_LIMIT) != cudaSuccess) cudaGetLastError();
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, kq, &q) != cudaSuccess || ncl < 1) {
+        cudaGetLastError();
+        ncl = c->sms / 2 - 4;
+    }
+    c->pair_clusters = std::min(ncl, c->sms / 2);
+    return c->pair_clusters;
 }
 
 // Runs ops [0, upto] (upto < 0: the whole program) for the planes of P.
@@ -1989,6 +2068,66 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
             c->n_launch += 1;
             continue;
         }
+        // (B2SR_PAIR2_MASK, measurements: bit 0 = 32-channel convolutions, bit 1 = 64-channel ones, bit 2 = the fused-shortcut one)
+        static const int p2mask = getenv("B2SR_PAIR2_MASK") ? atoi(getenv("B2SR_PAIR2_MASK")) : 7;
+        const int p2kind = o.sc_cin ? 4 : (o.cout == 64 ? 2 : 1);
+        if (c->pair2 && !c->flip_rows && c->fop_pair2[i] >= 0 && (p2mask & p2kind)) {
+            // the CTA-pair form: ONE launch of 2-CTA clusters over band pairs for the whole convolution
+            const FusedLaunch& L = c->flaunch2[c->fop_pair2[i]];
+            ResItems* R = nullptr;
+            TRY(fused_items(c, P, o.res, pair_cluster_count(c), &R, 1));
+            TcgParams p{};
+            fused_fill_params2(c, P, i, L, p);
+            p.items = R->d_items, p.item_first = R->d_first;
+            const bool dbg2 = c->pipe_debug && i < c->pipe_debug;
+            if (dbg2) {
+                if (!c->d_dbg) CUDA_TRY(cudaMalloc(&c->d_dbg, B2SR_DBG_WORDS * sizeof(long long)));
+                CUDA_TRY(cudaMemsetAsync(c->d_dbg, 0, B2SR_DBG_WORDS * sizeof(long long), c->stream));
+                p.dbg = c->d_dbg;
+            }
+            TRY(prof_begin(c, 1, R->out_px));
+            const int outs = (o.out16_buf >= 0 ? 1 : 0) | (o.out32_buf >= 0 ? 2 : 0);
+            bool resf32 = true, resf16 = true;
+            for (int q = 0; q < o.nres; ++q) {
+                resf32 = resf32 && c->fbufs[o.res_buf[q]].dtype == 4;
+                resf16 = resf16 && c->fbufs[o.res_buf[q]].dtype == 2;
+            }
+            const int key = resf32 ? o.nres * 4 + outs : (resf16 ? 100 + o.nres * 4 + outs : -1);
+            int rc;
+            if (L.NOUT == 64) {
+                switch (key) {
+                    case 0 * 4 + 1: rc = launch_tcg2<64, 0, 1>(c, L, R, p); break;
+                    case 0 * 4 + 3: rc = launch_tcg2<64, 0, 3>(c, L, R, p); break;
+                    case 1 * 4 + 1: rc = launch_tcg2<64, 1, 1>(c, L, R, p); break;
+                    case 1 * 4 + 3: rc = launch_tcg2<64, 1, 3>(c, L, R, p); break;
+                    case 100 + 1 * 4 + 1: rc = launch_tcg2<64, 1, 1, true>(c, L, R, p); break;
+                    default: rc = launch_tcg2<64, -1, 0>(c, L, R, p);
+                }
+            } else if (L.sc_ks) {
+                rc = launch_tcg2<32, 0, 1, false, true>(c, L, R, p);
+            } else {
+                switch (key) {
+                    case 0 * 4 + 1: rc = launch_tcg2<32, 0, 1>(c, L, R, p); break;
+                    case 100 + 1 * 4 + 1: rc = launch_tcg2<32, 1, 1, true>(c, L, R, p); break;
+                    default: rc = launch_tcg2<32, -1, 0>(c, L, R, p);
+                }
+            }
+            TRY(rc);
+            TRY(prof_end(c));
+            if (dbg2) {
+                std::vector<long long> h(B2SR_DBG_WORDS);
+                CUDA_TRY(cudaStreamSynchronize(c->stream));
+                CUDA_TRY(cudaMemcpy(h.data(), c->d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                double v[2][16] = {{0}, {0}};
+                for (int k = 0; k < 2 * R->n_cta; ++k)
+                    for (int j = 0; j < 16; ++j) v[k & 1][j] += (double)h[(size_t)k * 16 + j] / R->n_cta / 1e3;
+                fprintf(stderr, "b2sr pair launch op %3d (%3d->%2d, G %d, slots %d, %d clusters), kcycles: leader issuer %6.0f (waits: own row %5.0f, peer row %5.0f, own block %5.0f, peer block %5.0f) | "
+                        "producer r0 %6.0f (slot wait %5.0f) r1 %6.0f (%5.0f) | epilogue w2 r0 %6.0f (tfull wait %5.0f, tmem %4.0f) r1 %6.0f (%5.0f, %4.0f)\n",
+                        i, o.cin, o.cout, L.G, L.slots, R->n_cta, v[0][0], v[0][1], v[0][8], v[0][2], v[0][3], v[0][7], v[0][4], v[1][7], v[1][4], v[0][6], v[0][5], v[0][10],
+                        v[1][6], v[1][5], v[1][10]);
+            }
+            continue;
+        }
         for (int li = c->fop_first[i]; li < c->fop_first[i + 1]; ++li) {
             const FusedLaunch& L = c->flaunch[li];
             if (L.pair && !c->pair_clusters) {
@@ -2001,7 +2140,7 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
                 qa[0].val.clusterDim.x = 2, qa[0].val.clusterDim.y = 1, qa[0].val.clusterDim.z = 1;
                 q.attrs = qa, q.numAttrs = 1;
                 auto kq = tcg_conv_kernel<32, 0, false, 1, 3>;
-                CUDA_TRY(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q.dynamicSmemBytes));
+                CUDA_TRY(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, B2SR_SMEM_LIMIT));
                 int ncl = 0;
                 if (cudaOccupancyMaxActiveClusters(&ncl, kq, &q) != cudaSuccess || ncl < 1) {
                     cudaGetLastError();
@@ -2398,6 +2537,9 @@ extern "C" int b2sr_set_option(b2sr_ctx* c, int key, int64_t value) {
             return 0;
         case B2SR_OPT_SEG_PIPE:
             c->seg_pipe = value != 0;
+            return 0;
+        case B2SR_OPT_PAIR2:
+            c->pair2 = value != 0;
             return 0;
         case B2SR_OPT_RING_ROWS:
             if (value != 0 && (value < 4 || value > 4096)) return fail(B2SR_E_INVALID, "ring rows %lld (need 0 = auto, or 4..4096)", (long long)value);

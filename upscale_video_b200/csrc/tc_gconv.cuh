@@ -111,10 +111,53 @@ __device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mas
                  : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) helpers: one instruction stream drives the tensor cores of two SMs (M = 256) ----
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// arrive (once all MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `target` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t target) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(target)
+        : "memory");
+}
+// wait on a local barrier that a thread of the PEER CTA arrives on (cluster-scope acquire)
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int who) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 6000000000LL) mbar_timeout(bar, parity, who);
+    }
+}
+
 constexpr int TCG_PB = 128;                      // bytes per pixel of one channel group == one SW128 swizzle row
 constexpr int TCG_SUBROWB = TC_PITCH * TCG_PB;   // one ring slot
 constexpr int TCG_PIPE_WORDS = 8;  // 8-byte slots for the pipelined mode's shared words (progress, polled minima)
-constexpr int TCG_BAR_WORDS = 2 * TC_MAX_SLOTS + 2 * TC_NBLK + 2 + TCG_PIPE_WORDS;
+constexpr int TCG_PAIR_WORDS = TC_MAX_SLOTS + TC_NBLK + 2;  // CTA-pair mode: the peer's full / tempty / weights barriers in the leader
+constexpr int TCG_BAR_WORDS = 2 * TC_MAX_SLOTS + 2 * TC_NBLK + 2 + TCG_PIPE_WORDS + TCG_PAIR_WORDS;
 
 template <int NOUT, int MODE, bool SC = false>
 struct TcgCfg {
@@ -138,6 +181,9 @@ struct TcgCfg {
     static constexpr int weight_bytes(int groups) { return groups * 9 * NOUT * TCG_PB + SCB; }
     static constexpr int ring_fit(int groups) { return (B2SR_SMEM_LIMIT - 1024 - weight_bytes(groups) - STG - MISC) / TCG_SUBROWB; }
     static constexpr int smem_bytes(int groups, int slots) { return 1024 + weight_bytes(groups) + slots * TCG_SUBROWB + STG + MISC; }
+    // CTA-pair mode: every CTA keeps HALF of the stacked weights (its half of the B rows of every MMA)
+    static constexpr int ring_fit2(int groups) { return (B2SR_SMEM_LIMIT - 1024 - weight_bytes(groups) / 2 - STG - MISC) / TCG_SUBROWB; }
+    static constexpr int smem_bytes2(int groups, int slots) { return 1024 + weight_bytes(groups) / 2 + slots * TCG_SUBROWB + STG + MISC; }
 };
 
 // NRES / OUTS specialise the MODE 0 epilogue (a lone warp per scheduler runs it: its instruction count is its speed):
@@ -145,11 +191,22 @@ struct TcgCfg {
 // from the parameters at run time; OUTS = bit 0: fp16 copy, bit 1: fp32 copy, or 0 = decided at run time.  NRES = 0, OUTS = 1 is the
 // plain bias + LeakyReLU -> fp16 epilogue.
 template <int NOUT, int MODE /*0 = activation buffers, 1 = network output frames*/, bool F32OUT, int NRES, int OUTS, bool RF16,
-          bool SC /*fused 1x1 shortcut*/, bool PIPE /*CTA = (stage, band) of a persistent segment launch*/>
+          bool SC /*fused 1x1 shortcut*/, bool PIPE /*CTA = (stage, band) of a persistent segment launch*/,
+          bool P2 = false /*CTA pair: the two CTAs of a cluster take neighbouring bands of the same rows, cta_group::2 MMAs*/>
 __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin, const int it_end, const int band, const uint32_t rank,
                                          uint8_t* smem_raw) {
     using C = TcgCfg<NOUT, MODE, SC>;
     static_assert(!PIPE || MODE == 0, "pipelined stages write activation buffers");
+    static_assert(!P2 || (!PIPE && MODE == 0), "the CTA-pair form exists for per-launch activation convolutions");
+    // CTA-pair mode (P2).  Both CTAs walk the same rows; CTA r owns band 2 * pair + r: its own input rows (own TMA ring), its
+    // own accumulators and epilogue warps, and HALF of the stacked weights (rows [r * N/2, (r+1) * N/2) of every tile).  The
+    // leader (r = 0) issues tcgen05.mma.cta_group::2 (M = 256: both bands, N = 3 * NOUT) once both rings hold the row; its
+    // commits arrive on the barriers of both CTAs.  One instruction stream per two bands halves the per-band issue cost of
+    // these issue-bound layers, and half the weights per CTA leaves room for a deeper input ring.  Windows are ALWAYS full
+    // (N = 3 * NOUT, the B split must not move): the two output rows above and below a CTA range are accumulated as
+    // phantom rows and drained without being stored.
+    const uint32_t prank = P2 ? cluster_ctarank() : 0u;
+    [[maybe_unused]] const bool leader = prank == 0u;
     const uint8_t* wimg = P.wimg + (size_t)rank * P.pair_wbytes;
     const float* bias_g = P.bias + rank * NOUT;
     const float* slope_g = P.slope + rank * NOUT;
@@ -161,7 +218,7 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
         res_ptr[r] = reinterpret_cast<const uint8_t*>(P.res_ptr[r]) + (size_t)rank * NOUT * (P.res_f32[r] ? 4 : 2);
     const int G = P.groups, R = P.ring_slots;
     constexpr int NB = C::NB;
-    const uint32_t WB = (uint32_t)(G * 9 * NOUT * TCG_PB) + C::SCB;  // stacked 3x3 weights of all groups [+ the shortcut image]
+    const uint32_t WB = ((uint32_t)(G * 9 * NOUT * TCG_PB) + C::SCB) / (P2 ? 2u : 1u);  // stacked 3x3 weights of all groups [+ the shortcut image]
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
     uint8_t* gbase = smem_raw + (sbase - raw);
@@ -188,6 +245,10 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
     volatile uint32_t* s_bpmin = s_prog + 4 * TC_NSETS + 1;
     uint32_t* s_finished = const_cast<uint32_t*>(s_prog) + 4 * TC_NSETS + 2;
     static_assert((4 * TC_NSETS + 3) * 4 <= TCG_PIPE_WORDS * 8, "pipelined-mode words do not fit their slots");
+    constexpr int PAIR_BASE = 2 * TC_MAX_SLOTS + 2 * TC_NBLK + 2 + TCG_PIPE_WORDS;
+    [[maybe_unused]] auto pfull_bar = [&](int s_) { return bar_s + 8u * (PAIR_BASE + s_); };                    // (leader) the peer's row has landed
+    [[maybe_unused]] auto ptempty_bar = [&](int b_) { return bar_s + 8u * (PAIR_BASE + TC_MAX_SLOTS + b_); };     // (leader) the peer drained its block
+    [[maybe_unused]] const uint32_t pw_bar = bar_s + 8u * (PAIR_BASE + TC_MAX_SLOTS + TC_NBLK);                  // (leader) the peer's weights are loaded
     const bool ring_in = PIPE && P.n_in > 0, ring_out = PIPE && (P.out16_ring || P.out32_ring);
     const uint32_t RR = PIPE ? (uint32_t)P.RR : 1u;
     const int nb_lo = band > 0 ? band - 1 : 0, nb_hi = PIPE && band + 1 < P.nb ? band + 1 : (PIPE ? P.nb - 1 : 0);
@@ -210,6 +271,11 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
             mbar_init(tempty_bar(b), 4);
         }
         mbar_init(w_bar, 1);
+        if constexpr (P2) {
+            for (int s_ = 0; s_ < R; ++s_) mbar_init(pfull_bar(s_), 1);
+            for (int b_ = 0; b_ < NB; ++b_) mbar_init(ptempty_bar(b_), 4);
+            mbar_init(pw_bar, 1);
+        }
         if constexpr (PIPE) {
             for (int w = 0; w < 4 * TC_NSETS; ++w) s_prog[w] = (uint32_t)(w >> 2);
             *s_avail = 0u;
@@ -219,10 +285,15 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
-                     "r"((uint32_t)C::TCOLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (P2) {  // one warp in EACH CTA of the pair performs the pair allocation
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)C::TCOLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                         "r"((uint32_t)C::TCOLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     if (warp >= 2) {
         for (int i = threadIdx.x - 64; i < NOUT; i += TC_THREADS - 64) {
@@ -233,16 +304,30 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (!PIPE && P.pair) cluster_sync_all();  // the peer's barriers exist before anything (multicast data, commits) can reach them
+    if (P2 || (!PIPE && P.pair)) cluster_sync_all();  // the peer's barriers exist before anything (multicast data, commits, arrives) can reach them
     const uint32_t tmem_base = *s_tmem;
+    // pair mode: this CTA's band of a work item (items describe the band PAIR: x0 = first column of band 2 * pair)
+    auto my_item = [&](int it_) {
+        TcItem I_ = P.items[it_];
+        if constexpr (P2) {
+            I_.x0 += (int)prank * TC_BW;
+            I_.w = max(0, min(TC_BW, I_.Wt - I_.x0));  // (an odd band count leaves the last pair's second CTA without columns: it still runs the protocol)
+        }
+        return I_;
+    };
 
     if (warp == 0) {
         // ======================= TMA producer =======================
         if (lane == 0) {
             mbar_expect_tx(w_bar, WB);
             const uint32_t chunk = 3u * NOUT * TCG_PB;  // one (group, kx) tile
-            for (int t = 0; t < 3 * G; ++t) bulk_g2s(w_s + t * chunk, wimg + (size_t)t * chunk, chunk, w_bar);
-            if constexpr (SC) bulk_g2s(w_s + 3 * G * chunk, wimg + (size_t)3 * G * chunk, C::SCB, w_bar);
+            if constexpr (P2) {  // this CTA's half of the rows of every tile (the swizzle pattern repeats every 8 rows = 1 KB: halves keep it)
+                for (int t = 0; t < 3 * G; ++t) bulk_g2s(w_s + t * (chunk / 2), wimg + (size_t)t * chunk + prank * (chunk / 2), chunk / 2, w_bar);
+                if constexpr (SC) bulk_g2s(w_s + 3 * G * (chunk / 2), wimg + (size_t)3 * G * chunk + prank * (C::SCB / 2), C::SCB / 2, w_bar);
+            } else {
+                for (int t = 0; t < 3 * G; ++t) bulk_g2s(w_s + t * chunk, wimg + (size_t)t * chunk, chunk, w_bar);
+                if constexpr (SC) bulk_g2s(w_s + 3 * G * chunk, wimg + (size_t)3 * G * chunk, C::SCB, w_bar);
+            }
             int slot = 0;
             uint32_t phase = 0;
             long long w_empty = 0, w_gate = 0;
@@ -250,7 +335,7 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
             if constexpr (!PIPE) griddep_wait();  // everything above (barriers, TMEM, weights: constants) overlapped the previous launch's tail
             uint32_t seen = 0u;  // last value read from s_avail
             for (int it = it_begin; it < it_end; ++it) {
-                const TcItem I = P.items[it];
+                const TcItem I = my_item(it);
                 if (PIPE && I.w <= 0) continue;
                 const CUtensorMap* map = P.maps + (P.map_base + I.map);
                 [[maybe_unused]] const CUtensorMap* rmap = PIPE ? P.maps + (P.ring_map_base + I.map) : nullptr;
@@ -303,6 +388,125 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
         }
     } else if (warp == 1) {
         // ======================= MMA issuer =======================
+      if constexpr (P2) {
+        // ---- CTA-pair mode.  Every input row is issued with its FULL window: output rows y-1, y, y+1 of input row y, N = 3 * NOUT.
+        // Row sequence of a work item [y0, y0 + rows): input rows y0-1 .. y0+rows (rho = 0 .. rows+1), output rows
+        // y0-2 .. y0+rows+1 (the first and last two are phantom rows: accumulated, drained, never stored).
+        const uint32_t desc_hi = ((8u * TCG_PB) >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B | version | SWIZZLE_128B
+        const uint64_t hi64 = (uint64_t)desc_hi << 32;
+        const uint32_t w_lo = (w_s >> 4) | (1u << 16);
+        const uint32_t ring_lo = (ring_s >> 4) | (1u << 16);
+        constexpr uint32_t KXB = (3 * NOUT * TCG_PB / 2) >> 4;  // descriptor units between this CTA's half tiles of kx, kx + 1
+        constexpr uint32_t GRPB = 3 * KXB;                      // ... between channel groups
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)((3 * NOUT) >> 3) << 17) | ((256u >> 4) << 24);  // D f32, A = B = f16, M = 256, N = 3 NOUT
+        const int itb = __shfl_sync(0xffffffffu, it_begin, 0), ite = __shfl_sync(0xffffffffu, it_end, 0);
+        int slot = 0;
+        uint32_t phase = 0;
+        if (!leader) {
+            // the peer: forwards "my row has landed" (and, first, "my weights are loaded") to the leader's barriers
+            if (lane == 0) {
+                mbar_wait(w_bar, 0, 1);
+                mbar_arrive_remote(pw_bar, 0u);
+                for (int it = itb; it < ite; ++it) {
+                    const int rows = P.items[it].rows;
+                    for (int rg = 0; rg < (rows + 2) * G; ++rg) {
+                        mbar_wait(full_bar(slot), phase, 2);
+                        mbar_arrive_remote(pfull_bar(slot), 0u);
+                        if (++slot == R) slot = 0, phase ^= 1u;
+                    }
+                }
+            }
+        } else {
+            mbar_wait(w_bar, 0, 1);
+            mbar_wait_cluster(pw_bar, 0, 1);
+            uint32_t tmask = 0;  // bit h: parity of the next use of accumulator block h
+            long long w_te = 0, w_pte = 0, w_fu = 0, w_pfu = 0;
+            const long long t_begin = clock64();
+            auto take_block = [&](uint32_t h) {  // block h drained and zeroed by the epilogue warps of BOTH CTAs?
+                const long long t0 = P.dbg ? clock64() : 0;
+                mbar_wait(tempty_bar(h), (tmask >> h) & 1u, 3);
+                const long long t1 = P.dbg ? clock64() : 0;
+                mbar_wait_cluster(ptempty_bar(h), (tmask >> h) & 1u, 3);
+                if (P.dbg) w_te += t1 - t0, w_pte += clock64() - t1;
+                tmask ^= 1u << h;
+            };
+            for (int it = itb; it < ite; ++it) {
+                const int rows = __shfl_sync(0xffffffffu, P.items[it].rows, 0);
+                const uint32_t y0 = (uint32_t)__shfl_sync(0xffffffffu, P.items[it].y0, 0);
+                for (int rho = 0; rho < rows + 2; ++rho) {
+                    // window = homes of output rows y0+rho-2, y0+rho-1, y0+rho (it may run into the extension blocks NB, NB+1)
+                    const uint32_t home0 = (y0 + (uint32_t)rho + 2u * NB - 2u) % NB;
+                    if (rho == 0) {
+                        take_block(home0);
+                        take_block((home0 + 1u) % NB);
+                    }
+                    take_block((home0 + 2u) % NB);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + home0 * NOUT;
+                    if (elect_one_sync()) {
+                        int sl = slot;
+                        uint32_t ph = phase;
+                        for (int g = 0; g < G; ++g) {
+                            const long long t0 = P.dbg ? clock64() : 0;
+                            mbar_wait(full_bar(sl), ph, 2);
+                            const long long t1 = P.dbg ? clock64() : 0;
+                            mbar_wait_cluster(pfull_bar(sl), ph, 2);
+                            if (P.dbg) w_fu += t1 - t0, w_pfu += clock64() - t1;
+                            tc_fence_after();
+                            const int ks = min(4, (P.cin - g * 64) >> 4);  // K = 16 slabs present in this group
+                            const uint64_t a0 = hi64 | (uint64_t)(ring_lo + (uint32_t)sl * (TCG_SUBROWB >> 4));
+                            const uint64_t b0 = hi64 | (uint64_t)(w_lo + (uint32_t)g * GRPB);
+                            if (ks == 4) {
+#pragma unroll
+                                for (int m = 0; m < 12; ++m) {
+                                    const int kx = m >> 2, k = m & 3;
+                                    umma2_f16(d, a0 + (uint64_t)((kx * TCG_PB + k * 32) >> 4), b0 + (uint64_t)(kx * KXB + ((k * 32) >> 4)), idesc, 1u);
+                                }
+                            } else {
+                                for (int kx = 0; kx < 3; ++kx)
+                                    for (int k = 0; k < ks; ++k)
+                                        umma2_f16(d, a0 + (uint64_t)((kx * TCG_PB + k * 32) >> 4), b0 + (uint64_t)(kx * KXB + ((k * 32) >> 4)), idesc, 1u);
+                            }
+                            if constexpr (SC) {
+                                // input row rho is the centre row of output row rho - 1 (real rows only): its first channels through
+                                // the 1x1 weights (column tap kx = 1) into that row's shortcut block
+                                if (g == 0 && rho >= 1 && rho <= rows) {
+                                    const uint32_t ds = tmem_base + C::SC_COL0 + ((y0 + (uint32_t)rho - 1u) % NB) * NOUT;
+                                    const uint64_t bs = hi64 | (uint64_t)(w_lo + (uint32_t)G * GRPB);
+                                    constexpr uint32_t ids = (1u << 4) | ((uint32_t)(NOUT >> 3) << 17) | ((256u >> 4) << 24);
+                                    for (int k = 0; k < P.sc_ks; ++k)
+                                        umma2_f16(ds, a0 + (uint64_t)((TCG_PB + k * 32) >> 4), bs + (uint64_t)((k * 32) >> 4), ids, 1u);
+                                }
+                            }
+                            umma2_commit_both(empty_bar(sl));  // this (row, group) slot may be refilled in both CTAs
+                            if (++sl == R) sl = 0, ph ^= 1u;
+                        }
+                        umma2_commit_both(tfull_bar(home0));  // output row y0+rho-2 is complete
+                        if (rho == rows + 1) {                // the range is over: its last two (phantom) rows are as complete as they get
+                            umma2_commit_both(tfull_bar((home0 + 1u) % NB));
+                            umma2_commit_both(tfull_bar((home0 + 2u) % NB));
+                        }
+                    }
+                    __syncwarp();
+                    slot += G;
+                    if (slot >= R) slot -= R, phase ^= 1u;
+                }
+            }
+            if (P.dbg) {  // (the elected lane holds the full / pfull waits, every lane the block waits)
+                const long long a = __shfl_sync(0xffffffffu, w_fu, 0) , b = __shfl_sync(0xffffffffu, w_pfu, 0);
+                (void)a, (void)b;
+                if (lane == 0) {
+                    P.dbg[blockIdx.x * 16 + 0] = clock64() - t_begin;
+                    P.dbg[blockIdx.x * 16 + 2] = w_te;
+                    P.dbg[blockIdx.x * 16 + 3] = w_pte;
+                }
+                if (w_fu || w_pfu) {
+                    P.dbg[blockIdx.x * 16 + 1] = w_fu;
+                    P.dbg[blockIdx.x * 16 + 8] = w_pfu;
+                }
+            }
+        }
+      } else {
         // The whole warp runs the (warp-uniform) control flow, one elected lane issues.  Work unit: one channel group
         // of one input row; all groups of a row accumulate into the same window of accumulator blocks.
         const uint32_t desc_hi = ((8u * TCG_PB) >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B | version | SWIZZLE_128B
@@ -418,6 +622,7 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
             P.dbg[blockIdx.x * 16 + 8] = t_mma;
             P.dbg[blockIdx.x * 16 + 9] = t_commit;
         }
+      }
     } else if (warp < 2 + 4 * TC_NSETS) {
         // ======================= epilogue =======================
         const int q = warp & 3;
@@ -433,7 +638,9 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(b));
+            if (lane == 0) {
+                if (P2 && !leader) mbar_arrive_remote(ptempty_bar(b), 0u); else mbar_arrive(tempty_bar(b));
+            }
         }
         const float scale_acc = P.acc_scale;
         const int c = q * 32 + lane;
@@ -443,14 +650,35 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
         [[maybe_unused]] uint32_t bp_seen = 0u;  // last value read from s_bpmin
         [[maybe_unused]] uint32_t av_seen = 0u;  // last value read from s_avail (gate of ring residual prefetches)
         for (int it = it_begin; it < it_end; ++it) {
-            const TcItem I = P.items[it];
+            const TcItem I = my_item(it);
             if (PIPE && I.w <= 0) continue;
             const bool valid = c < I.w;
-            for (int t = 0; t < I.rows; ++t, ++tile_cnt) {
-                const uint32_t buf = (uint32_t)(I.y0 + t) % NB;  // home block of this output row
+            for (int t = P2 ? -2 : 0; t < I.rows + (P2 ? 2 : 0); ++t, ++tile_cnt) {
+                const uint32_t buf = (uint32_t)(I.y0 + t + 2 * NB) % NB;  // home block of this output row
                 const uint32_t par = (emask >> buf) & 1u;        // parity of this use of the block (both sets' rows count)
                 emask ^= 1u << buf;
                 if (tile_cnt % TC_NSETS != set) continue;
+                if constexpr (P2) {
+                    if (t < 0 || t >= I.rows) {
+                        // phantom row (pair mode issues full windows only): wait until its partial sums are final, throw them
+                        // away -- the block (and its extension block) must be zero for the next row that lives there
+                        mbar_wait_clocked(tfull_bar(buf), par, 4, w_tfull);
+                        tc_fence_after();
+                        const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NOUT;
+#pragma unroll
+                        for (int j = 0; j < NOUT; j += 16) {
+                            tmem_st16_zero(taddr0 + j);
+                            if (buf < 2) tmem_st16_zero(taddr0 + (uint32_t)(NB * NOUT) + j);
+                        }
+                        tmem_wait_st();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (!leader) mbar_arrive_remote(ptempty_bar(buf), 0u); else mbar_arrive(tempty_bar(buf));
+                        }
+                        continue;
+                    }
+                }
                 // residual terms of this thread's pixel are fetched BEFORE the wait for the accumulator, so their
                 // latency (measured: ~700 cycles per dependent chunk, 4-8 chunks per row) hides behind the MMAs
                 [[maybe_unused]] long long pix = -1;
@@ -527,7 +755,9 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(buf));
+                if (lane == 0) {
+                    if (P2 && !leader) mbar_arrive_remote(ptempty_bar(buf), 0u); else mbar_arrive(tempty_bar(buf));
+                }
                 if (P.dbg) t_tmem += clock64() - tq0;
                 if constexpr (PIPE) {
                     // The ring slot of this row still holds row grow - RR.  Input row i is read by output rows i-1, i, i+1 of
@@ -805,12 +1035,15 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
 
     tc_fence_before();
     __syncthreads();
-    if (!PIPE && P.pair) cluster_sync_all();  // the peer's last commits / multicast writes target this CTA's shared memory: stay until it is done
+    if (P2 || (!PIPE && P.pair)) cluster_sync_all();  // the peer's last commits / arrives / multicast writes target this CTA's shared memory: stay until it is done
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TCOLS)
-                     : "memory");
+        if constexpr (P2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TCOLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TCOLS)
+                         : "memory");
     }
 }
 
@@ -822,6 +1055,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tcg_conv_kernel(const __grid_co
     const uint32_t rank = P.pair ? cluster_ctarank() : 0u;
     const int range = P.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     tcg_body<NOUT, MODE, F32OUT, NRES, OUTS, RF16, SC, false>(P, P.item_first[range], P.item_first[range + 1], 0, rank, smem_raw);
+}
+
+// CTA-pair form (cta_group::2): clusters of two CTAs = two neighbouring 128-column bands over the same rows (work items describe band pairs)
+template <int NOUT, int NRES, int OUTS, bool RF16 = false, bool SC = false>
+__global__ void __launch_bounds__(TC_THREADS, 1) tcg_pair2_kernel(const __grid_constant__ TcgParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const int range = (int)(blockIdx.x >> 1);
+    tcg_body<NOUT, 0, false, NRES, OUTS, RF16, SC, false, true>(P, P.item_first[range], P.item_first[range + 1], 0, 0u, smem_raw);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -272,21 +272,31 @@ def side_configs(E, ncnn_model, torch, device, steps=10):
     try:
         hurr = E.Engine.from_files(mdir, "1x_HurrDeblur_SubCompact_nf24-nc8_244k_net_g", device)
         comp = E.Engine.from_files(mdir, "2x_Compact_Pretrain", device)
-        n = 8
+        # Frames per hand-over: measured on one box (tools/chain_ab.py) 2 frames, two hand-over buffers: 329 fps; 4: 306-310; 8: 300-308;
+        # 16: 298 -- both networks run at the board's power cap, and short alternating phases leave the upscaler more clock headroom.
+        n = int(os.environ.get("B2SR_BENCH_CHAIN_N", "2"))
+        nbuf = int(os.environ.get("B2SR_BENCH_CHAIN_BUFS", "2"))
+        steps = steps * max(1, 8 // n)  # the same 80 frames per measurement whatever the hand-over size
         d_in = torch.randint(0, 256, (n, H, W, 3), dtype=torch.uint8, device="cuda")
-        d_mid = torch.empty_like(d_in)
+        d_mids = [torch.empty_like(d_in), torch.empty_like(d_in)]  # two hand-over buffers: the pre-pass of step k+1 may run under step k's upscale
+        d_mid = d_mids[0]
         d_out = torch.empty((n, 2 * H, 2 * W, 3), dtype=torch.uint8, device="cuda")
         sh, sc = torch.cuda.ExternalStream(hurr.stream, device=dev), torch.cuda.ExternalStream(comp.stream, device=dev)
-        mid_ready, mid_free = torch.cuda.Event(), torch.cuda.Event()
+        mid_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        mid_free = [torch.cuda.Event(), torch.cuda.Event()]
+        turn = [0]
 
-        def chain():  # the two engines own one stream each: events order d_mid's producer and consumer, nothing blocks the host
-            sh.wait_event(mid_free)
-            hurr.run_batch_device(d_in, d_mid, n, H, W, 0, 0, sync=False)       # apply_model: untiled, u8 out
-            mid_ready.record(sh)
-            sc.wait_event(mid_ready)
-            comp.run_batch_device(d_mid, d_out, n, H, W, TILE, HALO, sync=False)  # upscale_image: 960 + 10 tiling
-            mid_free.record(sc)
-        mid_free.record(sc)
+        def chain():  # the two engines own one stream each: events order each hand-over buffer's producer and consumer, nothing blocks the host
+            k = turn[0] % nbuf
+            turn[0] += 1
+            sh.wait_event(mid_free[k])
+            hurr.run_batch_device(d_in, d_mids[k], n, H, W, 0, 0, sync=False)       # apply_model: untiled, u8 out
+            mid_ready[k].record(sh)
+            sc.wait_event(mid_ready[k])
+            comp.run_batch_device(d_mids[k], d_out, n, H, W, TILE, HALO, sync=False)  # upscale_image: 960 + 10 tiling
+            mid_free[k].record(sc)
+        mid_free[0].record(sc)
+        mid_free[1].record(sc)
         for _ in range(2):
             chain()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

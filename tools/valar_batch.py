@@ -15,11 +15,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--passes", type=int, default=2)
 ap.add_argument("--n", type=int, default=4)
 ap.add_argument("--seg", type=int, default=0)
+ap.add_argument("--h", type=int, default=540)
 a = ap.parse_args()
 eng = E.Engine.from_files(ncnn_model.packaged_model_dir(), "4x_Valar_v1", 0)
 eng.set_option(E.OPT_SEG_PIPE, a.seg)
-d_in = torch.randint(0, 256, (a.n, 540, 960, 3), dtype=torch.uint8, device="cuda")
-d_out = torch.empty((a.n, 2160, 3840, 3), dtype=torch.uint8, device="cuda")
+d_in = torch.randint(0, 256, (a.n, a.h, 960, 3), dtype=torch.uint8, device="cuda")
+d_out = torch.empty((a.n, a.h * 4, 3840, 3), dtype=torch.uint8, device="cuda")
 for _ in range(a.passes):
-    eng.run_batch_device(d_in, d_out, a.n, 540, 960, sync=True)
+    eng.run_batch_device(d_in, d_out, a.n, a.h, 960, sync=True)
 print("launches", int(eng.stat(E.STAT_LAUNCHES)))

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <string>
 #include <tuple>
@@ -65,6 +66,24 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 extern "C" const char* b2sr_last_error(void) { return g_err.c_str(); }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the (function, device) pair, shared by every engine of the process:
+// it is only ever raised, under a lock, so that engines on other threads that launch the same instance with another
+// ring depth can never lower it under a launch in flight.
+static int raise_dyn_smem(const void* fn, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> cur;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    int& v = cur[std::make_pair(fn, dev)];
+    if (bytes > v) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        v = bytes;
+    }
+    return 0;
+}
+
 extern "C" int b2sr_abi_version(void) { return B2SR_ABI_VERSION; }
 
 // ------------------------------------------------------------------------------------------------
@@ -712,7 +731,7 @@ static int launch_tc(b2sr_ctx* c, const Plan* plan, TcParams P) {
     P.item_first = plan->d_item_first;
     const int smem = Cfg::smem_bytes();
     auto kern = tc_conv_kernel<CPIX, NOUT, SHUF, F32OUT>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TRY(raise_dyn_smem((const void*)kern, smem));
     const int grid = plan->n_cta;
     kern<<<grid, TC_THREADS, smem, c->stream>>>(P);
     CUDA_TRY(cudaGetLastError());
@@ -819,7 +838,7 @@ template <int CF, int NL, int S, bool F32OUT>
 static int launch_pipe(b2sr_ctx* c, const PipeParams& Q) {
     const int smem = TcPipeCfg<CF, NL, S>::smem_bytes();
     auto kern = tc_pipe_kernel<CF, NL, S, F32OUT>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TRY(raise_dyn_smem((const void*)kern, smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(Q.n_layers * Q.nb)), cfg.blockDim = dim3(TC_THREADS), cfg.dynamicSmemBytes = (size_t)smem, cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
@@ -1142,7 +1161,7 @@ static int run_graph(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
                         const unsigned nbw = (unsigned)(((H + GW_TY - 1) / GW_TY) * ((W + GW_TX - 1) / GW_TX));
 #define WMMA_CASE(kk, nf)                                                                                                   \
     if (o.k == kk && o.cout == nf * 16) {                                                                                   \
-        CUDA_TRY(cudaFuncSetAttribute(g_conv_wmma_kernel<kk, nf>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2SR_SMEM_LIMIT)); \
+        TRY(raise_dyn_smem((const void*)g_conv_wmma_kernel<kk, nf>, (int)smem)); \
         g_conv_wmma_kernel<kk, nf><<<nbw, GW_THREADS, smem, c->stream>>>(in0, ld0, H, W, o.cin, g.wh, g.b, o.act, o.slope, outp, ldo); \
     }
                         WMMA_CASE(3, 2)
@@ -1725,9 +1744,7 @@ template <int NOUT, int MODE, bool F32OUT, int NRES, int OUTS, bool RF16 = false
 static int launch_tcg(b2sr_ctx* c, const FusedLaunch& L, const ResItems* R, const TcgParams& p) {
     auto kern = tcg_conv_kernel<NOUT, MODE, F32OUT, NRES, OUTS, RF16, SC>;
     const int smem = TcgCfg<NOUT, MODE, SC>::smem_bytes(L.G, L.slots);
-    // (the attribute is per function and process-wide: always the limit, so that engines of other threads that launch the same
-    // instance with another ring depth can never lower it under a launch in flight)
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B2SR_SMEM_LIMIT));
+    TRY(raise_dyn_smem((const void*)kern, smem));
     // programmatic dependent launch: this launch's prologue (barrier init, TMEM allocation, weight load) overlaps the tail
     // of the previous launch of the stream; the kernel waits (griddepcontrol.wait) before it touches activation buffers
     cudaLaunchConfig_t cfg{};
@@ -1891,7 +1908,7 @@ static int launch_segment(b2sr_ctx* c, Plan* P, const FusedSegment& S) {
         const FusedLaunch& L = c->flaunch[st.launch];
         smem = std::max(smem, L.sc_ks ? TcgCfg<32, 0, true>::smem_bytes(L.G, L.slots) : TcgCfg<32, 0>::smem_bytes(L.G, L.slots));
     }
-    CUDA_TRY(cudaFuncSetAttribute(tcg_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2SR_SMEM_LIMIT));
+    TRY(raise_dyn_smem((const void*)tcg_pipe_kernel, smem));
     CUDA_TRY(cudaMemsetAsync(P->d_fflags, 0, (size_t)ns * nb * B2SR_FLAG_STRIDE * sizeof(uint32_t), c->stream));
     TcgPipeParams Q{};
     Q.stages = P->d_fstages + S.stage_base, Q.n_stages = ns, Q.nb = nb;
@@ -1938,7 +1955,7 @@ template <int NOUT, int NRES, int OUTS, bool RF16 = false, bool SC = false>
 static int launch_tcg2(b2sr_ctx* c, const FusedLaunch& L, const ResItems* R, const TcgParams& p) {
     auto kern = tcg_pair2_kernel<NOUT, NRES, OUTS, RF16, SC>;
     const int smem = TcgCfg<NOUT, 0, SC>::smem_bytes2(L.G, L.slots);
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B2SR_SMEM_LIMIT));
+    TRY(raise_dyn_smem((const void*)kern, smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(R->n_cta * 2)), cfg.blockDim = dim3(TC_THREADS), cfg.dynamicSmemBytes = (size_t)smem, cfg.stream = c->stream;
     cudaLaunchAttribute attr[2];
@@ -1968,7 +1985,7 @@ static int pair_cluster_count(b2sr_ctx* c) {
     qa[0].val.clusterDim.x = 2, qa[0].val.clusterDim.y = 1, qa[0].val.clusterDim.z = 1;
     q.attrs = qa, q.numAttrs = 1;
     auto kq = tcg_conv_kernel<32, 0, false, 1, 3>;
-    if (cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, B2SR_SMEM_LIMIT) != cudaSuccess) cudaGetLastError();
+    if (raise_dyn_smem((const void*)kq, (int)q.dynamicSmemBytes) != 0) cudaGetLastError();
     int ncl = 0;
     if (cudaOccupancyMaxActiveClusters(&ncl, kq, &q) != cudaSuccess || ncl < 1) {
         cudaGetLastError();
@@ -2140,7 +2157,7 @@ static int run_fused(b2sr_ctx* c, Plan* P, const uint8_t* d_frames, void* d_out,
                 qa[0].val.clusterDim.x = 2, qa[0].val.clusterDim.y = 1, qa[0].val.clusterDim.z = 1;
                 q.attrs = qa, q.numAttrs = 1;
                 auto kq = tcg_conv_kernel<32, 0, false, 1, 3>;
-                CUDA_TRY(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, B2SR_SMEM_LIMIT));
+                TRY(raise_dyn_smem((const void*)kq, (int)q.dynamicSmemBytes));
                 int ncl = 0;
                 if (cudaOccupancyMaxActiveClusters(&ncl, kq, &q) != cudaSuccess || ncl < 1) {
                     cudaGetLastError();

@@ -1777,6 +1777,8 @@ static void fused_fill_params(b2sr_ctx* c, Plan* P, int li, void* d_out, TcgPara
     p.acc_scale = o.in_buf < 0 ? (1.f / 255.f) : 1.f;
     p.groups = L.G, p.cin = L.cinp, p.k1 = o.k == 1, p.ring_slots = L.slots;
     p.sc_ks = L.sc_ks, p.sc_cv = o.sc_coef_v, p.sc_cr = o.sc_coef_r;
+    static const int ablate = getenv("B2SR_ABLATE") ? atoi(getenv("B2SR_ABLATE")) : 0;  // measurement only: see TcgParams::ablate
+    p.ablate = ablate;
     p.pair = L.pair, p.pair_wbytes = L.G * 9 * L.NOUT * TCG_PB;
     p.nres = o.nres;
     for (int q = 0; q < o.nres; ++q) {

@@ -82,6 +82,9 @@ struct TcgParams {
     int32_t nogate;             // measurement only (B2SR_SEG_NOGATE=1): ignore every counter -- stages free-run on stale data, results are garbage
     int32_t half;               // which 32-channel half of a 64-channel convolution this stage computes (weights / bias /
                                 // output / residual slices are offset like a cluster rank's in the paired launch)
+    int32_t ablate;             // measurement only (B2SR_ABLATE, energy accounting; results are garbage): bit 0 = no MMAs are issued
+                                // (commits only), bit 1 = the epilogue drains the accumulators but neither reads residuals nor
+                                // computes / stores anything, bit 2 = the producer arrives on the full barriers without loading rows
 };
 
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may become resident
@@ -362,6 +365,11 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
                     }
                     for (int g = 0; g < G; ++g) {
                         mbar_wait_clocked(empty_bar(slot), phase ^ 1u, 0, w_empty);
+                        if (P.ablate & 4) {
+                            mbar_arrive(full_bar(slot));
+                            if (++slot == R) slot = 0, phase ^= 1u;
+                            continue;
+                        }
                         mbar_expect_tx(full_bar(slot), TCG_SUBROWB);
                         if (PIPE && P.grp_ring[g])
                             tma_load_4d(ring_s + slot * TCG_SUBROWB, rmap, full_bar(slot), g * 64, I.x0 - 1, ry, 0);
@@ -578,7 +586,8 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
                         const int ks = min(4, (P.cin - g * 64) >> 4);  // K = 16 slabs present in this group
                         const uint64_t a0 = hi64 | (uint64_t)(ring_lo + (uint32_t)sl * (TCG_SUBROWB >> 4));
                         const uint64_t b0 = hi64 | (uint64_t)(w_lo + (uint32_t)g * GRPB + brow0 * BLKB);
-                        if (ks == 4 && !P.k1) {  // the common case, straight-line: 12 MMAs, one 64-bit add per descriptor
+                        if (P.ablate & 1) {
+                        } else if (ks == 4 && !P.k1) {  // the common case, straight-line: 12 MMAs, one 64-bit add per descriptor
 #pragma unroll
                             for (int m = 0; m < 12; ++m) {
                                 const int kx = m >> 2, k = m & 3;
@@ -592,7 +601,7 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
                         if constexpr (SC) {
                             // input row rho is the centre row of output row rho - 1: its first channels through the 1x1 weights
                             // (column tap kx = 1) into that row's shortcut block
-                            if (g == 0 && rho >= 1 && rho <= rows) {
+                            if (g == 0 && rho >= 1 && rho <= rows && !(P.ablate & 1)) {
                                 const uint32_t ds = tmem_base + C::SC_COL0 + ((y0 + (uint32_t)rho - 1u) % NB) * NOUT;
                                 const uint64_t bs = hi64 | (uint64_t)(w_lo + (uint32_t)G * GRPB);
                                 constexpr uint32_t ids = C::IDESC0 | ((uint32_t)(NOUT >> 3) << 17);
@@ -707,7 +716,7 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
                 if constexpr (MODE == 0 && !PLAIN) {
 #pragma unroll
                     for (int r = 0; r < NPRE; ++r) {
-                        if (r >= nres || pix < 0) continue;
+                        if (r >= nres || pix < 0 || (P.ablate & 2)) continue;
                         // (pipelined mode reads residuals with ld.global.cg: a ring slot is rewritten by another SM during
                         // the launch, so a stale L1 line must never be hit)
                         if (NRES >= 0 ? !RF16 : P.res_f32[r] != 0) {
@@ -759,6 +768,7 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
                     if (P2 && !leader) mbar_arrive_remote(ptempty_bar(buf), 0u); else mbar_arrive(tempty_bar(buf));
                 }
                 if (P.dbg) t_tmem += clock64() - tq0;
+                if (!PIPE && (P.ablate & 2)) continue;
                 if constexpr (PIPE) {
                     // The ring slot of this row still holds row grow - RR.  Input row i is read by output rows i-1, i, i+1 of
                     // the stages that read this ring (and by their epilogues as a residual of row i): all of that is over

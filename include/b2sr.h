@@ -242,6 +242,20 @@ int b2sr_run_batch_device(b2sr_ctx *ctx, const uint8_t *d_in, uint8_t *d_out, in
 int b2sr_run_batch_host(b2sr_ctx *ctx, const uint8_t *h_in, uint8_t *h_out, int n, int h, int w, int tile,
                         int halo);
 
+/*
+ * The same pipeline without the host waiting for it: the call returns once the copies and launches are enqueued, and
+ * `b2sr_wait_batch(ctx, *ticket)` returns once this submission's last output frame is in `h_out`.  Submissions of one context
+ * complete in order, and the first H2D copy of one runs under the network of the previous one (equal chunks, no tapered
+ * ends), so a caller that keeps two submissions in flight on two pairs of PINNED buffers sees the device-resident rate
+ * (pageable memory makes the copies, and therefore the call, synchronous).  `h_in` / `h_out` must stay valid and
+ * untouched until the wait returns.  Any other call on the context first waits for all pending submissions.  This is the
+ * reference's `pool.apply_async(upscale_image, ...)` + callback (upscale_processing.py:586-598) for a caller that holds
+ * raw frames instead of PNG names.
+ */
+int b2sr_submit_batch_host(b2sr_ctx *ctx, const uint8_t *h_in, uint8_t *h_out, int n, int h, int w, int tile,
+                           int halo, uint64_t *ticket);
+int b2sr_wait_batch(b2sr_ctx *ctx, uint64_t ticket);
+
 /* Bring-up aid: activations after convolution `layer` (0-based, post-PReLU) of a single untiled u8 image,
  * as float h x w x nf on the host. */
 int b2sr_debug_layer(b2sr_ctx *ctx, const uint8_t *in, int h, int w, int layer, float *out);

@@ -303,6 +303,34 @@ def test_host_pipeline_tapered_chunks(E, engines):
         assert np.array_equal(h_out.numpy(), d_out.cpu().numpy()), n
 
 
+def test_host_pipeline_submit_wait(E, engines):
+    """b2sr_submit_batch_host / b2sr_wait_batch: several submissions in flight on their own pinned buffers (more than the
+    ticket ring holds, mixed sizes so the staging buffers are replaced under pending work, waits out of order, a synchronous
+    call and a single-frame call in between) produce the frames of the device-resident batch."""
+    import torch
+    eng = engines("2x_Compact_Pretrain")
+    jobs = []
+    for k in range(11):
+        n, (h, w) = 1 + (k * 3) % 6, ((96, 200), (270, 480), (64, 1000))[k % 3]
+        frames = np.stack([natural(h, w, seed=500 + 10 * k + s) for s in range(n)])
+        h_in = torch.from_numpy(frames).pin_memory()
+        h_out = torch.zeros((n, 2 * h, 2 * w, 3), dtype=torch.uint8).pin_memory()
+        jobs.append((frames, h_in, h_out, n, h, w, eng.submit_batch_host(h_in, h_out, n, h, w)))
+        if k == 4:  # a synchronous call between submissions waits for them and must not disturb them
+            assert np.array_equal(eng.run_u8(frames[0]), eng.run_u8(frames[0]))
+        if k == 7:
+            eng.wait_batch(jobs[6][6])
+    for j in (10, 2, 9, 0, 1, 3, 4, 5, 6, 7, 8):  # any order; an early ticket's event slot has been reused by then
+        eng.wait_batch(jobs[j][6])
+    for frames, h_in, h_out, n, h, w, _ in jobs:
+        d_in = torch.from_numpy(frames).cuda()
+        d_out = torch.empty((n, 2 * h, 2 * w, 3), dtype=torch.uint8, device="cuda")
+        eng.run_batch_device(d_in, d_out, n, h, w, sync=True)
+        assert np.array_equal(h_out.numpy(), d_out.cpu().numpy()), (n, h, w)
+    with pytest.raises(E.EngineError):
+        eng.wait_batch(10 ** 6)
+
+
 def test_strides_and_device_memory(E, engines):
     import torch
     eng = engines("2x_Compact_Pretrain")

@@ -432,6 +432,41 @@ def test_raw_stream_multi_gpu_dynamic_queue(tmp_path):
         k = 37 if mf is None else mf
         assert n == k and out.getvalue() == want[:k * 12 * 16 * 3]
     assert len(seen) == 3  # every worker took chunks
+
+    # engines with the streaming call (Engine.submit_batch_host / wait_batch): a worker keeps two chunks in flight
+    class Deferred(Jitter):
+        def __init__(self, gpu):
+            super().__init__(gpu)
+            self.jobs, self.tickets, self.in_flight, self.max_in_flight = {}, 0, 0, 0
+
+        def submit_batch_host(self, h_in, h_out, n, h, w, *a, **k):
+            self.tickets += 1
+            self.jobs[self.tickets] = (h_in, h_out, n, h, w)
+            self.in_flight += 1
+            self.max_in_flight = max(self.max_in_flight, self.in_flight)
+            return self.tickets
+
+        def wait_batch(self, ticket):
+            assert ticket == min(self.jobs), "submissions are waited for in order"
+            self.run_batch_host(*self.jobs.pop(ticket))  # (the output appears only now: nothing may be written before its wait)
+            self.in_flight -= 1
+
+    made = []
+    for chunk, gpus in ((1, [0]), (3, [0, 1, 1]), (40, [0, 1])):
+        seen.clear()
+        out = io.BytesIO()
+        n = raw_stream.stream_multi(Pipe(frames.tobytes()), out, 8, 6, scale=2, gpus=gpus, chunk=chunk,
+                                    make_engines=lambda g: (None, None, made.append(Deferred(g)) or made[-1]))
+        assert n == 37 and out.getvalue() == want and sum(seen.values()) == 37
+    assert all(e.in_flight == 0 and not e.jobs and e.max_in_flight <= 2 for e in made) and any(e.max_in_flight == 2 for e in made)
+
+    class BrokenWait(Deferred):
+        def wait_batch(self, ticket):
+            raise RuntimeError("device lost in flight")
+
+    with pytest.raises(RuntimeError, match="device lost in flight"):
+        raw_stream.stream_multi(Pipe(frames.tobytes()), io.BytesIO(), 8, 6, scale=2, gpus=[0, 1], chunk=2,
+                                make_engines=lambda g: (None, None, BrokenWait(g) if g == 1 else Deferred(g)))
     # rgb24 in and out, denoise -> pre-pass -> upscale chain per worker
     class Neg:
         def run_batch_host(self, h_in, h_out, n, h, w, level, level_color=None):

@@ -27,6 +27,7 @@ ap.add_argument("--gpus", default="0")
 ap.add_argument("--input", default="file", choices=["file", "memory"])
 ap.add_argument("--chain", action="store_true", help="-m a: HurrDeblur pre-pass in front of the upscaler")
 ap.add_argument("--chunk", type=int, default=4)
+ap.add_argument("--multi", action="store_true", help="one GPU through stream_multi (streaming workers) instead of stream")
 ap.add_argument("--check", type=int, default=0, help="also verify the first N output frames against the single-GPU stream")
 a = ap.parse_args()
 gpus = [int(g) for g in a.gpus.split(",")]
@@ -72,7 +73,7 @@ def run(n_frames, sink):
     models = ["a"] if a.chain else []
     pool = list(prebuilt)
     t = time.time()
-    if len(gpus) == 1:
+    if len(gpus) == 1 and not a.multi:
         k = raw_stream.stream(fin, sink, W, H, 2, models, gpus[0], 8, max_frames=n_frames, overlap=True, upscaler=prebuilt[0][2],
                               prepass=prebuilt[0][1])
     else:

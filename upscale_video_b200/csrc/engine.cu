@@ -280,6 +280,14 @@ struct b2sr_ctx {
     std::vector<float*> slot_buf;
     std::vector<size_t> slot_cap;
     cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
+    // host-batch pipeline (b2sr_run_batch_host / b2sr_submit_batch_host): events that order the two staging slots across chunks AND
+    // across calls, the chunk counter that alternates the slots, and one event per recent submission (its last D2H)
+    cudaEvent_t hb_in_ready[2] = {nullptr, nullptr}, hb_compute_done[2] = {nullptr, nullptr}, hb_out_done[2] = {nullptr, nullptr};
+    cudaEvent_t hb_ticket[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool hb_used[2] = {false, false};
+    unsigned hb_seq = 0;
+    uint64_t hb_next_ticket = 1;
+    bool hb_pending = false;  // submissions that nobody has waited for may still be using d_in / d_out
     b2sr_net_desc desc{};
     int CF = 0, NL = 0, cout_last = 0;
     std::vector<LayerDev> layers;
@@ -395,6 +403,11 @@ extern "C" void b2sr_destroy(b2sr_ctx* c) {
     }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
+    for (cudaEvent_t* ev : {c->hb_in_ready, c->hb_compute_done, c->hb_out_done})
+        for (int i = 0; i < 2; ++i)
+            if (ev[i]) cudaEventDestroy(ev[i]);
+    for (cudaEvent_t e : c->hb_ticket)
+        if (e) cudaEventDestroy(e);
     if (c->copy_in) cudaStreamDestroy(c->copy_in);
     if (c->copy_out) cudaStreamDestroy(c->copy_out);
     delete c;
@@ -2404,10 +2417,12 @@ static int grow(uint8_t** p, size_t* cap, size_t need) {
     return 0;
 }
 
+static int drain_host_pipeline(b2sr_ctx* c);
 static int run_one(b2sr_ctx* c, const uint8_t* in, int h, int w, int in_stride, void* out, int out_stride, bool f32out,
                    int tile, int halo, int memspace) {
     if (!c || !in || !out) return fail(B2SR_E_INVALID, "b2sr_run: null argument");
     TRY(check_geom(1, h, w, tile, halo));
+    TRY(drain_host_pipeline(c));  // (pending b2sr_submit_batch_host work shares this call's staging buffers)
     const int S = c->desc.scale;
     const size_t in_row = (size_t)w * 3, out_row = (size_t)w * S * 3 * (f32out ? 4 : 1);
     if (in_stride == 0) in_stride = (int)in_row;
@@ -2444,30 +2459,41 @@ extern "C" int b2sr_run_f32(b2sr_ctx* c, const uint8_t* in, int h, int w, int in
 
 // Host frames -> H2D -> network -> D2H, chunk by chunk, copies overlapped with compute on separate streams
 // (double-buffered staging).  The reference moves every frame through PNG files instead (upscale_processing.py:487,:519).
-extern "C" int b2sr_run_batch_host(b2sr_ctx* c, const uint8_t* h_in, uint8_t* h_out, int n, int h, int w, int tile, int halo) {
-    if (!c || !h_in || !h_out) return fail(B2SR_E_INVALID, "b2sr_run_batch_host: null argument");
-    TRY(check_geom(n, h, w, tile, halo));
-    CUDA_TRY(cudaSetDevice(c->device));
+// Waits for every submission of the host-batch pipeline (they use d_in / d_out and the copy streams).
+static int drain_host_pipeline(b2sr_ctx* c) {
+    if (!c->hb_pending) return 0;
+    c->hb_pending = false;
+    cudaError_t e1 = cudaStreamSynchronize(c->copy_in), e2 = cudaStreamSynchronize(c->stream), e3 = cudaStreamSynchronize(c->copy_out);
+    for (cudaError_t e : {e1, e2, e3})
+        if (e != cudaSuccess) return fail(B2SR_E_CUDA, "host-batch pipeline: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// Enqueues n host frames as chunks on the three streams: H2D of chunk k+1 (copy_in), the network on chunk k (stream) and D2H of
+// chunk k-1 (copy_out) run concurrently; two staging slots, ordered by events that persist across calls, so that the first copy
+// of one call may run under the last compute of the previous one.  Nothing here waits on the host.
+static int enqueue_batch_host(b2sr_ctx* c, const uint8_t* h_in, uint8_t* h_out, int n, int h, int w, int tile, int halo, bool taper) {
     const int S = c->desc.scale;
-    // small chunks: H2D of chunk k+1, the network on chunk k and D2H of chunk k-1 run concurrently on three streams
-    const int B = std::min(frames_per_pass(c, h, w, tile), c->max_batch > 0 ? c->max_batch : 4);
+    // frames per chunk (B2SR_OPT_MAX_BATCH overrides): 4 in a synchronous call, 8 in a submission whose ends overlap with its
+    // neighbours (measured at 1080p, tools/e2e_stream_sweep.py: 393 / 396 / 394 fps end to end with chunks of 4 / 8 / 16)
+    const int B = std::min(frames_per_pass(c, h, w, tile), c->max_batch > 0 ? c->max_batch : (taper ? 4 : 8));
     const size_t in_frame = (size_t)h * w * 3, out_frame = in_frame * S * S;
+    if (in_frame * B > c->cap_in || out_frame * B > c->cap_out || in_frame * B > c->cap_in2 || out_frame * B > c->cap_out2)
+        TRY(drain_host_pipeline(c));  // the staging buffers are about to be replaced
     TRY(grow(&c->d_in, &c->cap_in, in_frame * B));
     TRY(grow(&c->d_out, &c->cap_out, out_frame * B));
     TRY(grow(&c->d_in2, &c->cap_in2, in_frame * B));
     TRY(grow(&c->d_out2, &c->cap_out2, out_frame * B));
     uint8_t* din[2] = {c->d_in, c->d_in2};
     uint8_t* dout[2] = {c->d_out, c->d_out2};
-    cudaEvent_t in_ready[2], compute_done[2], out_done[2];
     for (int i = 0; i < 2; ++i) {
-        CUDA_TRY(cudaEventCreateWithFlags(&in_ready[i], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&compute_done[i], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&out_done[i], cudaEventDisableTiming));
+        if (!c->hb_in_ready[i]) CUDA_TRY(cudaEventCreateWithFlags(&c->hb_in_ready[i], cudaEventDisableTiming));
+        if (!c->hb_compute_done[i]) CUDA_TRY(cudaEventCreateWithFlags(&c->hb_compute_done[i], cudaEventDisableTiming));
+        if (!c->hb_out_done[i]) CUDA_TRY(cudaEventCreateWithFlags(&c->hb_out_done[i], cudaEventDisableTiming));
     }
-    // Chunk schedule.  The call is synchronous, so the H2D of the first chunk and the D2H of the last one are not hidden
-    // behind compute: both are one frame long (tapered ends), the chunks in between hold B frames.  B2SR_E2E_TAPER=0
-    // restores equal chunks.
-    static const bool taper = !(getenv("B2SR_E2E_TAPER") && atoi(getenv("B2SR_E2E_TAPER")) == 0);
+    // Chunk schedule.  In a synchronous call the H2D of the first chunk and the D2H of the last one are not hidden behind
+    // compute: both are one frame long there (tapered ends), the chunks in between hold B frames.  Submissions that overlap
+    // with their neighbours use equal chunks.
     std::vector<int> chunks;
     {
         int left = n;
@@ -2476,33 +2502,68 @@ extern "C" int b2sr_run_batch_host(b2sr_ctx* c, const uint8_t* h_in, uint8_t* h_
         for (; left > 0; left -= B) chunks.push_back(std::min(B, left));
         if (tail) chunks.push_back(1);
     }
-    int rc = 0, k = 0;
-    for (int f = 0; k < (int)chunks.size() && !rc; f += chunks[k], ++k) {
-        const int nb = chunks[k], s = k & 1;
-        // staging slot s is free once the compute that read din[s] and the D2H that read dout[s] (chunk k-2) are done
-        if (k >= 2) {
-            cudaStreamWaitEvent(c->copy_in, compute_done[s], 0);
-            cudaStreamWaitEvent(c->stream, out_done[s], 0);
+    c->hb_pending = true;
+    int f = 0;
+    for (size_t k = 0; k < chunks.size(); f += chunks[k], ++k) {
+        const int nb = chunks[k], s = (int)(c->hb_seq++ & 1u);
+        // staging slot s is free once the compute that read din[s] and the D2H that read dout[s] (two chunks ago, maybe in the
+        // previous call) are done
+        if (c->hb_used[s]) {
+            CUDA_TRY(cudaStreamWaitEvent(c->copy_in, c->hb_compute_done[s], 0));
+            CUDA_TRY(cudaStreamWaitEvent(c->stream, c->hb_out_done[s], 0));
         }
-        cudaMemcpyAsync(din[s], h_in + (size_t)f * in_frame, in_frame * nb, cudaMemcpyHostToDevice, c->copy_in);
-        cudaEventRecord(in_ready[s], c->copy_in);
-        cudaStreamWaitEvent(c->stream, in_ready[s], 0);
-        rc = run_batch_dev(c, din[s], dout[s], false, nb, h, w, tile, halo);
-        if (rc) break;
-        cudaEventRecord(compute_done[s], c->stream);
-        cudaStreamWaitEvent(c->copy_out, compute_done[s], 0);
-        cudaMemcpyAsync(h_out + (size_t)f * out_frame, dout[s], out_frame * nb, cudaMemcpyDeviceToHost, c->copy_out);
-        cudaEventRecord(out_done[s], c->copy_out);
+        c->hb_used[s] = true;
+        CUDA_TRY(cudaMemcpyAsync(din[s], h_in + (size_t)f * in_frame, in_frame * nb, cudaMemcpyHostToDevice, c->copy_in));
+        CUDA_TRY(cudaEventRecord(c->hb_in_ready[s], c->copy_in));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->hb_in_ready[s], 0));
+        TRY(run_batch_dev(c, din[s], dout[s], false, nb, h, w, tile, halo));
+        CUDA_TRY(cudaEventRecord(c->hb_compute_done[s], c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->copy_out, c->hb_compute_done[s], 0));
+        CUDA_TRY(cudaMemcpyAsync(h_out + (size_t)f * out_frame, dout[s], out_frame * nb, cudaMemcpyDeviceToHost, c->copy_out));
+        CUDA_TRY(cudaEventRecord(c->hb_out_done[s], c->copy_out));
     }
-    cudaError_t e1 = cudaStreamSynchronize(c->copy_in), e2 = cudaStreamSynchronize(c->stream), e3 = cudaStreamSynchronize(c->copy_out);
-    for (int i = 0; i < 2; ++i) {
-        cudaEventDestroy(in_ready[i]);
-        cudaEventDestroy(compute_done[i]);
-        cudaEventDestroy(out_done[i]);
+    return 0;
+}
+
+extern "C" int b2sr_run_batch_host(b2sr_ctx* c, const uint8_t* h_in, uint8_t* h_out, int n, int h, int w, int tile, int halo) {
+    if (!c || !h_in || !h_out) return fail(B2SR_E_INVALID, "b2sr_run_batch_host: null argument");
+    TRY(check_geom(n, h, w, tile, halo));
+    CUDA_TRY(cudaSetDevice(c->device));
+    static const bool taper = !(getenv("B2SR_E2E_TAPER") && atoi(getenv("B2SR_E2E_TAPER")) == 0);  // B2SR_E2E_TAPER=0: equal chunks
+    const int rc = enqueue_batch_host(c, h_in, h_out, n, h, w, tile, halo, taper);
+    const int rd = drain_host_pipeline(c);  // (also after a failed enqueue: nothing of this call may still be running when it returns)
+    return rc ? rc : rd;
+}
+
+extern "C" int b2sr_submit_batch_host(b2sr_ctx* c, const uint8_t* h_in, uint8_t* h_out, int n, int h, int w, int tile, int halo,
+                                      uint64_t* ticket) {
+    if (!c || !h_in || !h_out || !ticket) return fail(B2SR_E_INVALID, "b2sr_submit_batch_host: null argument");
+    TRY(check_geom(n, h, w, tile, halo));
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int rc = enqueue_batch_host(c, h_in, h_out, n, h, w, tile, halo, false);
+    if (rc) {
+        const std::string keep = b2sr_last_error();
+        drain_host_pipeline(c);
+        fail(rc, "%s", keep.c_str());
+        return rc;
     }
-    if (rc) return rc;
-    for (cudaError_t e : {e1, e2, e3})
-        if (e != cudaSuccess) return fail(B2SR_E_CUDA, "b2sr_run_batch_host: %s", cudaGetErrorString(e));
+    const uint64_t t = c->hb_next_ticket++;
+    cudaEvent_t& ev = c->hb_ticket[t % 8];
+    if (!ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ev, c->copy_out));  // the D2H copies of a context complete in submission order
+    *ticket = t;
+    return 0;
+}
+
+extern "C" int b2sr_wait_batch(b2sr_ctx* c, uint64_t ticket) {
+    if (!c) return fail(B2SR_E_INVALID, "b2sr_wait_batch: null context");
+    if (ticket == 0 || ticket >= c->hb_next_ticket) return fail(B2SR_E_INVALID, "b2sr_wait_batch: unknown ticket %llu", (unsigned long long)ticket);
+    CUDA_TRY(cudaSetDevice(c->device));
+    // a ticket whose event slot has been reused by a later submission: that one's copies finish after this one's
+    uint64_t t = ticket;
+    while (t + 8 < c->hb_next_ticket) t += 8;
+    CUDA_TRY(cudaEventSynchronize(c->hb_ticket[t % 8]));
+    if (ticket + 1 == c->hb_next_ticket) c->hb_pending = false;  // the newest submission is complete: so is every earlier one
     return 0;
 }
 
@@ -2510,6 +2571,7 @@ extern "C" int b2sr_debug_layer(b2sr_ctx* c, const uint8_t* in, int h, int w, in
     if (!c || !in || !out) return fail(B2SR_E_INVALID, "b2sr_debug_layer: null argument");
     TRY(check_geom(1, h, w, 0, 0));
     if (c->family != B2SR_FAMILY_COMPACT) return fail(B2SR_E_UNSUPPORTED, "b2sr_debug_layer: Compact family only");
+    TRY(drain_host_pipeline(c));
     if (layer < 0 || layer >= (int)c->layers.size() - 1) return fail(B2SR_E_INVALID, "layer %d has no activation output", layer);
     CUDA_TRY(cudaSetDevice(c->device));
     const size_t in_bytes = (size_t)h * w * 3;

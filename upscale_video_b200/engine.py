@@ -26,7 +26,8 @@ IMPL_AUTO, IMPL_SIMPLE, IMPL_TCGEN05, IMPL_PIPELINED = 0, 1, 2, 3  # IMPL_TCGEN0
 SYMBOLS = [
     "b2sr_abi_version", "b2sr_device_count", "b2sr_default_device", "b2sr_device_name", "b2sr_create", "b2sr_create_graph",
     "b2sr_create_fused", "b2sr_fused_describe_segments", "b2sr_debug_fused", "b2sr_destroy",
-    "b2sr_run_u8", "b2sr_run_f32", "b2sr_run_batch_device", "b2sr_run_batch_host", "b2sr_debug_layer",
+    "b2sr_run_u8", "b2sr_run_f32", "b2sr_run_batch_device", "b2sr_run_batch_host", "b2sr_submit_batch_host", "b2sr_wait_batch",
+    "b2sr_debug_layer",
     "b2sr_set_option", "b2sr_get_stat", "b2sr_reset_stats", "b2sr_synchronize", "b2sr_stream", "b2sr_last_error",
     "b2sr_bcast_weights", "b2sr_nccl_unique_id", "b2sr_nccl_comm_init", "b2sr_nccl_comm_destroy",
     "b2sr_nlm_create", "b2sr_nlm_destroy", "b2sr_nlm_run_u8", "b2sr_nlm_run_batch_device", "b2sr_nlm_run_batch_host",
@@ -95,6 +96,8 @@ def load_library(path: str = LIB_PATH):
     lib.b2sr_run_f32.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, i32, i32]
     lib.b2sr_run_batch_device.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32]
     lib.b2sr_run_batch_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32]
+    lib.b2sr_submit_batch_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_uint64)]
+    lib.b2sr_wait_batch.argtypes = [vp, ctypes.c_uint64]
     lib.b2sr_debug_layer.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.b2sr_set_option.argtypes = [vp, i32, i64]
     lib.b2sr_get_stat.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_double)]
@@ -330,6 +333,19 @@ class Engine:
         pi, _ = _ptr(h_in)
         po, _ = _ptr(h_out)
         _check(self._lib.b2sr_run_batch_host(self._h, pi, po, n, h, w, tile, halo), "b2sr_run_batch_host")
+
+    def submit_batch_host(self, h_in, h_out, n: int, h: int, w: int, tile: int = 960, halo: int = 10) -> int:
+        """``run_batch_host`` without waiting: returns a ticket for ``wait_batch``.  Keep ``h_in`` / ``h_out`` (pinned) alive and
+        untouched until then; two submissions in flight on two buffer pairs hide every copy behind the network."""
+        pi, _ = _ptr(h_in)
+        po, _ = _ptr(h_out)
+        ticket = ctypes.c_uint64(0)
+        _check(self._lib.b2sr_submit_batch_host(self._h, pi, po, n, h, w, tile, halo, ctypes.byref(ticket)), "b2sr_submit_batch_host")
+        return int(ticket.value)
+
+    def wait_batch(self, ticket: int):
+        """Returns once the submission's last output frame is in its host buffer (submissions complete in order)."""
+        _check(self._lib.b2sr_wait_batch(self._h, ticket), "b2sr_wait_batch")
 
     # ---- bring-up / measurement ---------------------------------------------------------------
     def debug_layer(self, img: np.ndarray, layer: int) -> np.ndarray:

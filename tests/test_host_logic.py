@@ -451,6 +451,11 @@ def test_raw_stream_multi_gpu_dynamic_queue(tmp_path):
             self.run_batch_host(*self.jobs.pop(ticket))  # (the output appears only now: nothing may be written before its wait)
             self.in_flight -= 1
 
+    class Deferred1(Deferred):
+        def __init__(self, gpu):
+            super().__init__(gpu)
+            self.scale = 1
+
     made = []
     for chunk, gpus in ((1, [0]), (3, [0, 1, 1]), (40, [0, 1])):
         seen.clear()
@@ -478,6 +483,17 @@ def test_raw_stream_multi_gpu_dynamic_queue(tmp_path):
     raw_stream.stream_multi(Pipe(frames.tobytes()), out, 8, 6, scale=2, models=["n=3", "a"], gpus=[0, 0], chunk=3, pix_fmt="rgb24",
                             make_engines=lambda g: (Neg(), _FakeEngine(1), _FakeEngine(2)))
     assert out.getvalue() == np.repeat(np.repeat(255 - frames, 2, 1), 2, 2).tobytes()
+    # the same chain with a streaming last stage: the earlier stages of chunk k+1 run while chunk k's upscale is in flight, each
+    # chunk on its own set of intermediate buffers (Deferred produces its output only at the wait, from the buffers it was given)
+    for chunk in (1, 3):
+        out = io.BytesIO()
+        raw_stream.stream_multi(Pipe(frames.tobytes()), out, 8, 6, scale=2, models=["n=3", "a"], gpus=[0, 0], chunk=chunk, pix_fmt="rgb24",
+                                make_engines=lambda g: (Neg(), _FakeEngine(1), Deferred(g)))
+        assert out.getvalue() == np.repeat(np.repeat(255 - frames, 2, 1), 2, 2).tobytes()
+    out = io.BytesIO()  # scale 1: the pre-pass is the last stage
+    raw_stream.stream_multi(Pipe(frames.tobytes()), out, 8, 6, scale=1, models=["n=3", "a"], gpus=[0, 1], chunk=2,
+                            make_engines=lambda g: (Neg(), Deferred1(g), None))
+    assert out.getvalue() == (255 - frames).tobytes()
     # truncated inputs, a failing engine, a closed output pipe
     with pytest.raises(ValueError, match="truncated"):
         raw_stream.stream_multi(Pipe(frames.tobytes()[:-5]), io.BytesIO(), 8, 6, scale=2, gpus=[0, 1], chunk=2, make_engines=lambda g: (None, None, _FakeEngine(2)))

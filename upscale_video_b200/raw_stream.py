@@ -204,29 +204,49 @@ class _Worker:
             raise ValueError("nothing to do: scale 1 and no pre-pass model")
         self.scale = self.upscaler.scale if self.upscaler is not None else 1
         stages = sum(e is not None for e in (self.denoiser, self.prepass, self.upscaler))
-        self.tmp = [_Stage((chunk, height, width, 3)) for _ in range(min(2, stages - 1))]  # ping / pong between the stages
-        self.single_stage = stages == 1 and self.upscaler is not None and hasattr(self.upscaler, "submit_batch_host")
+        # ping / pong between the stages, two sets: the set of a chunk whose last stage is still in flight is not reused by the next
+        self.tmps = [[_Stage((chunk, height, width, 3)) for _ in range(min(2, stages - 1))] for _ in range(2)]
+        self.tmp = self.tmps[0]
+        self.last = self.upscaler if self.upscaler is not None else self.prepass  # the stage that may run without the host waiting
+        self.can_stream = self.last is not None and hasattr(self.last, "submit_batch_host")
+        self.n_submitted = 0
 
-    def submit(self, st_in, st_out, n):
-        """The upscaler alone, without waiting (``single_stage`` workers): returns the ticket for ``upscaler.wait_batch``."""
-        buf = lambda st: st.tensor if st.tensor is not None else st.array  # noqa: E731
-        return self.upscaler.submit_batch_host(buf(st_in), buf(st_out), n, self.height, self.width)
-
-    def process(self, st_in, st_out, n):
-        """denoise -> 1x pre-pass -> upscaler (the reference's order, test_images.py:82-110) over ``n`` frames."""
-        buf = lambda st: st.tensor if st.tensor is not None else st.array  # noqa: E731
+    def _steps(self, n, last_async):
         steps = []
         if self.denoiser is not None:
             steps.append(lambda a, b: self.denoiser.run_batch_host(a, b, n, self.height, self.width, self.level))
         if self.prepass is not None:
-            steps.append(lambda a, b: self.prepass.run_batch_host(a, b, n, self.height, self.width, tile=0, halo=0))
+            if last_async and self.upscaler is None:
+                steps.append(lambda a, b: self.prepass.submit_batch_host(a, b, n, self.height, self.width, tile=0, halo=0))
+            else:
+                steps.append(lambda a, b: self.prepass.run_batch_host(a, b, n, self.height, self.width, tile=0, halo=0))
         if self.upscaler is not None:
-            steps.append(lambda a, b: self.upscaler.run_batch_host(a, b, n, self.height, self.width))
-        src = st_in
+            if last_async:
+                steps.append(lambda a, b: self.upscaler.submit_batch_host(a, b, n, self.height, self.width))
+            else:
+                steps.append(lambda a, b: self.upscaler.run_batch_host(a, b, n, self.height, self.width))
+        return steps
+
+    def _run(self, st_in, st_out, n, last_async, tmp):
+        buf = lambda st: st.tensor if st.tensor is not None else st.array  # noqa: E731
+        steps = self._steps(n, last_async)
+        src, ret = st_in, None
         for i, step in enumerate(steps):
-            dst = st_out if i == len(steps) - 1 else self.tmp[i % 2]
-            step(buf(src), buf(dst))
+            dst = st_out if i == len(steps) - 1 else tmp[i % 2]
+            ret = step(buf(src), buf(dst))
             src = dst
+        return ret
+
+    def process(self, st_in, st_out, n):
+        """denoise -> 1x pre-pass -> upscaler (the reference's order, test_images.py:82-110) over ``n`` frames."""
+        self._run(st_in, st_out, n, False, self.tmp)
+
+    def submit(self, st_in, st_out, n):
+        """``process`` with the LAST stage submitted instead of run (``can_stream`` workers): the earlier stages run
+        synchronously -- on the same GPU as, and concurrently with, the previous chunk's last stage -- and the ticket returned is
+        for ``last.wait_batch``.  At most two chunks may be in flight: each uses its own set of intermediate buffers."""
+        self.n_submitted += 1
+        return self._run(st_in, st_out, n, True, self.tmps[self.n_submitted & 1])
 
 
 def stream_multi(fin, fout, width, height, scale=2, models=(), gpus=(0,), chunk=4, pix_fmt="bgr24", model_path=None, max_frames=None,
@@ -362,9 +382,9 @@ def stream_multi(fin, fout, width, height, scale=2, models=(), gpus=(0,), chunk=
             work.put(None)
 
     def worker(i):
-        """One ``-g`` entry.  With the upscaler as the only stage the worker keeps TWO chunks in flight (``Engine.submit_batch_host``
-        / ``wait_batch``): the next chunk's first H2D copy runs under this chunk's network and this chunk's last D2H under the
-        next one's -- but a chunk is never held back waiting for a successor that is not already queued."""
+        """One ``-g`` entry.  The worker keeps TWO chunks in flight on its last engine (``Engine.submit_batch_host`` /
+        ``wait_batch``): the next chunk's first H2D copy (and its earlier stages) run under this chunk's network and this chunk's
+        last D2H under the next one's -- but a chunk is never held back waiting for a successor that is not already queued."""
         w = workers[i]
         pending = None  # (ticket, seq, st_in, st_out, n) submitted, not yet waited for
 
@@ -375,7 +395,7 @@ def stream_multi(fin, fout, width, height, scale=2, models=(), gpus=(0,), chunk=
                 done_cv.notify_all()
 
         def finish(p):
-            w.upscaler.wait_batch(p[0])
+            w.last.wait_batch(p[0])
             publish(*p[1:])
 
         try:
@@ -394,7 +414,7 @@ def stream_multi(fin, fout, width, height, scale=2, models=(), gpus=(0,), chunk=
                 seq, st_in, st_out, n = item
                 if n > 0 and swap:
                     st_in.array[:n] = st_in.array[:n, :, :, ::-1].copy()
-                if n > 0 and w.single_stage:
+                if n > 0 and w.can_stream:
                     nxt_p = (w.submit(st_in, st_out, n), seq, st_in, st_out, n)
                     if pending is not None:
                         finish(pending)

@@ -211,7 +211,7 @@ def run_reference(args, rank):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
 
 
 def _event_timed(torch, stream_int, device, fn, steps, warm=2):
@@ -387,6 +387,9 @@ def denoise_1080p(E, torch, device, level=3):
         return {"workload": "denoise 1080p", "unavailable": str(e)[:200]}
 
 
+_JSON_OUT = None  # the process's original stdout (see main)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -406,6 +409,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries ONE JSON line: everything libraries write to file descriptor 1 meanwhile (NCCL's version banner ignores
+    # NCCL_DEBUG_FILE on this image) goes to stderr; the line itself is written to the saved descriptor
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -631,7 +640,7 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_torch": cpu_torch, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": sampler.summary(), "other_configs": extra,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 

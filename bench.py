@@ -501,7 +501,7 @@ def main():
         h_in = torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()
         h_in.copy_(d_in.cpu())
         h_out = torch.empty((B, H * SCALE, W * SCALE, 3), dtype=torch.uint8).pin_memory()
-        e_steps = max(4, args.steps // 2)
+        e_steps = max(4, args.steps)
 
         def timed(fn):
             barrier()

@@ -404,8 +404,8 @@ def stream_multi(fin, fout, width, height, scale=2, models=(), gpus=(0,), chunk=
                     try:
                         item = work.get_nowait()
                     except queue.Empty:
-                        finish(pending)
-                        pending = None
+                        p, pending = pending, None
+                        finish(p)
                         continue
                 else:
                     item = get(work)
@@ -416,20 +416,27 @@ def stream_multi(fin, fout, width, height, scale=2, models=(), gpus=(0,), chunk=
                     st_in.array[:n] = st_in.array[:n, :, :, ::-1].copy()
                 if n > 0 and w.can_stream:
                     nxt_p = (w.submit(st_in, st_out, n), seq, st_in, st_out, n)
-                    if pending is not None:
-                        finish(pending)
-                    pending = nxt_p
+                    p, pending = pending, nxt_p
+                    if p is not None:
+                        finish(p)
                     continue
                 if pending is not None:
-                    finish(pending)
-                    pending = None
+                    p, pending = pending, None
+                    finish(p)
                 if n > 0:
                     w.process(st_in, st_out, n)
                 publish(seq, st_in, st_out, n)
             if pending is not None:
-                finish(pending)
+                p, pending = pending, None
+                finish(p)
         except BaseException as e:  # noqa: BLE001
             fail(e)
+        finally:
+            if pending is not None:  # an error elsewhere: the device may still be copying into this chunk's staging slots
+                try:
+                    w.last.wait_batch(pending[0])
+                except BaseException:  # noqa: BLE001 -- already failing
+                    pass
 
     threads = [threading.Thread(target=dispatcher, daemon=True)] + [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(nw)]
     if direct:

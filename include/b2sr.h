@@ -84,6 +84,9 @@ extern "C" {
                                   accumulator ring is shorter; measured 33.4 vs 28.3 ms per 540p frame on B200 -- DESIGN.md section 3),
                                   0 (default) = one CTA per band */
 
+#define B2SR_OPT_ABLATE 9      /* fused family, MEASUREMENT ONLY (results are garbage): bit 0 = no MMAs, bit 1 = epilogues drain TMEM only,
+                                  bit 2 = no row loads, bit 3 = epilogues without their global loads / stores (energy accounting) */
+
 /* b2sr_get_stat keys */
 #define B2SR_STAT_LAUNCHES 1       /* kernels launched by this context since creation / last reset */
 #define B2SR_STAT_TC_LAUNCHES 2    /* ... of which tcgen05 convolution kernels */

@@ -19,6 +19,7 @@ ap.add_argument("--w", type=int, default=960)
 ap.add_argument("--scale", type=int, default=4)
 ap.add_argument("--batch", type=int, default=4)
 ap.add_argument("--secs", type=float, default=5.0)
+ap.add_argument("--ablate", type=int, default=0, help="B2SR_OPT_ABLATE bits, switched on AFTER two real passes (the buffers keep real activations)")
 a = ap.parse_args()
 pynvml.nvmlInit()
 h = pynvml.nvmlDeviceGetHandleByIndex(0)
@@ -28,6 +29,9 @@ d_out = torch.empty((a.batch, a.h * a.scale, a.w * a.scale, 3), dtype=torch.uint
 time.sleep(1)
 print("idle power %.0f W" % (pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0))
 for _ in range(2):
+    eng.run_batch_device(d_in, d_out, a.batch, a.h, a.w, sync=True)
+if a.ablate:
+    eng.set_option(E.OPT_ABLATE, a.ablate)
     eng.run_batch_device(d_in, d_out, a.batch, a.h, a.w, sync=True)
 samples, stop = [], [False]
 
@@ -55,5 +59,5 @@ ck = sum(x[1] for x in s) / len(s)
 reasons = 0
 for x in s:
     reasons |= x[2]
-print("%s %dx%d batch %d: %.1f fps  power %.0f W  sm clock %.0f MHz  throttle reasons 0x%x  => %.2f J/frame" % (
-    a.model, a.h, a.w, a.batch, n / dt, pw, ck, reasons, pw * dt / n))
+print("ablate %d | %s %dx%d batch %d: %.1f fps  power %.0f W  sm clock %.0f MHz  throttle reasons 0x%x  => %.2f J/frame" % (
+    a.ablate, a.model, a.h, a.w, a.batch, n / dt, pw, ck, reasons, pw * dt / n))

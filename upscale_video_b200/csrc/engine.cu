@@ -255,6 +255,7 @@ struct b2sr_ctx {
     std::vector<FusedLaunch> flaunch;
     std::vector<FusedLaunch> flaunch2;  // CTA-pair (cta_group::2) form of the ops that have one: whole convolution, full weight image
     std::vector<int> fop_pair2;         // op -> index into flaunch2, or -1
+    int ablate = 0;                     // measurement only (B2SR_ABLATE / B2SR_OPT_ABLATE): see TcgParams::ablate
     int pair2 = 0;                      // use the CTA-pair form where it exists (B2SR_PAIR2=1 / B2SR_OPT_PAIR2); measured slower: opt-in
     std::vector<int> fop_first;   // launches of op i: flaunch[fop_first[i] .. fop_first[i+1])
     std::vector<void*> fbuf_ptr;
@@ -1790,8 +1791,8 @@ static void fused_fill_params(b2sr_ctx* c, Plan* P, int li, void* d_out, TcgPara
     p.acc_scale = o.in_buf < 0 ? (1.f / 255.f) : 1.f;
     p.groups = L.G, p.cin = L.cinp, p.k1 = o.k == 1, p.ring_slots = L.slots;
     p.sc_ks = L.sc_ks, p.sc_cv = o.sc_coef_v, p.sc_cr = o.sc_coef_r;
-    static const int ablate = getenv("B2SR_ABLATE") ? atoi(getenv("B2SR_ABLATE")) : 0;  // measurement only: see TcgParams::ablate
-    p.ablate = ablate;
+    static const int ablate_env = getenv("B2SR_ABLATE") ? atoi(getenv("B2SR_ABLATE")) : 0;  // measurement only: see TcgParams::ablate
+    p.ablate = c->ablate ? c->ablate : ablate_env;
     p.pair = L.pair, p.pair_wbytes = L.G * 9 * L.NOUT * TCG_PB;
     p.nres = o.nres;
     for (int q = 0; q < o.nres; ++q) {
@@ -2621,6 +2622,9 @@ extern "C" int b2sr_set_option(b2sr_ctx* c, int key, int64_t value) {
             return 0;
         case B2SR_OPT_PAIR2:
             c->pair2 = value != 0;
+            return 0;
+        case B2SR_OPT_ABLATE:
+            c->ablate = (int)value;
             return 0;
         case B2SR_OPT_RING_ROWS:
             if (value != 0 && (value < 4 || value > 4096)) return fail(B2SR_E_INVALID, "ring rows %lld (need 0 = auto, or 4..4096)", (long long)value);

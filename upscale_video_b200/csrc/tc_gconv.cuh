@@ -84,7 +84,8 @@ struct TcgParams {
                                 // output / residual slices are offset like a cluster rank's in the paired launch)
     int32_t ablate;             // measurement only (B2SR_ABLATE, energy accounting; results are garbage): bit 0 = no MMAs are issued
                                 // (commits only), bit 1 = the epilogue drains the accumulators but neither reads residuals nor
-                                // computes / stores anything, bit 2 = the producer arrives on the full barriers without loading rows
+                                // computes / stores anything, bit 2 = the producer arrives on the full barriers without loading rows,
+                                // bit 3 = the epilogue does everything but its global loads and stores
 };
 
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may become resident
@@ -716,7 +717,7 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
                 if constexpr (MODE == 0 && !PLAIN) {
 #pragma unroll
                     for (int r = 0; r < NPRE; ++r) {
-                        if (r >= nres || pix < 0 || (P.ablate & 2)) continue;
+                        if (r >= nres || pix < 0 || (P.ablate & 10)) continue;
                         // (pipelined mode reads residuals with ld.global.cg: a ring slot is rewritten by another SM during
                         // the launch, so a stale L1 line must never be hit)
                         if (NRES >= 0 ? !RF16 : P.res_f32[r] != 0) {
@@ -820,7 +821,7 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
                         const int qi = i * 32 + lane;
                         const uint4 v4 = stg[qi ^ ((qi >> 3) & 7)];
                         const long long o = __shfl_sync(0xffffffffu, pix16, qi / CH);
-                        if (o >= 0) *reinterpret_cast<uint4*>(outp + (size_t)o * P.out16_ld * 2 + (qi % CH) * 16) = v4;
+                        if (o >= 0 && !(P.ablate & 8)) *reinterpret_cast<uint4*>(outp + (size_t)o * P.out16_ld * 2 + (qi % CH) * 16) = v4;
                     }
                     __syncwarp();
                 } else if constexpr (MODE == 0) {
@@ -890,7 +891,7 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
                                 const int qi = i * 32 + lane;
                                 const uint4 v4 = stg[qi ^ ((qi >> 3) & 7)];
                                 const long long o = __shfl_sync(0xffffffffu, pix32, qi / CH);
-                                if (o >= 0) *reinterpret_cast<uint4*>(outp + ((size_t)o * P.out32_ld + half * (NOUT / 2)) * 4 + (qi % CH) * 16) = v4;
+                                if (o >= 0 && !(P.ablate & 8)) *reinterpret_cast<uint4*>(outp + ((size_t)o * P.out32_ld + half * (NOUT / 2)) * 4 + (qi % CH) * 16) = v4;
                             }
                         }
                     }
@@ -914,7 +915,7 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
                             const int qi = i * 32 + lane;
                             const uint4 v4 = stg[qi ^ ((qi >> 3) & 7)];
                             const long long o = __shfl_sync(0xffffffffu, pix16, qi / CH);
-                            if (o >= 0) *reinterpret_cast<uint4*>(outp + (size_t)o * P.out16_ld * 2 + (qi % CH) * 16) = v4;
+                            if (o >= 0 && !(P.ablate & 8)) *reinterpret_cast<uint4*>(outp + (size_t)o * P.out16_ld * 2 + (qi % CH) * 16) = v4;
                         }
                     }
                     __syncwarp();

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2sr.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
-OPT_IMPL, OPT_PROFILE, OPT_MAX_BATCH, OPT_RING_ROWS, OPT_PIPE_DEBUG, OPT_SM_LIMIT, OPT_SEG_PIPE, OPT_PAIR2 = 1, 2, 3, 4, 5, 6, 7, 8
+OPT_IMPL, OPT_PROFILE, OPT_MAX_BATCH, OPT_RING_ROWS, OPT_PIPE_DEBUG, OPT_SM_LIMIT, OPT_SEG_PIPE, OPT_PAIR2, OPT_ABLATE = 1, 2, 3, 4, 5, 6, 7, 8, 9
 STAT_LAUNCHES, STAT_TC_LAUNCHES, STAT_TC_MID_MS, STAT_TC_MID_COUNT, STAT_ALL_MS, STAT_TC_MID_PIXELS = 1, 2, 3, 4, 5, 6
 STAT_PIPE_LAUNCHES, STAT_PIPE_MS, STAT_HMMA_LAUNCHES, STAT_PIPE_FALLBACKS = 7, 8, 9, 10
 IMPL_AUTO, IMPL_SIMPLE, IMPL_TCGEN05, IMPL_PIPELINED = 0, 1, 2, 3  # IMPL_TCGEN05 = tcgen05 kernels launched layer by layer

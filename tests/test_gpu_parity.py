@@ -329,6 +329,14 @@ def test_host_pipeline_submit_wait(E, engines):
         assert np.array_equal(h_out.numpy(), d_out.cpu().numpy()), (n, h, w)
     with pytest.raises(E.EngineError):
         eng.wait_batch(10 ** 6)
+    # a rejected submission (bad geometry) leaves the pipeline usable
+    frames, h_in, h_out, n, h, w, _ = jobs[1]
+    with pytest.raises(E.EngineError):
+        eng.submit_batch_host(h_in, h_out, n, 0, w)
+    before = h_out.numpy().copy()
+    h_out.zero_()
+    eng.wait_batch(eng.submit_batch_host(h_in, h_out, n, h, w))
+    assert np.array_equal(h_out.numpy(), before)
 
 
 def test_strides_and_device_memory(E, engines):

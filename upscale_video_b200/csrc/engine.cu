@@ -379,7 +379,9 @@ static void free_layers(b2sr_ctx* c) {
 extern "C" void b2sr_destroy(b2sr_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->copy_in) cudaStreamSynchronize(c->copy_in);  // (pending b2sr_submit_batch_host work: copies into / out of the caller's buffers)
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_out) cudaStreamSynchronize(c->copy_out);
     c->plans.clear();
     free_layers(c);
     for (auto& g : c->gops) {

@@ -273,11 +273,12 @@ def side_configs(E, ncnn_model, torch, device, steps=10):
     try:
         hurr = E.Engine.from_files(mdir, "1x_HurrDeblur_SubCompact_nf24-nc8_244k_net_g", device)
         comp = E.Engine.from_files(mdir, "2x_Compact_Pretrain", device)
-        # Frames per hand-over: measured on one box (tools/chain_ab.py) 2 frames, two hand-over buffers: 329 fps; 4: 306-310; 8: 300-308;
-        # 16: 298 -- both networks run at the board's power cap, and short alternating phases leave the upscaler more clock headroom.
+        # Frames per hand-over, measured on one box with equal warm-up and duration (tools/chain_ab.py): 2 or 4 frames through two
+        # hand-over buffers 316-317 fps, 8 frames 310, 16 frames 299.
         n = int(os.environ.get("B2SR_BENCH_CHAIN_N", "2"))
         nbuf = int(os.environ.get("B2SR_BENCH_CHAIN_BUFS", "2"))
-        steps = steps * max(1, 8 // n)  # the same 80 frames per measurement whatever the hand-over size
+        steps = max(1, steps * 16 // n)  # the same 160 frames per measurement (and 32 of warm-up) whatever the hand-over size:
+        # the board's power governor settles over some 100 ms, so runs of different length or warmth do not compare
         d_in = torch.randint(0, 256, (n, H, W, 3), dtype=torch.uint8, device="cuda")
         d_mids = [torch.empty_like(d_in), torch.empty_like(d_in)]  # two hand-over buffers: the pre-pass of step k+1 may run under step k's upscale
         d_mid = d_mids[0]
@@ -298,7 +299,7 @@ def side_configs(E, ncnn_model, torch, device, steps=10):
             mid_free[k].record(sc)
         mid_free[0].record(sc)
         mid_free[1].record(sc)
-        for _ in range(2):
+        for _ in range(max(2, 32 // n)):
             chain()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(sh)

@@ -8,6 +8,8 @@
  * `ncnn_vulkan` wheel (version unpinned, reference README.md:29; call sites
  * upscale/upscale_processing.py:265-281 and :437-453), which is not in /root/reference, not installable
  * offline, and the reference ships no golden outputs or known-answer tests.
+ * (What CAN be pinned is: tests/test_architecture_cross_check.py shows that this restatement equals the published PyTorch
+ * architectures the model files were exported from -- SRVGGNetCompact, ESRGAN-plus RRDB_Net -- to < 1e-8.)
  * This file therefore restates ncnn's *published layer definitions* for exactly the layers the reference's
  * model files use (reference models/2x_Compact_Pretrain.param:3-42, 1x_HurrDeblur...param:3-26,
  * 4x_Valar_v1.param:3-1208):

@@ -73,6 +73,28 @@ def test_upscale_goldens(name, model, engines):
     assert_parity(engines(model).run_u8(g["x"]), g["y"], name)
 
 
+@pytest.mark.parametrize("name,model,scale,fn", [
+    ("hurr_upscale_14x1000", HURR, 1, "upscale_image"), ("hurr_upscale_1000x12", HURR, 1, "upscale_image"),
+    ("hurr_upscale_12x965", HURR, 1, "upscale_image"), ("hurr_upscale_12x969", HURR, 1, "upscale_image"),
+    ("hurr_upscale_12x970", HURR, 1, "upscale_image"), ("hurr_upscale_12x971", HURR, 1, "upscale_image"),
+    ("hurr_upscale_969x11", HURR, 1, "upscale_image"), ("hurr_upscale_970x11", HURR, 1, "upscale_image"),
+    ("hurr_upscale_9x9", HURR, 1, "upscale_image"), ("hurr_apply_40x60", HURR, 1, "apply_model"),
+    ("compact2x_10x980", "2x_Compact_Pretrain", 2, "upscale_image"), ("compact2x_972x8", "2x_Compact_Pretrain", 2, "upscale_image"),
+    ("compact4x_8x975", "4x_Compact_Pretrain", 4, "upscale_image"), ("valar4x_5x964", "4x_Valar_v1", 4, "upscale_image"),
+])
+def test_reference_code_goldens(name, model, scale, fn, engines, model_dir):
+    """The device against files written by the reference's OWN upscale_processing.py (tools/make_ref_glue_goldens.py: the reference
+    module imported unmodified, only ncnn_vulkan replaced by a numpy stand-in running the oracle's float32 layers): the tile grid,
+    halo rule, crops and rounding the device reproduces are the reference's, not a restatement's."""
+    if model == "4x_Valar_v1" and not os.path.exists(os.path.join(model_dir, "4x_Valar_v1.b2sr")):
+        pytest.skip("4x_Valar_v1 not packaged")
+    g = golden("ref_glue")
+    x, want = g[name + "__x"], g[name + "__y"]
+    eng = engines(model)
+    got = eng.run_u8(x) if fn == "upscale_image" else eng.run_u8(x, tile=0, halo=0)
+    assert_parity(got, want, name, max_mismatch=0.05)
+
+
 def test_hurr_goldens_and_chain(engines):
     """1x pre-pass (apply_model, untiled) and the chained config with its u8 hop between the two networks
     (reference apply_model :288 writes u8, upscale_image :487 re-reads it)."""

@@ -148,3 +148,47 @@ def test_rrdb_op_semantics_hand_vectors():
     # Eltwise operand order matters: swapping the bottoms must change the result
     layers[4] = layer("Eltwise", ["c", "z"], ["e"], {0: 1, 1: [0.2, 1.0]})
     assert np.allclose(oracle.run_graph(layers, x, "f64")[0, 0, 3:], [0.2 * 1.0 - 2.0, 0.2 * -2.0 + 1.0], atol=1e-7)
+
+
+REF_GLUE_CASES = [  # (name, model, scale, reference function) -- tools/make_ref_glue_goldens.py
+    ("hurr_upscale_14x1000", HURR, 1, "upscale_image"), ("hurr_upscale_1000x12", HURR, 1, "upscale_image"),
+    ("hurr_upscale_12x965", HURR, 1, "upscale_image"), ("hurr_upscale_12x969", HURR, 1, "upscale_image"),
+    ("hurr_upscale_12x970", HURR, 1, "upscale_image"), ("hurr_upscale_12x971", HURR, 1, "upscale_image"),
+    ("hurr_upscale_969x11", HURR, 1, "upscale_image"), ("hurr_upscale_970x11", HURR, 1, "upscale_image"),
+    ("hurr_upscale_9x9", HURR, 1, "upscale_image"), ("hurr_apply_40x60", HURR, 1, "apply_model"),
+    ("compact2x_10x980", "2x_Compact_Pretrain", 2, "upscale_image"), ("compact2x_972x8", "2x_Compact_Pretrain", 2, "upscale_image"),
+    ("compact4x_8x975", "4x_Compact_Pretrain", 4, "upscale_image"), ("valar4x_5x964", "4x_Valar_v1", 4, "upscale_image"),
+]
+
+
+def ref_glue_big_input():
+    """Same generator as tools/make_ref_glue_goldens.py::big_case_input (the four-tile case stores no input)."""
+    yy, xx = np.mgrid[0:975, 0:972]
+    rng = np.random.default_rng(975972)
+    base = np.stack([120 + 90 * np.sin(xx / 37.0) * np.cos(yy / 53.0), 40 + 0.2 * xx + 30 * ((xx // 16 + yy // 12) % 2), 200 - 0.15 * yy], -1)
+    return np.clip(base + rng.normal(0, 6, base.shape), 0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("name,model,scale,fn", REF_GLUE_CASES)
+def test_oracle_glue_equals_reference_code(name, model, scale, fn, oracle_models):
+    """PINS THE GLUE: tests/golden/ref_glue.npz holds what the reference's OWN upscale_processing.py (imported unmodified in the
+    build container, init_worker -> upscale_image -> process_tile / apply_model, PNG in, PNG out) wrote when only ncnn_vulkan was
+    replaced by a numpy stand-in whose network run is the oracle's float32 layer interpreter.  The oracle's restatement of that
+    glue -- tile grid, the '>= 10 px remain' halo rule on every side, crop of the halo, unswapped BGR, 1/255 and *255 in float32,
+    float64 canvas, imwrite rounding -- must reproduce those files bit for bit (reference upscale_processing.py:258-299, :395-519)."""
+    g = golden("ref_glue")
+    x, want = g[name + "__x"], g[name + "__y"]
+    layers = oracle_models(model)
+    got = oracle.upscale_image_array(layers, x, scale, "f32") if fn == "upscale_image" else oracle.apply_model_array(layers, x, "f32")
+    assert got.shape == want.shape and np.array_equal(got, want), (name, int(np.abs(got.astype(int) - want.astype(int)).max()))
+
+
+def test_oracle_glue_equals_reference_code_four_tiles(oracle_models):
+    """The same for a 975 x 972 frame: four tiles, three of them slivers whose halo exists on one side only (digest of the whole
+    output + the strips around both seams, as written by the reference's own code)."""
+    import hashlib
+    g = golden("ref_glue")
+    got = oracle.upscale_image_array(oracle_models(HURR), ref_glue_big_input(), 1, "f32")
+    assert np.array_equal(got[940:975], g["hurr_upscale_975x972__rows_940_975"])
+    assert np.array_equal(got[:, 940:972], g["hurr_upscale_975x972__cols_940_972"])
+    assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).digest() == g["hurr_upscale_975x972__sha256"].tobytes()

@@ -9,7 +9,9 @@
  * upscale/upscale_processing.py:265-281 and :437-453), which is not in /root/reference, not installable
  * offline, and the reference ships no golden outputs or known-answer tests.
  * (What CAN be pinned is: tests/test_architecture_cross_check.py shows that this restatement equals the published PyTorch
- * architectures the model files were exported from -- SRVGGNetCompact, ESRGAN-plus RRDB_Net -- to < 1e-8.)
+ * architectures the model files were exported from -- SRVGGNetCompact, ESRGAN-plus RRDB_Net -- to < 1e-8; and the Python side's
+ * restatement of the reference's glue reproduces, bit for bit, files written by the reference's own upscale_processing.py run with
+ * an ncnn stand-in -- tools/make_ref_glue_goldens.py, tests/golden/ref_glue.npz.)
  * This file therefore restates ncnn's *published layer definitions* for exactly the layers the reference's
  * model files use (reference models/2x_Compact_Pretrain.param:3-42, 1x_HurrDeblur...param:3-26,
  * 4x_Valar_v1.param:3-1208):

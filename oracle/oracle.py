@@ -3,8 +3,11 @@
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs
 may import this module; product code under ``upscale_video_b200/`` must never do so.
 
-PARITY UNPINNED (see oracle.c header): the reference delegates its arithmetic to the un-vendored, unpinned
-``ncnn_vulkan`` wheel and ships no golden outputs, so this file restates
+PARITY UNPINNED for ncnn's own arithmetic (see oracle.c header): the reference delegates it to the un-vendored, unpinned
+``ncnn_vulkan`` wheel and ships no golden outputs.  PINNED for the rest: the glue below reproduces, bit for bit, files written by the
+reference's own ``upscale_processing.py`` run with an ncnn stand-in (``tools/make_ref_glue_goldens.py`` ->
+``tests/golden/ref_glue.npz``), and the graph interpreter equals the published PyTorch architectures the models were exported from
+(``tests/test_architecture_cross_check.py``).  This file restates
 
 * the ncnn model format and layer semantics for the layers the reference's models use
   (own, independent reader below -- it deliberately does not share code with

@@ -502,8 +502,6 @@ __device__ __forceinline__ void tcg_body(const TcgParams& P, const int it_begin,
                 }
             }
             if (P.dbg) {  // (the elected lane holds the full / pfull waits, every lane the block waits)
-                const long long a = __shfl_sync(0xffffffffu, w_fu, 0) , b = __shfl_sync(0xffffffffu, w_pfu, 0);
-                (void)a, (void)b;
                 if (lane == 0) {
                     P.dbg[blockIdx.x * 16 + 0] = clock64() - t_begin;
                     P.dbg[blockIdx.x * 16 + 2] = w_te;

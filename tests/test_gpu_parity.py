@@ -351,6 +351,11 @@ def test_host_pipeline_submit_wait(E, engines):
         assert np.array_equal(h_out.numpy(), d_out.cpu().numpy()), (n, h, w)
     with pytest.raises(E.EngineError):
         eng.wait_batch(10 ** 6)
+    # pageable (numpy) buffers: the copies become synchronous, the result is the same
+    frames, _, h_out, n, h, w, _ = jobs[3]
+    np_out = np.zeros((n, 2 * h, 2 * w, 3), np.uint8)
+    eng.wait_batch(eng.submit_batch_host(frames, np_out, n, h, w))
+    assert np.array_equal(np_out, h_out.numpy())
     # a rejected submission (bad geometry) leaves the pipeline usable
     frames, h_in, h_out, n, h, w, _ = jobs[1]
     with pytest.raises(E.EngineError):

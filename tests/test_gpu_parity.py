@@ -17,7 +17,8 @@ from oracle import oracle
 pytestmark = pytest.mark.gpu
 
 MAX_LSB = 1            # tolerance stated by BASELINE.json north_star
-MAX_MISMATCH = 0.06    # fraction of u8 values allowed to differ by exactly 1 LSB (measured ~0.5-2.5 %)
+MAX_MISMATCH = 0.045   # fraction of u8 values allowed to differ by exactly 1 LSB (measured, profiles/r02zz_parity_measured.jsonl:
+                       # 0.2-0.5 % on natural content, 2.5-3.0 % on uniform noise, 4x_Valar_v1 1.1-2.1 %)
 
 
 @pytest.fixture(scope="module")
@@ -51,9 +52,20 @@ def natural(h, w, seed=0):
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
+def _record(name, **kv):
+    """Measured parity figures go to gpurun_out/ (when that scratch dir exists) so tolerances can be set from data."""
+    import json
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_measured.jsonl"), "a") as f:
+            f.write(json.dumps(dict(name=name, **kv)) + "\n")
+
+
 def assert_parity(got, ref, what="", max_mismatch=MAX_MISMATCH):
     assert got.shape == ref.shape and got.dtype == np.uint8, what
     d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+    _record(what, max_lsb=int(d.max()) if d.size else 0, mismatch_fraction=float((d > 0).mean()) if d.size else 0.0, bound=max_mismatch,
+            values=int(d.size))
     assert d.max() <= MAX_LSB, "%s: max |diff| = %d LSB at %s" % (what, d.max(), np.unravel_index(d.argmax(), d.shape))
     # the fraction bound is only meaningful on images with enough values (a 1x1 frame has 12)
     assert (d > 0).sum() <= max(2, max_mismatch * d.size), "%s: %.2f%% of values differ" % (what, 100 * (d > 0).mean())
@@ -92,7 +104,7 @@ def test_reference_code_goldens(name, model, scale, fn, engines, model_dir):
     x, want = g[name + "__x"], g[name + "__y"]
     eng = engines(model)
     got = eng.run_u8(x) if fn == "upscale_image" else eng.run_u8(x, tile=0, halo=0)
-    assert_parity(got, want, name, max_mismatch=0.05)
+    assert_parity(got, want, name, max_mismatch=0.045)
 
 
 def test_hurr_goldens_and_chain(engines):
@@ -532,24 +544,24 @@ def test_valar_rrdb_fused_tcgen05(E, model_dir, oracle_models):
     assert eng.stat(E.STAT_PIPE_LAUNCHES) == 23 and eng.stat(E.STAT_TC_LAUNCHES) == 1 + 23 + 1 + 4
     assert np.array_equal(out, piped), "persistent segments and per-convolution launches must agree bit for bit"
     eng.set_option(E.OPT_SEG_PIPE, 0)
-    assert_parity(out, g["y"], "valar golden (tcgen05)", max_mismatch=0.05)
+    assert_parity(out, g["y"], "valar golden (tcgen05)", max_mismatch=0.03)
     assert np.array_equal(out, eng.run_u8(g["x"]))
     img = natural(20, 980, seed=13)  # seam at x = 960
     models = oracle_models("4x_Valar_v1")
     ref = oracle.upscale_image_array(models, img, 4, "f32")
     out = eng.run_u8(img)
-    assert_parity(out, ref, "valar 20x980 (tcgen05)", max_mismatch=0.05)
+    assert_parity(out, ref, "valar 20x980 (tcgen05)", max_mismatch=0.03)
     canvas = eng.run_f32(img)
     assert np.array_equal(oracle.saturate_u8(canvas), out)
     img = natural(37, 300, seed=14)  # three bands, the last one 44 columns wide; CTA ranges cut inside bands
-    assert_parity(eng.run_u8(img), oracle.upscale_image_array(models, img, 4, "f32"), "valar 37x300 (tcgen05)", max_mismatch=0.05)
+    assert_parity(eng.run_u8(img), oracle.upscale_image_array(models, img, 4, "f32"), "valar 37x300 (tcgen05)", max_mismatch=0.03)
     # worst case found for the storage types: salt-and-pepper extremes drive the largest activations through all 23 blocks
     # (CPU emulation of the device arithmetic: 0.70 LSB max float error with the fp32 trunk -- an all-fp16 trunk reaches
     # 1.17 LSB here and is why the trunk is kept in fp32, ncnn_model.compile_fused fp32_chain)
     rng = np.random.default_rng(5)
     rng.integers(0, 256, (40, 64, 3))  # (keeps the generator state of the CPU study this case comes from)
     harsh = np.where(rng.random((40, 64, 1)) > 0.5, 250, 5).astype(np.uint8).repeat(3, 2)
-    assert_parity(eng.run_u8(harsh), oracle.upscale_image_array(models, harsh, 4, "f64"), "valar salt-and-pepper (tcgen05)", max_mismatch=0.12)
+    assert_parity(eng.run_u8(harsh), oracle.upscale_image_array(models, harsh, 4, "f64"), "valar salt-and-pepper (tcgen05)", max_mismatch=0.10)
     # batch == single frame, bit for bit (accumulator homes follow plane rows, not CTA ranges)
     import torch
     frames = np.stack([natural(64, 200, seed=s) for s in (21, 22, 23)])
@@ -600,7 +612,7 @@ def test_valar_cta_pair_schedule(E, model_dir, oracle_models):
     assert eng.stat(E.STAT_TC_LAUNCHES) == 420 - 69
     d = np.abs(pair.astype(int) - base.astype(int))
     assert d.max() <= 1 and (d > 0).mean() < 0.06, "pair form vs default: max %d, %.3f%%" % (d.max(), 100 * (d > 0).mean())
-    assert_parity(pair, oracle.upscale_image_array(models, img, 4, "f32"), "valar 37x300 (cta pairs)", max_mismatch=0.05)
+    assert_parity(pair, oracle.upscale_image_array(models, img, 4, "f32"), "valar 37x300 (cta pairs)", max_mismatch=0.03)
     assert np.array_equal(pair, eng.run_u8(img)), "pair form is not deterministic"
     frames = np.stack([natural(150, 1000, seed=s) for s in (31, 32)])  # two tiles per frame (seam at 960), 8 + 1 bands
     d_in = torch.from_numpy(frames).cuda()
@@ -623,7 +635,7 @@ def test_valar_edge_shapes(E, model_dir, oracle_models, shape):
     eng = E.Engine.from_files(model_dir, "4x_Valar_v1", 0)
     img = natural(shape[0], shape[1], seed=31 + shape[1])
     ref = oracle.upscale_image_array(oracle_models("4x_Valar_v1"), img, 4, "f64")
-    assert_parity(eng.run_u8(img), ref, "valar %dx%d" % shape, max_mismatch=0.05)
+    assert_parity(eng.run_u8(img), ref, "valar %dx%d" % shape, max_mismatch=0.03)
     eng.close()
 
 
@@ -638,7 +650,7 @@ def test_valar_rrdb_generic_graph_engine(E, model_dir, oracle_models):
     g = golden("valar4x_crop")
     out = eng.run_u8(g["x"])
     assert eng.stat(E.STAT_TC_LAUNCHES) == 0 and eng.stat(E.STAT_HMMA_LAUNCHES) >= 400
-    assert_parity(out, g["y"], "valar golden (hmma)", max_mismatch=0.09)
+    assert_parity(out, g["y"], "valar golden (hmma)", max_mismatch=0.03)
     # fp32 CUDA-core kernels everywhere: essentially exact
     eng.set_option(E.OPT_IMPL, E.IMPL_SIMPLE)
     eng.reset_stats()
@@ -666,15 +678,6 @@ def test_compact_models_through_generic_engine(E, engines, model_dir, oracle_mod
         gen.close()
 
 
-def _record(name, **kv):
-    """Measured parity figures go to gpurun_out/ (when that scratch dir exists) so tolerances can be set from data."""
-    import json
-    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
-    if os.path.isdir(d):
-        with open(os.path.join(d, "parity_measured.jsonl"), "a") as f:
-            f.write(json.dumps(dict(name=name, **kv)) + "\n")
-
-
 def test_valar_540p_full_frame_vs_oracle(E, model_dir, oracle_models):
     """BASELINE configs[3] at its stated size: one 960x540 frame of natural-looking content through 4x_Valar_v1
     (reference models/4x_Valar_v1.param:1-1208, 420 convolutions, no input residual) against the f32 CPU oracle run on
@@ -698,7 +701,7 @@ def test_valar_540p_full_frame_vs_oracle(E, model_dir, oracle_models):
     d = np.abs(out.astype(np.int32) - ref.astype(np.int32))
     _record("valar_540p_full_frame", content=what, max_lsb=int(d.max()), mismatch_fraction=float((d > 0).mean()))
     assert out.shape == (2160, 3840, 3) and d.max() <= 1, "valar 540p %s: max |diff| = %d LSB" % (what, d.max())
-    assert (d > 0).mean() <= 0.05, "valar 540p %s: %.2f%% of values differ" % (what, 100 * (d > 0).mean())
+    assert (d > 0).mean() <= 0.025, "valar 540p %s: %.2f%% of values differ" % (what, 100 * (d > 0).mean())
 
 
 def test_persistent_grid_guard_falls_back(E, model_dir, oracle_models):

@@ -517,3 +517,47 @@ def test_raw_stream_multi_gpu_dynamic_queue(tmp_path):
 
     with pytest.raises(BrokenPipeError):
         raw_stream.stream_multi(Pipe(frames.tobytes()), ClosedPipe(), 8, 6, scale=2, gpus=[0, 1, 2], chunk=2, make_engines=lambda g: (None, None, Jitter(g)))
+
+
+def test_host_helpers_behave_like_the_reference_code(caplog):
+    """`get_frames` and `logging_callback` against the reference's own functions, imported unmodified with the two modules it
+    cannot import here stubbed (tools/make_ref_glue_goldens.py::import_reference) -- only where /root/reference exists."""
+    import logging
+    if not os.path.exists("/root/reference/upscale/upscale_processing.py"):
+        pytest.skip("the reference tree is only present in the build container")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import make_ref_glue_goldens as glue
+    finally:
+        sys.path.pop(0)
+    keep = {m: sys.modules.get(m) for m in ("ncnn_vulkan", "wakepy")}
+    try:
+        ref = glue.import_reference()
+    finally:
+        for m, v in keep.items():
+            if v is None:
+                sys.modules.pop(m, None)
+            else:
+                sys.modules[m] = v
+    from upscale_video_b200 import upscale_processing as up
+
+    def outcome(fn, *a):
+        try:
+            return ("ok", fn(*a))
+        except SystemExit as e:
+            return ("exit", str(e.code))
+        except Exception as e:  # noqa: BLE001 -- the exception TYPE is part of the behaviour compared
+            return ("raise", type(e).__name__)
+
+    for spec in ("1", "1,3-5", "7-7", "5-3", "10,2,2", "1-3,2-4", " 4 , 6-8", "", "a", "1-", "1-2-3", "3,,4"):
+        assert outcome(up.get_frames, spec) == outcome(ref.get_frames, spec), spec
+    for items in ([], [["info", "a"], ["debug", "b"]], [["info", "a"], ["error", "boom"], ["info", "never logged"]], [["error", ValueError("x")]],
+                  [["warning", "ignored level"]]):
+        caplog.clear()
+        with caplog.at_level(logging.DEBUG):
+            mine = outcome(up.logging_callback, items)
+        mine_log = [(r.levelname, r.getMessage()) for r in caplog.records]
+        caplog.clear()
+        with caplog.at_level(logging.DEBUG):
+            theirs = outcome(ref.logging_callback, items)
+        assert mine == theirs and mine_log == [(r.levelname, r.getMessage()) for r in caplog.records], items

@@ -452,6 +452,30 @@ def test_worker_functions_on_png_files(engines, oracle_models, model_dir, tmp_pa
     up._release_engine()
 
 
+def test_log_items_equal_the_reference_codes(model_dir, tmp_path, monkeypatch):
+    """The result protocol (lists of [level, message], reference logging_callback :40-51): the items `upscale_image` returns for
+    every form of `frame_batch` (:521-540), without an output file (test_gpus.py:22-31), and `apply_model` (:298) are the ones the
+    reference's own functions returned for the same calls (tests/golden/ref_glue.npz, tools/make_ref_glue_goldens.py)."""
+    import json
+    import cv2
+    from upscale_video_b200 import upscale_processing as up
+    g = golden("ref_glue")
+    want = json.loads(bytes(g["log_items_json"]).decode())
+    img = g["log_items_input"]
+    monkeypatch.chdir(tmp_path)
+    up.init_worker([0], 0, model_dir, "x_Compact_Pretrain", 2, "input", "output")
+    for key, frame_batch, out_name in (("batch_none", None, "7.png"), ("batch_int", 3, "7.png"), ("batch_list", [7, 9], "7.png"),
+                                       ("no_output_file", None, None)):
+        cv2.imwrite("7.extract.png", img)
+        got = up.upscale_image("7.extract.png", out_name, 2, frame_batch, 7, 12, remove=key != "no_output_file")
+        assert got == want[key], key
+        assert os.path.exists("7.extract.png") == (key == "no_output_file")
+    up.init_worker([0], 0, model_dir, "x_HurrDeblur_SubCompact_nf24-nc8_244k_net_g", 1, "input", "output")
+    cv2.imwrite("7.extract.png", img)
+    assert up.apply_model("7.extract.png", "7.anime.png", True) == want["apply_model"]
+    up._release_engine()
+
+
 def test_upscale_frames_pool_two_workers_one_gpu(oracle_models, model_dir, tmp_path, monkeypatch):
     """`-g 0,0`: two spawned workers sharing GPU 0, dynamic frame queue, inputs deleted when done, missing
     inputs skipped (reference upscale_frames :545-601)."""

@@ -163,6 +163,28 @@ def main():
                 out[name + "__x"] = np.ascontiguousarray(img)
                 out[name + "__y"] = got
             print("%-26s %s -> %s  (%s, scale %d, %s)" % (name, img.shape, got.shape, fn, scale, model_file), flush=True)
+    # the log items the reference's functions return (the result protocol of logging_callback, upscale_processing.py:40-51):
+    # every frame_batch form of upscale_image :521-540 and apply_model :298, with relative file names in a scratch directory
+    import json
+    logs = {}
+    img = sample[600:612, 500:1480]  # two tiles
+    with tempfile.TemporaryDirectory() as tmp:
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            ref.init_worker([0], 0, os.path.join(REF, "models"), "x_Compact_Pretrain", 2, "input", "output")
+            for key, frame_batch, out_name in (("batch_none", None, "7.png"), ("batch_int", 3, "7.png"), ("batch_list", [7, 9], "7.png"),
+                                               ("no_output_file", None, None)):
+                cv2.imwrite("7.extract.png", img)
+                logs[key] = ref.upscale_image("7.extract.png", out_name, 2, frame_batch, 7, 12, remove=key != "no_output_file")
+            ref.init_worker([0], 0, os.path.join(REF, "models"), HURR, 1, "input", "output")
+            cv2.imwrite("7.extract.png", img)
+            logs["apply_model"] = ref.apply_model("7.extract.png", "7.anime.png", True)
+        finally:
+            os.chdir(cwd)
+    out["log_items_input"] = np.ascontiguousarray(img)
+    out["log_items_json"] = np.frombuffer(json.dumps(logs).encode(), np.uint8)
+    print("log items:", json.dumps(logs)[:300], "...")
     path = os.path.join(ROOT, "tests", "golden", "ref_glue.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

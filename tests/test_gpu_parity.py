@@ -510,6 +510,32 @@ def test_upscale_frames_pool_two_workers_one_gpu(oracle_models, model_dir, tmp_p
     assert not up._pools
 
 
+def test_pool_functions_leave_what_the_reference_codes_leave(model_dir, tmp_path, monkeypatch, caplog):
+    """`process_model` then `upscale_frames` over a directory of frames with a gap, two workers on GPU 0: the files that exist
+    afterwards and the lines logged in the parent are the ones the reference's OWN two functions (spawn pools and all) left in the
+    build container for the same calls (tests/golden/ref_glue.npz "pool", tools/make_ref_glue_goldens.py::pool_behaviour)."""
+    import json
+    import logging
+    import cv2
+    import multiprocessing.process as mpp
+    from upscale_video_b200 import upscale_processing as up
+    want = json.loads(bytes(golden("ref_glue")["log_items_json"]).decode())["pool"]
+    monkeypatch.chdir(tmp_path)
+    for n in (1, 2, 4, 5):
+        cv2.imwrite("%d.extract.png" % n, natural(10, 24, seed=70 + n))
+    used = next(mpp._process_counter)
+    with caplog.at_level(logging.DEBUG):
+        up.process_model(5, model_dir, HURR[1:] if HURR[0].isdigit() else HURR, 1, "input", "output", "extract", "anime", [0, 0], used)
+    lines = sorted([r.levelname, r.getMessage()] for r in caplog.records if r.name == "root")
+    assert sorted(os.listdir(".")) == want["after_process_model"] and lines == want["log_process_model"]
+    caplog.clear()
+    with caplog.at_level(logging.DEBUG):
+        up.upscale_frames(2, 1, 5, "anime", 2, [0, 0], used + 2, model_dir, "x_Compact_Pretrain", "input", "output")
+    lines = sorted([r.levelname, r.getMessage()] for r in caplog.records if r.name == "root")
+    assert sorted(os.listdir(".")) == want["after_upscale_frames"] and lines == want["log_upscale_frames"]
+    up.release_workers()
+
+
 def test_raw_stream_matches_worker_functions(engines, model_dir, tmp_path):
     """the raw-frame stream (no PNG hop, chained pre-pass on the device) produces exactly the pixels
     the per-frame worker functions produce: apply_model (u8) -> upscale_image."""

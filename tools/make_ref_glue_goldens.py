@@ -113,6 +113,59 @@ def import_reference():
     return mod
 
 
+def pool_behaviour(sample):
+    """The reference's `process_model` and `upscale_frames` themselves (spawn pools, one worker per -g entry, upscale_processing.py
+    :302-347, :545-601) on a scratch directory of PNG frames with a gap: which files exist afterwards, what was logged.  The
+    third-party modules are importable stubs here (tools/ref_stubs), so the spawned workers import the reference by its real name."""
+    import importlib
+    import logging
+    stubs = os.path.join(ROOT, "tools", "ref_stubs")
+    for pth in (REF, os.path.join(ROOT, "tools"), stubs):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    for m in ("ncnn_vulkan", "wakepy", "upscale", "upscale.upscale_processing"):
+        sys.modules.pop(m, None)
+    refpkg = importlib.import_module("upscale.upscale_processing")
+    assert refpkg.__file__ == os.path.join(REF, "upscale", "upscale_processing.py")
+    records = []
+
+    class Collect(logging.Handler):
+        def emit(self, record):
+            records.append([record.levelname, record.getMessage()])
+
+    root = logging.getLogger()
+    handler, level = Collect(), root.level
+    root.addHandler(handler)
+    root.setLevel(logging.DEBUG)
+    result = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            frames = {}
+            for n in (1, 2, 4, 5):  # frame 3 is missing: finished by an earlier run (the resume contract)
+                frames[n] = np.ascontiguousarray(sample[100 * n:100 * n + 10, 300:324])
+                cv2.imwrite("%d.extract.png" % n, frames[n])
+            workers = 0
+            refpkg.process_model(5, os.path.join(REF, "models"), HURR, 1, "input", "output", "extract", "anime", [0, 0], workers)
+            result["after_process_model"] = sorted(os.listdir("."))
+            result["log_process_model"] = sorted(records)
+            del records[:]
+            workers += 2
+            refpkg.upscale_frames(2, 1, 5, "anime", 2, [0, 0], workers, os.path.join(REF, "models"), "x_Compact_Pretrain", "input", "output")
+            result["after_upscale_frames"] = sorted(os.listdir("."))
+            result["log_upscale_frames"] = sorted(records)
+            del records[:]
+            for n in frames:
+                assert cv2.imread("%d.png" % n).shape == (20, 48, 3)
+        finally:
+            os.chdir(cwd)
+            root.removeHandler(handler)
+            root.setLevel(level)
+    print("pool behaviour:", result)
+    return result
+
+
 def main():
     ref = import_reference()
     import multiprocessing
@@ -182,6 +235,7 @@ def main():
             logs["apply_model"] = ref.apply_model("7.extract.png", "7.anime.png", True)
         finally:
             os.chdir(cwd)
+    logs["pool"] = pool_behaviour(sample)
     out["log_items_input"] = np.ascontiguousarray(img)
     out["log_items_json"] = np.frombuffer(json.dumps(logs).encode(), np.uint8)
     print("log items:", json.dumps(logs)[:300], "...")
